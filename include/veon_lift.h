@@ -1,0 +1,205 @@
+/*
+ * veon_lift.h -- C ABI of libveonlift.so: the B200 (sm_100a) implementation of
+ * VEON's 2D->3D lifting hot path.
+ *
+ * Plain pointers and sizes only; no torch / ATen types.  All pointers are
+ * DEVICE pointers on the current CUDA device unless the parameter is marked
+ * [host].  `stream` is a cudaStream_t passed as void* (NULL = legacy default
+ * stream, which is what the reference launches on, bev_pool_cuda.cu:127,136).
+ * Nothing here allocates, synchronises the host, or keeps state between calls;
+ * the caller owns every buffer (same ownership rule as the reference,
+ * bev_pool.py:27,67-68).
+ *
+ * Return value: 0 on success, a positive cudaError_t on a CUDA failure, or a
+ * negative VEON_E_* code for argument errors.  (The reference checks nothing:
+ * bev_pool.cpp has no CHECK_* macros and no cudaGetLastError.)
+ *
+ * Citations are relative to /root/reference.
+ */
+#ifndef VEON_LIFT_H_
+#define VEON_LIFT_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VEON_ABI_VERSION 1
+
+#define VEON_E_BADARG    (-1)  /* NULL pointer / non-positive dimension          */
+#define VEON_E_WORKSPACE (-2)  /* workspace smaller than *_workspace_bytes()     */
+#define VEON_E_RANGE     (-3)  /* index space does not fit the int32 rank arrays */
+#define VEON_E_UNSUPPORTED (-4)
+
+/* Feature-volume layouts.  The reference kernel writes channels-last
+ * (out[rank*C + c], bev_pool_cuda.cu:46) and bev_pool.py:91 then transposes to
+ * channels-first; the fast path here emits channels-first directly. */
+#define VEON_LAYOUT_BZYXC 0   /* [B, Z, Y, X, C]  (reference kernel layout)     */
+#define VEON_LAYOUT_BCZYX 1   /* [B, C, Z, Y, X]  (what bev_pool_v2() returns)  */
+
+/* plan-validation flag bits written by veon_pool_plan_build() */
+#define VEON_PLAN_UNSORTED       1   /* ranks_bev not non-decreasing                       */
+#define VEON_PLAN_BAD_INTERVALS  2   /* intervals are not exactly the runs of ranks_bev    */
+#define VEON_PLAN_NONCANONICAL   4   /* ranks_feat != pixel-of(ranks_depth)                */
+#define VEON_PLAN_OUT_OF_RANGE   8   /* an index outside its tensor                        */
+#define VEON_PLAN_DUPLICATE     16   /* a depth element referenced twice                   */
+
+int veon_abi_version(void);
+/* static string for any code returned by this library */
+const char* veon_error_string(int code);
+
+/* ------------------------------------------------------------------------
+ * (1) Literal drop-ins for the two functions bev_pool.cpp binds
+ *     (bev_pool.cpp:7-14; kernels bev_pool_cuda.cu:21-48, 67-121; launchers
+ *     :125-140).  Same arguments in the same order plus a stream; same
+ *     semantics: channels-last `out` / `out_grad`, caller-zeroed outputs, one
+ *     output row per interval, intervals taken as given (for the backward they
+ *     are the by-ranks_feat intervals built at bev_pool.py:47-57).  Indexing is
+ *     64-bit (the reference's 32-bit `rank * c` overflows at C4).
+ * ------------------------------------------------------------------------ */
+int veon_bev_pool_v2(int c, int n_intervals,
+                     const float* depth, const float* feat,
+                     const int32_t* ranks_depth, const int32_t* ranks_feat,
+                     const int32_t* ranks_bev,
+                     const int32_t* interval_starts,
+                     const int32_t* interval_lengths,
+                     float* out, void* stream);
+
+int veon_bev_pool_v2_grad(int c, int n_intervals, const float* out_grad,
+                          const float* depth, const float* feat,
+                          const int32_t* ranks_depth, const int32_t* ranks_feat,
+                          const int32_t* ranks_bev,
+                          const int32_t* interval_starts,
+                          const int32_t* interval_lengths,
+                          float* depth_grad, float* feat_grad, void* stream);
+
+/* Same two operations for arbitrary (unsorted / non-canonical) rank arrays but
+ * with a selectable volume layout; `voxels_per_sample` = Z*Y*X is needed to
+ * split a rank into (b, voxel) for VEON_LAYOUT_BCZYX.  Used by the Python
+ * operator when veon_pool_plan_build() rejects the ranks.  The backward is
+ * point-driven (it needs no by-ranks_feat intervals): feat_grad is accumulated
+ * with float atomics (order not deterministic).  Outputs must be zeroed by the
+ * caller. */
+int veon_bev_pool_v2_generic(int c, int n_intervals, int layout,
+                             int64_t voxels_per_sample,
+                             const float* depth, const float* feat,
+                             const int32_t* ranks_depth, const int32_t* ranks_feat,
+                             const int32_t* ranks_bev,
+                             const int32_t* interval_starts,
+                             const int32_t* interval_lengths,
+                             float* out, void* stream);
+
+int veon_bev_pool_v2_grad_generic(int c, int64_t n_points, int layout,
+                                  int64_t voxels_per_sample, const float* out_grad,
+                                  const float* depth, const float* feat,
+                                  const int32_t* ranks_depth, const int32_t* ranks_feat,
+                                  const int32_t* ranks_bev,
+                                  float* depth_grad, float* feat_grad, void* stream);
+
+/* ------------------------------------------------------------------------
+ * (2) voxel_pooling_prepare_v2 (view_transformer.py:202-260; duplicated at
+ *     view_transformer_raw.py:244-302).
+ *
+ *  coor            [B,N,D,H,W,3] float32, contiguous
+ *  lower/interval/grid_size  [host] float32[3] = grid_lower_bound,
+ *                  grid_interval, grid_size (view_transformer.py:79-82; all
+ *                  three are FLOAT tensors in the reference and every rank is
+ *                  computed in float32, :241-244 -- reproduced bit for bit)
+ *  outputs, each with capacity P = B*N*D*H*W int32:
+ *      ranks_bev, ranks_depth, ranks_feat   first n_kept entries valid
+ *      interval_starts, interval_lengths    first n_int  entries valid
+ *  counts          device int64[2] = {n_kept, n_int}
+ *  Order: points sorted by ranks_bev; inside one voxel by ascending
+ *  ranks_depth (the reference's argsort is unstable, so its in-voxel order is
+ *  arbitrary; ours is the canonical stable one).
+ *
+ *  Optional by-products ("plan") consumed by the *_planar pool entry points
+ *  (pass NULL to skip all three):
+ *      tile_start   int32[n_tiles+1]  first point of each 32-voxel tile
+ *      tile_istart  int32[n_tiles+1]  first interval of each tile
+ *      point_interval int32[P]        interval index of depth element
+ *                   (b,n,d,h,w) stored PIXEL-major at ((b*N+n)*H*W+hw)*D+d,
+ *                   -1 where the point was dropped
+ *    with n_tiles = B * ceil(Z*Y*X / 32), see veon_pool_num_tiles().
+ * ------------------------------------------------------------------------ */
+size_t veon_prepare_v2_workspace_bytes(int B, int N, int D, int H, int W,
+                                       const float* grid_size /*[host]*/);
+int64_t veon_pool_num_tiles(int B, int64_t voxels_per_sample);
+
+int veon_prepare_v2(const float* coor, int B, int N, int D, int H, int W,
+                    const float* lower, const float* interval,
+                    const float* grid_size,
+                    int32_t* ranks_bev, int32_t* ranks_depth, int32_t* ranks_feat,
+                    int32_t* interval_starts, int32_t* interval_lengths,
+                    int64_t* counts,
+                    int32_t* tile_start, int32_t* tile_istart,
+                    int32_t* point_interval,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* Build the same plan from rank arrays the caller already holds (the
+ * `accelerate=True` cache, view_transformer.py:154-173, or any user input) and
+ * validate them.  *flags (device int32) receives an OR of VEON_PLAN_* bits; the
+ * planar entry points are only valid for flags == 0. */
+int veon_pool_plan_build(const int32_t* ranks_depth, const int32_t* ranks_feat,
+                         const int32_t* ranks_bev,
+                         const int32_t* interval_starts,
+                         const int32_t* interval_lengths,
+                         int64_t n_points, int64_t n_intervals,
+                         int B, int N, int D, int H, int W,
+                         int64_t voxels_per_sample,
+                         int32_t* tile_start, int32_t* tile_istart,
+                         int32_t* point_interval, int32_t* flags, void* stream);
+
+/* ------------------------------------------------------------------------
+ * (3) Fast pooling path: bev_pool_v2() INCLUDING its transpose
+ *     (bev_pool.py:86-92 = QuickCumsumCuda.forward :17-41 + permute :91).
+ *     `out` is [B,C,Z,Y,X]; every element is written exactly once (zeros for
+ *     empty voxels), so the caller need not zero it.  Requires a valid plan.
+ * ------------------------------------------------------------------------ */
+int veon_bev_pool_v2_fwd_planar(const float* depth, const float* feat,
+                                const int32_t* ranks_depth,
+                                const int32_t* ranks_feat,
+                                const int32_t* ranks_bev,
+                                const int32_t* tile_start,
+                                int B, int C, int64_t voxels_per_sample,
+                                float* out, void* stream);
+
+/* QuickCumsumCuda.backward (bev_pool.py:43-83) for a [B,C,Z,Y,X] out_grad.
+ *   rows_ws      float[n_intervals * C] scratch (compacted gradient rows)
+ *   depth_grad   [B,N,D,H,W], feat_grad [B,N,H,W,C]: fully written (no need to
+ *                zero).  Deterministic: no atomics, fixed summation order. */
+int veon_bev_pool_v2_bwd_planar(const float* out_grad,
+                                const float* depth, const float* feat,
+                                const int32_t* ranks_bev,
+                                const int32_t* interval_starts,
+                                const int32_t* tile_start,
+                                const int32_t* tile_istart,
+                                const int32_t* point_interval,
+                                int64_t n_intervals,
+                                int B, int N, int D, int H, int W, int C,
+                                int64_t voxels_per_sample,
+                                float* rows_ws,
+                                float* depth_grad, float* feat_grad,
+                                void* stream);
+
+/* ------------------------------------------------------------------------
+ * (4) Open-vocabulary tail: voxel-feature x text-embedding logits, per-class
+ *     max over prompts, argmax, occupancy gate, uint8 labels.
+ *       semantic_inference_3d   san_in_veon_temporal.py:257-259
+ *       _merge_classes_prob     san_in_veon_entry_temporal.py:273-297
+ *       label rule              veon_temporal.py:223-229,240
+ *   feat_occ [B,C,Z,Y,X] f32; text_w [Q,C] f32; class_of_prompt [Q] int32
+ *   (non-decreasing, the merged class of every prompt row incl. the trailing
+ *   background row); bin_occ [B,2,Z,Y,X] f32; labels uint8 [B,X,Y,Z].
+ * ------------------------------------------------------------------------ */
+int veon_voxel_text_argmax(const float* feat_occ, const float* text_w,
+                           const int32_t* class_of_prompt, const float* bin_occ,
+                           int B, int C, int Q, int Z, int Y, int X,
+                           int free_label, uint8_t* labels, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* VEON_LIFT_H_ */

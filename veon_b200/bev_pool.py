@@ -1,0 +1,360 @@
+"""BEVPoolv2 operator surface on libveonlift (B200 / sm_100a).
+
+Mirrors `mmdet3d/ops/bev_pool_v2/bev_pool.py` of the reference:
+
+    bev_pool_v2(depth, feat, ranks_depth, ranks_feat, ranks_bev,
+                bev_feat_shape, interval_starts, interval_lengths)   :86-92
+    QuickCumsumCuda (torch.autograd.Function)                         :11-83
+    TRTBEVPoolv2                                                      :95-142
+
+plus the index preparation the necks call before it,
+
+    voxel_pooling_prepare_v2(coor, grid_lower_bound, grid_interval, grid_size)
+        = LSSViewTransformer.voxel_pooling_prepare_v2, view_transformer.py:202-260
+
+What differs underneath: the volume is produced channels-first
+in one pass (no memset, no permute copy), the backward needs no argsort, and a
+"plan" (tile tables + point->interval table) rides along with the rank
+tensors.  Everything runs in CUDA through the C ABI; there is no CPU path.
+"""
+import collections
+import ctypes
+
+import torch
+
+from . import _lib
+
+__all__ = ["bev_pool_v2", "QuickCumsumCuda", "TRTBEVPoolv2",
+           "voxel_pooling_prepare_v2", "prepare_ranks", "PreparedRanks",
+           "pool_prepared"]
+
+LAYOUT_BZYXC, LAYOUT_BCZYX = 0, 1
+TILE_VOXELS = 32
+
+
+def _stream_ptr(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if not t.is_cuda:
+            raise RuntimeError(
+                "veon_b200 runs on CUDA tensors only (there is no CPU fallback); "
+                f"got a tensor on {t.device}")
+
+
+class PoolPlan:
+    """By-products of the index preparation used by the planar kernels."""
+    __slots__ = ("tile_start", "tile_istart", "point_interval", "dims", "V",
+                 "flags", "_n_intervals", "_n_points", "counts_dev", "counts_host",
+                 "counts_event", "keepalive")
+
+    def __init__(self):
+        self.flags = 0
+        self._n_intervals = None
+        self._n_points = None
+        self.counts_dev = self.counts_host = self.counts_event = None
+        self.keepalive = None
+
+    def _resolve(self):
+        if self._n_intervals is None:
+            self.counts_event.synchronize()
+            self._n_points = int(self.counts_host[0])
+            self._n_intervals = int(self.counts_host[1])
+
+    @property
+    def n_intervals(self):
+        self._resolve()
+        return self._n_intervals
+
+    @property
+    def n_points(self):
+        self._resolve()
+        return self._n_points
+
+    @property
+    def ok(self):
+        return self.flags == 0
+
+
+class PreparedRanks:
+    """Device-side result of the index preparation (capacity-sized buffers;
+    the valid prefix lengths live in `plan.counts_dev` / `plan.n_points`)."""
+    __slots__ = ("ranks_bev", "ranks_depth", "ranks_feat", "interval_starts",
+                 "interval_lengths", "plan", "shape")
+
+
+def prepare_ranks(coor, grid_lower_bound, grid_interval, grid_size):
+    """Launch the GPU index preparation; returns without a host sync.
+
+    coor: [B,N,D,H,W,3] float tensor on CUDA.  The three grid vectors are the
+    reference's float32 tensors (view_transformer.py:79-82) or any 3-sequence.
+    """
+    _require_cuda(coor)
+    if coor.dim() != 6 or coor.shape[-1] != 3:
+        raise ValueError(f"coor must be [B,N,D,H,W,3], got {tuple(coor.shape)}")
+    lib = _lib.load()
+    coor = coor.detach().contiguous().float()
+    B, N, D, H, W, _ = coor.shape
+    P = B * N * D * H * W
+    dev = coor.device
+    lower = [float(v) for v in grid_lower_bound]
+    interval = [float(v) for v in grid_interval]
+    size = [float(v) for v in grid_size]
+    V = int(size[0]) * int(size[1]) * int(size[2])
+    c_size = _lib.float3(size)
+    ws_bytes = lib.veon_prepare_v2_workspace_bytes(B, N, D, H, W, c_size)
+    if ws_bytes == 0:
+        raise _lib.VeonError(-3, "veon_prepare_v2_workspace_bytes")
+    n_tiles = lib.veon_pool_num_tiles(B, V)
+    with torch.cuda.device(dev):
+        ranks = torch.empty((5, P), dtype=torch.int32, device=dev)
+        tiles = torch.empty((2, n_tiles + 1), dtype=torch.int32, device=dev)
+        point_interval = torch.empty(P, dtype=torch.int32, device=dev)
+        counts = torch.empty(2, dtype=torch.int64, device=dev)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        rc = lib.veon_prepare_v2(
+            _ptr(coor), B, N, D, H, W, _lib.float3(lower), _lib.float3(interval), c_size,
+            _ptr(ranks[0]), _ptr(ranks[1]), _ptr(ranks[2]), _ptr(ranks[3]), _ptr(ranks[4]),
+            _ptr(counts), _ptr(tiles[0]), _ptr(tiles[1]), _ptr(point_interval),
+            _ptr(ws), ws_bytes, _stream_ptr(dev))
+        _lib.check(rc, "veon_prepare_v2")
+        counts_host = torch.empty(2, dtype=torch.int64, pin_memory=True)
+        counts_host.copy_(counts, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev))
+    plan = PoolPlan()
+    plan.tile_start, plan.tile_istart = tiles[0], tiles[1]
+    plan.point_interval = point_interval
+    plan.dims = (B, N, D, H, W)
+    plan.V = V
+    plan.counts_dev, plan.counts_host, plan.counts_event = counts, counts_host, ev
+    out = PreparedRanks()
+    out.ranks_bev, out.ranks_depth, out.ranks_feat = ranks[0], ranks[1], ranks[2]
+    out.interval_starts, out.interval_lengths = ranks[3], ranks[4]
+    out.plan = plan
+    out.shape = (B, N, D, H, W)
+    return out
+
+
+# ---------------------------------------------------------------- plan cache
+_PLAN_CACHE = collections.OrderedDict()
+_PLAN_CACHE_SIZE = 8
+
+
+def _plan_key(rd, rf, rb, ist, iln, dims, V):
+    return (rd.data_ptr(), rf.data_ptr(), rb.data_ptr(), ist.data_ptr(), iln.data_ptr(),
+            rd.numel(), ist.numel(), rd._version, rf._version, rb._version,
+            ist._version, iln._version, dims, V, rd.device.index)
+
+
+def _remember_plan(key, plan, tensors):
+    plan.keepalive = tensors  # pins the addresses the key is made of
+    _PLAN_CACHE[key] = plan
+    _PLAN_CACHE.move_to_end(key)
+    while len(_PLAN_CACHE) > _PLAN_CACHE_SIZE:
+        _PLAN_CACHE.popitem(last=False)
+
+
+def _plan_for(rd, rf, rb, ist, iln, dims, V):
+    """Plan for caller-held rank tensors: cached, else built + validated."""
+    key = _plan_key(rd, rf, rb, ist, iln, dims, V)
+    plan = _PLAN_CACHE.get(key)
+    if plan is not None:
+        _PLAN_CACHE.move_to_end(key)
+        return plan
+    lib = _lib.load()
+    B, N, D, H, W = dims
+    dev = rb.device
+    P = B * N * D * H * W
+    n_tiles = lib.veon_pool_num_tiles(B, V)
+    with torch.cuda.device(dev):
+        tiles = torch.empty((2, n_tiles + 1), dtype=torch.int32, device=dev)
+        point_interval = torch.empty(P, dtype=torch.int32, device=dev)
+        flags = torch.zeros(1, dtype=torch.int32, device=dev)
+        rc = lib.veon_pool_plan_build(
+            _ptr(rd), _ptr(rf), _ptr(rb), _ptr(ist), _ptr(iln), rd.numel(), ist.numel(),
+            B, N, D, H, W, V, _ptr(tiles[0]), _ptr(tiles[1]), _ptr(point_interval),
+            _ptr(flags), _stream_ptr(dev))
+        _lib.check(rc, "veon_pool_plan_build")
+        plan = PoolPlan()
+        plan.flags = int(flags.item())  # one sync per distinct rank set
+    plan.tile_start, plan.tile_istart = tiles[0], tiles[1]
+    plan.point_interval = point_interval
+    plan.dims, plan.V = dims, V
+    plan._n_points, plan._n_intervals = rd.numel(), ist.numel()
+    _remember_plan(key, plan, (rd, rf, rb, ist, iln))
+    return plan
+
+
+def voxel_pooling_prepare_v2(coor, grid_lower_bound, grid_interval, grid_size):
+    """Same contract as the reference method (view_transformer.py:202-260):
+    returns (ranks_bev, ranks_depth, ranks_feat, interval_starts,
+    interval_lengths), int32 contiguous on coor.device, or five `None`s when
+    nothing can be pooled (:236-237, :253-254)."""
+    if coor.numel() == 0:
+        return None, None, None, None, None
+    prep = prepare_ranks(coor, grid_lower_bound, grid_interval, grid_size)
+    n_kept, n_int = prep.plan.n_points, prep.plan.n_intervals  # host sync
+    if n_int == 0:
+        return None, None, None, None, None
+    rb, rd, rf = prep.ranks_bev[:n_kept], prep.ranks_depth[:n_kept], prep.ranks_feat[:n_kept]
+    ist, iln = prep.interval_starts[:n_int], prep.interval_lengths[:n_int]
+    key = _plan_key(rd, rf, rb, ist, iln, prep.shape, prep.plan.V)
+    _remember_plan(key, prep.plan, (rd, rf, rb, ist, iln))
+    return rb, rd, rf, ist, iln
+
+
+# ------------------------------------------------------------------ pooling
+def _fwd_planar(depth, feat, rd, rf, rb, plan, B, C, V, shape5):
+    lib = _lib.load()
+    dev = feat.device
+    with torch.cuda.device(dev):
+        out = torch.empty(shape5, dtype=torch.float32, device=dev)  # [B,C,Z,Y,X]
+        rc = lib.veon_bev_pool_v2_fwd_planar(
+            _ptr(depth), _ptr(feat), _ptr(rd), _ptr(rf), _ptr(rb), _ptr(plan.tile_start),
+            B, C, V, _ptr(out), _stream_ptr(dev))
+    _lib.check(rc, "veon_bev_pool_v2_fwd_planar")
+    return out
+
+
+def _bwd_planar(grad_planar, depth, feat, rb, ist, plan, C):
+    lib = _lib.load()
+    dev = feat.device
+    B, N, D, H, W = plan.dims
+    n_int = plan.n_intervals
+    with torch.cuda.device(dev):
+        depth_grad = torch.empty_like(depth)
+        feat_grad = torch.empty_like(feat)
+        rows = torch.empty(max(n_int, 1) * C, dtype=torch.float32, device=dev)
+        rc = lib.veon_bev_pool_v2_bwd_planar(
+            _ptr(grad_planar), _ptr(depth), _ptr(feat), _ptr(rb), _ptr(ist),
+            _ptr(plan.tile_start), _ptr(plan.tile_istart), _ptr(plan.point_interval),
+            n_int, B, N, D, H, W, C, plan.V, _ptr(rows), _ptr(depth_grad), _ptr(feat_grad),
+            _stream_ptr(dev))
+    _lib.check(rc, "veon_bev_pool_v2_bwd_planar")
+    return depth_grad, feat_grad
+
+
+class QuickCumsumCuda(torch.autograd.Function):
+    """Same signature and result as the reference Function (bev_pool.py:11-83):
+    returns the pooled volume shaped [B,Z,Y,X,C].  It is a permuted VIEW of a
+    channels-first buffer, so the `.permute(0,4,1,2,3).contiguous()` that
+    `bev_pool_v2` applies next (bev_pool.py:91) is free."""
+
+    @staticmethod
+    def forward(ctx, depth, feat, ranks_depth, ranks_feat, ranks_bev,
+                bev_feat_shape, interval_starts, interval_lengths, *extra):
+        # `extra` = (PoolPlan,) when called from this package; the reference's
+        # 8-argument call is accepted unchanged
+        plan = extra[0] if extra else None
+        ctx.n_extra = len(extra)
+        _require_cuda(depth, feat, ranks_depth, ranks_feat, ranks_bev,
+                      interval_starts, interval_lengths)
+        if depth.dim() != 5 or feat.dim() != 5:
+            raise ValueError("depth must be [B,N,D,H,W] and feat [B,N,H,W,C]")
+        ranks_bev = ranks_bev.int().contiguous()
+        depth = depth.contiguous().float()
+        feat = feat.contiguous().float()
+        ranks_depth = ranks_depth.contiguous().int()
+        ranks_feat = ranks_feat.contiguous().int()
+        interval_lengths = interval_lengths.contiguous().int()
+        interval_starts = interval_starts.contiguous().int()
+        B, Z, Y, X, C = (int(v) for v in bev_feat_shape)
+        if feat.shape[-1] != C:
+            raise ValueError("bev_feat_shape[-1] must equal feat.shape[-1]")
+        V = Z * Y * X
+        dims = tuple(int(v) for v in depth.shape)
+        if plan is None:
+            plan = _plan_for(ranks_depth, ranks_feat, ranks_bev, interval_starts,
+                             interval_lengths, dims, V)
+        if plan.ok:
+            out = _fwd_planar(depth, feat, ranks_depth, ranks_feat, ranks_bev, plan,
+                              B, C, V, (B, C, Z, Y, X))
+        else:
+            lib = _lib.load()
+            out = feat.new_zeros((B, C, Z, Y, X))
+            with torch.cuda.device(feat.device):
+                rc = lib.veon_bev_pool_v2_generic(
+                    C, interval_starts.numel(), LAYOUT_BCZYX, V, _ptr(depth), _ptr(feat),
+                    _ptr(ranks_depth), _ptr(ranks_feat), _ptr(ranks_bev),
+                    _ptr(interval_starts), _ptr(interval_lengths), _ptr(out),
+                    _stream_ptr(feat.device))
+            _lib.check(rc, "veon_bev_pool_v2_generic")
+        ctx.save_for_backward(ranks_bev, depth, feat, ranks_feat, ranks_depth, interval_starts)
+        ctx.plan = plan
+        ctx.vol = (B, C, Z, Y, X)
+        return out.permute(0, 2, 3, 4, 1)
+
+    @staticmethod
+    def backward(ctx, out_grad):
+        ranks_bev, depth, feat, ranks_feat, ranks_depth, interval_starts = ctx.saved_tensors
+        B, C, Z, Y, X = ctx.vol
+        plan = ctx.plan
+        g = out_grad.permute(0, 4, 1, 2, 3)  # back to the channels-first storage order
+        if g.dtype != torch.float32 or not g.is_contiguous():
+            g = g.float().contiguous()
+        if plan.ok:
+            depth_grad, feat_grad = _bwd_planar(g, depth, feat, ranks_bev, interval_starts,
+                                                plan, C)
+        else:
+            lib = _lib.load()
+            depth_grad = torch.zeros_like(depth)
+            feat_grad = torch.zeros_like(feat)
+            with torch.cuda.device(feat.device):
+                rc = lib.veon_bev_pool_v2_grad_generic(
+                    C, ranks_bev.numel(), LAYOUT_BCZYX, Z * Y * X, _ptr(g), _ptr(depth),
+                    _ptr(feat), _ptr(ranks_depth), _ptr(ranks_feat), _ptr(ranks_bev),
+                    _ptr(depth_grad), _ptr(feat_grad), _stream_ptr(feat.device))
+            _lib.check(rc, "veon_bev_pool_v2_grad_generic")
+        return (depth_grad, feat_grad, None, None, None, None, None, None) + (None,) * ctx.n_extra
+
+
+def bev_pool_v2(depth, feat, ranks_depth, ranks_feat, ranks_bev,
+                bev_feat_shape, interval_starts, interval_lengths):
+    """Drop-in for the reference `bev_pool_v2` (bev_pool.py:86-92).
+
+    depth [B,N,D,H,W]; feat [B,N,H,W,C] (any strides); int32 rank / interval
+    tensors; bev_feat_shape = (B,Z,Y,X,C).  Returns [B,C,Z,Y,X] float32
+    contiguous, differentiable w.r.t. depth and feat."""
+    x = QuickCumsumCuda.apply(depth, feat, ranks_depth, ranks_feat, ranks_bev,
+                              bev_feat_shape, interval_starts, interval_lengths)
+    x = x.permute(0, 4, 1, 2, 3).contiguous()  # no copy: already channels-first
+    return x
+
+
+def pool_prepared(depth, feat, prep, bev_feat_shape):
+    """bev_pool_v2 on a `PreparedRanks` without any host synchronisation in the
+    forward (the counts are only needed, and by then long available, when the
+    backward sizes its scratch)."""
+    x = QuickCumsumCuda.apply(depth, feat, prep.ranks_depth, prep.ranks_feat, prep.ranks_bev,
+                              bev_feat_shape, prep.interval_starts, prep.interval_lengths,
+                              prep.plan)
+    return x.permute(0, 4, 1, 2, 3).contiguous()
+
+
+class TRTBEVPoolv2(torch.autograd.Function):
+    """ONNX/TensorRT export shim with the reference's symbolic
+    (bev_pool.py:95-142): emits `mmdeploy::bev_pool_v2`; eager `forward`
+    evaluates through `bev_pool_v2` for a single un-batched sample."""
+
+    @staticmethod
+    def symbolic(g, depth, feat, ranks_depth, ranks_feat, ranks_bev, interval_starts,
+                 interval_lengths, out_height=128, out_width=128):
+        return g.op("mmdeploy::bev_pool_v2", depth, feat, ranks_depth, ranks_feat, ranks_bev,
+                    interval_starts, interval_lengths, out_height_i=out_height,
+                    out_width_i=out_width)
+
+    @staticmethod
+    def forward(g, depth, feat, ranks_depth, ranks_feat, ranks_bev, interval_starts,
+                interval_lengths, out_height=128, out_width=128):
+        depth5, feat5 = depth[None], feat[None]          # N,D,H,W -> 1,N,D,H,W
+        shape = (1, 1, out_height, out_width, feat5.shape[-1])
+        bev = bev_pool_v2(depth5, feat5, ranks_depth, ranks_feat, ranks_bev, shape,
+                          interval_starts, interval_lengths)
+        return bev[:, :, 0].permute(0, 2, 3, 1)         # [1, Y, X, C]

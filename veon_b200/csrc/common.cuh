@@ -1,0 +1,44 @@
+// Shared helpers for libveonlift (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/veon_lift.h"
+
+#define VEON_CUDA_TRY(expr)                         \
+  do {                                              \
+    cudaError_t _e = (expr);                        \
+    if (_e != cudaSuccess) return (int)_e;          \
+  } while (0)
+
+#define VEON_LAUNCH_CHECK()                         \
+  do {                                              \
+    cudaError_t _e = cudaGetLastError();            \
+    if (_e != cudaSuccess) return (int)_e;          \
+  } while (0)
+
+namespace veon {
+
+constexpr int kTileVoxels = 32;  // one warp-wide x-run of the output volume
+
+static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// Streaming stores/loads: the feature volume is written once and never re-read
+// by the same kernel, so keep it from evicting the (L2-resident) rank / depth /
+// feature inputs.
+__device__ __forceinline__ void st_stream(float* p, float v) {
+  asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ float ld_stream(const float* p) {
+  float v;
+  asm volatile("ld.global.cs.f32 %0, [%1];" : "=f"(v) : "l"(p));
+  return v;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace veon

@@ -1,0 +1,266 @@
+// bev_pool_v2 backward for a channels-first [B,C,Z,Y,X] out_grad.
+//
+// Reference behaviour: QuickCumsumCuda.backward (bev_pool.py:43-83): argsort by
+// ranks_feat + interval rebuild on every call, `out_grad.contiguous()` (a full
+// transpose back to channels-last, :69), then bev_pool_grad_kernel
+// (bev_pool_cuda.cu:67-121) with ONE THREAD per feature pixel walking all its
+// points and all channels twice, stride-C uncoalesced.
+//
+// Here, two atomic-free passes:
+//   k_bwd_rows    one warp per occupied 32-voxel tile: reads the tile's
+//                 out_grad lines (only the 32-byte sectors that hold an
+//                 occupied voxel), transposes through shared memory and emits
+//                 one compact channel-contiguous row per interval
+//                 (rows[interval, C]).  Empty tiles are never read.
+//   k_bwd_pixels  one warp per feature pixel (the reference's by-ranks_feat
+//                 interval): its kept points come from the pixel-major
+//                 point->interval table the prepare step emitted (no sort),
+//                 the pixel's feature row lives in registers, each point costs
+//                 one row read:  depth_grad[p] = <row, feat>,
+//                 feat_grad += depth[p] * row.  Both outputs are written
+//                 densely (zeros for dropped points), so no memset either.
+// Every output element has exactly one writer and a fixed summation order
+// (ascending depth bin) => bitwise run-to-run deterministic.
+#include "common.cuh"
+
+namespace veon {
+
+constexpr int kBwdWarps = 8;
+constexpr int kPitch = kTileVoxels + 1;
+
+template <int KCH>
+__global__ void __launch_bounds__(kBwdWarps * 32)
+k_bwd_rows(const float* __restrict__ out_grad, const int32_t* __restrict__ ranks_bev,
+           const int32_t* __restrict__ interval_starts,
+           const int32_t* __restrict__ tile_start, const int32_t* __restrict__ tile_istart,
+           int64_t tile_begin, int64_t tile_end, int64_t tiles_per_sample, int64_t V, int C,
+           int n_chunks, float* __restrict__ rows) {
+  constexpr int CC = 32 * KCH;
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* tile = smem + warp * (CC * kPitch);
+  const int64_t group = blockIdx.x / n_chunks;
+  const int cbase = (int)(blockIdx.x - group * n_chunks) * CC;
+  const int64_t t = tile_begin + group * kBwdWarps + warp;
+  if (t >= tile_end) return;
+  const int32_t i0 = __ldg(tile_istart + t);
+  const int ni = __ldg(tile_istart + t + 1) - i0;  // intervals in this tile, <= 32
+  if (ni <= 0) return;                              // empty tile: nothing read
+  const int64_t b = t / tiles_per_sample;
+  const int64_t v0 = (t - b * tiles_per_sample) * kTileVoxels;
+  const int64_t g0 = b * V + v0;
+
+  int vl = 0;
+  if (lane < ni) vl = (int)(__ldg(ranks_bev + __ldg(interval_starts + i0 + lane)) - g0);
+  const uint32_t occ = __reduce_or_sync(0xffffffffu, lane < ni ? (1u << (vl & 31)) : 0u);
+  // fetch only 32-byte sectors (8 voxels) that contain an occupied voxel
+  const bool want = ((occ >> (lane & 24)) & 0xffu) != 0u && (v0 + lane < V);
+  const float* g = out_grad + ((int64_t)b * C + cbase) * V + v0 + lane;
+  const int cmax = min(CC, C - cbase);
+#pragma unroll 8
+  for (int cl = 0; cl < cmax; ++cl)
+    tile[cl * kPitch + lane] = want ? ld_stream(g + (int64_t)cl * V) : 0.f;
+  __syncwarp();
+  for (int j = 0; j < ni; ++j) {
+    const int vj = __shfl_sync(0xffffffffu, vl, j);
+    float* row = rows + (int64_t)(i0 + j) * C + cbase + lane;
+#pragma unroll
+    for (int k = 0; k < KCH; ++k)
+      if (lane + 32 * k < cmax) row[32 * k] = tile[(lane + 32 * k) * kPitch + vj];
+  }
+}
+
+// One warp per feature pixel; a CTA's 8 warps are 8 consecutive pixels so that
+// their strided depth / depth_grad accesses share 32-byte sectors.
+template <int KCH>
+__global__ void __launch_bounds__(kBwdWarps * 32)
+k_bwd_pixels(const float* __restrict__ rows, const float* __restrict__ depth,
+             const float* __restrict__ feat, const int32_t* __restrict__ point_interval,
+             int64_t pix_begin, int64_t pix_end, int D, int HW, int C,
+             float* __restrict__ depth_grad, float* __restrict__ feat_grad) {
+  constexpr int CC = 32 * KCH;
+  constexpr int U = 4;
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // per warp: dots[D] | dep[D] | iis[D] | kd[D]
+  float* dots = smem + (size_t)warp * 4 * D;
+  float* dep = dots + D;
+  int* iis = reinterpret_cast<int*>(dep + D);
+  int* kd = iis + D;
+  const int64_t pix = pix_begin + (int64_t)blockIdx.x * kBwdWarps + warp;
+  if (pix >= pix_end) return;
+  const int64_t bn = pix / HW;
+  const int hw = (int)(pix - bn * HW);
+  const int64_t dbase = bn * (int64_t)D * HW + hw;
+
+  int nk = 0;
+  for (int d0 = 0; d0 < D; d0 += 32) {
+    const int d = d0 + lane;
+    int ii = -1;
+    float dv = 0.f;
+    if (d < D) {
+      ii = __ldg(point_interval + pix * D + d);
+      dv = __ldg(depth + dbase + (int64_t)d * HW);
+      dots[d] = 0.f;
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, ii >= 0);
+    if (ii >= 0) {
+      const int pos = nk + __popc(m & ((1u << lane) - 1u));
+      kd[pos] = d;
+      iis[pos] = ii;
+      dep[pos] = dv;
+    }
+    nk += __popc(m);
+  }
+  __syncwarp();
+
+  const int n_chunks = (C + CC - 1) / CC;
+  for (int ch = 0; ch < n_chunks; ++ch) {
+    const int cbase = ch * CC;
+    float f[KCH], acc[KCH];
+#pragma unroll
+    for (int k = 0; k < KCH; ++k) {
+      const int c = cbase + lane + 32 * k;
+      f[k] = c < C ? __ldg(feat + pix * C + c) : 0.f;
+      acc[k] = 0.f;
+    }
+    for (int j0 = 0; j0 < nk; j0 += U) {
+      float g[U][KCH];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int j = min(j0 + u, nk - 1);
+        const float* row = rows + (int64_t)iis[j] * C + cbase + lane;
+#pragma unroll
+        for (int k = 0; k < KCH; ++k)
+          g[u][k] = (cbase + lane + 32 * k < C) ? __ldg(row + 32 * k) : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (j0 + u < nk) {
+          const float dv = dep[j0 + u];
+          float dot = 0.f;
+#pragma unroll
+          for (int k = 0; k < KCH; ++k) {
+            dot = fmaf(g[u][k], f[k], dot);
+            acc[k] = fmaf(dv, g[u][k], acc[k]);
+          }
+          dot = warp_sum(dot);
+          if (lane == 0) dots[kd[j0 + u]] += dot;
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < KCH; ++k) {
+      const int c = cbase + lane + 32 * k;
+      if (c < C) feat_grad[pix * C + c] = acc[k];
+    }
+  }
+  __syncwarp();
+  // dense depth_grad column: dots[] is zero for dropped bins
+  for (int d = lane; d < D; d += 32) depth_grad[dbase + (int64_t)d * HW] = dots[d];
+}
+
+template <int KCH>
+static int launch_rows(const float* out_grad, const int32_t* rb, const int32_t* istarts,
+                       const int32_t* tile_start, const int32_t* tile_istart,
+                       int64_t tile_begin, int64_t tile_end, int64_t tps, int64_t V, int C,
+                       float* rows, cudaStream_t stream) {
+  constexpr int CC = 32 * KCH;
+  const size_t smem = sizeof(float) * kBwdWarps * CC * kPitch;
+  static bool attr_set = false;
+  if (!attr_set) {
+    VEON_CUDA_TRY(cudaFuncSetAttribute(k_bwd_rows<KCH>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_set = true;
+  }
+  const int n_chunks = (C + CC - 1) / CC;
+  const int64_t blocks = ceil_div64(tile_end - tile_begin, kBwdWarps) * n_chunks;
+  if (blocks <= 0) return 0;
+  if (blocks > 0x7fffffffLL) return VEON_E_RANGE;
+  k_bwd_rows<KCH><<<(unsigned)blocks, kBwdWarps * 32, smem, stream>>>(
+      out_grad, rb, istarts, tile_start, tile_istart, tile_begin, tile_end, tps, V, C, n_chunks,
+      rows);
+  VEON_LAUNCH_CHECK();
+  return 0;
+}
+
+template <int KCH>
+static int launch_pixels(const float* rows, const float* depth, const float* feat,
+                         const int32_t* point_interval, int64_t pix_begin, int64_t pix_end,
+                         int D, int HW, int C, float* depth_grad, float* feat_grad,
+                         cudaStream_t stream) {
+  const size_t smem = sizeof(float) * kBwdWarps * 4 * (size_t)D;
+  if (smem > 200 * 1024) return VEON_E_UNSUPPORTED;
+  static size_t attr_smem = 48 * 1024;
+  if (smem > attr_smem) {
+    VEON_CUDA_TRY(cudaFuncSetAttribute(k_bwd_pixels<KCH>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem = smem;
+  }
+  const int64_t blocks = ceil_div64(pix_end - pix_begin, kBwdWarps);
+  if (blocks <= 0) return 0;
+  if (blocks > 0x7fffffffLL) return VEON_E_RANGE;
+  k_bwd_pixels<KCH><<<(unsigned)blocks, kBwdWarps * 32, smem, stream>>>(
+      rows, depth, feat, point_interval, pix_begin, pix_end, D, HW, C, depth_grad, feat_grad);
+  VEON_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace veon
+
+using namespace veon;
+
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
+extern "C" int veon_bev_pool_v2_bwd_planar(
+    const float* out_grad, const float* depth, const float* feat, const int32_t* ranks_bev,
+    const int32_t* interval_starts, const int32_t* tile_start, const int32_t* tile_istart,
+    const int32_t* point_interval, int64_t n_intervals, int B, int N, int D, int H, int W,
+    int C, int64_t V, float* rows_ws, float* depth_grad, float* feat_grad, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!out_grad || !depth || !feat || !ranks_bev || !interval_starts || !tile_start ||
+      !tile_istart || !point_interval || !rows_ws || !depth_grad || !feat_grad || B <= 0 ||
+      N <= 0 || D <= 0 || H <= 0 || W <= 0 || C <= 0 || V <= 0 || n_intervals < 0)
+    return VEON_E_BADARG;
+  (void)tile_start;
+  const int64_t tps = ceil_div64(V, kTileVoxels);
+  const int HW = H * W;
+  const int64_t pix_per_sample = (int64_t)N * HW;
+  // Samples are processed in groups so that the compact rows of a group are
+  // still L2-resident (126 MB) when the pixel pass gathers them.
+  static int group_env = env_int("VEON_BWD_SAMPLES_PER_LAUNCH", 0);
+  int group = group_env;
+  if (group <= 0) {
+    const double rows_per_sample = (double)n_intervals / B * C * sizeof(float);
+    group = (int)(48.0e6 / (rows_per_sample + 1.0));
+    if (group < 1) group = 1;
+  }
+  if (group > B) group = B;
+  static int rows_kch = env_int("VEON_BWD_ROWS_KCH", 0);
+  static int pix_kch = env_int("VEON_BWD_PIX_KCH", 0);
+  int rk = rows_kch ? rows_kch : (C <= 32 ? 1 : 2);
+  int pk = pix_kch ? pix_kch : (C <= 32 ? 1 : (C <= 64 ? 2 : 4));
+  for (int b0 = 0; b0 < B; b0 += group) {
+    const int b1 = b0 + group < B ? b0 + group : B;
+    int rc;
+    switch (rk) {
+      case 1: rc = launch_rows<1>(out_grad, ranks_bev, interval_starts, tile_start, tile_istart, b0 * tps, b1 * tps, tps, V, C, rows_ws, stream); break;
+      case 2: rc = launch_rows<2>(out_grad, ranks_bev, interval_starts, tile_start, tile_istart, b0 * tps, b1 * tps, tps, V, C, rows_ws, stream); break;
+      case 4: rc = launch_rows<4>(out_grad, ranks_bev, interval_starts, tile_start, tile_istart, b0 * tps, b1 * tps, tps, V, C, rows_ws, stream); break;
+      default: return VEON_E_BADARG;
+    }
+    if (rc) return rc;
+    switch (pk) {
+      case 1: rc = launch_pixels<1>(rows_ws, depth, feat, point_interval, b0 * pix_per_sample, b1 * pix_per_sample, D, HW, C, depth_grad, feat_grad, stream); break;
+      case 2: rc = launch_pixels<2>(rows_ws, depth, feat, point_interval, b0 * pix_per_sample, b1 * pix_per_sample, D, HW, C, depth_grad, feat_grad, stream); break;
+      case 4: rc = launch_pixels<4>(rows_ws, depth, feat, point_interval, b0 * pix_per_sample, b1 * pix_per_sample, D, HW, C, depth_grad, feat_grad, stream); break;
+      case 8: rc = launch_pixels<8>(rows_ws, depth, feat, point_interval, b0 * pix_per_sample, b1 * pix_per_sample, D, HW, C, depth_grad, feat_grad, stream); break;
+      default: return VEON_E_BADARG;
+    }
+    if (rc) return rc;
+  }
+  return 0;
+}

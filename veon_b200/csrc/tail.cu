@@ -1,0 +1,127 @@
+// Open-vocabulary tail: voxel-feature x text-embedding logits with fused
+// per-class max, argmax, occupancy gate and uint8 label emission.
+//
+// Reference behaviour (three separate stages, ~25 launches, the [B,Q,Z,Y,X]
+// logits and [B,18,Z,Y,X] merged tensor both materialised):
+//   semantic_inference_3d  einsum "qc,bczhw->bqzhw"   san_in_veon_temporal.py:257-259
+//   _merge_classes_prob    max over each class's prompts   san_in_veon_entry_temporal.py:273-297
+//   label rule             softmax/max/gate/where/permute/uint8   veon_temporal.py:223-229,240
+//
+// v1 (this file): fp32 FFMA contraction, one thread per voxel, text rows staged
+// in shared memory per prompt tile, everything after the dot products fused in
+// registers; feat_occ is read once per prompt tile and nothing but the uint8
+// labels is written.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace veon {
+
+constexpr int kTailThreads = 128;
+constexpr int kTailQT = 24;  // prompts held in registers per pass
+
+__global__ void __launch_bounds__(kTailThreads)
+k_voxel_text_argmax(const float* __restrict__ feat_occ, const float* __restrict__ text_w,
+                    const int32_t* __restrict__ class_of_prompt,
+                    const float* __restrict__ bin_occ, int C, int Q, int Z, int Y, int X,
+                    int free_label, uint8_t* __restrict__ labels) {
+  extern __shared__ float w_s[];  // [kTailQT][C] of the current prompt tile
+  const int64_t V = (int64_t)Z * Y * X;
+  const int b = blockIdx.y;
+  const int64_t v = (int64_t)blockIdx.x * kTailThreads + threadIdx.x;
+  const bool live = v < V;
+  const float* f = feat_occ + (int64_t)b * C * V + (live ? v : 0);
+
+  float best = 0.f, cur = 0.f;
+  int best_cls = -1, cur_cls = -1;
+  bool bad = false;  // NaN / +inf anywhere => softmax score is NaN => free
+
+  for (int q0 = 0; q0 < Q; q0 += kTailQT) {
+    const int nq = min(kTailQT, Q - q0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < nq * C; i += kTailThreads) w_s[i] = text_w[(int64_t)q0 * C + i];
+    __syncthreads();
+    float acc[kTailQT];
+#pragma unroll
+    for (int q = 0; q < kTailQT; ++q) acc[q] = 0.f;
+    int c = 0;
+    for (; c + 4 <= C; c += 4) {
+      const float f0 = __ldg(f + (int64_t)(c + 0) * V), f1 = __ldg(f + (int64_t)(c + 1) * V);
+      const float f2 = __ldg(f + (int64_t)(c + 2) * V), f3 = __ldg(f + (int64_t)(c + 3) * V);
+#pragma unroll
+      for (int q = 0; q < kTailQT; ++q) {
+        if (q < nq) {
+          const float* w = w_s + q * C + c;
+          acc[q] = fmaf(w[0], f0, acc[q]);
+          acc[q] = fmaf(w[1], f1, acc[q]);
+          acc[q] = fmaf(w[2], f2, acc[q]);
+          acc[q] = fmaf(w[3], f3, acc[q]);
+        }
+      }
+    }
+    for (; c < C; ++c) {
+      const float f0 = __ldg(f + (int64_t)c * V);
+#pragma unroll
+      for (int q = 0; q < kTailQT; ++q)
+        if (q < nq) acc[q] = fmaf(w_s[q * C + c], f0, acc[q]);
+    }
+    // group-max over prompts of one class, then first-index argmax over classes
+#pragma unroll
+    for (int q = 0; q < kTailQT; ++q) {
+      if (q < nq) {
+        const int cls = class_of_prompt[q0 + q];
+        const float x = acc[q];
+        bad |= !(x < INFINITY);  // NaN or +inf
+        if (cls != cur_cls) {
+          if (cur_cls >= 0 && (best_cls < 0 || cur > best)) { best = cur; best_cls = cur_cls; }
+          cur_cls = cls;
+          cur = x;
+        } else {
+          cur = fmaxf(cur, x);
+        }
+      }
+    }
+  }
+  if (cur_cls >= 0 && (best_cls < 0 || cur > best)) { best = cur; best_cls = cur_cls; }
+  if (!live) return;
+  bad |= (best == -INFINITY);  // all logits -inf => softmax NaN
+  const float b0 = bin_occ[((int64_t)b * 2 + 0) * V + v];
+  const float b1 = bin_occ[((int64_t)b * 2 + 1) * V + v];
+  // softmax(bin_occ)[0] > 0.5, evaluated like torch.softmax
+  const float m = fmaxf(b0, b1);
+  const float e0 = expf(b0 - m), e1 = expf(b1 - m);
+  const bool occupied = (e0 / (e0 + e1)) > 0.5f;
+  const int label = (occupied && !bad) ? best_cls : free_label;
+  // [B,Z,Y,X] -> permute(0,3,2,1) -> [B,X,Y,Z]
+  const int x = (int)(v % X);
+  const int y = (int)((v / X) % Y);
+  const int z = (int)(v / ((int64_t)X * Y));
+  labels[(((int64_t)b * X + x) * Y + y) * Z + z] = (uint8_t)label;
+}
+
+}  // namespace veon
+
+using namespace veon;
+
+extern "C" int veon_voxel_text_argmax(const float* feat_occ, const float* text_w,
+                                      const int32_t* class_of_prompt, const float* bin_occ,
+                                      int B, int C, int Q, int Z, int Y, int X, int free_label,
+                                      uint8_t* labels, void* stream) {
+  if (!feat_occ || !text_w || !class_of_prompt || !bin_occ || !labels || B <= 0 || C <= 0 ||
+      Q <= 0 || Z <= 0 || Y <= 0 || X <= 0 || B > 65535)
+    return VEON_E_BADARG;
+  const size_t smem = sizeof(float) * (size_t)kTailQT * C;
+  if (smem > 200 * 1024) return VEON_E_UNSUPPORTED;
+  static size_t attr_smem = 48 * 1024;
+  if (smem > attr_smem) {
+    VEON_CUDA_TRY(cudaFuncSetAttribute(k_voxel_text_argmax,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem = smem;
+  }
+  const int64_t V = (int64_t)Z * Y * X;
+  dim3 grid((unsigned)ceil_div64(V, kTailThreads), (unsigned)B);
+  k_voxel_text_argmax<<<grid, kTailThreads, smem, (cudaStream_t)stream>>>(
+      feat_occ, text_w, class_of_prompt, bin_occ, C, Q, Z, Y, X, free_label, labels);
+  VEON_LAUNCH_CHECK();
+  return 0;
+}

@@ -1,0 +1,211 @@
+"""Host-side mirror of the reference's Lift-Splat view transformer, restricted
+to the lifting path.
+
+Same class name, constructor arguments, attribute names and method names as
+`mmdet3d/models/necks/view_transformer.py::LSSViewTransformer` (and the
+`forward` convention of `view_transformer_raw.py::LSSViewTransformerRaw`,
+:537-555), so reference-side code and tests that drive the neck read the same.
+The tensor work underneath goes to libveonlift through `veon_b200.bev_pool`.
+
+Out of scope here: DepthNet / ASPP / stereo cost
+volumes and every other conv stack of the reference file.
+"""
+import torch
+import torch.nn as nn
+
+from . import bev_pool as _bp
+
+__all__ = ["LSSViewTransformer", "LSSViewTransformerRaw"]
+
+
+class LSSViewTransformer(nn.Module):
+    """Lift-Splat view transformer (reference: view_transformer.py:15-319).
+
+    Args mirror the reference (:40-50): grid_config {x,y,z,depth: (lo,hi,step)},
+    input_size (H_in, W_in), downsample, in_channels, out_channels,
+    accelerate, sid, collapse_z.
+
+    Extra (not in the reference): `sync_free` -- when True the non-accelerated
+    path skips the host read-back of the point / interval counts (the
+    reference's boolean-mask indexing syncs at the same place); the only
+    behavioural difference is that an input with no point inside the grid
+    yields an all-zero volume of the regular shape instead of the reference's
+    warning + dummy tensor (:179-189).
+    """
+
+    def __init__(self, grid_config, input_size, downsample=16, in_channels=512,
+                 out_channels=64, accelerate=False, sid=False, collapse_z=True,
+                 sync_free=False):
+        super().__init__()
+        self.grid_config = grid_config
+        self.downsample = downsample
+        self.create_grid_infos(**grid_config)
+        self.sid = sid
+        self.frustum = self.create_frustum(grid_config["depth"], input_size, downsample)
+        self.out_channels = out_channels
+        self.in_channels = in_channels
+        # the reference's 1x1 depth/context head (:59-60); a library conv, kept
+        # so that `forward` is a complete drop-in
+        self.depth_net = nn.Conv2d(in_channels, self.D + self.out_channels, kernel_size=1)
+        self.accelerate = accelerate
+        self.initial_flag = True
+        self.collapse_z = collapse_z
+        self.sync_free = sync_free
+
+    # -- a1 ------------------------------------------------------------------
+    def create_grid_infos(self, x, y, z, **kwargs):
+        """float32 grid vectors exactly as the reference builds them (:66-82):
+        python-float arithmetic, then a float32 tensor."""
+        axes = (x, y, z)
+        self.grid_lower_bound = torch.tensor([a[0] for a in axes], dtype=torch.float32)
+        self.grid_interval = torch.tensor([a[2] for a in axes], dtype=torch.float32)
+        self.grid_size = torch.tensor([(a[1] - a[0]) / a[2] for a in axes],
+                                      dtype=torch.float32)
+
+    def create_frustum(self, depth_cfg, input_size, downsample):
+        """[D,H,W,3] frustum of (x_img, y_img, depth) (reference :84-112)."""
+        h_in, w_in = input_size
+        h, w = h_in // downsample, w_in // downsample
+        depth = torch.arange(*depth_cfg, dtype=torch.float)
+        self.D = depth.numel()
+        if self.sid:
+            lo = torch.tensor(float(depth_cfg[0]))
+            hi = torch.tensor(float(depth_cfg[1]))
+            idx = torch.arange(self.D).float()
+            depth = torch.exp(torch.log(lo) + idx / (self.D - 1) * torch.log((hi - 1) / lo))
+        xs = torch.linspace(0, w_in - 1, w, dtype=torch.float)
+        ys = torch.linspace(0, h_in - 1, h, dtype=torch.float)
+        fr = torch.empty(self.D, h, w, 3, dtype=torch.float)
+        fr[..., 0] = xs.view(1, 1, w)
+        fr[..., 1] = ys.view(1, h, 1)
+        fr[..., 2] = depth.view(self.D, 1, 1)
+        return fr
+
+    # -- a2 ------------------------------------------------------------------
+    def get_lidar_coor(self, sensor2ego, ego2global, cam2imgs, post_rots, post_trans, bda):
+        """Frustum points in the ego/lidar frame, [B,N,D,H,W,3]
+        (reference :114-152; same operation order so that float32 results
+        agree to rounding): undo image augmentation, un-project with depth,
+        camera->ego, BEV augmentation."""
+        B, N = sensor2ego.shape[:2]
+        fr = self.frustum.to(sensor2ego)                      # [D,H,W,3]
+        undo_aug = torch.inverse(post_rots)                   # [B,N,3,3]
+        cam2ego = sensor2ego[..., :3, :3] @ torch.inverse(cam2imgs)
+        ego_t = sensor2ego[..., :3, 3]
+        img = fr[None, None] - post_trans[:, :, None, None, None, :]
+        img = torch.einsum("bnij,bndhwj->bndhwi", undo_aug, img)
+        depth = img[..., 2:3]
+        cam = torch.cat((img[..., :2] * depth, depth), dim=-1)   # pixel * depth, depth
+        ego = torch.einsum("bnij,bndhwj->bndhwi", cam2ego, cam)
+        ego = ego + ego_t[:, :, None, None, None, :]
+        return torch.einsum("bij,bndhwj->bndhwi", bda, ego)
+
+    # -- a3 ------------------------------------------------------------------
+    def voxel_pooling_prepare_v2(self, coor):
+        """(ranks_bev, ranks_depth, ranks_feat, interval_starts,
+        interval_lengths) or five Nones -- reference :202-260."""
+        return _bp.voxel_pooling_prepare_v2(coor, self.grid_lower_bound, self.grid_interval,
+                                            self.grid_size)
+
+    def init_acceleration_v2(self, coor):
+        """Cache the ranks for constant calibration (reference :154-173)."""
+        ranks_bev, ranks_depth, ranks_feat, interval_starts, interval_lengths = \
+            self.voxel_pooling_prepare_v2(coor)
+        self.ranks_bev = ranks_bev.int().contiguous()
+        self.ranks_feat = ranks_feat.int().contiguous()
+        self.ranks_depth = ranks_depth.int().contiguous()
+        self.interval_starts = interval_starts.int().contiguous()
+        self.interval_lengths = interval_lengths.int().contiguous()
+
+    def _bev_shape(self, depth, channels):
+        gs = self.grid_size
+        return (depth.shape[0], int(gs[2]), int(gs[1]), int(gs[0]), channels)  # B,Z,Y,X,C
+
+    # -- a4 ------------------------------------------------------------------
+    def voxel_pooling_v2(self, coor, depth, feat):
+        """coor [B,N,D,H,W,3], depth [B,N,D,H,W], feat [B,N,C,H,W] ->
+        [B,C,Z,Y,X] (or [B,C*Z,Y,X] with collapse_z) -- reference :175-200."""
+        feat_last = feat.permute(0, 1, 3, 4, 2)
+        shape = self._bev_shape(depth, feat_last.shape[-1])
+        if self.sync_free:
+            prep = _bp.prepare_ranks(coor, self.grid_lower_bound, self.grid_interval,
+                                     self.grid_size)
+            bev_feat = _bp.pool_prepared(depth, feat_last, prep, shape)
+        else:
+            ranks_bev, ranks_depth, ranks_feat, interval_starts, interval_lengths = \
+                self.voxel_pooling_prepare_v2(coor)
+            if ranks_feat is None:
+                print("warning ---> no points within the predefined bev receptive field")
+                gs = self.grid_size
+                dummy = torch.zeros(size=[feat.shape[0], feat.shape[2], int(gs[2]),
+                                          int(gs[0]), int(gs[1])]).to(feat)
+                return torch.cat(dummy.unbind(dim=2), 1)
+            bev_feat = _bp.bev_pool_v2(depth, feat_last, ranks_depth, ranks_feat, ranks_bev,
+                                       shape, interval_starts, interval_lengths)
+        if self.collapse_z:
+            bev_feat = torch.cat(bev_feat.unbind(dim=2), 1)
+        return bev_feat
+
+    # -- a10 -----------------------------------------------------------------
+    def pre_compute(self, input):
+        if self.initial_flag:
+            coor = self.get_lidar_coor(*input[1:7])
+            self.init_acceleration_v2(coor)
+            self.initial_flag = False
+
+    def view_transform_core(self, input, depth, tran_feat):
+        """reference :268-290"""
+        B, N, C, H, W = input[0].shape
+        if self.accelerate:
+            feat = tran_feat.view(B, N, self.out_channels, H, W).permute(0, 1, 3, 4, 2)
+            depth = depth.view(B, N, self.D, H, W)
+            bev_feat = _bp.bev_pool_v2(depth, feat, self.ranks_depth, self.ranks_feat,
+                                       self.ranks_bev, self._bev_shape(depth, feat.shape[-1]),
+                                       self.interval_starts, self.interval_lengths)
+            bev_feat = bev_feat.squeeze(2)
+        else:
+            coor = self.get_lidar_coor(*input[1:7])
+            bev_feat = self.voxel_pooling_v2(coor, depth.view(B, N, self.D, H, W),
+                                             tran_feat.view(B, N, self.out_channels, H, W))
+        return bev_feat, depth
+
+    def view_transform(self, input, depth, tran_feat):
+        if self.accelerate:
+            self.pre_compute(input)
+        return self.view_transform_core(input, depth, tran_feat)
+
+    def forward(self, input):
+        """input = (img_feat [B,N,C_in,H,W], sensor2ego, ego2global, cam2imgs,
+        post_rots, post_trans, bda) -> (bev_feat, depth) -- reference :297-319."""
+        x = input[0]
+        B, N, C, H, W = x.shape
+        x = self.depth_net(x.view(B * N, C, H, W))
+        depth = x[:, :self.D].softmax(dim=1)
+        tran_feat = x[:, self.D:self.D + self.out_channels]
+        return self.view_transform(input, depth, tran_feat)
+
+
+class LSSViewTransformerRaw(LSSViewTransformer):
+    """VEON's neck entry (reference view_transformer_raw.py:537-555): takes
+    ready-made features and a depth distribution, lifts, then (use_ds)
+    max-pools the volume 2x2x2."""
+
+    def __init__(self, *args, use_ds=True, ds=(2, 2, 2), **kwargs):
+        kwargs.setdefault("collapse_z", False)
+        super().__init__(*args, **kwargs)
+        self.use_ds = use_ds
+        self.ds = tuple(ds)
+
+    def forward(self, input, depth, stereo_metas=None):
+        tran_feat = input[0]
+        B, N, C, H, W = tran_feat.shape
+        tran_feat = tran_feat.reshape(B * N, C, H, W)
+        Bd, Nd, Dd, Hd, Wd = depth.shape
+        depth = depth.reshape(Bd * Nd, Dd, Hd, Wd)
+        bev_feat, _ = self.view_transform(input, depth, tran_feat)
+        if self.use_ds:
+            dz, dy, dx = self.ds
+            b, c, z, y, x = bev_feat.shape
+            bev_feat = bev_feat.view(b, c, z // dz, dz, y // dy, dy, x // dx, dx) \
+                .amax(dim=(3, 5, 7))
+        return bev_feat
