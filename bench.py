@@ -1,0 +1,356 @@
+#!/usr/bin/env python
+"""bench.py -- 6-camera samples/s of the lift (voxel_pooling_prepare_v2 +
+bev_pool_v2 forward + backward) on N B200s, with the roofline of the dominant
+kernel and the CPU baseline beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the hot path over one batch of synthetic
+nuScenes-shaped input: BASELINE.json configs[1] (6 cams 16x44 feats, D=88,
+C=64, batch 8 per GPU; weak scaling: every rank lifts its own 8 samples, no
+data-path collective).  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "6-cam samples/sec for lift (bev_pool_v2 fwd+bwd)"
+UNIT = "samples/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2", help="veon_b200.synthetic.CONFIGS key")
+    ap.add_argument("--batch", type=int, default=0, help="override samples per GPU per step")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0,
+                    help="budget of the cpu_baseline leg (rank 0, N=1 only)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sync-free", type=int, default=0,
+                    help="1: skip the host read-back of the counts (see LSSViewTransformer)")
+    return ap.parse_args()
+
+
+def workload_dict(cfg, batch, extra=None):
+    H, W = cfg.feat_hw
+    d = {"workload": f"{cfg.name}: {cfg.n_cams} cams {cfg.input_size[0]}x{cfg.input_size[1]} -> "
+                     f"{H}x{W} feats, D={cfg.D}, C={cfg.channels} -> 200x200x16, "
+                     f"prepare_v2 + bev_pool_v2 fwd + bwd",
+         "samples_per_gpu_per_step": batch, "parallelism": "sample-sharded, no collective"}
+    if extra:
+        d.update(extra)
+    return d
+
+
+# ---------------------------------------------------------------- clocks
+class ClockSampler:
+    """nvidia-smi-equivalent (NVML) clock / throttle sampling during the timed region."""
+
+    def __init__(self, index):
+        self.samples, self.reasons = [], set()
+        self._stop = threading.Event()
+        self.max_mhz = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "hw_thermal_slowdown": 0x40,
+                 "sw_thermal_slowdown": 0x20, "hw_power_brake": 0x80}
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) \
+                    if hasattr(nv, "nvmlDeviceGetCurrentClocksEventReasons") \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for k, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def __enter__(self):
+        if self.nv:
+            self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self.nv:
+            self.t.join(timeout=1)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml unavailable"]}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ------------------------------------------------------------ CPU baseline
+def cpu_lift_once(cfg, batch, seed=0):
+    """inputs for the CPU port (oracle.lift_oracle.torch_cpu_lift)"""
+    import torch
+    from veon_b200 import synthetic as S
+    coor = torch.from_numpy(S.lidar_coor_np(cfg, batch=batch, sample_offset=seed))
+    B, N, D, H, W, _ = coor.shape
+    g = torch.Generator().manual_seed(seed)
+    depth = torch.softmax(torch.randn(B, N, D, H, W, generator=g) * 4, dim=2)
+    feat = torch.randn(B, N, cfg.channels, H, W, generator=g)
+    og = torch.randn(B, cfg.channels, 16, 200, 200, generator=g)
+    return coor, depth, feat, og
+
+
+def time_cpu_port(cfg, budget_s, steps=None, warmup=1, batch=1):
+    """Times the reference's pure-PyTorch CPU lift (BASELINE.json configs[0]) as restated in
+    oracle/ (kind "port").  Returns (samples/s, cores, description, ms per step)."""
+    import torch
+    from oracle import lift_oracle as O
+    from veon_b200 import synthetic as S
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    lower, interval, size = S.grid_vectors(cfg.grid_config)
+    coor, depth, feat, og = cpu_lift_once(cfg, batch)
+    for _ in range(warmup):
+        O.torch_cpu_lift(coor, depth, feat, lower, interval, size, og)
+    times = []
+    t_end = time.perf_counter() + budget_s
+    while True:
+        t0 = time.perf_counter()
+        O.torch_cpu_lift(coor, depth, feat, lower, interval, size, og)
+        times.append(time.perf_counter() - t0)
+        if steps is not None and len(times) >= steps:
+            break
+        if steps is None and (time.perf_counter() > t_end and len(times) >= 3):
+            break
+    times.sort()
+    med = times[len(times) // 2]
+    desc = (f"{len(times)} timed passes (median) of prepare_v2 + scatter-add pool fwd + autograd bwd "
+            f"on {batch} sample(s) of {cfg.name} (6 cams, D={cfg.D}, C={cfg.channels}), torch CPU fp32, "
+            f"{cores} threads")
+    return batch / med, cores, desc, med * 1e3, len(times)
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (oracle port; the
+    reference is Python + CUDA, its CPU path is the pure-PyTorch lift of BASELINE configs[0])."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from veon_b200 import synthetic as S
+    cfg = S.CONFIGS[args.workload]
+    # each step = ONE sample of the workload (bounded so K steps end in minutes)
+    val, cores, desc, ms, n = time_cpu_port(cfg, 0.0, steps=max(args.steps, 1),
+                                            warmup=max(args.warmup, 1), batch=1)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT,
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": workload_dict(cfg, 1, {"note": "CPU port; one sample per step"}),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": desc},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------- ours
+def algorithmic_bytes(cfg, B, n_kept, n_int):
+    """compulsory traffic per step (every input element read once, every
+    output element written once)."""
+    V, C = 640000, cfg.channels
+    H, W = cfg.feat_hw
+    NHW = cfg.n_cams * H * W
+    P = NHW * cfg.D * B
+    fwd = 4 * V * C * B + 4 * NHW * C * B + 4 * n_kept + 8 * n_kept + 12 * n_int
+    n_bp = NHW * B
+    bwd = 4 * n_int * C + 4 * NHW * C * B + 4 * n_kept + 4 * P + 4 * NHW * C * B + 12 * n_kept + 8 * n_bp
+    prep = 12 * P + 12 * n_kept + 8 * n_int
+    return {"prepare": prep, "pool_fwd": fwd, "pool_bwd": bwd}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from veon_b200 import _lib, bev_pool as BP, synthetic as S
+    from veon_b200.view_transformer import LSSViewTransformer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+
+    cfg = S.CONFIGS[args.workload]
+    B = args.batch or cfg.batch
+    C = cfg.channels
+    neck = LSSViewTransformer(cfg.grid_config, cfg.input_size, cfg.downsample, in_channels=8,
+                              out_channels=C, collapse_z=False, sync_free=bool(args.sync_free))
+    lower, interval, size = S.grid_vectors(cfg.grid_config)
+
+    # rotating input sets so that a step's inputs are not L2-hot from the previous step
+    n_sets = 4
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    host_sets, dev_sets = [], []
+    for i in range(n_sets):
+        coor = torch.from_numpy(S.lidar_coor_np(cfg, batch=B, sample_offset=rank * 1000 + i * B))
+        Bc, N, D, H, W, _ = coor.shape
+        depth = torch.softmax(torch.randn(B, N, D, H, W, device=dev, generator=g) * 4, dim=2)
+        feat = torch.randn(B, N, C, H, W, device=dev, generator=g)
+        host_sets.append((coor.pin_memory(), depth.cpu().pin_memory(), feat.cpu().pin_memory()))
+        dev_sets.append((coor.to(dev), depth, feat))
+    out_grad = torch.randn(B, C, 16, 200, 200, device=dev, generator=g)
+
+    def step_device(i):
+        coor, depth, feat = dev_sets[i % n_sets]
+        depth = depth.detach().requires_grad_()
+        feat = feat.detach().requires_grad_()
+        bev = neck.voxel_pooling_v2(coor, depth, feat)
+        bev.backward(out_grad)
+        return depth.grad, feat.grad
+
+    dg_host = torch.empty((B, N, D, H, W), dtype=torch.float32).pin_memory()
+    fg_host = torch.empty((B, N, C, H, W), dtype=torch.float32).pin_memory()
+
+    def step_e2e(i):
+        hc, hd, hf = host_sets[i % n_sets]
+        coor = hc.to(dev, non_blocking=True)
+        depth = hd.to(dev, non_blocking=True).requires_grad_()
+        feat = hf.to(dev, non_blocking=True).requires_grad_()
+        bev = neck.voxel_pooling_v2(coor, depth, feat)
+        bev.backward(out_grad)
+        dg_host.copy_(depth.grad, non_blocking=True)
+        fg_host.copy_(feat.grad, non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = lib.veon_kernel_launch_count()
+        e0.record()
+        for i in range(steps):
+            fn(i)
+        e1.record()
+        barrier()
+        launches = lib.veon_kernel_launch_count() - l0
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item()), launches
+
+    K, Wm = max(args.steps, 1), max(args.warmup, 3)
+    with ClockSampler(local) as clocks:
+        ms_total, launches = timed(step_device, K, Wm)
+    ms_e2e, _ = timed(step_e2e, K, max(3, Wm // 2))
+
+    # live per-call device times (CUDA events on the launching stream) over K more steps
+    BP.enable_kernel_timing(True)
+    for i in range(K):
+        step_device(i)
+    t = BP.kernel_timings_ms()
+    BP.enable_kernel_timing(False)
+    avg = {k: sum(v) / len(v) for k, v in t.items()}
+
+    # counts for the algorithmic-byte denominators
+    prep = BP.prepare_ranks(dev_sets[0][0], lower, interval, size)
+    n_kept, n_int = prep.plan.n_points, prep.plan.n_intervals
+    alg = algorithmic_bytes(cfg, B, n_kept, n_int)
+
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "6650 GB/s (of fallback)"
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
+            traffic = json.load(f).get(args.workload, {}).get("pool_fwd_dram_bytes_per_launch")
+    except Exception:
+        pass
+    fwd_ms = avg.get("pool_fwd")
+    achieved = alg["pool_fwd"] / (fwd_ms * 1e-3) / 1e9 if fwd_ms else None
+
+    value = world * B * K / (ms_total * 1e-3)
+    e2e_value = world * B * K / (ms_e2e * 1e-3)
+    h2d = sum(x.numel() * x.element_size() for x in host_sets[0])
+    d2h = dg_host.numel() * 4 + fg_host.numel() * 4
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+        "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_dict(cfg, B, {
+            "l2": f"inputs rotate over {n_sets} sets; each step streams a "
+                  f"{4 * 640000 * C * B / 1e9:.2f} GB volume (>> 126 MB L2)",
+            "host_sync_per_step": 0 if args.sync_free else 1,
+            "n_kept": n_kept, "n_intervals": n_int}),
+        "gpu_launches": int(launches),
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / K,
+                "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "what": "pinned host coor+depth+feat -> LSSViewTransformer.voxel_pooling_v2 -> "
+                        "backward -> depth_grad+feat_grad back to pinned host"},
+        "roofline": {"bound": "hbm", "kernel": "k_pool_fwd (veon_bev_pool_v2_fwd_planar)",
+                     "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
+                     "frac": (achieved / peak_gbs) if achieved else None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": alg["pool_fwd"],
+                     "ms_per_launch": fwd_ms, "traffic": traffic},
+        "phases_ms": {k: round(v, 4) for k, v in avg.items()},
+        "phases_gbs_algorithmic": {
+            k: round(alg[a] / (avg[k] * 1e-3) / 1e9, 1)
+            for k, a in (("prepare_v2", "prepare"), ("pool_fwd", "pool_fwd"), ("pool_bwd", "pool_bwd"))
+            if k in avg},
+        "clocks": clocks.summary(),
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        c1 = S.CONFIGS["C1"] if args.workload == "C2" else cfg
+        v, cores, desc, _, _ = time_cpu_port(c1, args.cpu_seconds)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": desc}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -49,6 +49,8 @@ extern "C" {
 int veon_abi_version(void);
 /* static string for any code returned by this library */
 const char* veon_error_string(int code);
+/* number of CUDA kernels this library has launched in this process so far */
+uint64_t veon_kernel_launch_count(void);
 
 /* ------------------------------------------------------------------------
  * (1) Literal drop-ins for the two functions bev_pool.cpp binds

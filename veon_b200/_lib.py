@@ -26,6 +26,7 @@ _SIGNATURES = {
     # name: (restype, argtypes)
     "veon_abi_version": (c_int, []),
     "veon_error_string": (c_char_p, [c_int]),
+    "veon_kernel_launch_count": (ctypes.c_uint64, []),
     "veon_bev_pool_v2": (c_int, [c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "veon_bev_pool_v2_grad": (c_int, [c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "veon_bev_pool_v2_generic": (c_int, [c_int, c_int, c_int, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

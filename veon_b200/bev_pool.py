@@ -40,6 +40,39 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr())
 
 
+# Opt-in device timing of the library calls (bench.py / profiling only): CUDA
+# events recorded on the stream the kernels are launched on.
+_TIMERS = None
+
+
+def enable_kernel_timing(on=True):
+    global _TIMERS
+    _TIMERS = {} if on else None
+
+
+def kernel_timings_ms():
+    """{call name: [ms, ...]} of everything recorded since enable_kernel_timing()."""
+    torch.cuda.synchronize()
+    return {k: [s.elapsed_time(e) for s, e in v] for k, v in (_TIMERS or {}).items()}
+
+
+class _timed:
+    def __init__(self, name, dev):
+        self.name, self.dev = name, dev
+
+    def __enter__(self):
+        if _TIMERS is not None:
+            self.s = torch.cuda.Event(enable_timing=True)
+            self.e = torch.cuda.Event(enable_timing=True)
+            self.s.record(torch.cuda.current_stream(self.dev))
+
+    def __exit__(self, *exc):
+        if _TIMERS is not None:
+            self.e.record(torch.cuda.current_stream(self.dev))
+            _TIMERS.setdefault(self.name, []).append((self.s, self.e))
+        return False
+
+
 def _require_cuda(*tensors):
     for t in tensors:
         if not t.is_cuda:
@@ -118,11 +151,12 @@ def prepare_ranks(coor, grid_lower_bound, grid_interval, grid_size):
         point_interval = torch.empty(P, dtype=torch.int32, device=dev)
         counts = torch.empty(2, dtype=torch.int64, device=dev)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        rc = lib.veon_prepare_v2(
-            _ptr(coor), B, N, D, H, W, _lib.float3(lower), _lib.float3(interval), c_size,
-            _ptr(ranks[0]), _ptr(ranks[1]), _ptr(ranks[2]), _ptr(ranks[3]), _ptr(ranks[4]),
-            _ptr(counts), _ptr(tiles[0]), _ptr(tiles[1]), _ptr(point_interval),
-            _ptr(ws), ws_bytes, _stream_ptr(dev))
+        with _timed("prepare_v2", dev):
+            rc = lib.veon_prepare_v2(
+                _ptr(coor), B, N, D, H, W, _lib.float3(lower), _lib.float3(interval), c_size,
+                _ptr(ranks[0]), _ptr(ranks[1]), _ptr(ranks[2]), _ptr(ranks[3]), _ptr(ranks[4]),
+                _ptr(counts), _ptr(tiles[0]), _ptr(tiles[1]), _ptr(point_interval),
+                _ptr(ws), ws_bytes, _stream_ptr(dev))
         _lib.check(rc, "veon_prepare_v2")
         counts_host = torch.empty(2, dtype=torch.int64, pin_memory=True)
         counts_host.copy_(counts, non_blocking=True)
@@ -216,9 +250,10 @@ def _fwd_planar(depth, feat, rd, rf, rb, plan, B, C, V, shape5):
     dev = feat.device
     with torch.cuda.device(dev):
         out = torch.empty(shape5, dtype=torch.float32, device=dev)  # [B,C,Z,Y,X]
-        rc = lib.veon_bev_pool_v2_fwd_planar(
-            _ptr(depth), _ptr(feat), _ptr(rd), _ptr(rf), _ptr(rb), _ptr(plan.tile_start),
-            B, C, V, _ptr(out), _stream_ptr(dev))
+        with _timed("pool_fwd", dev):
+            rc = lib.veon_bev_pool_v2_fwd_planar(
+                _ptr(depth), _ptr(feat), _ptr(rd), _ptr(rf), _ptr(rb), _ptr(plan.tile_start),
+                B, C, V, _ptr(out), _stream_ptr(dev))
     _lib.check(rc, "veon_bev_pool_v2_fwd_planar")
     return out
 
@@ -232,11 +267,12 @@ def _bwd_planar(grad_planar, depth, feat, rb, ist, plan, C):
         depth_grad = torch.empty_like(depth)
         feat_grad = torch.empty_like(feat)
         rows = torch.empty(max(n_int, 1) * C, dtype=torch.float32, device=dev)
-        rc = lib.veon_bev_pool_v2_bwd_planar(
-            _ptr(grad_planar), _ptr(depth), _ptr(feat), _ptr(rb), _ptr(ist),
-            _ptr(plan.tile_start), _ptr(plan.tile_istart), _ptr(plan.point_interval),
-            n_int, B, N, D, H, W, C, plan.V, _ptr(rows), _ptr(depth_grad), _ptr(feat_grad),
-            _stream_ptr(dev))
+        with _timed("pool_bwd", dev):
+            rc = lib.veon_bev_pool_v2_bwd_planar(
+                _ptr(grad_planar), _ptr(depth), _ptr(feat), _ptr(rb), _ptr(ist),
+                _ptr(plan.tile_start), _ptr(plan.tile_istart), _ptr(plan.point_interval),
+                n_int, B, N, D, H, W, C, plan.V, _ptr(rows), _ptr(depth_grad), _ptr(feat_grad),
+                _stream_ptr(dev))
     _lib.check(rc, "veon_bev_pool_v2_bwd_planar")
     return depth_grad, feat_grad
 

@@ -1,5 +1,11 @@
 // ABI version + error strings for libveonlift.
+#include <atomic>
+
 #include "common.cuh"
+
+static std::atomic<unsigned long long> g_launches{0};
+extern "C" void veon_count_launch(void) { g_launches.fetch_add(1, std::memory_order_relaxed); }
+extern "C" uint64_t veon_kernel_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int veon_abi_version(void) { return VEON_ABI_VERSION; }
 

@@ -11,11 +11,15 @@
     if (_e != cudaSuccess) return (int)_e;          \
   } while (0)
 
+// every kernel launch of this library goes through here (counted for bench.py)
 #define VEON_LAUNCH_CHECK()                         \
   do {                                              \
     cudaError_t _e = cudaGetLastError();            \
     if (_e != cudaSuccess) return (int)_e;          \
+    veon_count_launch();                            \
   } while (0)
+
+extern "C" void veon_count_launch(void);
 
 namespace veon {
 
@@ -28,6 +32,18 @@ static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b;
 // feature inputs.
 __device__ __forceinline__ void st_stream(float* p, float v) {
   asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+__device__ __forceinline__ void st_stream4(float* p, float4 v) {
+  asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+               "f"(v.w)
+               : "memory");
+}
+__device__ __forceinline__ float4 ld_stream4(const float* p) {
+  float4 v;
+  asm volatile("ld.global.cs.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "l"(p));
+  return v;
 }
 __device__ __forceinline__ float ld_stream(const float* p) {
   float v;

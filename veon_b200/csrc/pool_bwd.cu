@@ -25,23 +25,24 @@
 
 namespace veon {
 
-constexpr int kBwdWarps = 8;
+constexpr int kBwdWarps = 8;   // pixel pass: 8 consecutive pixels per CTA
+constexpr int kRowWarps = 4;   // row pass
 constexpr int kPitch = kTileVoxels + 1;
 
 template <int KCH>
-__global__ void __launch_bounds__(kBwdWarps * 32)
+__global__ void __launch_bounds__(kRowWarps * 32)
 k_bwd_rows(const float* __restrict__ out_grad, const int32_t* __restrict__ ranks_bev,
            const int32_t* __restrict__ interval_starts,
            const int32_t* __restrict__ tile_start, const int32_t* __restrict__ tile_istart,
            int64_t tile_begin, int64_t tile_end, int64_t tiles_per_sample, int64_t V, int C,
-           int n_chunks, float* __restrict__ rows) {
+           int n_chunks, int vec_ok, float* __restrict__ rows) {
   constexpr int CC = 32 * KCH;
   extern __shared__ float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* tile = smem + warp * (CC * kPitch);
   const int64_t group = blockIdx.x / n_chunks;
   const int cbase = (int)(blockIdx.x - group * n_chunks) * CC;
-  const int64_t t = tile_begin + group * kBwdWarps + warp;
+  const int64_t t = tile_begin + group * kRowWarps + warp;
   if (t >= tile_end) return;
   const int32_t i0 = __ldg(tile_istart + t);
   const int ni = __ldg(tile_istart + t + 1) - i0;  // intervals in this tile, <= 32
@@ -53,13 +54,27 @@ k_bwd_rows(const float* __restrict__ out_grad, const int32_t* __restrict__ ranks
   int vl = 0;
   if (lane < ni) vl = (int)(__ldg(ranks_bev + __ldg(interval_starts + i0 + lane)) - g0);
   const uint32_t occ = __reduce_or_sync(0xffffffffu, lane < ni ? (1u << (vl & 31)) : 0u);
-  // fetch only 32-byte sectors (8 voxels) that contain an occupied voxel
-  const bool want = ((occ >> (lane & 24)) & 0xffu) != 0u && (v0 + lane < V);
-  const float* g = out_grad + ((int64_t)b * C + cbase) * V + v0 + lane;
+  // fetch only 32-byte sectors (8 voxels) that contain an occupied voxel.
+  // lane (r = lane/8, q = lane%8) loads voxels 4q..4q+3 of channel 4*it + r with
+  // one 16-byte load; the 4 scalar smem stores hit banks (c + 4q + i) mod 32.
   const int cmax = min(CC, C - cbase);
-#pragma unroll 8
-  for (int cl = 0; cl < cmax; ++cl)
-    tile[cl * kPitch + lane] = want ? ld_stream(g + (int64_t)cl * V) : 0.f;
+  const int q4 = (lane & 7) * 4, r = lane >> 3;
+  const bool want = ((occ >> (q4 & 24)) & 0xffu) != 0u;
+  if (vec_ok && v0 + kTileVoxels <= V) {
+    const float* g = out_grad + ((int64_t)b * C + cbase + r) * V + v0 + q4;
+    float* trow = tile + r * kPitch + q4;
+#pragma unroll 4
+    for (int c = r; c < cmax; c += 4, g += 4 * V, trow += 4 * kPitch) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (want) v = ld_stream4(g);
+      trow[0] = v.x; trow[1] = v.y; trow[2] = v.z; trow[3] = v.w;
+    }
+  } else {
+    const bool wants = ((occ >> (lane & 24)) & 0xffu) != 0u && (v0 + lane < V);
+    const float* g = out_grad + ((int64_t)b * C + cbase) * V + v0 + lane;
+    for (int cl = 0; cl < cmax; ++cl)
+      tile[cl * kPitch + lane] = wants ? ld_stream(g + (int64_t)cl * V) : 0.f;
+  }
   __syncwarp();
   for (int j = 0; j < ni; ++j) {
     const int vj = __shfl_sync(0xffffffffu, vl, j);
@@ -79,7 +94,7 @@ k_bwd_pixels(const float* __restrict__ rows, const float* __restrict__ depth,
              int64_t pix_begin, int64_t pix_end, int D, int HW, int C,
              float* __restrict__ depth_grad, float* __restrict__ feat_grad) {
   constexpr int CC = 32 * KCH;
-  constexpr int U = 4;
+  constexpr int U = (KCH <= 2) ? 8 : 4;  // gradient rows in flight per warp
   extern __shared__ float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // per warp: dots[D] | dep[D] | iis[D] | kd[D]
@@ -166,7 +181,7 @@ static int launch_rows(const float* out_grad, const int32_t* rb, const int32_t* 
                        int64_t tile_begin, int64_t tile_end, int64_t tps, int64_t V, int C,
                        float* rows, cudaStream_t stream) {
   constexpr int CC = 32 * KCH;
-  const size_t smem = sizeof(float) * kBwdWarps * CC * kPitch;
+  const size_t smem = sizeof(float) * kRowWarps * CC * kPitch;
   static bool attr_set = false;
   if (!attr_set) {
     VEON_CUDA_TRY(cudaFuncSetAttribute(k_bwd_rows<KCH>,
@@ -174,12 +189,13 @@ static int launch_rows(const float* out_grad, const int32_t* rb, const int32_t* 
     attr_set = true;
   }
   const int n_chunks = (C + CC - 1) / CC;
-  const int64_t blocks = ceil_div64(tile_end - tile_begin, kBwdWarps) * n_chunks;
+  const int vec_ok = ((V & 3) == 0) && (((uintptr_t)out_grad & 15) == 0);
+  const int64_t blocks = ceil_div64(tile_end - tile_begin, kRowWarps) * n_chunks;
   if (blocks <= 0) return 0;
   if (blocks > 0x7fffffffLL) return VEON_E_RANGE;
-  k_bwd_rows<KCH><<<(unsigned)blocks, kBwdWarps * 32, smem, stream>>>(
+  k_bwd_rows<KCH><<<(unsigned)blocks, kRowWarps * 32, smem, stream>>>(
       out_grad, rb, istarts, tile_start, tile_istart, tile_begin, tile_end, tps, V, C, n_chunks,
-      rows);
+      vec_ok, rows);
   VEON_LAUNCH_CHECK();
   return 0;
 }

@@ -10,9 +10,9 @@
 // 32*KCH channels.  Because points are sorted by voxel, the tile's points are
 // one contiguous slice [tile_start[t], tile_start[t+1]) of the rank arrays.
 // Lanes run over CHANNELS while accumulating (feature rows are read as full
-// 128-byte lines) and over VOXELS while storing (every store is one full
-// 128-byte line of a channel plane); a padded shared-memory tile [c][33] does
-// the transposition conflict-free in both directions.  Empty voxels are
+// 128-byte lines) and over VOXELS while storing (one 16-byte store per lane =
+// four full 128-byte lines of four channel planes per instruction); a padded
+// shared-memory tile [c][33] does the transposition conflict-free both ways.  Empty voxels are
 // written as zeros from an occupancy mask, so the volume is touched exactly
 // once: no memset, no permute pass, no atomics.  Accumulation order inside a
 // voxel is the rank order, fma(feat, depth, acc) starting from 0 -- the same
@@ -21,7 +21,7 @@
 
 namespace veon {
 
-constexpr int kFwdWarps = 8;
+constexpr int kFwdWarps = 4;
 constexpr int kTilePitch = kTileVoxels + 1;  // 33: conflict-free both ways
 
 template <int KCH>
@@ -30,7 +30,7 @@ k_pool_fwd(const float* __restrict__ depth, const float* __restrict__ feat,
            const int32_t* __restrict__ ranks_depth, const int32_t* __restrict__ ranks_feat,
            const int32_t* __restrict__ ranks_bev, const int32_t* __restrict__ tile_start,
            int64_t n_tiles, int64_t tiles_per_sample, int64_t V, int C, int n_chunks,
-           float* __restrict__ out) {
+           int vec_ok, float* __restrict__ out) {
   constexpr int CC = 32 * KCH;
   constexpr int U = 4;  // points whose feature rows are in flight together
   extern __shared__ float smem[];
@@ -102,14 +102,36 @@ k_pool_fwd(const float* __restrict__ depth, const float* __restrict__ feat,
   }
   __syncwarp();
 
-  const bool occl = (occ >> lane) & 1u;
-  const bool inb = v0 + lane < V;
-  float* o = out + ((int64_t)b * C + cbase) * V + v0 + lane;
+  // Write-out: lane (r = lane/8, q = lane%8) stores voxels 4q..4q+3 of channel
+  // 4*it + r as one 16-byte store, so one instruction covers 4 channel planes x
+  // 128 bytes.  The four scalar shared-memory reads behind it hit banks
+  // (c + 4q + i) mod 32 = all distinct (pitch 33).
+  const int q4 = (lane & 7) * 4, r = lane >> 3;
+  const uint32_t occ4 = (occ >> q4) & 0xfu;
   const int cmax = min(CC, C - cbase);
-#pragma unroll 8
-  for (int cl = 0; cl < cmax; ++cl) {
-    const float val = occl ? tile[cl * kTilePitch + lane] : 0.f;
-    if (inb) st_stream(o + (int64_t)cl * V, val);
+  float* o = out + ((int64_t)b * C + cbase + r) * V + v0 + q4;
+  const int64_t ostep = 4 * V;
+  const float* trow = tile + r * kTilePitch + q4;
+  if (vec_ok && v0 + kTileVoxels <= V) {  // full, 16-byte aligned tile (the usual case)
+    if (occ == 0u) {
+#pragma unroll 4
+      for (int c = r; c < cmax; c += 4, o += ostep) st_stream4(o, make_float4(0.f, 0.f, 0.f, 0.f));
+    } else {
+#pragma unroll 4
+      for (int c = r; c < cmax; c += 4, o += ostep, trow += 4 * kTilePitch) {
+        float4 v;
+        v.x = (occ4 & 1u) ? trow[0] : 0.f;
+        v.y = (occ4 & 2u) ? trow[1] : 0.f;
+        v.z = (occ4 & 4u) ? trow[2] : 0.f;
+        v.w = (occ4 & 8u) ? trow[3] : 0.f;
+        st_stream4(o, v);
+      }
+    }
+  } else {  // ragged volume edge: scalar, bounds-checked
+    for (int c = r; c < cmax; c += 4, o += ostep, trow += 4 * kTilePitch)
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (v0 + q4 + i < V) st_stream(o + i, ((occ4 >> i) & 1u) ? trow[i] : 0.f);
   }
 }
 
@@ -127,10 +149,11 @@ static int launch_fwd(const float* depth, const float* feat, const int32_t* rd,
   }
   const int64_t tps = ceil_div64(V, kTileVoxels), n_tiles = (int64_t)B * tps;
   const int n_chunks = (C + CC - 1) / CC;
+  const int vec_ok = ((V & 3) == 0) && (((uintptr_t)out & 15) == 0);
   const int64_t blocks = ceil_div64(n_tiles, kFwdWarps) * n_chunks;
   if (blocks > 0x7fffffffLL) return VEON_E_RANGE;
   k_pool_fwd<KCH><<<(unsigned)blocks, kFwdWarps * 32, smem, stream>>>(
-      depth, feat, rd, rf, rb, tile_start, n_tiles, tps, V, C, n_chunks, out);
+      depth, feat, rd, rf, rb, tile_start, n_tiles, tps, V, C, n_chunks, vec_ok, out);
   VEON_LAUNCH_CHECK();
   return 0;
 }

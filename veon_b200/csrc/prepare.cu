@@ -218,23 +218,34 @@ k_scan(const int32_t* __restrict__ count, int32_t* __restrict__ offset,
     if (w < warp) wprefix += v;
     btotal += v;
   }
-  if (tid == 0) {
+  // decoupled look-back, one warp wide: lane l inspects predecessor tile-1-l;
+  // the window slides back 32 tiles at a time until an inclusive prefix is seen
+  if (warp == 0) {
     unsigned long long excl = 0;
     if (tile == 0) {
-      st_relaxed(desc, kFlagIncl | btotal);
+      if (lane == 0) st_relaxed(desc, kFlagIncl | btotal);
     } else {
-      st_relaxed(desc + tile, kFlagAgg | btotal);
-      int64_t j = (int64_t)tile - 1;
+      if (lane == 0) st_relaxed(desc + tile, kFlagAgg | btotal);
+      int64_t hi = (int64_t)tile - 1;  // newest predecessor of the window
       while (true) {
-        unsigned long long d = ld_relaxed(desc + j);
-        if ((d >> 62) == 0) continue;  // predecessor not published yet
-        excl += d & kValMask;
-        if (d & kFlagIncl) break;
-        --j;
+        const int64_t j = hi - lane;
+        unsigned long long d = kFlagIncl;  // virtual tile -1: inclusive prefix 0
+        if (j >= 0) {
+          do { d = ld_relaxed(desc + j); } while ((d >> 62) == 0);
+        }
+        const uint32_t incl_mask = __ballot_sync(0xffffffffu, (d & kFlagIncl) != 0);
+        // lanes nearer than (and including) the first inclusive one contribute
+        const int stop = incl_mask ? __ffs(incl_mask) - 1 : 31;
+        unsigned long long v = (lane <= stop) ? (d & kValMask) : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        excl += v;
+        if (incl_mask) break;
+        hi -= 32;
       }
-      st_relaxed(desc + tile, kFlagIncl | (excl + btotal));
+      if (lane == 0) st_relaxed(desc + tile, kFlagIncl | (excl + btotal));
     }
-    s_excl = excl;
+    if (lane == 0) s_excl = excl;
   }
   __syncthreads();
   unsigned long long run = s_excl + wprefix + (incl - tsum);
