@@ -166,6 +166,7 @@ int veon_bev_pool_v2_fwd_planar(const float* depth, const float* feat,
                                 const int32_t* ranks_bev,
                                 const int32_t* tile_start,
                                 int B, int C, int64_t voxels_per_sample,
+                                int64_t n_feat_rows /* B*N*H*W rows of feat */,
                                 float* out, void* stream);
 
 /* QuickCumsumCuda.backward (bev_pool.py:43-83) for a [B,C,Z,Y,X] out_grad.

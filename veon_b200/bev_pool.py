@@ -253,7 +253,7 @@ def _fwd_planar(depth, feat, rd, rf, rb, plan, B, C, V, shape5):
         with _timed("pool_fwd", dev):
             rc = lib.veon_bev_pool_v2_fwd_planar(
                 _ptr(depth), _ptr(feat), _ptr(rd), _ptr(rf), _ptr(rb), _ptr(plan.tile_start),
-                B, C, V, _ptr(out), _stream_ptr(dev))
+                B, C, V, feat.numel() // C, _ptr(out), _stream_ptr(dev))
     _lib.check(rc, "veon_bev_pool_v2_fwd_planar")
     return out
 

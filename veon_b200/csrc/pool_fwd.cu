@@ -6,154 +6,301 @@
 // thread per (interval, channel), writes only occupied voxels of a
 // channels-last volume, and needs a memset before and a full transpose after.
 //
-// Here one warp owns one 32-voxel x-run of the output ("tile") for a chunk of
-// 32*KCH channels.  Because points are sorted by voxel, the tile's points are
-// one contiguous slice [tile_start[t], tile_start[t+1]) of the rank arrays.
-// Lanes run over CHANNELS while accumulating (feature rows are read as full
-// 128-byte lines) and over VOXELS while storing (one 16-byte store per lane =
-// four full 128-byte lines of four channel planes per instruction); a padded
-// shared-memory tile [c][33] does the transposition conflict-free both ways.  Empty voxels are
-// written as zeros from an occupancy mask, so the volume is touched exactly
-// once: no memset, no permute pass, no atomics.  Accumulation order inside a
-// voxel is the rank order, fma(feat, depth, acc) starting from 0 -- the same
-// sequence of roundings as the reference kernel's `psum += feat * depth`.
+// Here one warp handles one 32-voxel x-run of the output ("tile") for a chunk of
+// 32*KCH channels at a time (persistent grid, warps stride over the tiles).
+// Because points are sorted by voxel, the tile's points are one contiguous
+// slice [tile_start[t], tile_start[t+1]) of the rank arrays.  Lanes run over
+// CHANNELS while gathering (feature rows are read as full 128-byte lines, the
+// per-voxel sum lives in registers) and over VOXELS while storing (one 16-byte
+// store per lane = four full 128-byte lines of four channel planes per
+// instruction); a padded shared tile [c][33] does the transposition
+// conflict-free both ways.  Empty voxels are written as zeros from an
+// occupancy mask, so the volume is touched exactly once: no memset, no permute
+// pass, no atomics.  Accumulation order inside a voxel is the rank order,
+// fma(feat, depth, acc) starting from 0 -- the same sequence of roundings as
+// the reference kernel's `psum += feat * depth`.
 #include "common.cuh"
 
 namespace veon {
 
-constexpr int kFwdWarps = 4;
-constexpr int kTilePitch = kTileVoxels + 1;  // 33: conflict-free both ways
+constexpr int kFwdWarps = 8;                 // x 2 CTAs/SM = 16 warps/SM at 64 channels
+constexpr int kRowPitch = kTileVoxels + 4;   // 36 floats: rows stay 16-byte aligned
 
+// ---- per-warp prefetch ring in shared memory (cp.async, no registers held) ----
+// slot (ints): [0]=s [1]=e [2]=tile [3]=cbase, then one int4 per point (lane j):
+//   landing   {ranks_bev, ranks_feat, ranks_depth, depth}
+//   fixed up  {ranks_bev, row offset (floats), voxel | first<<8, depth}
+constexpr int kDist = 2;                     // prefetch distance in items per stage
+constexpr int kRingSlots = 4 * kDist;        // bounds run 3*kDist ahead
+constexpr int kSlotInts = 4 + 4 * 32;
+
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+// every group except the (kDist-1) most recent ones has landed
+__device__ __forceinline__ void cp_async_wait_dist() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(kDist - 1) : "memory");
+}
+
+// Persistent: every warp strides over (tile, channel-chunk) items.
+//  * index prefetch: tile bounds -> rank triple -> depth value run 3 / 2 / 1 x kDist
+//    items ahead as 4-byte cp.async copies into a per-warp ring (no registers held;
+//    `wait_group kDist-1` leaves the youngest group in flight, so short items do not
+//    expose the latency); a lanes=points fix-up turns the landed ranks into
+//    (row offset, voxel | first-of-voxel) so that the gather loop needs ONE
+//    broadcast LDS.128 per point;
+//  * gather: lanes = channels, 8 points' rows in flight, per-voxel sums in registers
+//    (fma(feat, depth, acc) in rank order), one store per occupied voxel into the
+//    zero-filled [c][36] shared tile;
+//  * write-out: lanes = voxels, LDS.128 + one 16-byte streaming store covers
+//    4 channel planes x 128 B per instruction.
+// (A TMA tensor-store write-out was measured slower here: ~17 B/clk/SM for boxes
+//  of 128-byte rows vs ~23 B/clk/SM for st.global.v4; see profiles/README.md.)
 template <int KCH>
 __global__ void __launch_bounds__(kFwdWarps * 32)
 k_pool_fwd(const float* __restrict__ depth, const float* __restrict__ feat,
            const int32_t* __restrict__ ranks_depth, const int32_t* __restrict__ ranks_feat,
            const int32_t* __restrict__ ranks_bev, const int32_t* __restrict__ tile_start,
-           int64_t n_tiles, int64_t tiles_per_sample, int64_t V, int C, int n_chunks,
+           uint32_t n_items, uint32_t tiles_per_sample, int64_t V, int C, uint32_t n_chunks,
            int vec_ok, float* __restrict__ out) {
   constexpr int CC = 32 * KCH;
-  constexpr int U = 4;  // points whose feature rows are in flight together
-  extern __shared__ float smem[];
+  constexpr int U = 8;  // feature rows in flight per warp
+  constexpr int kTileFloats = CC * kRowPitch;
+  constexpr int kWarpFloats = kTileFloats + kRingSlots * kSlotInts;
+  extern __shared__ __align__(16) float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* tile = smem + warp * (CC * kTilePitch);
+  float* tile = smem + warp * kWarpFloats;
+  int32_t* ring = reinterpret_cast<int32_t*>(tile + kTileFloats);
+  const uint32_t TW = gridDim.x * kFwdWarps;
+  const uint32_t first_item = blockIdx.x * kFwdWarps + warp;
+  if (first_item >= n_items) return;
+  const uint32_t my_items = (n_items - first_item + TW - 1) / TW;
 
-  // consecutive CTAs share a tile group and differ in channel chunk, so the
-  // rank slice they all read stays in L1/L2
-  const int64_t group = blockIdx.x / n_chunks;
-  const int cbase = (int)(blockIdx.x - group * n_chunks) * CC;
-  const int64_t t = group * kFwdWarps + warp;
-  if (t >= n_tiles) return;  // no block-level barrier below
-  const int64_t b = t / tiles_per_sample;
-  const int64_t v0 = (t - b * tiles_per_sample) * kTileVoxels;
-  const int64_t g0 = b * V + v0;
-
-  const int32_t s = __ldg(tile_start + t), e = __ldg(tile_start + t + 1);
-  uint32_t occ = 0;
-  int32_t prev_rb = -1;
-  for (int32_t base = s; base < e; base += 32) {
-    const int32_t i = base + lane;
-    const bool valid = i < e;
-    int32_t my_rb = -1, my_rf = 0;
-    float my_d = 0.f;
-    if (valid) {
-      my_rb = __ldg(ranks_bev + i);
-      my_rf = __ldg(ranks_feat + i);
-      my_d = __ldg(depth + __ldg(ranks_depth + i));
-    }
-    int32_t up = __shfl_up_sync(0xffffffffu, my_rb, 1);
-    if (lane == 0) up = prev_rb;
-    const bool first = valid && (my_rb != up);
-    const int32_t vl = (int32_t)(my_rb - g0);  // 0..31 when valid
-    const int32_t packed = (vl & 0xff) | (first ? 0x100 : 0);
-    prev_rb = __shfl_sync(0xffffffffu, my_rb, 31);
-    occ |= __reduce_or_sync(0xffffffffu, first ? (1u << (vl & 31)) : 0u);
-    const int cnt = min(32, e - base);
-    for (int j0 = 0; j0 < cnt; j0 += U) {
-      float f[U][KCH];
-      float dj[U];
-      int pj[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int j = min(j0 + u, 31);
-        pj[u] = __shfl_sync(0xffffffffu, packed, j);
-        dj[u] = __shfl_sync(0xffffffffu, my_d, j);
-        const int32_t fj = __shfl_sync(0xffffffffu, my_rf, j);
-        const float* frow = feat + (int64_t)fj * C + cbase + lane;
-#pragma unroll
-        for (int k = 0; k < KCH; ++k) {
-          const bool in = (j0 + u < cnt) && (cbase + lane + 32 * k < C);
-          f[u][k] = in ? __ldg(frow + 32 * k) : 0.f;
+  auto slot_of = [&](uint32_t m) { return ring + (m & (kRingSlots - 1)) * kSlotInts; };
+  auto issue_bounds = [&](uint32_t m) {  // tile_start[t], tile_start[t+1] -> slot[0..1]
+    int32_t* sl = slot_of(m);
+    if (lane < 2) {
+      if (m < my_items) {
+        const uint32_t item = first_item + m * TW;
+        const uint32_t t = (n_chunks == 1) ? item : item / n_chunks;
+        cp_async4(sl + lane, tile_start + t + lane);
+        if (lane == 0) {
+          sl[2] = (int32_t)t;
+          sl[3] = (int32_t)(item - t * n_chunks) * CC;
         }
+      } else {
+        sl[lane] = 0;
       }
+    }
+  };
+  auto issue_ranks = [&](uint32_t m) {  // needs bounds(m)
+    int32_t* sl = slot_of(m);
+    int32_t* pt = sl + 4 + 4 * lane;
+    const int32_t i = sl[0] + lane;
+    if (i < sl[1]) {
+      cp_async4(pt + 0, ranks_bev + i);
+      cp_async4(pt + 1, ranks_feat + i);
+      cp_async4(pt + 2, ranks_depth + i);
+    } else {
+      pt[0] = -1;
+    }
+  };
+  // needs ranks(m): depth gather + fix-up of the landed ranks (lanes = points)
+  auto issue_depth = [&](uint32_t m) {
+    int32_t* sl = slot_of(m);
+    int32_t* pt = sl + 4 + 4 * lane;
+    const int32_t rb = pt[0];
+    if (rb >= 0) {
+      cp_async4(pt + 3, depth + pt[2]);
+      const uint32_t t = (uint32_t)sl[2];
+      const uint32_t b = t / tiles_per_sample;
+      const int32_t g0 = (int32_t)((int64_t)b * V) + (int32_t)(t - b * tiles_per_sample) * kTileVoxels;
+      const int32_t up = lane ? pt[-4] : -1;
+      pt[1] = (int32_t)((uint32_t)pt[1] * (uint32_t)C);    // row offset in floats (< 2^32)
+      pt[2] = (rb - g0) | ((rb != up) ? 0x100 : 0);        // voxel | first-of-voxel
+    }
+  };
+
+  // prologue: fill the pipeline (three serialized latencies, once per warp)
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (j0 + u < cnt) {
-          const int vlj = pj[u] & 0xff;
-          const bool fst = (pj[u] & 0x100) != 0;
+  for (int i = 0; i < 3 * kDist; ++i) issue_bounds(i);
+  cp_async_commit(); cp_async_wait_all(); __syncwarp();
 #pragma unroll
-          for (int k = 0; k < KCH; ++k) {
-            float* a = tile + (lane + 32 * k) * kTilePitch + vlj;
-            const float acc = fst ? 0.f : *a;
-            *a = fmaf(f[u][k], dj[u], acc);
+  for (int i = 0; i < 2 * kDist; ++i) issue_ranks(i);
+  cp_async_commit(); cp_async_wait_all(); __syncwarp();
+#pragma unroll
+  for (int i = 0; i < kDist; ++i) issue_depth(i);
+  cp_async_commit(); cp_async_wait_all(); __syncwarp();
+
+  const int q4 = (lane & 7) * 4, r = lane >> 3;  // write-out role of this lane
+  float* const tlane = tile + lane * kRowPitch;   // flush base: channel = lane (+32k)
+
+  for (uint32_t m = 0; m < my_items; ++m) {
+    cp_async_wait_dist();
+    __syncwarp();
+    int32_t* sl = slot_of(m);
+    const int32_t s0 = sl[0], e0 = sl[1];
+    const uint32_t t = (uint32_t)sl[2];
+    const int cbase = sl[3];
+    issue_bounds(m + 3 * kDist);  // lands in the slot item m-kDist used
+    issue_ranks(m + 2 * kDist);
+    issue_depth(m + kDist);
+    cp_async_commit();
+
+    const uint32_t b = t / tiles_per_sample;
+    const int v0 = (int)(t - b * tiles_per_sample) * kTileVoxels;
+    const int cmax = min(CC, C - cbase);
+    float* o = out + ((int64_t)b * C + cbase + r) * V + v0 + q4;
+    const int64_t ostep = 4 * V;
+    const bool fast = vec_ok && (v0 + kTileVoxels <= V);
+
+    if (e0 <= s0 && fast) {  // empty tile
+#pragma unroll 4
+      for (int c = r; c < cmax; c += 4, o += ostep) st_stream4(o, make_float4(0.f, 0.f, 0.f, 0.f));
+      continue;
+    }
+
+    __syncwarp();
+    {  // zero the tile (empty voxels must read as 0)
+      float4* t4 = reinterpret_cast<float4*>(tile);
+#pragma unroll
+      for (int i = 0; i < kTileFloats / 4 / 32; ++i) t4[lane + 32 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncwarp();
+
+    float acc[KCH];
+    int acc_vl = -1;
+    const float* feat_lane = feat + cbase + lane;
+    const bool full_chunk = (cmax == CC);
+    for (int32_t base = s0; base < e0; base += 32) {
+      const int cnt = min(32, e0 - base);
+      if (base != s0) {  // long tile: later chunks are fetched synchronously
+        const int32_t i = base + lane;
+        const int32_t g0 = (int32_t)((int64_t)b * V) + v0;
+        __syncwarp();
+        int32_t rb = -1, rf = 0;
+        float d = 0.f;
+        if (i < e0) {
+          rb = __ldg(ranks_bev + i);
+          rf = __ldg(ranks_feat + i);
+          d = __ldg(depth + __ldg(ranks_depth + i));
+        }
+        const int32_t up = __shfl_up_sync(0xffffffffu, rb, 1);
+        const bool first = (lane > 0) && (rb != up);  // lane 0 continues or starts: see below
+        int32_t* pt = sl + 4 + 4 * lane;
+        pt[1] = (int32_t)((uint32_t)rf * (uint32_t)C);
+        pt[2] = (rb - g0) | (first ? 0x100 : 0);
+        pt[3] = __float_as_int(d);
+        if (lane == 0) {  // first point of the chunk: new voxel iff it differs from the last one
+          const int32_t last = sl[4 + 4 * 31 + 0];
+          pt[2] = (rb - g0) | ((rb != last) ? 0x100 : 0);
+        }
+        __syncwarp();
+        pt[0] = rb;
+        __syncwarp();
+      }
+      const int4* pts = reinterpret_cast<const int4*>(sl + 4);
+      for (int j0 = 0; j0 < cnt; j0 += U) {
+        int4 p[U];
+        float f[U][KCH];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {  // U points' rows in flight
+          p[u] = pts[min(j0 + u, cnt - 1)];
+          const float* row = feat_lane + (uint32_t)p[u].y;
+#pragma unroll
+          for (int k = 0; k < KCH; ++k)
+            f[u][k] = (full_chunk || lane + 32 * k < cmax) ? __ldg(row + 32 * k) : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (j0 + u < cnt) {
+            const float dj = __int_as_float(p[u].w);
+            if (p[u].z & 0x100) {  // first point of its voxel (warp-uniform)
+              if (acc_vl >= 0) {
+#pragma unroll
+                for (int k = 0; k < KCH; ++k) tlane[32 * k * kRowPitch + acc_vl] = acc[k];
+              }
+              acc_vl = p[u].z & 0xff;
+#pragma unroll
+              for (int k = 0; k < KCH; ++k) acc[k] = fmaf(f[u][k], dj, 0.f);
+            } else {
+#pragma unroll
+              for (int k = 0; k < KCH; ++k) acc[k] = fmaf(f[u][k], dj, acc[k]);
+            }
           }
         }
       }
     }
-  }
-  __syncwarp();
-
-  // Write-out: lane (r = lane/8, q = lane%8) stores voxels 4q..4q+3 of channel
-  // 4*it + r as one 16-byte store, so one instruction covers 4 channel planes x
-  // 128 bytes.  The four scalar shared-memory reads behind it hit banks
-  // (c + 4q + i) mod 32 = all distinct (pitch 33).
-  const int q4 = (lane & 7) * 4, r = lane >> 3;
-  const uint32_t occ4 = (occ >> q4) & 0xfu;
-  const int cmax = min(CC, C - cbase);
-  float* o = out + ((int64_t)b * C + cbase + r) * V + v0 + q4;
-  const int64_t ostep = 4 * V;
-  const float* trow = tile + r * kTilePitch + q4;
-  if (vec_ok && v0 + kTileVoxels <= V) {  // full, 16-byte aligned tile (the usual case)
-    if (occ == 0u) {
-#pragma unroll 4
-      for (int c = r; c < cmax; c += 4, o += ostep) st_stream4(o, make_float4(0.f, 0.f, 0.f, 0.f));
-    } else {
-#pragma unroll 4
-      for (int c = r; c < cmax; c += 4, o += ostep, trow += 4 * kTilePitch) {
-        float4 v;
-        v.x = (occ4 & 1u) ? trow[0] : 0.f;
-        v.y = (occ4 & 2u) ? trow[1] : 0.f;
-        v.z = (occ4 & 4u) ? trow[2] : 0.f;
-        v.w = (occ4 & 8u) ? trow[3] : 0.f;
-        st_stream4(o, v);
-      }
-    }
-  } else {  // ragged volume edge: scalar, bounds-checked
-    for (int c = r; c < cmax; c += 4, o += ostep, trow += 4 * kTilePitch)
+    if (acc_vl >= 0) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if (v0 + q4 + i < V) st_stream(o + i, ((occ4 >> i) & 1u) ? trow[i] : 0.f);
+      for (int k = 0; k < KCH; ++k) tlane[32 * k * kRowPitch + acc_vl] = acc[k];
+    }
+    __syncwarp();
+
+    // Write-out: lane (r = lane/8, q = lane%8) moves voxels 4q..4q+3 of channel
+    // 4*it + r with one LDS.128 + one 16-byte streaming store.
+    const float* trow = tile + r * kRowPitch + q4;
+    if (fast) {
+#pragma unroll 4
+      for (int c = r; c < cmax; c += 4, o += ostep, trow += 4 * kRowPitch)
+        st_stream4(o, *reinterpret_cast<const float4*>(trow));
+    } else {  // ragged volume edge / unaligned volume: scalar, bounds-checked
+      for (int c = r; c < cmax; c += 4, o += ostep, trow += 4 * kRowPitch)
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (v0 + q4 + i < V) st_stream(o + i, trow[i]);
+    }
+    // (the __syncwarp before the next zero-fill protects the tile reuse)
   }
+  cp_async_wait_all();
+}
+
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+static int env_flag(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
 }
 
 template <int KCH>
 static int launch_fwd(const float* depth, const float* feat, const int32_t* rd,
                       const int32_t* rf, const int32_t* rb, const int32_t* tile_start, int B,
-                      int C, int64_t V, float* out, cudaStream_t stream) {
+                      int C, int64_t V, bool feat_rows_fit_32bit, float* out,
+                      cudaStream_t stream) {
   constexpr int CC = 32 * KCH;
-  const size_t smem = sizeof(float) * kFwdWarps * CC * kTilePitch;
-  static bool attr_set = false;
-  if (!attr_set) {
+  const size_t smem = sizeof(float) * kFwdWarps * (CC * kRowPitch + kRingSlots * kSlotInts);
+  static int ctas_per_sm = 0;
+  if (ctas_per_sm == 0) {
     VEON_CUDA_TRY(cudaFuncSetAttribute(k_pool_fwd<KCH>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_set = true;
+    VEON_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_pool_fwd<KCH>,
+                                                                kFwdWarps * 32, smem));
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
   }
   const int64_t tps = ceil_div64(V, kTileVoxels), n_tiles = (int64_t)B * tps;
   const int n_chunks = (C + CC - 1) / CC;
+  if (n_tiles * n_chunks > 0x7fffffffLL || (int64_t)B * V > 0x7fffffffLL) return VEON_E_RANGE;
+  // the gather addresses rows with 32-bit float offsets
+  if (!feat_rows_fit_32bit) return VEON_E_RANGE;
   const int vec_ok = ((V & 3) == 0) && (((uintptr_t)out & 15) == 0);
-  const int64_t blocks = ceil_div64(n_tiles, kFwdWarps) * n_chunks;
-  if (blocks > 0x7fffffffLL) return VEON_E_RANGE;
+  int64_t blocks = ceil_div64(n_tiles * n_chunks, kFwdWarps);
+  const int64_t resident = (int64_t)ctas_per_sm * sm_count();  // persistent grid
+  if (blocks > resident) blocks = resident;
   k_pool_fwd<KCH><<<(unsigned)blocks, kFwdWarps * 32, smem, stream>>>(
-      depth, feat, rd, rf, rb, tile_start, n_tiles, tps, V, C, n_chunks, vec_ok, out);
+      depth, feat, rd, rf, rb, tile_start, (uint32_t)(n_tiles * n_chunks), (uint32_t)tps, V, C,
+      (uint32_t)n_chunks, vec_ok, out);
   VEON_LAUNCH_CHECK();
   return 0;
 }
@@ -177,17 +324,18 @@ extern "C" int veon_bev_pool_v2_fwd_planar(const float* depth, const float* feat
                                            const int32_t* ranks_feat,
                                            const int32_t* ranks_bev,
                                            const int32_t* tile_start, int B, int C, int64_t V,
-                                           float* out, void* stream_) {
+                                           int64_t n_feat_rows, float* out, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!depth || !feat || !ranks_depth || !ranks_feat || !ranks_bev || !tile_start || !out ||
-      B <= 0 || C <= 0 || V <= 0)
+      B <= 0 || C <= 0 || V <= 0 || n_feat_rows <= 0)
     return VEON_E_BADARG;
+  const bool fit32 = n_feat_rows * (int64_t)C <= 0xffffffffLL;
   int kch = fwd_kch_override();
   if (kch == 0) kch = (C <= 32) ? 1 : 2;
   switch (kch) {
-    case 1: return launch_fwd<1>(depth, feat, ranks_depth, ranks_feat, ranks_bev, tile_start, B, C, V, out, stream);
-    case 2: return launch_fwd<2>(depth, feat, ranks_depth, ranks_feat, ranks_bev, tile_start, B, C, V, out, stream);
-    case 4: return launch_fwd<4>(depth, feat, ranks_depth, ranks_feat, ranks_bev, tile_start, B, C, V, out, stream);
+    case 1: return launch_fwd<1>(depth, feat, ranks_depth, ranks_feat, ranks_bev, tile_start, B, C, V, fit32, out, stream);
+    case 2: return launch_fwd<2>(depth, feat, ranks_depth, ranks_feat, ranks_bev, tile_start, B, C, V, fit32, out, stream);
+    case 4: return launch_fwd<4>(depth, feat, ranks_depth, ranks_feat, ranks_bev, tile_start, B, C, V, fit32, out, stream);
     default: return VEON_E_BADARG;
   }
 }
