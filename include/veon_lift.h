@@ -118,9 +118,10 @@ int veon_bev_pool_v2_grad_generic(int c, int64_t n_points, int layout,
  *  arbitrary; ours is the canonical stable one).
  *
  *  Optional by-products ("plan") consumed by the *_planar pool entry points
- *  (pass NULL to skip all three):
+ *  (pass NULL to skip all four):
  *      tile_start   int32[n_tiles+1]  first point of each 32-voxel tile
  *      tile_istart  int32[n_tiles+1]  first interval of each tile
+ *      tile_occ     uint32[n_tiles+1] bit v set <=> voxel v of the tile is occupied
  *      point_interval int32[P]        interval index of depth element
  *                   (b,n,d,h,w) stored PIXEL-major at ((b*N+n)*H*W+hw)*D+d,
  *                   -1 where the point was dropped
@@ -136,7 +137,7 @@ int veon_prepare_v2(const float* coor, int B, int N, int D, int H, int W,
                     int32_t* ranks_bev, int32_t* ranks_depth, int32_t* ranks_feat,
                     int32_t* interval_starts, int32_t* interval_lengths,
                     int64_t* counts,
-                    int32_t* tile_start, int32_t* tile_istart,
+                    int32_t* tile_start, int32_t* tile_istart, uint32_t* tile_occ,
                     int32_t* point_interval,
                     void* workspace, size_t workspace_bytes, void* stream);
 
@@ -151,7 +152,7 @@ int veon_pool_plan_build(const int32_t* ranks_depth, const int32_t* ranks_feat,
                          int64_t n_points, int64_t n_intervals,
                          int B, int N, int D, int H, int W,
                          int64_t voxels_per_sample,
-                         int32_t* tile_start, int32_t* tile_istart,
+                         int32_t* tile_start, int32_t* tile_istart, uint32_t* tile_occ,
                          int32_t* point_interval, int32_t* flags, void* stream);
 
 /* ------------------------------------------------------------------------
@@ -175,10 +176,8 @@ int veon_bev_pool_v2_fwd_planar(const float* depth, const float* feat,
  *                zero).  Deterministic: no atomics, fixed summation order. */
 int veon_bev_pool_v2_bwd_planar(const float* out_grad,
                                 const float* depth, const float* feat,
-                                const int32_t* ranks_bev,
-                                const int32_t* interval_starts,
-                                const int32_t* tile_start,
                                 const int32_t* tile_istart,
+                                const uint32_t* tile_occ,
                                 const int32_t* point_interval,
                                 int64_t n_intervals,
                                 int B, int N, int D, int H, int W, int C,

@@ -83,7 +83,7 @@ def _require_cuda(*tensors):
 
 class PoolPlan:
     """By-products of the index preparation used by the planar kernels."""
-    __slots__ = ("tile_start", "tile_istart", "point_interval", "dims", "V",
+    __slots__ = ("tile_start", "tile_istart", "tile_occ", "point_interval", "dims", "V",
                  "flags", "_n_intervals", "_n_points", "counts_dev", "counts_host",
                  "counts_event", "keepalive")
 
@@ -147,7 +147,7 @@ def prepare_ranks(coor, grid_lower_bound, grid_interval, grid_size):
     n_tiles = lib.veon_pool_num_tiles(B, V)
     with torch.cuda.device(dev):
         ranks = torch.empty((5, P), dtype=torch.int32, device=dev)
-        tiles = torch.empty((2, n_tiles + 1), dtype=torch.int32, device=dev)
+        tiles = torch.empty((3, n_tiles + 1), dtype=torch.int32, device=dev)
         point_interval = torch.empty(P, dtype=torch.int32, device=dev)
         counts = torch.empty(2, dtype=torch.int64, device=dev)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
@@ -155,7 +155,7 @@ def prepare_ranks(coor, grid_lower_bound, grid_interval, grid_size):
             rc = lib.veon_prepare_v2(
                 _ptr(coor), B, N, D, H, W, _lib.float3(lower), _lib.float3(interval), c_size,
                 _ptr(ranks[0]), _ptr(ranks[1]), _ptr(ranks[2]), _ptr(ranks[3]), _ptr(ranks[4]),
-                _ptr(counts), _ptr(tiles[0]), _ptr(tiles[1]), _ptr(point_interval),
+                _ptr(counts), _ptr(tiles[0]), _ptr(tiles[1]), _ptr(tiles[2]), _ptr(point_interval),
                 _ptr(ws), ws_bytes, _stream_ptr(dev))
         _lib.check(rc, "veon_prepare_v2")
         counts_host = torch.empty(2, dtype=torch.int64, pin_memory=True)
@@ -163,7 +163,7 @@ def prepare_ranks(coor, grid_lower_bound, grid_interval, grid_size):
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(dev))
     plan = PoolPlan()
-    plan.tile_start, plan.tile_istart = tiles[0], tiles[1]
+    plan.tile_start, plan.tile_istart, plan.tile_occ = tiles[0], tiles[1], tiles[2]
     plan.point_interval = point_interval
     plan.dims = (B, N, D, H, W)
     plan.V = V
@@ -208,17 +208,17 @@ def _plan_for(rd, rf, rb, ist, iln, dims, V):
     P = B * N * D * H * W
     n_tiles = lib.veon_pool_num_tiles(B, V)
     with torch.cuda.device(dev):
-        tiles = torch.empty((2, n_tiles + 1), dtype=torch.int32, device=dev)
+        tiles = torch.empty((3, n_tiles + 1), dtype=torch.int32, device=dev)
         point_interval = torch.empty(P, dtype=torch.int32, device=dev)
         flags = torch.zeros(1, dtype=torch.int32, device=dev)
         rc = lib.veon_pool_plan_build(
             _ptr(rd), _ptr(rf), _ptr(rb), _ptr(ist), _ptr(iln), rd.numel(), ist.numel(),
-            B, N, D, H, W, V, _ptr(tiles[0]), _ptr(tiles[1]), _ptr(point_interval),
-            _ptr(flags), _stream_ptr(dev))
+            B, N, D, H, W, V, _ptr(tiles[0]), _ptr(tiles[1]), _ptr(tiles[2]),
+            _ptr(point_interval), _ptr(flags), _stream_ptr(dev))
         _lib.check(rc, "veon_pool_plan_build")
         plan = PoolPlan()
         plan.flags = int(flags.item())  # one sync per distinct rank set
-    plan.tile_start, plan.tile_istart = tiles[0], tiles[1]
+    plan.tile_start, plan.tile_istart, plan.tile_occ = tiles[0], tiles[1], tiles[2]
     plan.point_interval = point_interval
     plan.dims, plan.V = dims, V
     plan._n_points, plan._n_intervals = rd.numel(), ist.numel()
@@ -269,10 +269,9 @@ def _bwd_planar(grad_planar, depth, feat, rb, ist, plan, C):
         rows = torch.empty(max(n_int, 1) * C, dtype=torch.float32, device=dev)
         with _timed("pool_bwd", dev):
             rc = lib.veon_bev_pool_v2_bwd_planar(
-                _ptr(grad_planar), _ptr(depth), _ptr(feat), _ptr(rb), _ptr(ist),
-                _ptr(plan.tile_start), _ptr(plan.tile_istart), _ptr(plan.point_interval),
-                n_int, B, N, D, H, W, C, plan.V, _ptr(rows), _ptr(depth_grad), _ptr(feat_grad),
-                _stream_ptr(dev))
+                _ptr(grad_planar), _ptr(depth), _ptr(feat), _ptr(plan.tile_istart),
+                _ptr(plan.tile_occ), _ptr(plan.point_interval), n_int, B, N, D, H, W, C, plan.V,
+                _ptr(rows), _ptr(depth_grad), _ptr(feat_grad), _stream_ptr(dev))
     _lib.check(rc, "veon_bev_pool_v2_bwd_planar")
     return depth_grad, feat_grad
 

@@ -7,9 +7,11 @@
 // points and all channels twice, stride-C uncoalesced.
 //
 // Here, two atomic-free passes:
-//   k_bwd_rows    one warp per occupied 32-voxel tile: reads the tile's
-//                 out_grad lines (only the 32-byte sectors that hold an
-//                 occupied voxel), transposes through shared memory and emits
+//   k_bwd_rows    one warp per occupied 32-voxel tile (occupancy mask and first
+//                 interval come from the plan: one load latency), reads the
+//                 tile's out_grad lines (only the 32-byte sectors that hold an
+//                 occupied voxel, all loads in flight together), transposes
+//                 through shared memory and emits
 //                 one compact channel-contiguous row per interval
 //                 (rows[interval, C]).  Empty tiles are never read.
 //   k_bwd_pixels  one warp per feature pixel (the reference's by-ranks_feat
@@ -31,11 +33,10 @@ constexpr int kPitch = kTileVoxels + 1;
 
 template <int KCH>
 __global__ void __launch_bounds__(kRowWarps * 32)
-k_bwd_rows(const float* __restrict__ out_grad, const int32_t* __restrict__ ranks_bev,
-           const int32_t* __restrict__ interval_starts,
-           const int32_t* __restrict__ tile_start, const int32_t* __restrict__ tile_istart,
-           int64_t tile_begin, int64_t tile_end, int64_t tiles_per_sample, int64_t V, int C,
-           int n_chunks, int vec_ok, float* __restrict__ rows) {
+k_bwd_rows(const float* __restrict__ out_grad, const int32_t* __restrict__ tile_istart,
+           const uint32_t* __restrict__ tile_occ, int64_t tile_begin, int64_t tile_end,
+           int64_t tiles_per_sample, int64_t V, int C, int n_chunks, int vec_ok,
+           float* __restrict__ rows) {
   constexpr int CC = 32 * KCH;
   extern __shared__ float smem[];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -44,16 +45,12 @@ k_bwd_rows(const float* __restrict__ out_grad, const int32_t* __restrict__ ranks
   const int cbase = (int)(blockIdx.x - group * n_chunks) * CC;
   const int64_t t = tile_begin + group * kRowWarps + warp;
   if (t >= tile_end) return;
+  const uint32_t occ = __ldg(tile_occ + t);  // one independent load each: a single latency
   const int32_t i0 = __ldg(tile_istart + t);
-  const int ni = __ldg(tile_istart + t + 1) - i0;  // intervals in this tile, <= 32
-  if (ni <= 0) return;                              // empty tile: nothing read
+  if (occ == 0u) return;                     // empty tile: nothing read
   const int64_t b = t / tiles_per_sample;
   const int64_t v0 = (t - b * tiles_per_sample) * kTileVoxels;
-  const int64_t g0 = b * V + v0;
 
-  int vl = 0;
-  if (lane < ni) vl = (int)(__ldg(ranks_bev + __ldg(interval_starts + i0 + lane)) - g0);
-  const uint32_t occ = __reduce_or_sync(0xffffffffu, lane < ni ? (1u << (vl & 31)) : 0u);
   // fetch only 32-byte sectors (8 voxels) that contain an occupied voxel.
   // lane (r = lane/8, q = lane%8) loads voxels 4q..4q+3 of channel 4*it + r with
   // one 16-byte load; the 4 scalar smem stores hit banks (c + 4q + i) mod 32.
@@ -63,11 +60,22 @@ k_bwd_rows(const float* __restrict__ out_grad, const int32_t* __restrict__ ranks
   if (vec_ok && v0 + kTileVoxels <= V) {
     const float* g = out_grad + ((int64_t)b * C + cbase + r) * V + v0 + q4;
     float* trow = tile + r * kPitch + q4;
-#pragma unroll 4
-    for (int c = r; c < cmax; c += 4, g += 4 * V, trow += 4 * kPitch) {
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (want) v = ld_stream4(g);
-      trow[0] = v.x; trow[1] = v.y; trow[2] = v.z; trow[3] = v.w;
+    if (cmax == CC) {  // all CC/4 loads of the lane in flight at once
+      float4 v[CC / 4];
+#pragma unroll
+      for (int it = 0; it < CC / 4; ++it)
+        v[it] = want ? ld_stream4(g + (int64_t)it * 4 * V) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int it = 0; it < CC / 4; ++it) {
+        float* tr = trow + it * 4 * kPitch;
+        tr[0] = v[it].x; tr[1] = v[it].y; tr[2] = v[it].z; tr[3] = v[it].w;
+      }
+    } else {
+      for (int c = r; c < cmax; c += 4, g += 4 * V, trow += 4 * kPitch) {
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (want) v = ld_stream4(g);
+        trow[0] = v.x; trow[1] = v.y; trow[2] = v.z; trow[3] = v.w;
+      }
     }
   } else {
     const bool wants = ((occ >> (lane & 24)) & 0xffu) != 0u && (v0 + lane < V);
@@ -76,12 +84,16 @@ k_bwd_rows(const float* __restrict__ out_grad, const int32_t* __restrict__ ranks
       tile[cl * kPitch + lane] = wants ? ld_stream(g + (int64_t)cl * V) : 0.f;
   }
   __syncwarp();
-  for (int j = 0; j < ni; ++j) {
-    const int vj = __shfl_sync(0xffffffffu, vl, j);
-    float* row = rows + (int64_t)(i0 + j) * C + cbase + lane;
+  // j-th occupied voxel of the tile -> interval i0 + j
+  uint32_t rest = occ;
+  float* row = rows + (int64_t)i0 * C + cbase + lane;
+  while (rest) {
+    const int vj = __ffs(rest) - 1;
+    rest &= rest - 1;
 #pragma unroll
     for (int k = 0; k < KCH; ++k)
       if (lane + 32 * k < cmax) row[32 * k] = tile[(lane + 32 * k) * kPitch + vj];
+    row += C;
   }
 }
 
@@ -176,8 +188,7 @@ k_bwd_pixels(const float* __restrict__ rows, const float* __restrict__ depth,
 }
 
 template <int KCH>
-static int launch_rows(const float* out_grad, const int32_t* rb, const int32_t* istarts,
-                       const int32_t* tile_start, const int32_t* tile_istart,
+static int launch_rows(const float* out_grad, const int32_t* tile_istart, const uint32_t* tile_occ,
                        int64_t tile_begin, int64_t tile_end, int64_t tps, int64_t V, int C,
                        float* rows, cudaStream_t stream) {
   constexpr int CC = 32 * KCH;
@@ -194,8 +205,7 @@ static int launch_rows(const float* out_grad, const int32_t* rb, const int32_t* 
   if (blocks <= 0) return 0;
   if (blocks > 0x7fffffffLL) return VEON_E_RANGE;
   k_bwd_rows<KCH><<<(unsigned)blocks, kRowWarps * 32, smem, stream>>>(
-      out_grad, rb, istarts, tile_start, tile_istart, tile_begin, tile_end, tps, V, C, n_chunks,
-      vec_ok, rows);
+      out_grad, tile_istart, tile_occ, tile_begin, tile_end, tps, V, C, n_chunks, vec_ok, rows);
   VEON_LAUNCH_CHECK();
   return 0;
 }
@@ -232,28 +242,23 @@ static int env_int(const char* name, int dflt) {
 }
 
 extern "C" int veon_bev_pool_v2_bwd_planar(
-    const float* out_grad, const float* depth, const float* feat, const int32_t* ranks_bev,
-    const int32_t* interval_starts, const int32_t* tile_start, const int32_t* tile_istart,
-    const int32_t* point_interval, int64_t n_intervals, int B, int N, int D, int H, int W,
-    int C, int64_t V, float* rows_ws, float* depth_grad, float* feat_grad, void* stream_) {
+    const float* out_grad, const float* depth, const float* feat, const int32_t* tile_istart,
+    const uint32_t* tile_occ, const int32_t* point_interval, int64_t n_intervals, int B, int N,
+    int D, int H, int W, int C, int64_t V, float* rows_ws, float* depth_grad, float* feat_grad,
+    void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
-  if (!out_grad || !depth || !feat || !ranks_bev || !interval_starts || !tile_start ||
-      !tile_istart || !point_interval || !rows_ws || !depth_grad || !feat_grad || B <= 0 ||
-      N <= 0 || D <= 0 || H <= 0 || W <= 0 || C <= 0 || V <= 0 || n_intervals < 0)
+  if (!out_grad || !depth || !feat || !tile_istart || !tile_occ || !point_interval || !rows_ws ||
+      !depth_grad || !feat_grad || B <= 0 || N <= 0 || D <= 0 || H <= 0 || W <= 0 || C <= 0 ||
+      V <= 0 || n_intervals < 0)
     return VEON_E_BADARG;
-  (void)tile_start;
   const int64_t tps = ceil_div64(V, kTileVoxels);
   const int HW = H * W;
   const int64_t pix_per_sample = (int64_t)N * HW;
-  // Samples are processed in groups so that the compact rows of a group are
-  // still L2-resident (126 MB) when the pixel pass gathers them.
+  // One row launch + one pixel launch over all samples is fastest at every
+  // measured size (launch ramps cost more than keeping the rows L2-resident
+  // saves); VEON_BWD_SAMPLES_PER_LAUNCH > 0 groups samples instead.
   static int group_env = env_int("VEON_BWD_SAMPLES_PER_LAUNCH", 0);
-  int group = group_env;
-  if (group <= 0) {
-    const double rows_per_sample = (double)n_intervals / B * C * sizeof(float);
-    group = (int)(48.0e6 / (rows_per_sample + 1.0));
-    if (group < 1) group = 1;
-  }
+  int group = group_env > 0 ? group_env : B;
   if (group > B) group = B;
   static int rows_kch = env_int("VEON_BWD_ROWS_KCH", 0);
   static int pix_kch = env_int("VEON_BWD_PIX_KCH", 0);
@@ -263,9 +268,9 @@ extern "C" int veon_bev_pool_v2_bwd_planar(
     const int b1 = b0 + group < B ? b0 + group : B;
     int rc;
     switch (rk) {
-      case 1: rc = launch_rows<1>(out_grad, ranks_bev, interval_starts, tile_start, tile_istart, b0 * tps, b1 * tps, tps, V, C, rows_ws, stream); break;
-      case 2: rc = launch_rows<2>(out_grad, ranks_bev, interval_starts, tile_start, tile_istart, b0 * tps, b1 * tps, tps, V, C, rows_ws, stream); break;
-      case 4: rc = launch_rows<4>(out_grad, ranks_bev, interval_starts, tile_start, tile_istart, b0 * tps, b1 * tps, tps, V, C, rows_ws, stream); break;
+      case 1: rc = launch_rows<1>(out_grad, tile_istart, tile_occ, b0 * tps, b1 * tps, tps, V, C, rows_ws, stream); break;
+      case 2: rc = launch_rows<2>(out_grad, tile_istart, tile_occ, b0 * tps, b1 * tps, tps, V, C, rows_ws, stream); break;
+      case 4: rc = launch_rows<4>(out_grad, tile_istart, tile_occ, b0 * tps, b1 * tps, tps, V, C, rows_ws, stream); break;
       default: return VEON_E_BADARG;
     }
     if (rc) return rc;

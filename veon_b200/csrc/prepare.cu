@@ -184,7 +184,9 @@ __global__ void __launch_bounds__(kScanThreads)
 k_scan(const int32_t* __restrict__ count, int32_t* __restrict__ offset,
        int32_t* __restrict__ iidx, int32_t* __restrict__ istarts,
        int32_t* __restrict__ ilens, unsigned long long* desc, uint32_t* ctrl,
-       int32_t* __restrict__ long_list, int long_cap, int64_t* counts_out, int num_tiles) {
+       int32_t* __restrict__ long_list, int long_cap, int64_t* counts_out, int num_tiles,
+       int32_t* __restrict__ tile_start, int32_t* __restrict__ tile_istart,
+       uint32_t* __restrict__ tile_occ, int64_t n_pool_tiles) {
   __shared__ uint32_t s_tile;
   __shared__ unsigned long long s_warp[kScanThreads / 32];
   __shared__ unsigned long long s_excl;
@@ -249,13 +251,16 @@ k_scan(const int32_t* __restrict__ count, int32_t* __restrict__ offset,
   }
   __syncthreads();
   unsigned long long run = s_excl + wprefix + (incl - tsum);
+  int32_t off8[kScanItems], idx8[kScanItems];
+  uint32_t occ8 = 0;
 #pragma unroll
   for (int i = 0; i < kScanItems; ++i) {
     const int32_t pts = (int32_t)(run & 0x7fffffffull);
     const int32_t ints = (int32_t)((run >> 31) & 0x7fffffffull);
-    offset[base + i] = pts;
-    iidx[base + i] = ints;
+    off8[i] = pts;
+    idx8[i] = ints;
     if (c[i] > 0) {
+      occ8 |= 1u << i;
       istarts[ints] = pts;
       ilens[ints] = c[i];
       if (c[i] > kLongSeg) {
@@ -265,6 +270,27 @@ k_scan(const int32_t* __restrict__ count, int32_t* __restrict__ offset,
     }
     run += pack_count(c[i]);
   }
+  {  // one full 32-byte sector per thread and array
+    int4* o4 = reinterpret_cast<int4*>(offset + base);
+    int4* i4 = reinterpret_cast<int4*>(iidx + base);
+    o4[0] = make_int4(off8[0], off8[1], off8[2], off8[3]);
+    o4[1] = make_int4(off8[4], off8[5], off8[6], off8[7]);
+    i4[0] = make_int4(idx8[0], idx8[1], idx8[2], idx8[3]);
+    i4[1] = make_int4(idx8[4], idx8[5], idx8[6], idx8[7]);
+  }
+  // pooling-tile tables (V % 32 == 0: bin g starts tile g/32).  Four consecutive
+  // threads hold one 32-voxel tile; combine their 8-bit occupancy masks.
+  if (tile_start) {
+    uint32_t m = occ8 << (8 * (tid & 3));
+    m |= __shfl_xor_sync(0xffffffffu, m, 1);
+    m |= __shfl_xor_sync(0xffffffffu, m, 2);
+    const int64_t pt = base >> 5;
+    if ((tid & 3) == 0 && pt <= n_pool_tiles) {
+      tile_start[pt] = off8[0];
+      tile_istart[pt] = idx8[0];
+      tile_occ[pt] = m;
+    }
+  }
   if ((int)tile == num_tiles - 1 && tid == kScanThreads - 1) {
     counts_out[0] = (int64_t)(run & 0x7fffffffull);
     counts_out[1] = (int64_t)((run >> 31) & 0x7fffffffull);
@@ -272,15 +298,22 @@ k_scan(const int32_t* __restrict__ count, int32_t* __restrict__ offset,
 }
 
 // ------------------------------------------------------------------- k_tiles
-__global__ void k_tiles(const int32_t* __restrict__ offset, const int32_t* __restrict__ iidx,
-                        int64_t n_tiles, int64_t tiles_per_sample, int64_t V,
-                        int32_t* __restrict__ tile_start, int32_t* __restrict__ tile_istart) {
+// tile tables when V is not a multiple of 32 (otherwise k_scan emits them)
+__global__ void k_tiles(const int32_t* __restrict__ count, const int32_t* __restrict__ offset,
+                        const int32_t* __restrict__ iidx, int64_t n_tiles,
+                        int64_t tiles_per_sample, int64_t V, int32_t* __restrict__ tile_start,
+                        int32_t* __restrict__ tile_istart, uint32_t* __restrict__ tile_occ) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t > n_tiles) return;
   int64_t b = t / tiles_per_sample, vt = t % tiles_per_sample;
   int64_t g = b * V + vt * kTileVoxels;  // t == n_tiles -> g == B*V (sentinel)
   tile_start[t] = offset[g];
   tile_istart[t] = iidx[g];
+  uint32_t m = 0;
+  if (t < n_tiles)
+    for (int i = 0; i < kTileVoxels && vt * kTileVoxels + i < V; ++i)
+      if (count[g + i] > 0) m |= 1u << i;
+  tile_occ[t] = m;
 }
 
 // ----------------------------------------------------------------- k_scatter
@@ -398,7 +431,8 @@ __global__ void k_plan_tiles(const int32_t* __restrict__ ranks_bev, int64_t n_po
                              const int32_t* __restrict__ istarts, int64_t n_int,
                              int64_t n_tiles, int64_t tiles_per_sample, int64_t V,
                              int32_t* __restrict__ tile_start,
-                             int32_t* __restrict__ tile_istart) {
+                             int32_t* __restrict__ tile_istart,
+                             uint32_t* __restrict__ tile_occ) {
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t > n_tiles) return;
   int64_t b = t / tiles_per_sample, vt = t % tiles_per_sample;
@@ -406,6 +440,16 @@ __global__ void k_plan_tiles(const int32_t* __restrict__ ranks_bev, int64_t n_po
   int64_t ps = lower_bound_i32(ranks_bev, n_points, g);
   tile_start[t] = (int32_t)ps;
   tile_istart[t] = (int32_t)lower_bound_i32(istarts, n_int, ps);
+  uint32_t m = 0;
+  if (t < n_tiles) {
+    const int64_t gend = min(g + kTileVoxels, (b + 1) * V);
+    for (int64_t i = ps; i < n_points; ++i) {
+      const int64_t rbv = ranks_bev[i];
+      if (rbv >= gend || rbv < g) break;
+      m |= 1u << (int)(rbv - g);
+    }
+  }
+  tile_occ[t] = m;
 }
 
 __global__ void k_plan_points(const int32_t* __restrict__ ranks_depth,
@@ -496,7 +540,7 @@ extern "C" int veon_prepare_v2(const float* coor, int B, int N, int D, int H, in
                                int32_t* ranks_depth, int32_t* ranks_feat,
                                int32_t* interval_starts, int32_t* interval_lengths,
                                int64_t* counts, int32_t* tile_start, int32_t* tile_istart,
-                               int32_t* point_interval, void* workspace,
+                               uint32_t* tile_occ, int32_t* point_interval, void* workspace,
                                size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   int64_t P;
@@ -522,14 +566,17 @@ extern "C" int veon_prepare_v2(const float* coor, int B, int N, int D, int H, in
   k_classify<<<pblocks, 256, 0, stream>>>(coor, P, pts_per_sample, g, nbins, w.key, w.slot,
                                           w.count);
   VEON_LAUNCH_CHECK();
+  const bool want_tiles = tile_start && tile_istart && tile_occ;
+  const int64_t tps = ceil_div64(V, kTileVoxels), n_tiles = (int64_t)B * tps;
+  const bool fused_tiles = want_tiles && (V % kTileVoxels == 0);
   k_scan<<<(unsigned)w.scan_tiles, kScanThreads, 0, stream>>>(
       w.count, w.offset, w.iidx, interval_starts, interval_lengths, w.desc, w.ctrl,
-      w.long_list, (int)w.long_cap, counts, (int)w.scan_tiles);
+      w.long_list, (int)w.long_cap, counts, (int)w.scan_tiles,
+      fused_tiles ? tile_start : nullptr, tile_istart, tile_occ, n_tiles);
   VEON_LAUNCH_CHECK();
-  if (tile_start && tile_istart) {
-    const int64_t tps = ceil_div64(V, kTileVoxels), n_tiles = (int64_t)B * tps;
+  if (want_tiles && !fused_tiles) {
     k_tiles<<<(unsigned)ceil_div64(n_tiles + 1, 256), 256, 0, stream>>>(
-        w.offset, w.iidx, n_tiles, tps, V, tile_start, tile_istart);
+        w.count, w.offset, w.iidx, n_tiles, tps, V, tile_start, tile_istart, tile_occ);
     VEON_LAUNCH_CHECK();
   }
   k_scatter<<<pblocks, 256, 0, stream>>>(w.key, w.slot, w.offset, P, w.tmp, ranks_bev);
@@ -550,13 +597,15 @@ extern "C" int veon_pool_plan_build(const int32_t* ranks_depth, const int32_t* r
                                     const int32_t* interval_lengths, int64_t n_points,
                                     int64_t n_intervals, int B, int N, int D, int H, int W,
                                     int64_t V, int32_t* tile_start, int32_t* tile_istart,
-                                    int32_t* point_interval, int32_t* flags, void* stream_) {
+                                    uint32_t* tile_occ, int32_t* point_interval, int32_t* flags,
+                                    void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   int64_t P;
   int rc = check_dims(B, N, D, H, W, &P);
   if (rc) return rc;
   if (!ranks_depth || !ranks_feat || !ranks_bev || !interval_starts || !interval_lengths ||
-      !tile_start || !tile_istart || !point_interval || !flags || V <= 0 || n_points <= 0 ||
+      !tile_start || !tile_istart || !tile_occ || !point_interval || !flags || V <= 0 ||
+      n_points <= 0 ||
       n_intervals <= 0)
     return VEON_E_BADARG;
   if ((int64_t)B * V > 0x7fffffffLL) return VEON_E_RANGE;
@@ -574,7 +623,7 @@ extern "C" int veon_pool_plan_build(const int32_t* ranks_depth, const int32_t* r
   const int64_t tps = ceil_div64(V, kTileVoxels), n_tiles = (int64_t)B * tps;
   k_plan_tiles<<<(unsigned)ceil_div64(n_tiles + 1, 256), 256, 0, stream>>>(
       ranks_bev, n_points, interval_starts, n_intervals, n_tiles, tps, V, tile_start,
-      tile_istart);
+      tile_istart, tile_occ);
   VEON_LAUNCH_CHECK();
   return 0;
 }
