@@ -134,3 +134,61 @@ def test_all_gather_occupancy_world_size_2_gloo(tmp_path):
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
         assert "ok" in o
+
+
+@pytest.mark.needs_reference
+def test_operator_surface_matches_reference_call_sites():
+    """CPU-side drop-in check (the GPU-side one needs both a GPU and
+    /root/reference): run the UNMODIFIED reference neck with a recording stub
+    bound as `bev_pool_v2` and verify that exactly that call is accepted by our
+    operator's signature, and that our prepare wrapper has the reference
+    method's shape of result."""
+    import inspect
+    from _ref_loader import load_reference_view_transformer
+    from veon_b200 import bev_pool as BP, synthetic as S
+    calls = []
+
+    def recorder(*args, **kwargs):
+        calls.append((args, kwargs))
+        depth, feat = args[0], args[1]
+        B, Z, Y, X, C = args[5]
+        return torch.zeros(B, C, Z, Y, X)
+
+    mod = load_reference_view_transformer(recorder)
+    cfg = S.CONFIGS["tiny"]
+    neck = mod.LSSViewTransformer(grid_config=cfg.grid_config, input_size=cfg.input_size,
+                                  downsample=cfg.downsample, in_channels=8, out_channels=4,
+                                  collapse_z=False)
+    B, N, D = 1, cfg.n_cams, cfg.D
+    H, W = cfg.feat_hw
+    coor = torch.from_numpy(S.lidar_coor_np(cfg, batch=B))
+    neck.voxel_pooling_v2(coor, torch.rand(B, N, D, H, W), torch.rand(B, N, 4, H, W))
+    (args, kwargs), = calls
+    sig = inspect.signature(BP.bev_pool_v2)
+    bound = sig.bind(*args, **kwargs)               # raises TypeError if the surface differs
+    assert list(bound.arguments) == ["depth", "feat", "ranks_depth", "ranks_feat", "ranks_bev",
+                                     "bev_feat_shape", "interval_starts", "interval_lengths"]
+    assert bound.arguments["feat"].shape == (B, N, H, W, 4)          # permuted view, :190
+    assert not bound.arguments["feat"].is_contiguous()
+    assert all(bound.arguments[k].dtype == torch.int32 for k in
+               ("ranks_depth", "ranks_feat", "ranks_bev", "interval_starts", "interval_lengths"))
+    # same names on the module as the reference's bev_pool.py
+    for name in ("bev_pool_v2", "QuickCumsumCuda", "TRTBEVPoolv2"):
+        assert hasattr(BP, name)
+    ref_fwd = inspect.signature(BP.QuickCumsumCuda.forward)
+    assert list(ref_fwd.parameters)[:9] == ["ctx", "depth", "feat", "ranks_depth", "ranks_feat",
+                                            "ranks_bev", "bev_feat_shape", "interval_starts",
+                                            "interval_lengths"]
+    # the neck mirror exposes the reference neck's methods / attributes
+    from veon_b200.view_transformer import LSSViewTransformer
+    ours = LSSViewTransformer(cfg.grid_config, cfg.input_size, cfg.downsample, 8, 4, collapse_z=False)
+    for name in ("create_grid_infos", "create_frustum", "get_lidar_coor", "init_acceleration_v2",
+                 "voxel_pooling_v2", "voxel_pooling_prepare_v2", "pre_compute", "view_transform_core",
+                 "view_transform", "forward"):
+        assert callable(getattr(ours, name)) and hasattr(neck, name)
+        ref_params = list(inspect.signature(getattr(neck, name)).parameters)
+        our_params = list(inspect.signature(getattr(ours, name)).parameters)
+        assert ref_params == our_params, (name, ref_params, our_params)
+    for attr in ("grid_lower_bound", "grid_interval", "grid_size", "frustum", "D", "accelerate",
+                 "initial_flag", "collapse_z", "out_channels", "in_channels", "downsample", "sid"):
+        assert hasattr(ours, attr) and hasattr(neck, attr)

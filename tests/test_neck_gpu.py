@@ -1,0 +1,136 @@
+"""GPU: the host-side mirror of the neck (LSSViewTransformer) end to end, and
+the DROP-IN check: the reference's own, unmodified neck running on top of our
+operators."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import lift_oracle as O
+from veon_b200 import synthetic as S
+
+pytestmark = pytest.mark.gpu
+KEYS = ("sensor2ego", "ego2global", "intrins", "post_rots", "post_trans", "bda")
+
+
+def rel(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+def inputs(cfg, B, C, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    H, W = cfg.feat_hw
+    cal = S.calibration(cfg, batch=B)
+    metas = [torch.from_numpy(cal[k]).cuda() for k in KEYS]
+    depth = torch.softmax(torch.randn(B * cfg.n_cams, cfg.D, H, W, generator=g) * 4, dim=1).cuda()
+    feat = torch.randn(B * cfg.n_cams, C, H, W, generator=g).cuda()
+    img = torch.zeros(B, cfg.n_cams, 8, H, W, device="cuda")
+    return img, metas, depth, feat
+
+
+@pytest.mark.parametrize("sync_free", [False, True])
+def test_view_transform_matches_cpu_lift(sync_free):
+    from veon_b200.view_transformer import LSSViewTransformer
+    cfg = S.CONFIGS["small"]
+    B, C = 2, 32
+    neck = LSSViewTransformer(cfg.grid_config, cfg.input_size, cfg.downsample, 8, C,
+                              collapse_z=False, sync_free=sync_free)
+    img, metas, depth, feat = inputs(cfg, B, C)
+    bev, _ = neck.view_transform([img] + metas, depth, feat)
+    assert bev.shape == (B, C, 16, 200, 200)
+    coor = neck.get_lidar_coor(*metas)
+    H, W = cfg.feat_hw
+    want, _, _ = O.torch_cpu_lift(coor.cpu(), depth.view(B, cfg.n_cams, cfg.D, H, W).cpu(),
+                                  feat.view(B, cfg.n_cams, C, H, W).cpu(), neck.grid_lower_bound,
+                                  neck.grid_interval, neck.grid_size)
+    assert rel(bev.cpu().numpy(), want.numpy()) <= 1e-5
+
+
+def test_accelerate_equals_non_accelerate():
+    """the idea of the reference's own neck test (tests/test_models/test_necks/test_necks.py:137-195)"""
+    from veon_b200.view_transformer import LSSViewTransformer
+    cfg = S.CONFIGS["small"]
+    B, C = 1, 64
+    # collapse_z=False: the reference's accelerate branch squeezes Z (view_transformer.py:284)
+    # instead of collapsing it, so the two paths only agree in shape for un-collapsed volumes
+    neck = LSSViewTransformer(cfg.grid_config, cfg.input_size, cfg.downsample, 8, C, collapse_z=False)
+    img, metas, depth, feat = inputs(cfg, B, C, seed=1)
+    a, _ = neck.view_transform([img] + metas, depth, feat)
+    neck.accelerate = True
+    b, _ = neck.view_transform([img] + metas, depth, feat)
+    c, _ = neck.view_transform([img] + metas, depth, feat)       # cached ranks + cached plan
+    assert a.shape == (B, C, 16, 200, 200)
+    assert torch.equal(a, b) and torch.equal(b, c)
+
+
+def test_raw_neck_forward_downsamples():
+    from veon_b200.view_transformer import LSSViewTransformerRaw
+    cfg = S.CONFIGS["small"]
+    B, C = 1, 16
+    neck = LSSViewTransformerRaw(cfg.grid_config, cfg.input_size, cfg.downsample, 8, C)
+    img, metas, depth, feat = inputs(cfg, B, C, seed=2)
+    H, W = cfg.feat_hw
+    out = neck([feat.view(B, cfg.n_cams, C, H, W)] + metas, depth.view(B, cfg.n_cams, cfg.D, H, W))
+    assert out.shape == (B, C, 8, 100, 100)
+    neck.use_ds = False
+    full = neck([feat.view(B, cfg.n_cams, C, H, W)] + metas, depth.view(B, cfg.n_cams, cfg.D, H, W))
+    want = full.view(B, C, 8, 2, 100, 2, 100, 2).amax(dim=(3, 5, 7))
+    assert torch.equal(out, want)
+
+
+def test_no_point_in_grid_matches_reference_dummy():
+    from veon_b200.view_transformer import LSSViewTransformer
+    cfg = S.CONFIGS["tiny"]
+    neck = LSSViewTransformer(cfg.grid_config, cfg.input_size, cfg.downsample, 8, 4, collapse_z=True)
+    B, N, D = 1, cfg.n_cams, cfg.D
+    H, W = cfg.feat_hw
+    coor = torch.full((B, N, D, H, W, 3), 1000.0, device="cuda")
+    out = neck.voxel_pooling_v2(coor, torch.rand(B, N, D, H, W, device="cuda"),
+                                torch.rand(B, N, 4, H, W, device="cuda"))
+    assert out.shape == (1, 4 * 16, 200, 200) and float(out.abs().sum()) == 0.0
+
+
+@pytest.mark.needs_reference
+def test_reference_neck_runs_unchanged_on_our_operators():
+    """DROP-IN: the reference's LSSViewTransformer (unmodified file) with our
+    bev_pool_v2 bound in place of its extension and our prepare patched in;
+    compared with the same reference neck on the CPU oracle pooling."""
+    import torch as _t
+    from _ref_loader import load_reference_view_transformer
+    from veon_b200 import bev_pool as BP
+
+    def cpu_pool(depth, feat, rd, rf, rb, shape, st, ln):
+        out = O.bev_pool_v2(depth.numpy(), feat.contiguous().numpy(), rd.numpy(), rf.numpy(),
+                            rb.numpy(), tuple(shape), st.numpy(), ln.numpy())
+        return _t.from_numpy(out)
+
+    cfg = S.CONFIGS["small"]
+    B, C = 1, 16
+    H, W = cfg.feat_hw
+    g = _t.Generator().manual_seed(5)
+    cal = S.calibration(cfg, batch=B)
+    metas = [_t.from_numpy(cal[k]) for k in KEYS]
+    depth = _t.softmax(_t.randn(B * cfg.n_cams, cfg.D, H, W, generator=g) * 4, dim=1)
+    feat = _t.randn(B * cfg.n_cams, C, H, W, generator=g)
+    img = _t.zeros(B, cfg.n_cams, 8, H, W)
+    kw = dict(grid_config=cfg.grid_config, input_size=cfg.input_size, downsample=cfg.downsample,
+              in_channels=8, out_channels=C, collapse_z=False)
+
+    mod = load_reference_view_transformer(cpu_pool)
+    ref_neck = mod.LSSViewTransformer(**kw)
+    want, _ = ref_neck.view_transform([img] + metas, depth, feat)
+
+    mod = load_reference_view_transformer(BP.bev_pool_v2)
+    neck = mod.LSSViewTransformer(**kw)
+    got, _ = neck.view_transform([img.cuda()] + [m.cuda() for m in metas], depth.cuda(), feat.cuda())
+    assert rel(got.cpu().numpy(), want.numpy()) <= 1e-4     # get_lidar_coor runs on GPU vs CPU here
+
+    # and with the index preparation replaced as well (INTEGRATION.md route A)
+    mod.LSSViewTransformer.voxel_pooling_prepare_v2 = lambda self, coor: BP.voxel_pooling_prepare_v2(
+        coor, self.grid_lower_bound, self.grid_interval, self.grid_size)
+    neck2 = mod.LSSViewTransformer(**kw)
+    got2, _ = neck2.view_transform([img.cuda()] + [m.cuda() for m in metas], depth.cuda(), feat.cuda())
+    assert _t.equal(got2, got)
+    neck2.accelerate = True                                  # reference's cache path on our ranks
+    got3, _ = neck2.view_transform([img.cuda()] + [m.cuda() for m in metas], depth.cuda(), feat.cuda())
+    assert _t.equal(got3.unsqueeze(2) if got3.dim() == 4 else got3, got) or rel(got3.cpu().numpy().reshape(got.shape), got.cpu().numpy()) == 0.0
