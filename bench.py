@@ -232,33 +232,81 @@ def run_ours(args):
         bev.backward(out_grad)
         return depth.grad, feat.grad
 
-    dg_host = torch.empty((B, N, D, H, W), dtype=torch.float32).pin_memory()
-    fg_host = torch.empty((B, N, C, H, W), dtype=torch.float32).pin_memory()
+    # ---- end to end: the user's call, view_transform(input, depth, tran_feat), on HOST data.
+    # Per step: calibration + depth + feat from pinned host memory -> device (copy stream,
+    # overlapped with the previous step's compute), get_lidar_coor + prepare + pool forward +
+    # backward on device, depth_grad + feat_grad back to pinned host memory (D2H stream).
+    KEYS = ("sensor2ego", "ego2global", "intrins", "post_rots", "post_trans", "bda")
+    e2e_host = []
+    for i in range(n_sets):
+        cal = S.calibration(cfg, batch=B, sample_offset=rank * 1000 + i * B)
+        metas = [torch.from_numpy(cal[k]).pin_memory() for k in KEYS]
+        _, hd, hf = host_sets[i]
+        e2e_host.append((metas, hd.view(B * N, D, H, W), hf.view(B * N, C, H, W)))
+    img_shape = torch.zeros(B, N, 1, H, W, device=dev)      # only its shape is read
+    copy_stream, d2h_stream = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    dev_in = [None, None]
+    ready = [torch.cuda.Event(), torch.cuda.Event()]
+    consumed = [torch.cuda.Event(), torch.cuda.Event()]
+    dg_host = [torch.empty((B * N, D, H, W), dtype=torch.float32).pin_memory() for _ in range(2)]
+    fg_host = [torch.empty((B * N, C, H, W), dtype=torch.float32).pin_memory() for _ in range(2)]
 
-    def step_e2e(i):
-        hc, hd, hf = host_sets[i % n_sets]
-        coor = hc.to(dev, non_blocking=True)
-        depth = hd.to(dev, non_blocking=True).requires_grad_()
-        feat = hf.to(dev, non_blocking=True).requires_grad_()
-        bev = neck.voxel_pooling_v2(coor, depth, feat)
-        bev.backward(out_grad)
-        dg_host.copy_(depth.grad, non_blocking=True)
-        fg_host.copy_(feat.grad, non_blocking=True)
+    def e2e_prefetch(i):
+        slot = i % 2
+        metas, hd, hf = e2e_host[i % n_sets]
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])          # the slot's previous user is done
+            dev_in[slot] = ([m.to(dev, non_blocking=True) for m in metas],
+                            hd.to(dev, non_blocking=True), hf.to(dev, non_blocking=True))
+            ready[slot].record(copy_stream)
+
+    def run_e2e(steps):
+        main = torch.cuda.current_stream(dev)
+        for ev in consumed:
+            ev.record(main)
+        e2e_prefetch(0)
+        for i in range(steps):
+            slot = i % 2
+            if i + 1 < steps:
+                e2e_prefetch(i + 1)
+            main.wait_event(ready[slot])
+            metas, depth, feat = dev_in[slot]
+            for t_ in (depth, feat, *metas):
+                t_.record_stream(main)
+            depth = depth.requires_grad_()
+            feat = feat.requires_grad_()
+            bev, _ = neck.view_transform([img_shape] + metas, depth, feat)
+            bev.backward(out_grad)
+            consumed[slot].record(main)
+            dgrad, fgrad = depth.grad, feat.grad
+            with torch.cuda.stream(d2h_stream):
+                d2h_stream.wait_event(consumed[slot])
+                dgrad.record_stream(d2h_stream)
+                fgrad.record_stream(d2h_stream)
+                dg_host[slot].copy_(dgrad, non_blocking=True)
+                fg_host[slot].copy_(fgrad, non_blocking=True)
+        main.wait_stream(d2h_stream)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup):
-        for i in range(warmup):
-            fn(i)
+    def timed(fn, steps, warmup, whole_loop=False):
+        if whole_loop:
+            fn(warmup)
+        else:
+            for i in range(warmup):
+                fn(i)
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = lib.veon_kernel_launch_count()
         e0.record()
-        for i in range(steps):
-            fn(i)
+        if whole_loop:
+            fn(steps)
+        else:
+            for i in range(steps):
+                fn(i)
         e1.record()
         barrier()
         launches = lib.veon_kernel_launch_count() - l0
@@ -270,7 +318,7 @@ def run_ours(args):
     K, Wm = max(args.steps, 1), max(args.warmup, 3)
     with ClockSampler(local) as clocks:
         ms_total, launches = timed(step_device, K, Wm)
-    ms_e2e, _ = timed(step_e2e, K, max(3, Wm // 2))
+    ms_e2e, _ = timed(run_e2e, K, max(3, Wm // 2), whole_loop=True)
 
     # live per-call device times (CUDA events on the launching stream) over K more steps
     BP.enable_kernel_timing(True)
@@ -304,8 +352,8 @@ def run_ours(args):
 
     value = world * B * K / (ms_total * 1e-3)
     e2e_value = world * B * K / (ms_e2e * 1e-3)
-    h2d = sum(x.numel() * x.element_size() for x in host_sets[0])
-    d2h = dg_host.numel() * 4 + fg_host.numel() * 4
+    h2d = sum(x.numel() * x.element_size() for x in (*e2e_host[0][0], e2e_host[0][1], e2e_host[0][2]))
+    d2h = dg_host[0].numel() * 4 + fg_host[0].numel() * 4
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
@@ -319,8 +367,9 @@ def run_ours(args):
         "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / K,
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "what": "pinned host coor+depth+feat -> LSSViewTransformer.voxel_pooling_v2 -> "
-                        "backward -> depth_grad+feat_grad back to pinned host"},
+                "what": "pinned host calibration+depth+feat -> LSSViewTransformer.view_transform "
+                        "(get_lidar_coor + prepare_v2 + bev_pool_v2) -> backward -> depth_grad + "
+                        "feat_grad to pinned host; copies on side streams, double-buffered"},
         "roofline": {"bound": "hbm", "kernel": "k_pool_fwd (veon_bev_pool_v2_fwd_planar)",
                      "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                      "frac": (achieved / peak_gbs) if achieved else None, "peak_source": peak_src,

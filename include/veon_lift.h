@@ -101,6 +101,20 @@ int veon_bev_pool_v2_grad_generic(int c, int64_t n_points, int layout,
                                   float* depth_grad, float* feat_grad, void* stream);
 
 /* ------------------------------------------------------------------------
+ * (1b) get_lidar_coor (view_transformer.py:114-152; view_transformer_raw.py:121-158):
+ *      frustum [D,H,W,3] + per-camera calibration -> coor [B,N,D,H,W,3], the
+ *      input of voxel_pooling_prepare_v2.  sensor2ego [B,N,4,4], cam2imgs /
+ *      post_rots [B,N,3,3], post_trans [B,N,3], bda [B,3,3], all float32
+ *      contiguous on the device.  Float-tolerance parity (upstream of the
+ *      bit-exact boundary).
+ * ------------------------------------------------------------------------ */
+size_t veon_lidar_coor_workspace_bytes(int B, int N);
+int veon_lidar_coor(const float* frustum, const float* sensor2ego, const float* cam2imgs,
+                    const float* post_rots, const float* post_trans, const float* bda,
+                    int B, int N, int D, int H, int W, float* coor,
+                    void* workspace, size_t workspace_bytes, void* stream);
+
+/* ------------------------------------------------------------------------
  * (2) voxel_pooling_prepare_v2 (view_transformer.py:202-260; duplicated at
  *     view_transformer_raw.py:244-302).
  *

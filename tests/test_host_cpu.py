@@ -45,6 +45,14 @@ def test_argument_errors_do_not_need_a_gpu():
 
 def test_cpu_tensors_are_refused_loudly():
     from veon_b200.bev_pool import bev_pool_v2, voxel_pooling_prepare_v2
+    from veon_b200 import synthetic as S
+    from veon_b200.view_transformer import LSSViewTransformer
+    cfg = S.CONFIGS["tiny"]
+    neck = LSSViewTransformer(cfg.grid_config, cfg.input_size, cfg.downsample, 8, 4)
+    cal = S.calibration(cfg, batch=1)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        neck.get_lidar_coor(*[torch.from_numpy(cal[k]) for k in
+                              ("sensor2ego", "ego2global", "intrins", "post_rots", "post_trans", "bda")])
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         voxel_pooling_prepare_v2(torch.zeros(1, 1, 2, 2, 2, 3), [0, 0, 0], [1, 1, 1], [4, 4, 2])
     z = torch.zeros(1, 1, 2, 2, 2)
@@ -76,7 +84,7 @@ def test_view_transformer_mirror_geometry(golden_dir):
         np.testing.assert_array_equal(neck.grid_lower_bound.numpy(), lower)
         np.testing.assert_array_equal(neck.grid_interval.numpy(), interval)
         cal = S.calibration(cfg, batch=1)
-        coor = neck.get_lidar_coor(*[torch.from_numpy(cal[k]) for k in
+        coor = neck.get_lidar_coor_torch(*[torch.from_numpy(cal[k]) for k in
                                      ("sensor2ego", "ego2global", "intrins", "post_rots",
                                       "post_trans", "bda")]).numpy()
         if name == "tiny":

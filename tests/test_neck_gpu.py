@@ -28,6 +28,42 @@ def inputs(cfg, B, C, seed=0):
     return img, metas, depth, feat
 
 
+def test_get_lidar_coor_kernel_matches_reference_geometry(golden_dir):
+    """CUDA get_lidar_coor vs the reference's own get_lidar_coor output (golden) and vs the
+    torch formulation, incl. non-trivial post_rots / bda"""
+    import os
+    from veon_b200.view_transformer import LSSViewTransformer
+    geo = np.load(os.path.join(golden_dir, "geometry_tiny.npz"))
+    for name in ("tiny", "C1"):
+        cfg = S.CONFIGS[name]
+        neck = LSSViewTransformer(cfg.grid_config, cfg.input_size, cfg.downsample, 8, cfg.channels)
+        cal = S.calibration(cfg, batch=1)
+        metas = [torch.from_numpy(cal[k]).cuda() for k in KEYS]
+        coor = neck.get_lidar_coor(*metas).cpu().numpy()
+        if name == "tiny":
+            np.testing.assert_allclose(coor, geo["tiny.coor"], rtol=0, atol=3e-5)
+        else:
+            np.testing.assert_allclose(coor[:, :, ::11, ::5, ::7], geo["C1.coor_sample"], rtol=0, atol=3e-4)
+    # random rotations in post_rots (flip / rotate augmentation) and bda
+    cfg = S.CONFIGS["tiny"]
+    neck = LSSViewTransformer(cfg.grid_config, cfg.input_size, cfg.downsample, 8, 4)
+    g = torch.Generator().manual_seed(0)
+    B, N = 3, cfg.n_cams
+    cal = S.calibration(cfg, batch=B)
+    th = torch.rand(B, N, generator=g) * 0.4 - 0.2
+    pr = torch.zeros(B, N, 3, 3)
+    sc = 0.4 + 0.2 * torch.rand(B, N, generator=g)
+    pr[..., 0, 0] = sc * th.cos(); pr[..., 0, 1] = -sc * th.sin()
+    pr[..., 1, 0] = sc * th.sin(); pr[..., 1, 1] = sc * th.cos(); pr[..., 2, 2] = 1
+    bda = torch.eye(3).repeat(B, 1, 1) * torch.tensor([1.0, -1.0, 1.0]) * 1.05
+    metas = [torch.from_numpy(cal[k]) for k in KEYS]
+    metas[3], metas[5] = pr, bda
+    metas[4] = metas[4] + torch.randn(B, N, 3, generator=g) * torch.tensor([5.0, 5.0, 0.0])
+    want = neck.get_lidar_coor_torch(*metas).numpy()
+    got = neck.get_lidar_coor(*[m.cuda() for m in metas]).cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-4)
+
+
 @pytest.mark.parametrize("sync_free", [False, True])
 def test_view_transform_matches_cpu_lift(sync_free):
     from veon_b200.view_transformer import LSSViewTransformer

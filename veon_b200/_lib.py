@@ -31,6 +31,9 @@ _SIGNATURES = {
     "veon_bev_pool_v2_grad": (c_int, [c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "veon_bev_pool_v2_generic": (c_int, [c_int, c_int, c_int, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "veon_bev_pool_v2_grad_generic": (c_int, [c_int, c_int64, c_int, c_int64, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "veon_lidar_coor_workspace_bytes": (c_size_t, [c_int, c_int]),
+    "veon_lidar_coor": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P,
+                                c_size_t, _P]),
     "veon_prepare_v2_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, _P]),
     "veon_pool_num_tiles": (c_int64, [c_int, c_int64]),
     "veon_prepare_v2": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P,

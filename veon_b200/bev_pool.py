@@ -26,7 +26,7 @@ from . import _lib
 
 __all__ = ["bev_pool_v2", "QuickCumsumCuda", "TRTBEVPoolv2",
            "voxel_pooling_prepare_v2", "prepare_ranks", "PreparedRanks",
-           "pool_prepared"]
+           "pool_prepared", "lidar_coor"]
 
 LAYOUT_BZYXC, LAYOUT_BCZYX = 0, 1
 TILE_VOXELS = 32
@@ -79,6 +79,27 @@ def _require_cuda(*tensors):
             raise RuntimeError(
                 "veon_b200 runs on CUDA tensors only (there is no CPU fallback); "
                 f"got a tensor on {t.device}")
+
+
+def lidar_coor(frustum, sensor2ego, cam2imgs, post_rots, post_trans, bda):
+    """get_lidar_coor (view_transformer.py:114-152) as one fused CUDA pass.
+    frustum [D,H,W,3]; returns coor [B,N,D,H,W,3] float32."""
+    _require_cuda(frustum, sensor2ego, cam2imgs, post_rots, post_trans, bda)
+    lib = _lib.load()
+    dev = sensor2ego.device
+    B, N = sensor2ego.shape[:2]
+    D, H, W, _ = frustum.shape
+    args = [t.detach().contiguous().float() for t in
+            (frustum, sensor2ego, cam2imgs, post_rots, post_trans, bda)]
+    with torch.cuda.device(dev):
+        coor = torch.empty((B, N, D, H, W, 3), dtype=torch.float32, device=dev)
+        ws_bytes = lib.veon_lidar_coor_workspace_bytes(B, N)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        with _timed("lidar_coor", dev):
+            rc = lib.veon_lidar_coor(*[_ptr(a) for a in args], B, N, D, H, W, _ptr(coor), _ptr(ws),
+                                     ws_bytes, _stream_ptr(dev))
+    _lib.check(rc, "veon_lidar_coor")
+    return coor
 
 
 class PoolPlan:

@@ -26,11 +26,12 @@ class LSSViewTransformer(nn.Module):
     accelerate, sid, collapse_z.
 
     Extra (not in the reference): `sync_free` -- when True the non-accelerated
-    path skips the host read-back of the point / interval counts (the
-    reference's boolean-mask indexing syncs at the same place); the only
-    behavioural difference is that an input with no point inside the grid
-    yields an all-zero volume of the regular shape instead of the reference's
-    warning + dummy tensor (:179-189).
+    path never reads the point / interval counts back to the host (the default
+    reads them AFTER the pooling has been queued, where the reference's
+    boolean-mask indexing syncs before it); the only behavioural difference is
+    that an input with no point inside the grid yields an all-zero volume of
+    the regular shape instead of the reference's warning + dummy tensor
+    (:179-189).
     """
 
     def __init__(self, grid_config, input_size, downsample=16, in_channels=512,
@@ -87,7 +88,19 @@ class LSSViewTransformer(nn.Module):
         (reference :114-152; same operation order so that float32 results
         agree to rounding): undo image augmentation, un-project with depth,
         camera->ego, BEV augmentation."""
-        B, N = sensor2ego.shape[:2]
+        return _bp.lidar_coor(self._frustum_on(sensor2ego.device), sensor2ego, cam2imgs,
+                              post_rots, post_trans, bda)
+
+    def _frustum_on(self, device):
+        cache = self.__dict__.setdefault("_frustum_cache", {})
+        if device not in cache:
+            cache[device] = self.frustum.to(device).contiguous()
+        return cache[device]
+
+    def get_lidar_coor_torch(self, sensor2ego, ego2global, cam2imgs, post_rots, post_trans, bda):
+        """The same geometry written with torch ops (device-agnostic, like the
+        reference's).  NOT used by `get_lidar_coor` / `view_transform`: it exists as
+        the float reference the CUDA kernel is validated against."""
         fr = self.frustum.to(sensor2ego)                      # [D,H,W,3]
         undo_aug = torch.inverse(post_rots)                   # [B,N,3,3]
         cam2ego = sensor2ego[..., :3, :3] @ torch.inverse(cam2imgs)
@@ -127,24 +140,27 @@ class LSSViewTransformer(nn.Module):
         [B,C,Z,Y,X] (or [B,C*Z,Y,X] with collapse_z) -- reference :175-200."""
         feat_last = feat.permute(0, 1, 3, 4, 2)
         shape = self._bev_shape(depth, feat_last.shape[-1])
-        if self.sync_free:
-            prep = _bp.prepare_ranks(coor, self.grid_lower_bound, self.grid_interval,
-                                     self.grid_size)
-            bev_feat = _bp.pool_prepared(depth, feat_last, prep, shape)
-        else:
-            ranks_bev, ranks_depth, ranks_feat, interval_starts, interval_lengths = \
-                self.voxel_pooling_prepare_v2(coor)
-            if ranks_feat is None:
-                print("warning ---> no points within the predefined bev receptive field")
-                gs = self.grid_size
-                dummy = torch.zeros(size=[feat.shape[0], feat.shape[2], int(gs[2]),
-                                          int(gs[0]), int(gs[1])]).to(feat)
-                return torch.cat(dummy.unbind(dim=2), 1)
-            bev_feat = _bp.bev_pool_v2(depth, feat_last, ranks_depth, ranks_feat, ranks_bev,
-                                       shape, interval_starts, interval_lengths)
+        if coor.numel() == 0:
+            return self._no_points_dummy(feat)
+        # The pooling is queued BEFORE the point / interval counts are read back, so
+        # the host read-back (the reference syncs at the same place in its
+        # boolean-mask indexing) overlaps the forward kernel instead of draining
+        # the GPU; it only decides about the reference's empty-input result.
+        prep = _bp.prepare_ranks(coor, self.grid_lower_bound, self.grid_interval, self.grid_size)
+        bev_feat = _bp.pool_prepared(depth, feat_last, prep, shape)
+        if not self.sync_free and prep.plan.n_intervals == 0:
+            return self._no_points_dummy(feat)
         if self.collapse_z:
             bev_feat = torch.cat(bev_feat.unbind(dim=2), 1)
         return bev_feat
+
+    def _no_points_dummy(self, feat):
+        """reference :179-189 (note its X/Y order and that Z is always collapsed)"""
+        print("warning ---> no points within the predefined bev receptive field")
+        gs = self.grid_size
+        dummy = torch.zeros(size=[feat.shape[0], feat.shape[2], int(gs[2]), int(gs[0]),
+                                  int(gs[1])]).to(feat)
+        return torch.cat(dummy.unbind(dim=2), 1)
 
     # -- a10 -----------------------------------------------------------------
     def pre_compute(self, input):
