@@ -7,10 +7,10 @@
 //   _merge_classes_prob    max over each class's prompts   san_in_veon_entry_temporal.py:273-297
 //   label rule             softmax/max/gate/where/permute/uint8   veon_temporal.py:223-229,240
 //
-// v1 (this file): fp32 FFMA contraction, one thread per voxel, text rows staged
-// in shared memory per prompt tile, everything after the dot products fused in
-// registers; feat_occ is read once per prompt tile and nothing but the uint8
-// labels is written.
+// This file: the entry point and the fp32 FFMA kernel used for shapes the tensor-core
+// path (tail_tc.cu: tcgen05 3xTF32, TMEM accumulators) does not take (C % 32 != 0,
+// V % 4 != 0, more than 128 prompt rows) -- one thread per voxel, text rows staged in
+// shared memory per prompt tile, everything after the dot products fused in registers.
 #include <math.h>
 
 #include "common.cuh"
@@ -103,6 +103,11 @@ k_voxel_text_argmax(const float* __restrict__ feat_occ, const float* __restrict_
 
 using namespace veon;
 
+// tensor-core path (tail_tc.cu); VEON_E_UNSUPPORTED when the shape does not fit it
+int veon_tail_tc_launch(const float* feat_occ, const float* text_w, const int32_t* cls,
+                        const float* bin_occ, int B, int C, int Q, int Z, int Y, int X,
+                        int free_label, uint8_t* labels, cudaStream_t stream);
+
 extern "C" int veon_voxel_text_argmax(const float* feat_occ, const float* text_w,
                                       const int32_t* class_of_prompt, const float* bin_occ,
                                       int B, int C, int Q, int Z, int Y, int X, int free_label,
@@ -110,6 +115,18 @@ extern "C" int veon_voxel_text_argmax(const float* feat_occ, const float* text_w
   if (!feat_occ || !text_w || !class_of_prompt || !bin_occ || !labels || B <= 0 || C <= 0 ||
       Q <= 0 || Z <= 0 || Y <= 0 || X <= 0 || B > 65535)
     return VEON_E_BADARG;
+  {  // tcgen05 path unless VEON_TAIL_IMPL=ffma or the shape does not fit (C % 32, V % 4, Q > 128)
+    static int use_tc = -1;
+    if (use_tc < 0) {
+      const char* e = getenv("VEON_TAIL_IMPL");
+      use_tc = (e && e[0] == 'f') ? 0 : 1;
+    }
+    if (use_tc) {
+      const int rc = veon_tail_tc_launch(feat_occ, text_w, class_of_prompt, bin_occ, B, C, Q, Z, Y, X,
+                                         free_label, labels, (cudaStream_t)stream);
+      if (rc != VEON_E_UNSUPPORTED) return rc;
+    }
+  }
   const size_t smem = sizeof(float) * (size_t)kTailQT * C;
   if (smem > 200 * 1024) return VEON_E_UNSUPPORTED;
   static size_t attr_smem = 48 * 1024;
