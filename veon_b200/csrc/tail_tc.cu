@@ -23,7 +23,9 @@
 //     STS.128): 16 B of shared-memory traffic per element instead of 20-24 B if
 //     a TMA-landed tile had to be re-read to be split; at ~22 B/clk/SM of HBM the
 //     shared-memory port is the scarce resource of this kernel.
-// Warp roles (13 warps): 0-7 producers, 8 MMA issuer (+TMEM alloc), 9-12 epilogue.
+// Warp roles (21 warps): 0-15 producers (loads of the next stage are issued before the
+// current one is stored: 4 x LDG.128 in flight per lane), 16 MMA issuer (+TMEM alloc),
+// 17-20 epilogue.
 #include <math.h>
 
 #include "common.cuh"
@@ -33,10 +35,10 @@ namespace tc {
 
 constexpr int KC = 32;        // channels per pipeline stage = 4 UMMA K-steps of 8 (tf32)
 constexpr int TM = 128;       // voxels per tile = UMMA M
-constexpr int kProdWarps = 8;
-constexpr int kMmaWarp = 8;
-constexpr int kEpiWarp0 = 9;
-constexpr int kWarps = 13;
+constexpr int kProdWarps = 16;  // 2 channel rows of the 32-row stage each
+constexpr int kMmaWarp = 16;
+constexpr int kEpiWarp0 = 17;   // 17..20: warp % 4 = 1,2,3,0 -> the four TMEM lane quarters
+constexpr int kWarps = 21;
 constexpr int kMaxStages = 6;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -174,59 +176,105 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_tail_tc(const Params p) {
 
   if (warp < kProdWarps) {
     // ============================ PRODUCERS ============================
-    uint32_t it = 0;  // global stage counter
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    // Everything that does not change from stage to stage is set up once: the lane's
+    // two shared-memory offsets, and the (up to two) W pieces this thread owns.
+    const int ma = lane >> 3, j = lane & 7;
+    const int row0 = 2 * warp;  // this warp's two channel rows inside a 32-row stage
+    uint32_t a_off[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      // channel row kl of the chunk = row kl%4 of 4-row group kl/4; the lane's 16 bytes are
+      // half of 32-byte chunk j/2, which is XOR-swizzled by the row
+      const int kl = row0 + i, kg4 = kl >> 2, kin = kl & 3;
+      a_off[i] = (uint32_t)(kg4 * 4 + ma) * 512u + (uint32_t)kin * 128u +
+                 (uint32_t)(((j >> 1) ^ kin) << 5) + (uint32_t)((j & 1) << 4);
+    }
+    constexpr int kWPieces = 2;  // npad * 8 float4 pieces over 512 threads (npad <= 128)
+    const float4* w_src[kWPieces];
+    uint32_t w_hi_off[kWPieces], w_lo_off[kWPieces];
+    bool w_has[kWPieces], w_real[kWPieces];
+#pragma unroll
+    for (int q = 0; q < kWPieces; ++q) {
+      const int idx = threadIdx.x + q * kProdWarps * 32;
+      const int n = idx >> 3, j4 = idx & 7, n2 = n + npad;
+      w_has[q] = idx < npad * 8;
+      w_real[q] = w_has[q] && n < p.Q;
+      w_src[q] = reinterpret_cast<const float4*>(p.w + (int64_t)(w_real[q] ? n : 0) * p.C) + j4;
+      w_hi_off[q] = 2 * a_bytes + (uint32_t)(n >> 3) * 1024u + (uint32_t)(n & 7) * 128u +
+                    (uint32_t)((j4 ^ (n & 7)) << 4);
+      w_lo_off[q] = 2 * a_bytes + (uint32_t)(n2 >> 3) * 1024u + (uint32_t)(n2 & 7) * 128u +
+                    (uint32_t)((j4 ^ (n2 & 7)) << 4);
+    }
+    const int64_t chunk_stride = (int64_t)KC * p.V;  // floats between consecutive chunks
+    auto tile_src = [&](int64_t tile, bool& vin) -> const float* {
       const int64_t b = tile / vtiles;
-      const int64_t v0 = (tile - b * vtiles) * TM;
-      const int64_t v = v0 + 4 * lane;
-      const bool vin = v < p.V;  // V % 4 == 0: the float4 is fully in or fully out
-      const int ma = lane >> 3, j = lane & 7;
-      for (int ch = 0; ch < n_chunks; ++ch, ++it) {
-        const int s = it % stages;
-        const uint32_t round = it / stages;
-        if (round > 0) mbar_wait(empty + s, (round - 1) & 1);
+      const int64_t v = (tile - b * vtiles) * TM + 4 * lane;
+      vin = (tile < n_tiles) && (v < p.V);  // V % 4 == 0: the float4 is fully in or out
+      return p.feat + ((int64_t)b * p.C + row0) * p.V + v;
+    };
+    auto load_rows = [&](const float* src, bool vin, float4* a) {
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+        a[i] = vin ? ld_stream4(src + (int64_t)i * p.V) : make_float4(0.f, 0.f, 0.f, 0.f);
+    };
+    uint32_t s = 0, phase = 0;  // stage slot and the parity its `empty` barrier completes next
+    bool first_round = true;
+    float4 a_cur[2], a_nxt[2], w_cur[kWPieces], w_nxt[kWPieces];
+    int64_t tile = blockIdx.x;
+    bool vin;
+    const float* src = tile_src(tile, vin);
+    load_rows(src, vin, a_cur);
+#pragma unroll
+    for (int q = 0; q < kWPieces; ++q)
+      w_cur[q] = w_real[q] ? __ldg(w_src[q]) : make_float4(0.f, 0.f, 0.f, 0.f);
+    while (tile < n_tiles) {
+      for (int ch = 0; ch < n_chunks; ++ch) {
+        // the loads of the next stage go out before this stage is written
+        const int nch = (ch + 1 == n_chunks) ? 0 : ch + 1;
+        if (nch == 0) {
+          tile += gridDim.x;
+          src = tile_src(tile, vin);
+        } else {
+          src += chunk_stride;
+        }
+        load_rows(src, vin, a_nxt);
+#pragma unroll
+        for (int q = 0; q < kWPieces; ++q)
+          w_nxt[q] = w_real[q] ? __ldg(w_src[q] + nch * (KC / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+
+        if (!first_round) mbar_wait(empty + s, phase);
         uint8_t* st = stage_base + (size_t)s * stage_bytes;
-        const int c0 = ch * KC;
-        // --- A: this warp's 4 channel rows, 128 voxels each (4 x LDG.128 in flight)
-        float4 a[4];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int c = c0 + 4 * warp + i;
-          a[i] = vin ? ld_stream4(p.feat + ((int64_t)b * p.C + c) * p.V + v)
-                     : make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-        // --- W chunk: npad rows x 8 float4 pieces, split over the 256 producer threads
-        for (int idx = threadIdx.x; idx < npad * 8; idx += kProdWarps * 32) {
-          const int n = idx >> 3, j4 = idx & 7;
-          float4 wv = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (n < p.Q) wv = __ldg(reinterpret_cast<const float4*>(p.w + (int64_t)n * p.C + c0) + j4);
-          float4 hi, lo;
-          hi.x = tf32_hi(wv.x); hi.y = tf32_hi(wv.y); hi.z = tf32_hi(wv.z); hi.w = tf32_hi(wv.w);
-          lo.x = wv.x - hi.x; lo.y = wv.y - hi.y; lo.z = wv.z - hi.z; lo.w = wv.w - hi.w;
-          const uint32_t off = (uint32_t)(n >> 3) * 1024u + (uint32_t)(n & 7) * 128u +
-                               (uint32_t)((j4 ^ (n & 7)) << 4);
-          uint8_t* wb = st + 2 * a_bytes;
-          *reinterpret_cast<float4*>(wb + off) = hi;
-          const int n2 = n + npad;
-          const uint32_t off2 = (uint32_t)(n2 >> 3) * 1024u + (uint32_t)(n2 & 7) * 128u +
-                                (uint32_t)((j4 ^ (n2 & 7)) << 4);
-          *reinterpret_cast<float4*>(wb + off2) = lo;
+        for (int q = 0; q < kWPieces; ++q) {
+          if (w_has[q]) {
+            float4 hi, lo;
+            hi.x = tf32_hi(w_cur[q].x); hi.y = tf32_hi(w_cur[q].y);
+            hi.z = tf32_hi(w_cur[q].z); hi.w = tf32_hi(w_cur[q].w);
+            lo.x = w_cur[q].x - hi.x; lo.y = w_cur[q].y - hi.y;
+            lo.z = w_cur[q].z - hi.z; lo.w = w_cur[q].w - hi.w;
+            *reinterpret_cast<float4*>(st + w_hi_off[q]) = hi;
+            *reinterpret_cast<float4*>(st + w_lo_off[q]) = lo;
+          }
+          w_cur[q] = w_nxt[q];
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          // channel row 4*warp + i of the chunk = row i of 4-row group `warp`; the lane's
-          // 16 bytes are half of 32-byte chunk j/2, which is XOR-swizzled by the row
-          const uint32_t off = (uint32_t)(warp * 4 + ma) * 512u + (uint32_t)i * 128u +
-                               (uint32_t)(((j >> 1) ^ i) << 5) + (uint32_t)((j & 1) << 4);
+        for (int i = 0; i < 2; ++i) {
           float4 hi, lo;
-          hi.x = tf32_hi(a[i].x); hi.y = tf32_hi(a[i].y); hi.z = tf32_hi(a[i].z); hi.w = tf32_hi(a[i].w);
-          lo.x = a[i].x - hi.x; lo.y = a[i].y - hi.y; lo.z = a[i].z - hi.z; lo.w = a[i].w - hi.w;
-          *reinterpret_cast<float4*>(st + off) = hi;
-          *reinterpret_cast<float4*>(st + a_bytes + off) = lo;
+          hi.x = tf32_hi(a_cur[i].x); hi.y = tf32_hi(a_cur[i].y);
+          hi.z = tf32_hi(a_cur[i].z); hi.w = tf32_hi(a_cur[i].w);
+          lo.x = a_cur[i].x - hi.x; lo.y = a_cur[i].y - hi.y;
+          lo.z = a_cur[i].z - hi.z; lo.w = a_cur[i].w - hi.w;
+          *reinterpret_cast<float4*>(st + a_off[i]) = hi;
+          *reinterpret_cast<float4*>(st + a_bytes + a_off[i]) = lo;
+          a_cur[i] = a_nxt[i];
         }
         fence_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) mbar_arrive(full + s);
+        if (++s == (uint32_t)stages) {
+          s = 0;
+          if (first_round) first_round = false; else phase ^= 1;
+        }
       }
     }
   } else if (warp == kMmaWarp) {
