@@ -37,6 +37,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0,
                     help="budget of the cpu_baseline leg (rank 0, N=1 only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-tail", action="store_true", help="skip the secondary tail measurement")
     ap.add_argument("--sync-free", type=int, default=0,
                     help="1: skip the host read-back of the counts (see LSSViewTransformer)")
     return ap.parse_args()
@@ -382,6 +383,36 @@ def run_ours(args):
             if k in avg},
         "clocks": clocks.summary(),
     }
+    # ---- secondary: the open-vocabulary tail (tcgen05 3xTF32 logits + fused argmax), reported
+    # as samples/s, algorithmic GB/s and fraction of the HBM roofline (it is HBM-bound: 9 flop/B)
+    if not args.no_tail:
+        from veon_b200.tail import class_of_prompt, voxel_text_argmax
+        Bt, Ct, Qt = 2, 512, 18
+        gt = torch.Generator(device=dev).manual_seed(7)
+        feat_occ = torch.sigmoid(torch.randn(Bt, Ct, 16, 200, 200, device=dev, generator=gt)) - 0.5
+        wt = torch.randn(Qt, Ct, device=dev, generator=gt)
+        wt = 100.0 * wt / wt.norm(dim=1, keepdim=True)
+        bin_occ = torch.randn(Bt, 2, 16, 200, 200, device=dev, generator=gt)
+        cls_t = class_of_prompt(list(range(Qt - 1))).to(dev)
+        for _ in range(3):
+            voxel_text_argmax(feat_occ, wt, cls_t, bin_occ)
+        torch.cuda.synchronize()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        nt = 10
+        t0.record()
+        for _ in range(nt):
+            voxel_text_argmax(feat_occ, wt, cls_t, bin_occ)
+        t1.record()
+        torch.cuda.synchronize()
+        ms_t = t0.elapsed_time(t1) / nt
+        bytes_t = Bt * (4 * 640000 * Ct + 8 * 640000 + 640000) + 4 * Qt * Ct
+        line["tail"] = {"what": f"veon_voxel_text_argmax, C={Ct}, Q={Qt} prompt rows, {Bt} samples/call, "
+                                "3xTF32 tcgen05 + fused class-max/argmax/gate -> uint8 [B,200,200,16]",
+                        "samples_per_s_per_gpu": Bt / (ms_t * 1e-3), "ms_per_call": ms_t,
+                        "achieved_gbs_algorithmic": bytes_t / (ms_t * 1e-3) / 1e9,
+                        "frac_of_hbm_peak": bytes_t / (ms_t * 1e-3) / 1e9 / peak_gbs,
+                        "tf32_tflops_issued": 3 * 2.0 * Bt * 640000 * Ct * 32 / (ms_t * 1e-3) / 1e12}
+        del feat_occ, bin_occ
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         c1 = S.CONFIGS["C1"] if args.workload == "C2" else cfg
         v, cores, desc, _, _ = time_cpu_port(c1, args.cpu_seconds)
