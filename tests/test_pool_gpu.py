@@ -284,3 +284,42 @@ def test_full_size_properties_c2():
     via_depth = (depth.grad.double() * depth.detach().double()).sum().item()
     assert abs(lhs - via_feat) <= 1e-6 * abs(lhs) + 1e-3
     assert abs(lhs - via_depth) <= 1e-6 * abs(lhs) + 1e-3
+
+
+@pytest.mark.parametrize("name,batch", [("C3", 1), ("C4", 1)])
+def test_full_size_properties_wide_channels(name, batch):
+    """BASELINE configs[2]/[3] shapes (32x88 feats, C=512 / D=118, C=768; one sample):
+    multi-chunk channel path at full size.  Checked by size-independent properties
+    (empty voxels exactly zero, linearity, adjoint identity) and, on a slice of
+    channels, bit-exactness against the C oracle."""
+    from veon_b200.bev_pool import bev_pool_v2, voxel_pooling_prepare_v2
+    cfg = S.CONFIGS[name]
+    coor_np = S.lidar_coor_np(cfg, batch=batch)
+    coor = torch.from_numpy(coor_np).cuda()
+    lower, interval, size = S.grid_vectors(cfg.grid_config)
+    rb, rd, rf, st, ln = voxel_pooling_prepare_v2(coor, lower, interval, size)
+    B, N, D, H, W, _ = coor.shape
+    C = cfg.channels
+    shape = (B, 16, 200, 200, C)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    depth = torch.rand(B, N, D, H, W, device="cuda", generator=g).requires_grad_()
+    feat = torch.randn(B, N, H, W, C, device="cuda", generator=g).requires_grad_()
+    out = bev_pool_v2(depth, feat, rd, rf, rb, shape, st, ln)
+    assert out.shape == (B, C, 16, 200, 200) and out.is_contiguous()
+    occ_vox = torch.zeros(B * 640000, dtype=torch.bool, device="cuda")
+    occ_vox[rb.long()] = True
+    assert float(out.detach().view(B, C, -1)[:, :, ~occ_vox.view(B, -1)[0]].abs().max()) == 0.0
+    # a slice of channels against the oracle (bit-exact), incl. the last partial chunk
+    sel = [0, 1, 63, 64, 200, C - 65, C - 1]
+    feat_sel = feat.detach()[..., sel].contiguous()
+    want = O.bev_pool_v2(depth.detach().cpu().numpy(), feat_sel.cpu().numpy(), rd.cpu().numpy(),
+                         rf.cpu().numpy(), rb.cpu().numpy(), (B, 16, 200, 200, len(sel)),
+                         st.cpu().numpy(), ln.cpu().numpy())
+    np.testing.assert_array_equal(out.detach()[:, sel].cpu().numpy(), want)
+    og = torch.randn(out.shape, device="cuda", generator=g)
+    out.backward(og)
+    lhs = (out.detach().double() * og.double()).sum().item()
+    via_feat = (feat.grad.double() * feat.detach().double()).sum().item()
+    via_depth = (depth.grad.double() * depth.detach().double()).sum().item()
+    assert abs(lhs - via_feat) <= 1e-6 * abs(lhs) + 1e-2
+    assert abs(lhs - via_depth) <= 1e-6 * abs(lhs) + 1e-2

@@ -263,7 +263,7 @@ extern "C" int veon_bev_pool_v2_bwd_planar(
   static int rows_kch = env_int("VEON_BWD_ROWS_KCH", 0);
   static int pix_kch = env_int("VEON_BWD_PIX_KCH", 0);
   int rk = rows_kch ? rows_kch : (C <= 32 ? 1 : 2);
-  int pk = pix_kch ? pix_kch : (C <= 32 ? 1 : (C <= 64 ? 2 : 4));
+  int pk = pix_kch ? pix_kch : (C <= 32 ? 1 : (C <= 64 ? 2 : (C <= 256 ? 4 : 8)));
   for (int b0 = 0; b0 < B; b0 += group) {
     const int b1 = b0 + group < B ? b0 + group : B;
     int rc;
