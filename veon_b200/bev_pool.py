@@ -167,11 +167,19 @@ def prepare_ranks(coor, grid_lower_bound, grid_interval, grid_size):
         raise _lib.VeonError(-3, "veon_prepare_v2_workspace_bytes")
     n_tiles = lib.veon_pool_num_tiles(B, V)
     with torch.cuda.device(dev):
-        ranks = torch.empty((5, P), dtype=torch.int32, device=dev)
-        tiles = torch.empty((3, n_tiles + 1), dtype=torch.int32, device=dev)
-        point_interval = torch.empty(P, dtype=torch.int32, device=dev)
-        counts = torch.empty(2, dtype=torch.int64, device=dev)
-        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        # one allocation for every int32 output + the kernel workspace (fewer allocator
+        # round-trips per call); the pieces below are views of it
+        nt1 = (n_tiles + 1 + 3) // 4 * 4
+        ws_ints = (ws_bytes + 3) // 4
+        pool = torch.empty(6 * P + 3 * nt1 + 4 + ws_ints + 64, dtype=torch.int32, device=dev)
+        ranks = pool[:5 * P].view(5, P)
+        point_interval = pool[5 * P:6 * P]
+        o = 6 * P
+        tiles = pool[o:o + 3 * nt1].view(3, nt1)[:, :n_tiles + 1]
+        o += 3 * nt1
+        counts = pool[o:o + 4].view(torch.int64)
+        o = (o + 4 + 63) // 64 * 64           # 256-byte aligned workspace
+        ws = pool[o:o + ws_ints]
         with _timed("prepare_v2", dev):
             rc = lib.veon_prepare_v2(
                 _ptr(coor), B, N, D, H, W, _lib.float3(lower), _lib.float3(interval), c_size,
@@ -179,6 +187,7 @@ def prepare_ranks(coor, grid_lower_bound, grid_interval, grid_size):
                 _ptr(counts), _ptr(tiles[0]), _ptr(tiles[1]), _ptr(tiles[2]), _ptr(point_interval),
                 _ptr(ws), ws_bytes, _stream_ptr(dev))
         _lib.check(rc, "veon_prepare_v2")
+        # pinned read-back buffer: torch's caching host allocator makes this cheap
         counts_host = torch.empty(2, dtype=torch.int64, pin_memory=True)
         counts_host.copy_(counts, non_blocking=True)
         ev = torch.cuda.Event()

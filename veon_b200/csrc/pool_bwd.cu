@@ -97,6 +97,57 @@ k_bwd_rows(const float* __restrict__ out_grad, const int32_t* __restrict__ tile_
   }
 }
 
+// Sum U per-lane partials over the warp, for U values at once: after log2(U) exchange
+// steps every lane holds ONE value (the one selected by its upper lane bits), which is
+// then reduced over the remaining lane bits.  U + log2(32/U) - 1 shuffles instead of 5*U.
+// Returns the sum for value index `which` (valid in every lane).
+template <int U>
+__device__ __forceinline__ float reduce_many(float (&d)[U], int lane, int& which) {
+  static_assert(U == 4 || U == 8, "U must be 4 or 8");
+  int idx = 0;
+  if constexpr (U == 8) {
+    const bool hi = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float keep = hi ? d[4 + i] : d[i], send = hi ? d[i] : d[4 + i];
+      d[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+    idx = hi ? 4 : 0;
+    const bool h8 = lane & 8;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float keep = h8 ? d[2 + i] : d[i], send = h8 ? d[i] : d[2 + i];
+      d[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+    idx += h8 ? 2 : 0;
+    const bool h4 = lane & 4;
+    const float keep = h4 ? d[1] : d[0], send = h4 ? d[0] : d[1];
+    float v = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    idx += h4 ? 1 : 0;
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    which = idx;
+    return v;
+  } else {
+    const bool hi = lane & 16;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const float keep = hi ? d[2 + i] : d[i], send = hi ? d[i] : d[2 + i];
+      d[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+    idx = hi ? 2 : 0;
+    const bool h8 = lane & 8;
+    const float keep = h8 ? d[1] : d[0], send = h8 ? d[0] : d[1];
+    float v = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    idx += h8 ? 1 : 0;
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    which = idx;
+    return v;
+  }
+}
+
 // One warp per feature pixel; a CTA's 8 warps are 8 consecutive pixels so that
 // their strided depth / depth_grad accesses share 32-byte sectors.
 template <int KCH>
@@ -161,20 +212,23 @@ k_bwd_pixels(const float* __restrict__ rows, const float* __restrict__ depth,
         for (int k = 0; k < KCH; ++k)
           g[u][k] = (cbase + lane + 32 * k < C) ? __ldg(row + 32 * k) : 0.f;
       }
+      float dot[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
+        dot[u] = 0.f;
         if (j0 + u < nk) {
           const float dv = dep[j0 + u];
-          float dot = 0.f;
 #pragma unroll
           for (int k = 0; k < KCH; ++k) {
-            dot = fmaf(g[u][k], f[k], dot);
+            dot[u] = fmaf(g[u][k], f[k], dot[u]);
             acc[k] = fmaf(dv, g[u][k], acc[k]);
           }
-          dot = warp_sum(dot);
-          if (lane == 0) dots[kd[j0 + u]] += dot;
         }
       }
+      int which;
+      const float total = reduce_many<U>(dot, lane, which);
+      // one lane per point (the lanes whose low bits are zero) owns the result
+      if ((lane & (32 / U - 1)) == 0 && j0 + which < nk) dots[kd[j0 + which]] += total;
     }
 #pragma unroll
     for (int k = 0; k < KCH; ++k) {
