@@ -67,7 +67,7 @@ k_pool_fwd(const float* __restrict__ depth, const float* __restrict__ feat,
            uint32_t n_items, uint32_t tiles_per_sample, int64_t V, int C, uint32_t n_chunks,
            int vec_ok, float* __restrict__ out) {
   constexpr int CC = 32 * KCH;
-  constexpr int U = 8;  // feature rows in flight per warp
+  constexpr int U = (KCH <= 2) ? 16 : 8;  // feature rows in flight per warp
   constexpr int kTileFloats = CC * kRowPitch;
   constexpr int kWarpFloats = kTileFloats + kRingSlots * kSlotInts;
   extern __shared__ __align__(16) float smem[];
