@@ -186,6 +186,9 @@ int veon_bev_pool_v2_fwd_planar(const float* depth, const float* feat,
 
 /* QuickCumsumCuda.backward (bev_pool.py:43-83) for a [B,C,Z,Y,X] out_grad.
  *   rows_ws      float[n_intervals * C] scratch (compacted gradient rows)
+ *   ctrl_ws      int32[B + 1] scratch (work-queue ticket + per-sample completion
+ *                counters of the fused single-launch kernel; NULL selects the
+ *                two-launch path)
  *   depth_grad   [B,N,D,H,W], feat_grad [B,N,H,W,C]: fully written (no need to
  *                zero).  Deterministic: no atomics, fixed summation order. */
 int veon_bev_pool_v2_bwd_planar(const float* out_grad,
@@ -196,7 +199,7 @@ int veon_bev_pool_v2_bwd_planar(const float* out_grad,
                                 int64_t n_intervals,
                                 int B, int N, int D, int H, int W, int C,
                                 int64_t voxels_per_sample,
-                                float* rows_ws,
+                                float* rows_ws, int32_t* ctrl_ws,
                                 float* depth_grad, float* feat_grad,
                                 void* stream);
 

@@ -31,23 +31,17 @@ constexpr int kBwdWarps = 8;   // pixel pass: 8 consecutive pixels per CTA
 constexpr int kRowWarps = 4;   // row pass
 constexpr int kPitch = kTileVoxels + 1;
 
+// one warp: tile t, channel chunk starting at cbase -> compact rows
 template <int KCH>
-__global__ void __launch_bounds__(kRowWarps * 32)
-k_bwd_rows(const float* __restrict__ out_grad, const int32_t* __restrict__ tile_istart,
-           const uint32_t* __restrict__ tile_occ, int64_t tile_begin, int64_t tile_end,
-           int64_t tiles_per_sample, int64_t V, int C, int n_chunks, int vec_ok,
-           float* __restrict__ rows) {
+__device__ __forceinline__ void rows_tile(float* tile, int lane, const float* __restrict__ out_grad,
+                                          const int32_t* __restrict__ tile_istart,
+                                          const uint32_t* __restrict__ tile_occ, int64_t t,
+                                          int cbase, int64_t tiles_per_sample, int64_t V, int C,
+                                          int vec_ok, float* __restrict__ rows) {
   constexpr int CC = 32 * KCH;
-  extern __shared__ float smem[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  float* tile = smem + warp * (CC * kPitch);
-  const int64_t group = blockIdx.x / n_chunks;
-  const int cbase = (int)(blockIdx.x - group * n_chunks) * CC;
-  const int64_t t = tile_begin + group * kRowWarps + warp;
-  if (t >= tile_end) return;
   const uint32_t occ = __ldg(tile_occ + t);  // one independent load each: a single latency
   const int32_t i0 = __ldg(tile_istart + t);
-  if (occ == 0u) return;                     // empty tile: nothing read
+  if (occ == 0u) return;                     // empty tile: nothing read (warp-uniform)
   const int64_t b = t / tiles_per_sample;
   const int64_t v0 = (t - b * tiles_per_sample) * kTileVoxels;
 
@@ -95,6 +89,23 @@ k_bwd_rows(const float* __restrict__ out_grad, const int32_t* __restrict__ tile_
       if (lane + 32 * k < cmax) row[32 * k] = tile[(lane + 32 * k) * kPitch + vj];
     row += C;
   }
+}
+
+template <int KCH>
+__global__ void __launch_bounds__(kRowWarps * 32)
+k_bwd_rows(const float* __restrict__ out_grad, const int32_t* __restrict__ tile_istart,
+           const uint32_t* __restrict__ tile_occ, int64_t tile_begin, int64_t tile_end,
+           int64_t tiles_per_sample, int64_t V, int C, int n_chunks, int vec_ok,
+           float* __restrict__ rows) {
+  constexpr int CC = 32 * KCH;
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t group = blockIdx.x / n_chunks;
+  const int cbase = (int)(blockIdx.x - group * n_chunks) * CC;
+  const int64_t t = tile_begin + group * kRowWarps + warp;
+  if (t >= tile_end) return;
+  rows_tile<KCH>(smem + warp * (CC * kPitch), lane, out_grad, tile_istart, tile_occ, t, cbase,
+                 tiles_per_sample, V, C, vec_ok, rows);
 }
 
 // Sum U per-lane partials over the warp, for U values at once: after log2(U) exchange
@@ -150,23 +161,24 @@ __device__ __forceinline__ float reduce_many(float (&d)[U], int lane, int& which
 
 // One warp per feature pixel; a CTA's 8 warps are 8 consecutive pixels so that
 // their strided depth / depth_grad accesses share 32-byte sectors.
-template <int KCH>
-__global__ void __launch_bounds__(kBwdWarps * 32)
-k_bwd_pixels(const float* __restrict__ rows, const float* __restrict__ depth,
-             const float* __restrict__ feat, const int32_t* __restrict__ point_interval,
-             int64_t pix_begin, int64_t pix_end, int D, int HW, int C,
-             float* __restrict__ depth_grad, float* __restrict__ feat_grad) {
+// one warp: feature pixel `pix`; wsm = 4*D floats of per-warp shared memory.
+// COHERENT: true when `rows` was written earlier in the SAME kernel (fused path): the
+// read-only (.nc) path may then not be used.
+template <int KCH, bool COHERENT>
+__device__ __forceinline__ void pixel_warp(float* wsm, int lane, const float* __restrict__ rows,
+                                           const float* __restrict__ depth,
+                                           const float* __restrict__ feat,
+                                           const int32_t* __restrict__ point_interval,
+                                           int64_t pix, int D, int HW, int C,
+                                           float* __restrict__ depth_grad,
+                                           float* __restrict__ feat_grad) {
   constexpr int CC = 32 * KCH;
   constexpr int U = (KCH <= 2) ? 8 : 4;  // gradient rows in flight per warp
-  extern __shared__ float smem[];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   // per warp: dots[D] | dep[D] | iis[D] | kd[D]
-  float* dots = smem + (size_t)warp * 4 * D;
+  float* dots = wsm;
   float* dep = dots + D;
   int* iis = reinterpret_cast<int*>(dep + D);
   int* kd = iis + D;
-  const int64_t pix = pix_begin + (int64_t)blockIdx.x * kBwdWarps + warp;
-  if (pix >= pix_end) return;
   const int64_t bn = pix / HW;
   const int hw = (int)(pix - bn * HW);
   const int64_t dbase = bn * (int64_t)D * HW + hw;
@@ -210,7 +222,8 @@ k_bwd_pixels(const float* __restrict__ rows, const float* __restrict__ depth,
         const float* row = rows + (int64_t)iis[j] * C + cbase + lane;
 #pragma unroll
         for (int k = 0; k < KCH; ++k)
-          g[u][k] = (cbase + lane + 32 * k < C) ? __ldg(row + 32 * k) : 0.f;
+          g[u][k] = (cbase + lane + 32 * k < C) ? (COHERENT ? __ldcg(row + 32 * k) : __ldg(row + 32 * k))
+                                                : 0.f;
       }
       float dot[U];
 #pragma unroll
@@ -239,6 +252,138 @@ k_bwd_pixels(const float* __restrict__ rows, const float* __restrict__ depth,
   __syncwarp();
   // dense depth_grad column: dots[] is zero for dropped bins
   for (int d = lane; d < D; d += 32) depth_grad[dbase + (int64_t)d * HW] = dots[d];
+}
+
+template <int KCH>
+__global__ void __launch_bounds__(kBwdWarps * 32)
+k_bwd_pixels(const float* __restrict__ rows, const float* __restrict__ depth,
+             const float* __restrict__ feat, const int32_t* __restrict__ point_interval,
+             int64_t pix_begin, int64_t pix_end, int D, int HW, int C,
+             float* __restrict__ depth_grad, float* __restrict__ feat_grad) {
+  extern __shared__ float smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t pix = pix_begin + (int64_t)blockIdx.x * kBwdWarps + warp;
+  if (pix >= pix_end) return;
+  pixel_warp<KCH, false>(smem + (size_t)warp * 4 * D, lane, rows, depth, feat, point_interval, pix,
+                         D, HW, C, depth_grad, feat_grad);
+}
+
+// ---------------------------------------------------------------------------------
+// Fused backward: ONE persistent kernel, ordered work queue
+//     rows(0) | rows(1) pixels(0) | rows(2) pixels(1) | ... | pixels(B-1)
+// (a work item = 8 tiles x all channel chunks, or 8 pixels).  A pixel item of sample s
+// starts only when every row item of s has finished (per-sample completion counter).
+// Tickets are handed out in that order, so everything a waiting CTA depends on has
+// already been claimed by a running CTA that never waits itself: no deadlock with a
+// co-resident grid.  Effects: the compact rows of a sample are still L2-resident when
+// its pixels gather them (the 543 MB row round trip through HBM disappears), the
+// bandwidth-bound row pass overlaps the latency-bound pixel pass, no launch ramps.
+// ---------------------------------------------------------------------------------
+struct FusedBwdParams {
+  const float *out_grad, *depth, *feat;
+  const int32_t *tile_istart, *point_interval;
+  const uint32_t* tile_occ;
+  float *rows, *depth_grad, *feat_grad;
+  int32_t* ctrl;  // [0] ticket, [1 + s] finished row items of sample s
+  int64_t tiles_per_sample, V, pix_per_sample;
+  int B, D, HW, C, vec_ok;
+  int row_items, pix_items;  // per sample
+};
+
+__device__ __forceinline__ int ld_acquire_i32(const int32_t* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+template <int RK, int PK>
+__global__ void __launch_bounds__(kBwdWarps * 32)
+k_bwd_fused(const FusedBwdParams p) {
+  extern __shared__ float smem[];
+  __shared__ int s_ticket[2];
+  constexpr int CC = 32 * RK;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n_chunks = (p.C + CC - 1) / CC;
+  const int period = p.row_items + p.pix_items;
+  const int64_t total = (int64_t)p.B * period;
+  // the ticket for the NEXT item is fetched while the current one runs (the atomic's
+  // round trip would otherwise be serialised with every short item)
+  if (threadIdx.x == 0) s_ticket[0] = atomicAdd(p.ctrl, 1);
+  for (int it = 0;; ++it) {
+    __syncthreads();  // s_ticket[it & 1] published; previous item finished by every warp
+    const int64_t ticket = s_ticket[it & 1];
+    if (ticket >= total) break;
+    if (threadIdx.x == 0) s_ticket[(it + 1) & 1] = atomicAdd(p.ctrl, 1);
+    // decode: rows(0) first, then (rows(k+1), pixels(k)) periods, pixels(B-1) last
+    bool is_rows;
+    int sample, idx;
+    if (ticket < p.row_items) {
+      is_rows = true; sample = 0; idx = (int)ticket;
+    } else {
+      const int64_t t2 = ticket - p.row_items;
+      const int k = (int)(t2 / period), r = (int)(t2 - (int64_t)k * period);
+      if (k < p.B - 1) {
+        if (r < p.row_items) { is_rows = true; sample = k + 1; idx = r; }
+        else { is_rows = false; sample = k; idx = r - p.row_items; }
+      } else {
+        is_rows = false; sample = p.B - 1; idx = r;  // r < pix_items by construction of total
+      }
+    }
+    if (is_rows) {
+      const int64_t t = (int64_t)sample * p.tiles_per_sample + (int64_t)idx * kBwdWarps + warp;
+      if (t < (int64_t)(sample + 1) * p.tiles_per_sample) {
+        for (int ch = 0; ch < n_chunks; ++ch) {
+          rows_tile<RK>(smem + warp * (CC * kPitch), lane, p.out_grad, p.tile_istart, p.tile_occ, t,
+                        ch * CC, p.tiles_per_sample, p.V, p.C, p.vec_ok, p.rows);
+          __syncwarp();
+        }
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        __threadfence();  // this CTA's rows are visible before the counter moves
+        atomicAdd(p.ctrl + 1 + sample, 1);
+      }
+    } else {
+      if (threadIdx.x == 0) {
+        while (ld_acquire_i32(p.ctrl + 1 + sample) < p.row_items) __nanosleep(200);
+      }
+      __syncthreads();
+      const int64_t pix = (int64_t)sample * p.pix_per_sample + (int64_t)idx * kBwdWarps + warp;
+      if (pix < (int64_t)(sample + 1) * p.pix_per_sample)
+        pixel_warp<PK, true>(smem + (size_t)warp * 4 * p.D, lane, p.rows, p.depth, p.feat,
+                             p.point_interval, pix, p.D, p.HW, p.C, p.depth_grad, p.feat_grad);
+    }
+  }
+}
+
+template <int RK, int PK>
+static int launch_fused(const FusedBwdParams& p, cudaStream_t stream) {
+  constexpr int CC = 32 * RK;
+  size_t smem = sizeof(float) * kBwdWarps * CC * kPitch;
+  const size_t smem_pix = sizeof(float) * kBwdWarps * 4 * (size_t)p.D;
+  if (smem_pix > smem) smem = smem_pix;
+  if (smem > 200 * 1024) return VEON_E_UNSUPPORTED;
+  static size_t attr_smem = 0;
+  static int ctas_per_sm = 0;
+  if (smem > attr_smem) {
+    VEON_CUDA_TRY(cudaFuncSetAttribute(k_bwd_fused<RK, PK>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VEON_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_bwd_fused<RK, PK>,
+                                                                kBwdWarps * 32, smem));
+    attr_smem = smem;
+  }
+  if (ctas_per_sm < 1) return VEON_E_UNSUPPORTED;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  // the grid must be co-resident (CTAs wait on each other through the counters)
+  int64_t grid = (int64_t)ctas_per_sm * sms;
+  const int64_t total = (int64_t)p.B * (p.row_items + p.pix_items);
+  if (grid > total) grid = total;
+  VEON_CUDA_TRY(cudaMemsetAsync(p.ctrl, 0, sizeof(int32_t) * (p.B + 1), stream));
+  k_bwd_fused<RK, PK><<<(unsigned)grid, kBwdWarps * 32, smem, stream>>>(p);
+  VEON_LAUNCH_CHECK();
+  return 0;
 }
 
 template <int KCH>
@@ -298,8 +443,8 @@ static int env_int(const char* name, int dflt) {
 extern "C" int veon_bev_pool_v2_bwd_planar(
     const float* out_grad, const float* depth, const float* feat, const int32_t* tile_istart,
     const uint32_t* tile_occ, const int32_t* point_interval, int64_t n_intervals, int B, int N,
-    int D, int H, int W, int C, int64_t V, float* rows_ws, float* depth_grad, float* feat_grad,
-    void* stream_) {
+    int D, int H, int W, int C, int64_t V, float* rows_ws, int32_t* ctrl_ws, float* depth_grad,
+    float* feat_grad, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!out_grad || !depth || !feat || !tile_istart || !tile_occ || !point_interval || !rows_ws ||
       !depth_grad || !feat_grad || B <= 0 || N <= 0 || D <= 0 || H <= 0 || W <= 0 || C <= 0 ||
@@ -318,6 +463,29 @@ extern "C" int veon_bev_pool_v2_bwd_planar(
   static int pix_kch = env_int("VEON_BWD_PIX_KCH", 0);
   int rk = rows_kch ? rows_kch : (C <= 32 ? 1 : 2);
   int pk = pix_kch ? pix_kch : (C <= 32 ? 1 : (C <= 64 ? 2 : (C <= 256 ? 4 : 8)));
+  // Fused single-launch kernel vs two launches (measured, profiles/README.md): inside the
+  // fused kernel the latency-bound pixel work shares 24 warps/SM with the row work (as its own
+  // kernel it runs at 64 warps/SM), which loses at C = 64 (600 vs 389 us) and wins by 4-5 %
+  // for wide channels where the row pass dominates.  VEON_BWD_FUSED=0/1 overrides.
+  static int fused_env = env_int("VEON_BWD_FUSED", -1);
+  const bool fused = fused_env >= 0 ? fused_env != 0 : C >= 256;
+  if (fused && ctrl_ws && (int64_t)B * tps <= 0x7fffffffLL) {
+    FusedBwdParams p;
+    p.out_grad = out_grad; p.depth = depth; p.feat = feat; p.tile_istart = tile_istart;
+    p.point_interval = point_interval; p.tile_occ = tile_occ; p.rows = rows_ws;
+    p.depth_grad = depth_grad; p.feat_grad = feat_grad; p.ctrl = ctrl_ws;
+    p.tiles_per_sample = tps; p.V = V; p.pix_per_sample = pix_per_sample;
+    p.B = B; p.D = D; p.HW = HW; p.C = C;
+    p.vec_ok = ((V & 3) == 0) && (((uintptr_t)out_grad & 15) == 0);
+    p.row_items = (int)ceil_div64(tps, kBwdWarps);
+    p.pix_items = (int)ceil_div64(pix_per_sample, kBwdWarps);
+    int rc = VEON_E_UNSUPPORTED;
+    if (rk == 1 && pk == 1) rc = launch_fused<1, 1>(p, stream);
+    else if (rk == 2 && pk == 2) rc = launch_fused<2, 2>(p, stream);
+    else if (rk == 2 && pk == 4) rc = launch_fused<2, 4>(p, stream);
+    else if (rk == 2 && pk == 8) rc = launch_fused<2, 8>(p, stream);
+    if (rc != VEON_E_UNSUPPORTED) return rc;
+  }
   for (int b0 = 0; b0 < B; b0 += group) {
     const int b1 = b0 + group < B ? b0 + group : B;
     int rc;
