@@ -23,9 +23,8 @@
 //     STS.128): 16 B of shared-memory traffic per element instead of 20-24 B if
 //     a TMA-landed tile had to be re-read to be split; at ~22 B/clk/SM of HBM the
 //     shared-memory port is the scarce resource of this kernel.
-// Warp roles (21 warps): 0-15 producers (loads of the next stage are issued before the
-// current one is stored: 4 x LDG.128 in flight per lane), 16 MMA issuer (+TMEM alloc),
-// 17-20 epilogue.
+// Warp roles (21 warps): 0-15 producers (the loads of the next stage are in flight while the
+// current one is split and stored), 16 MMA issuer (+TMEM alloc), 17-20 epilogue.
 #include <math.h>
 
 #include "common.cuh"
@@ -219,63 +218,72 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_tail_tc(const Params p) {
     };
     uint32_t s = 0, phase = 0;  // stage slot and the parity its `empty` barrier completes next
     bool first_round = true;
-    float4 a_cur[2], a_nxt[2], w_cur[kWPieces], w_nxt[kWPieces];
-    int64_t tile = blockIdx.x;
+    // position of the stage whose data is being LOADED (runs one stage ahead of the stores)
+    int64_t ltile = blockIdx.x;
+    int lch = 0;
     bool vin;
-    const float* src = tile_src(tile, vin);
-    load_rows(src, vin, a_cur);
+    const float* src = tile_src(ltile, vin);
+    auto load_stage = [&](float4* a, float4* wv) {
+      load_rows(src, vin, a);
 #pragma unroll
-    for (int q = 0; q < kWPieces; ++q)
-      w_cur[q] = w_real[q] ? __ldg(w_src[q]) : make_float4(0.f, 0.f, 0.f, 0.f);
-    while (tile < n_tiles) {
-      for (int ch = 0; ch < n_chunks; ++ch) {
-        // the loads of the next stage go out before this stage is written
-        const int nch = (ch + 1 == n_chunks) ? 0 : ch + 1;
-        if (nch == 0) {
-          tile += gridDim.x;
-          src = tile_src(tile, vin);
-        } else {
-          src += chunk_stride;
-        }
-        load_rows(src, vin, a_nxt);
+      for (int q = 0; q < kWPieces; ++q)
+        wv[q] = w_real[q] ? __ldg(w_src[q] + lch * (KC / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      // advance the load position
+      if (++lch == n_chunks) {
+        lch = 0;
+        ltile += gridDim.x;
+        src = tile_src(ltile, vin);
+      } else {
+        src += chunk_stride;
+      }
+    };
+    auto store_stage = [&](const float4* a, const float4* wv) {
+      if (!first_round) mbar_wait(empty + s, phase);
+      uint8_t* st = stage_base + (size_t)s * stage_bytes;
 #pragma unroll
-        for (int q = 0; q < kWPieces; ++q)
-          w_nxt[q] = w_real[q] ? __ldg(w_src[q] + nch * (KC / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-
-        if (!first_round) mbar_wait(empty + s, phase);
-        uint8_t* st = stage_base + (size_t)s * stage_bytes;
-#pragma unroll
-        for (int q = 0; q < kWPieces; ++q) {
-          if (w_has[q]) {
-            float4 hi, lo;
-            hi.x = tf32_hi(w_cur[q].x); hi.y = tf32_hi(w_cur[q].y);
-            hi.z = tf32_hi(w_cur[q].z); hi.w = tf32_hi(w_cur[q].w);
-            lo.x = w_cur[q].x - hi.x; lo.y = w_cur[q].y - hi.y;
-            lo.z = w_cur[q].z - hi.z; lo.w = w_cur[q].w - hi.w;
-            *reinterpret_cast<float4*>(st + w_hi_off[q]) = hi;
-            *reinterpret_cast<float4*>(st + w_lo_off[q]) = lo;
-          }
-          w_cur[q] = w_nxt[q];
-        }
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
+      for (int q = 0; q < kWPieces; ++q) {
+        if (w_has[q]) {
           float4 hi, lo;
-          hi.x = tf32_hi(a_cur[i].x); hi.y = tf32_hi(a_cur[i].y);
-          hi.z = tf32_hi(a_cur[i].z); hi.w = tf32_hi(a_cur[i].w);
-          lo.x = a_cur[i].x - hi.x; lo.y = a_cur[i].y - hi.y;
-          lo.z = a_cur[i].z - hi.z; lo.w = a_cur[i].w - hi.w;
-          *reinterpret_cast<float4*>(st + a_off[i]) = hi;
-          *reinterpret_cast<float4*>(st + a_bytes + a_off[i]) = lo;
-          a_cur[i] = a_nxt[i];
-        }
-        fence_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
-        __syncwarp();
-        if (lane == 0) mbar_arrive(full + s);
-        if (++s == (uint32_t)stages) {
-          s = 0;
-          if (first_round) first_round = false; else phase ^= 1;
+          hi.x = tf32_hi(wv[q].x); hi.y = tf32_hi(wv[q].y);
+          hi.z = tf32_hi(wv[q].z); hi.w = tf32_hi(wv[q].w);
+          lo.x = wv[q].x - hi.x; lo.y = wv[q].y - hi.y;
+          lo.z = wv[q].z - hi.z; lo.w = wv[q].w - hi.w;
+          *reinterpret_cast<float4*>(st + w_hi_off[q]) = hi;
+          *reinterpret_cast<float4*>(st + w_lo_off[q]) = lo;
         }
       }
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        float4 hi, lo;
+        hi.x = tf32_hi(a[i].x); hi.y = tf32_hi(a[i].y);
+        hi.z = tf32_hi(a[i].z); hi.w = tf32_hi(a[i].w);
+        lo.x = a[i].x - hi.x; lo.y = a[i].y - hi.y;
+        lo.z = a[i].z - hi.z; lo.w = a[i].w - hi.w;
+        *reinterpret_cast<float4*>(st + a_off[i]) = hi;
+        *reinterpret_cast<float4*>(st + a_bytes + a_off[i]) = lo;
+      }
+      fence_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(full + s);
+      if (++s == (uint32_t)stages) {
+        s = 0;
+        if (first_round) first_round = false; else phase ^= 1;
+      }
+    };
+    // Two named register sets, loop unrolled by two: the loads of stage k+1 are issued
+    // before stage k is written, and no register is ever copied while its load is in flight
+    // (a rotating copy would wait for the load it copies; a third set spills at 672 threads).
+    const int64_t my_tiles = (n_tiles > (int64_t)blockIdx.x)
+                                 ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const int64_t n_stages_total = my_tiles * n_chunks;
+    float4 a0[2], a1[2], w0[kWPieces], w1[kWPieces];
+    if (n_stages_total > 0) load_stage(a0, w0);
+    for (int64_t k = 0; k < n_stages_total; k += 2) {
+      if (k + 1 < n_stages_total) load_stage(a1, w1);
+      store_stage(a0, w0);
+      if (k + 1 >= n_stages_total) break;
+      if (k + 2 < n_stages_total) load_stage(a0, w0);
+      store_stage(a1, w1);
     }
   } else if (warp == kMmaWarp) {
     // ============================ MMA ISSUER ============================
