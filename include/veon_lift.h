@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define VEON_ABI_VERSION 1
+#define VEON_ABI_VERSION 2
 
 #define VEON_E_BADARG    (-1)  /* NULL pointer / non-positive dimension          */
 #define VEON_E_WORKSPACE (-2)  /* workspace smaller than *_workspace_bytes()     */
@@ -132,18 +132,25 @@ int veon_lidar_coor(const float* frustum, const float* sensor2ego, const float* 
  *  arbitrary; ours is the canonical stable one).
  *
  *  Optional by-products ("plan") consumed by the *_planar pool entry points
- *  (pass NULL to skip all four):
+ *  (pass NULL to skip them all; tile_heavy may be NULL on its own):
  *      tile_start   int32[n_tiles+1]  first point of each 32-voxel tile
  *      tile_istart  int32[n_tiles+1]  first interval of each tile
  *      tile_occ     uint32[n_tiles+1] bit v set <=> voxel v of the tile is occupied
  *      point_interval int32[P]        interval index of depth element
  *                   (b,n,d,h,w) stored PIXEL-major at ((b*N+n)*H*W+hw)*D+d,
  *                   -1 where the point was dropped
+ *      tile_heavy   int32[veon_pool_heavy_list_ints(P, n_tiles)]: [0] = number of
+ *                   listed tiles, [1] = the point-count threshold used, [2..] = ids
+ *                   (arbitrary order) of the tiles holding at least that many
+ *                   points; the forward gives each of them to a whole thread
+ *                   block instead of one warp
  *    with n_tiles = B * ceil(Z*Y*X / 32), see veon_pool_num_tiles().
  * ------------------------------------------------------------------------ */
 size_t veon_prepare_v2_workspace_bytes(int B, int N, int D, int H, int W,
                                        const float* grid_size /*[host]*/);
 int64_t veon_pool_num_tiles(int B, int64_t voxels_per_sample);
+/* int32 elements a tile_heavy buffer needs for a plan over at most n_points points */
+int64_t veon_pool_heavy_list_ints(int64_t n_points, int64_t n_tiles);
 
 int veon_prepare_v2(const float* coor, int B, int N, int D, int H, int W,
                     const float* lower, const float* interval,
@@ -152,7 +159,7 @@ int veon_prepare_v2(const float* coor, int B, int N, int D, int H, int W,
                     int32_t* interval_starts, int32_t* interval_lengths,
                     int64_t* counts,
                     int32_t* tile_start, int32_t* tile_istart, uint32_t* tile_occ,
-                    int32_t* point_interval,
+                    int32_t* tile_heavy, int32_t* point_interval,
                     void* workspace, size_t workspace_bytes, void* stream);
 
 /* Build the same plan from rank arrays the caller already holds (the
@@ -167,6 +174,7 @@ int veon_pool_plan_build(const int32_t* ranks_depth, const int32_t* ranks_feat,
                          int B, int N, int D, int H, int W,
                          int64_t voxels_per_sample,
                          int32_t* tile_start, int32_t* tile_istart, uint32_t* tile_occ,
+                         int32_t* tile_heavy /* sized for n_points; may be NULL */,
                          int32_t* point_interval, int32_t* flags, void* stream);
 
 /* ------------------------------------------------------------------------
@@ -180,6 +188,8 @@ int veon_bev_pool_v2_fwd_planar(const float* depth, const float* feat,
                                 const int32_t* ranks_feat,
                                 const int32_t* ranks_bev,
                                 const int32_t* tile_start,
+                                const int32_t* tile_heavy /* may be NULL */,
+                                int64_t tile_heavy_ints /* its size in int32 */,
                                 int B, int C, int64_t voxels_per_sample,
                                 int64_t n_feat_rows /* B*N*H*W rows of feat */,
                                 float* out, void* stream);

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"libveonlift.so does not export {n}"
     assert set(names) == set(_lib.EXPORTED_SYMBOLS), "ctypes table and header disagree"
-    assert lib.veon_abi_version() == 1
+    assert lib.veon_abi_version() == 2
     assert b"bad argument" in lib.veon_error_string(-1)
 
 
@@ -35,7 +35,7 @@ def test_argument_errors_do_not_need_a_gpu():
     lib = _lib.load()
     null = ctypes.c_void_p(0)
     assert lib.veon_bev_pool_v2(64, 10, null, null, null, null, null, null, null, null, null) == -1
-    assert lib.veon_bev_pool_v2_fwd_planar(null, null, null, null, null, null, 1, 64, 640000, 4224, null, null) == -1
+    assert lib.veon_bev_pool_v2_fwd_planar(null, null, null, null, null, null, null, 0, 1, 64, 640000, 4224, null, null) == -1
     gs = _lib.float3([200, 200, 16])
     assert lib.veon_prepare_v2_workspace_bytes(8, 6, 88, 16, 44, gs) > 0
     assert lib.veon_prepare_v2_workspace_bytes(0, 6, 88, 16, 44, gs) == 0

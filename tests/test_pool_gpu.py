@@ -323,3 +323,81 @@ def test_full_size_properties_wide_channels(name, batch):
     via_depth = (depth.grad.double() * depth.detach().double()).sum().item()
     assert abs(lhs - via_feat) <= 1e-6 * abs(lhs) + 1e-2
     assert abs(lhs - via_depth) <= 1e-6 * abs(lhs) + 1e-2
+
+
+# ---------------------------------------------------------------- heavy tiles
+def _heavy_ids(plan):
+    h = plan.tile_heavy.cpu().numpy()
+    return int(h[0]), int(h[1]), np.sort(h[2:2 + int(h[0])])
+
+
+def test_heavy_tile_list_matches_point_counts():
+    """The plan lists exactly the tiles whose point count reaches the threshold
+    (veon_lift.h: tile_heavy), from both plan builders."""
+    from veon_b200 import bev_pool as BP
+    case = make_case("C1", 2, 8)
+    rb, rd, rf, st, ln = gpu_ranks(case["ranks"])
+    B, Z, Y, X, _ = case["shape"]
+    plan = BP._plan_for(rd, rf, rb, st, ln, case["dims"], Z * Y * X)
+    n, thr, ids = _heavy_ids(plan)
+    cnt = np.bincount(case["ranks"][0] // 32, minlength=B * Z * Y * X // 32)
+    want = np.nonzero(cnt >= thr)[0]
+    assert thr >= 32 and n == want.size and n > 0
+    assert np.array_equal(ids, want)
+    lower, interval, size = case["grid"]
+    prep = BP.prepare_ranks(torch.from_numpy(case["coor"]).cuda(), lower, interval, size)
+    n2, thr2, ids2 = _heavy_ids(prep.plan)
+    assert (n2, thr2) == (n, thr) and np.array_equal(ids2, want)
+
+
+@pytest.mark.parametrize("C", [64, 80, 6, 200])
+def test_heavy_tile_kernel_is_bit_identical_to_the_warp_path(C):
+    """The CTA-per-tile kernel for heavy tiles only re-schedules the loads: with and
+    without the heavy list the volume is the same bit for bit (C=80: ragged last
+    channel chunk; C=6: rows not 16-byte sized, the heavy list is ignored)."""
+    from veon_b200 import _lib, bev_pool as BP
+    case = make_case("C1", 1, C, seed=3)
+    rb, rd, rf, st, ln = gpu_ranks(case["ranks"])
+    B, Z, Y, X, _ = case["shape"]
+    V = Z * Y * X
+    plan = BP._plan_for(rd, rf, rb, st, ln, case["dims"], V)
+    assert _heavy_ids(plan)[0] > 0
+    depth, feat = case["depth"].cuda(), case["feat"].cuda()
+    with_heavy = BP._fwd_planar(depth, feat, rd, rf, rb, plan, B, C, V, (B, C, Z, Y, X))
+    lib = _lib.load()
+    without = torch.full((B, C, Z, Y, X), float("nan"), device="cuda")
+    rc = lib.veon_bev_pool_v2_fwd_planar(
+        BP._ptr(depth), BP._ptr(feat), BP._ptr(rd), BP._ptr(rf), BP._ptr(rb),
+        BP._ptr(plan.tile_start), None, 0, B, C, V, feat.numel() // C, BP._ptr(without),
+        BP._stream_ptr(depth.device))
+    assert rc == 0
+    torch.cuda.synchronize()
+    assert torch.equal(with_heavy, without)
+    want = O.bev_pool_v2(case["depth"].numpy(), case["feat"].numpy(), *case["ranks"][1:3],
+                         case["ranks"][0], case["shape"], *case["ranks"][3:])
+    assert np.array_equal(with_heavy.cpu().numpy(), np.ascontiguousarray(want))
+
+
+def test_heavy_tile_with_thousands_of_points_in_one_voxel():
+    """Many rounds of 128 points, all in one voxel + a second voxel that starts in the
+    middle of a round: partial sums carried across rounds keep the rank order."""
+    from veon_b200.bev_pool import bev_pool_v2
+    B, N, D, H, W, C = 1, 1, 40, 8, 16, 64
+    Z, Y, X = 1, 2, 64
+    g = torch.Generator().manual_seed(5)
+    depth = torch.rand(B, N, D, H, W, generator=g)
+    feat = torch.randn(B, N, H, W, C, generator=g)
+    P = D * H * W
+    n_a = 3000
+    rd = torch.randperm(P, generator=g)[:n_a + 333].int()
+    rd[:n_a] = rd[:n_a].sort().values
+    rd[n_a:] = rd[n_a:].sort().values
+    rf = (rd % (H * W)).int()
+    rb = torch.cat([torch.full((n_a,), 37), torch.full((333,), 41)]).int()
+    starts = torch.tensor([0, n_a]).int()
+    lengths = torch.tensor([n_a, 333]).int()
+    out = bev_pool_v2(depth.cuda(), feat.cuda(), rd.cuda(), rf.cuda(), rb.cuda(),
+                      (B, Z, Y, X, C), starts.cuda(), lengths.cuda())
+    want = O.bev_pool_v2(depth.numpy(), feat.numpy(), rd.numpy(), rf.numpy(), rb.numpy(),
+                         (B, Z, Y, X, C), starts.numpy(), lengths.numpy())
+    assert np.array_equal(out.cpu().numpy(), np.ascontiguousarray(want))

@@ -104,7 +104,7 @@ def lidar_coor(frustum, sensor2ego, cam2imgs, post_rots, post_trans, bda):
 
 class PoolPlan:
     """By-products of the index preparation used by the planar kernels."""
-    __slots__ = ("tile_start", "tile_istart", "tile_occ", "point_interval", "dims", "V",
+    __slots__ = ("tile_start", "tile_istart", "tile_occ", "tile_heavy", "point_interval", "dims", "V",
                  "flags", "_n_intervals", "_n_points", "counts_dev", "counts_host",
                  "counts_event", "keepalive")
 
@@ -171,12 +171,17 @@ def prepare_ranks(coor, grid_lower_bound, grid_interval, grid_size):
         # round-trips per call); the pieces below are views of it
         nt1 = (n_tiles + 1 + 3) // 4 * 4
         ws_ints = (ws_bytes + 3) // 4
-        pool = torch.empty(6 * P + 3 * nt1 + 4 + ws_ints + 64, dtype=torch.int32, device=dev)
+        nh = lib.veon_pool_heavy_list_ints(P, n_tiles)
+        nh4 = (nh + 3) // 4 * 4
+        pool = torch.empty(6 * P + 3 * nt1 + nh4 + 4 + ws_ints + 64, dtype=torch.int32,
+                           device=dev)
         ranks = pool[:5 * P].view(5, P)
         point_interval = pool[5 * P:6 * P]
         o = 6 * P
         tiles = pool[o:o + 3 * nt1].view(3, nt1)[:, :n_tiles + 1]
         o += 3 * nt1
+        heavy = pool[o:o + nh]
+        o += nh4
         counts = pool[o:o + 4].view(torch.int64)
         o = (o + 4 + 63) // 64 * 64           # 256-byte aligned workspace
         ws = pool[o:o + ws_ints]
@@ -184,8 +189,8 @@ def prepare_ranks(coor, grid_lower_bound, grid_interval, grid_size):
             rc = lib.veon_prepare_v2(
                 _ptr(coor), B, N, D, H, W, _lib.float3(lower), _lib.float3(interval), c_size,
                 _ptr(ranks[0]), _ptr(ranks[1]), _ptr(ranks[2]), _ptr(ranks[3]), _ptr(ranks[4]),
-                _ptr(counts), _ptr(tiles[0]), _ptr(tiles[1]), _ptr(tiles[2]), _ptr(point_interval),
-                _ptr(ws), ws_bytes, _stream_ptr(dev))
+                _ptr(counts), _ptr(tiles[0]), _ptr(tiles[1]), _ptr(tiles[2]), _ptr(heavy),
+                _ptr(point_interval), _ptr(ws), ws_bytes, _stream_ptr(dev))
         _lib.check(rc, "veon_prepare_v2")
         # pinned read-back buffer: torch's caching host allocator makes this cheap
         counts_host = torch.empty(2, dtype=torch.int64, pin_memory=True)
@@ -194,6 +199,7 @@ def prepare_ranks(coor, grid_lower_bound, grid_interval, grid_size):
         ev.record(torch.cuda.current_stream(dev))
     plan = PoolPlan()
     plan.tile_start, plan.tile_istart, plan.tile_occ = tiles[0], tiles[1], tiles[2]
+    plan.tile_heavy = heavy
     plan.point_interval = point_interval
     plan.dims = (B, N, D, H, W)
     plan.V = V
@@ -239,16 +245,19 @@ def _plan_for(rd, rf, rb, ist, iln, dims, V):
     n_tiles = lib.veon_pool_num_tiles(B, V)
     with torch.cuda.device(dev):
         tiles = torch.empty((3, n_tiles + 1), dtype=torch.int32, device=dev)
+        heavy = torch.empty(lib.veon_pool_heavy_list_ints(rd.numel(), n_tiles),
+                            dtype=torch.int32, device=dev)
         point_interval = torch.empty(P, dtype=torch.int32, device=dev)
         flags = torch.zeros(1, dtype=torch.int32, device=dev)
         rc = lib.veon_pool_plan_build(
             _ptr(rd), _ptr(rf), _ptr(rb), _ptr(ist), _ptr(iln), rd.numel(), ist.numel(),
-            B, N, D, H, W, V, _ptr(tiles[0]), _ptr(tiles[1]), _ptr(tiles[2]),
+            B, N, D, H, W, V, _ptr(tiles[0]), _ptr(tiles[1]), _ptr(tiles[2]), _ptr(heavy),
             _ptr(point_interval), _ptr(flags), _stream_ptr(dev))
         _lib.check(rc, "veon_pool_plan_build")
         plan = PoolPlan()
         plan.flags = int(flags.item())  # one sync per distinct rank set
     plan.tile_start, plan.tile_istart, plan.tile_occ = tiles[0], tiles[1], tiles[2]
+    plan.tile_heavy = heavy
     plan.point_interval = point_interval
     plan.dims, plan.V = dims, V
     plan._n_points, plan._n_intervals = rd.numel(), ist.numel()
@@ -283,6 +292,7 @@ def _fwd_planar(depth, feat, rd, rf, rb, plan, B, C, V, shape5):
         with _timed("pool_fwd", dev):
             rc = lib.veon_bev_pool_v2_fwd_planar(
                 _ptr(depth), _ptr(feat), _ptr(rd), _ptr(rf), _ptr(rb), _ptr(plan.tile_start),
+                _ptr(plan.tile_heavy), plan.tile_heavy.numel(),
                 B, C, V, feat.numel() // C, _ptr(out), _stream_ptr(dev))
     _lib.check(rc, "veon_bev_pool_v2_fwd_planar")
     return out

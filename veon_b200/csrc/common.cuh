@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/veon_lift.h"
 
@@ -24,6 +25,26 @@ extern "C" void veon_count_launch(void);
 namespace veon {
 
 constexpr int kTileVoxels = 32;  // one warp-wide x-run of the output volume
+
+// A tile holding at least this many points is "heavy": one warp would serialise
+// on it for longer than a whole average work share, so the plan lists such tiles
+// and the forward hands each of them to a whole CTA (pool_fwd.cu).  The list
+// capacity assumes the threshold never goes below kHeavyMinThreshold.
+constexpr int kHeavyMinThreshold = 32;
+constexpr int kHeavyDefaultThreshold = 128;
+inline int heavy_threshold() {
+  static int v = 0;
+  if (v == 0) {
+    const char* e = getenv("VEON_HEAVY_THRESHOLD");  // tuning knob
+    v = e ? atoi(e) : kHeavyDefaultThreshold;
+    if (v < kHeavyMinThreshold) v = kHeavyMinThreshold;
+  }
+  return v;
+}
+inline int64_t heavy_capacity(int64_t n_points, int64_t n_tiles) {
+  const int64_t by_points = n_points / kHeavyMinThreshold;
+  return by_points < n_tiles ? by_points : n_tiles;
+}
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 

@@ -21,9 +21,14 @@
 // the reference kernel's `psum += feat * depth`.
 #include "common.cuh"
 
+#ifndef VEON_FWD_WARPS
+#define VEON_FWD_WARPS 7
+#endif
+
 namespace veon {
 
-constexpr int kFwdWarps = 8;                 // x 2 CTAs/SM = 16 warps/SM at 64 channels
+constexpr int kFwdWarps = VEON_FWD_WARPS;     // x 2 CTAs/SM (8 warps/SM run as fast as 16: the
+                                             // store path is the shared bottleneck)
 constexpr int kRowPitch = kTileVoxels + 4;   // 36 floats: rows stay 16-byte aligned
 
 // ---- per-warp prefetch ring in shared memory (cp.async, no registers held) ----
@@ -64,8 +69,8 @@ __global__ void __launch_bounds__(kFwdWarps * 32)
 k_pool_fwd(const float* __restrict__ depth, const float* __restrict__ feat,
            const int32_t* __restrict__ ranks_depth, const int32_t* __restrict__ ranks_feat,
            const int32_t* __restrict__ ranks_bev, const int32_t* __restrict__ tile_start,
-           uint32_t n_items, uint32_t tiles_per_sample, int64_t V, int C, uint32_t n_chunks,
-           int vec_ok, float* __restrict__ out) {
+           const int32_t* __restrict__ heavy, uint32_t n_items, uint32_t tiles_per_sample,
+           int64_t V, int C, uint32_t n_chunks, int vec_ok, float* __restrict__ out) {
   constexpr int CC = 32 * KCH;
   constexpr int U = (KCH <= 2) ? 16 : 8;  // feature rows in flight per warp
   constexpr int kTileFloats = CC * kRowPitch;
@@ -78,6 +83,8 @@ k_pool_fwd(const float* __restrict__ depth, const float* __restrict__ feat,
   const uint32_t first_item = blockIdx.x * kFwdWarps + warp;
   if (first_item >= n_items) return;
   const uint32_t my_items = (n_items - first_item + TW - 1) / TW;
+  // tiles with at least this many points belong to k_pool_fwd_heavy
+  const int32_t heavy_thr = heavy ? __ldg(heavy + 1) : 0x7fffffff;
 
   auto slot_of = [&](uint32_t m) { return ring + (m & (kRingSlots - 1)) * kSlotInts; };
   auto issue_bounds = [&](uint32_t m) {  // tile_start[t], tile_start[t+1] -> slot[0..1]
@@ -149,6 +156,7 @@ k_pool_fwd(const float* __restrict__ depth, const float* __restrict__ feat,
     issue_ranks(m + 2 * kDist);
     issue_depth(m + kDist);
     cp_async_commit();
+    if (e0 - s0 >= heavy_thr) continue;
 
     const uint32_t b = t / tiles_per_sample;
     const int v0 = (int)(t - b * tiles_per_sample) * kTileVoxels;
@@ -258,6 +266,161 @@ k_pool_fwd(const float* __restrict__ depth, const float* __restrict__ feat,
   cp_async_wait_all();
 }
 
+
+// ---- heavy tiles -------------------------------------------------------------
+// A tile with hundreds of points (voxels next to the cameras collect a whole
+// frustum column each) would keep ONE warp of the kernel above busy for longer
+// than an average warp's entire share of the volume, one exposed load latency per
+// 16 points.  The plan lists such tiles and the kernel above skips them; here a
+// whole CTA takes one: 128 points per round, ALL their feature rows in flight at
+// once (cp.async into shared memory, the index records of the next two rounds
+// prefetched in registers), then each warp runs the fma chains of its voxels out
+// of shared memory.  Only the loads are parallelised -- every (voxel, channel) sum
+// is still accumulated point by point in rank order (partial sums are carried in
+// the shared tile between rounds), so the result stays bit-identical.
+constexpr int kHeavyThreads = 256;
+constexpr int kHeavyChunk = 128;  // points per round; one index record per thread < 128
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+
+template <int KCH>
+__global__ void __launch_bounds__(kHeavyThreads)
+k_pool_fwd_heavy(const float* __restrict__ depth, const float* __restrict__ feat,
+                 const int32_t* __restrict__ ranks_depth, const int32_t* __restrict__ ranks_feat,
+                 const int32_t* __restrict__ ranks_bev, const int32_t* __restrict__ tile_start,
+                 const int32_t* __restrict__ heavy, int heavy_cap, uint32_t tiles_per_sample,
+                 int64_t V, int C, uint32_t n_chunks, int vec_ok, float* __restrict__ out) {
+  constexpr int CC = 32 * KCH;
+  constexpr int kSegs = CC / 4;  // 16-byte segments per staged row
+  extern __shared__ __align__(16) float hsm[];
+  float* rows = hsm;                                            // [kHeavyChunk][CC]
+  float* tile = rows + kHeavyChunk * CC;                        // [CC][kRowPitch]
+  float* dep = tile + CC * kRowPitch;                           // [kHeavyChunk]
+  uint32_t* off = reinterpret_cast<uint32_t*>(dep + kHeavyChunk);  // [kHeavyChunk]
+  int32_t* bounds = reinterpret_cast<int32_t*>(off + kHeavyChunk); // [2][start 32 | end 32]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // let the main kernel (launched with programmatic stream serialization) start now:
+  // it writes a disjoint set of tiles, and this grid is small enough to share the SMs
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  const uint32_t n_heavy = (uint32_t)min(__ldg(heavy), heavy_cap);
+  const uint32_t n_work = n_heavy * n_chunks;
+
+  for (uint32_t w = blockIdx.x; w < n_work; w += gridDim.x) {
+    const uint32_t hi = w / n_chunks;
+    const int cbase = (int)(w - hi * n_chunks) * CC;
+    const uint32_t t = (uint32_t)__ldg(heavy + 2 + hi);
+    const int32_t s = __ldg(tile_start + t);
+    const int32_t n = __ldg(tile_start + t + 1) - s;
+    const uint32_t b = t / tiles_per_sample;
+    const int v0 = (int)(t - b * tiles_per_sample) * kTileVoxels;
+    const int32_t g0 = (int32_t)((int64_t)b * V) + v0;
+    const int cmax = min(CC, C - cbase);
+    const int n_rounds = (n + kHeavyChunk - 1) / kHeavyChunk;
+
+    // index records, one point per thread < kHeavyChunk, two rounds deep in registers:
+    //   stage A(k): ranks of round k            (rf, rb, previous point's rb, rd)
+    //   stage B(k): depth[rd] of round k        (needs A(k))
+    int32_t rf1 = 0, rb1 = -1, rp1 = -1, rd1 = 0, rf2 = 0, rb2 = -1, rp2 = -1, rd2 = 0;
+    float d1 = 0.f;
+    auto stage_a = [&](int k, int32_t& rf, int32_t& rb, int32_t& rp, int32_t& rd) {
+      const int32_t i = k * kHeavyChunk + tid;
+      rb = -1;
+      if (tid < kHeavyChunk && i < n) {
+        rf = __ldg(ranks_feat + s + i);
+        rd = __ldg(ranks_depth + s + i);
+        rb = __ldg(ranks_bev + s + i);
+        rp = i ? __ldg(ranks_bev + s + i - 1) : -1;
+      }
+    };
+    stage_a(0, rf1, rb1, rp1, rd1);
+    if (n_rounds > 1) stage_a(1, rf2, rb2, rp2, rd2);
+    if (rb1 >= 0) d1 = __ldg(depth + rd1);
+
+    {  // clear the tile and both boundary tables
+      float4* t4 = reinterpret_cast<float4*>(tile);
+      for (int i = tid; i < CC * kRowPitch / 4; i += kHeavyThreads)
+        t4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (tid < 128) bounds[tid] = 0;
+    }
+    __syncthreads();
+
+    for (int k = 0; k < n_rounds; ++k) {
+      const int cnt = min(kHeavyChunk, n - k * kHeavyChunk);
+      int32_t* cstart = bounds + (k & 1) * 64;
+      int32_t* cend = cstart + 32;
+      // publish round k's records and the [start, end) of every voxel inside the round
+      if (rb1 >= 0) {
+        const int vox = rb1 - g0, voxp = rp1 - g0;
+        off[tid] = (uint32_t)rf1 * (uint32_t)C;
+        dep[tid] = d1;
+        const bool first = (tid == 0) || (rb1 != rp1);
+        if (first) cstart[vox] = tid;
+        if (first && tid > 0) cend[voxp] = tid;
+        if (tid == cnt - 1) cend[vox] = cnt;
+      }
+      // advance the register pipeline: B(k+1) and A(k+2) fly during this round's row copy
+      rf1 = rf2; rb1 = rb2; rp1 = rp2; rd1 = rd2;
+      d1 = 0.f;
+      if (rb1 >= 0) d1 = __ldg(depth + rd1);
+      rb2 = -1;
+      if (k + 2 < n_rounds) stage_a(k + 2, rf2, rb2, rp2, rd2);
+      // the other table is free now (last read in round k-1): clear it for round k+1
+      if (tid >= 128 && tid < 192) bounds[((k + 1) & 1) * 64 + tid - 128] = 0;
+      __syncthreads();
+
+      // every feature row of the round in flight at once
+#pragma unroll
+      for (int i = 0; i < kHeavyChunk * kSegs / kHeavyThreads; ++i) {
+        const int idx = tid + kHeavyThreads * i;
+        const int r = idx / kSegs, seg = (idx % kSegs) * 4;
+        if (r < cnt && seg < cmax) cp_async16(rows + r * CC + seg, feat + off[r] + cbase + seg);
+      }
+      cp_async_commit();
+      cp_async_wait_all();
+      __syncthreads();
+
+      // fma chains: warp w owns voxels w, w+8, w+16, w+24; lanes = channels
+#pragma unroll 1
+      for (int v = warp; v < kTileVoxels; v += kHeavyThreads / 32) {
+        const int a = cstart[v], e = cend[v];
+        if (e <= a) continue;
+        float acc[KCH];
+#pragma unroll
+        for (int c = 0; c < KCH; ++c) acc[c] = tile[(lane + 32 * c) * kRowPitch + v];
+#pragma unroll 4
+        for (int j = a; j < e; ++j) {
+          const float dj = dep[j];
+#pragma unroll
+          for (int c = 0; c < KCH; ++c) acc[c] = fmaf(rows[j * CC + lane + 32 * c], dj, acc[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < KCH; ++c) tile[(lane + 32 * c) * kRowPitch + v] = acc[c];
+      }
+      __syncthreads();
+    }
+
+    {  // write-out: thread (row = tid/8, q = tid%8) moves voxels 4q..4q+3 of channel row (+32j)
+      const int q4 = (tid & 7) * 4;
+      const bool fast = vec_ok && (v0 + kTileVoxels <= V);
+      for (int c = tid >> 3; c < cmax; c += kHeavyThreads / 8) {
+        float* o = out + ((int64_t)b * C + cbase + c) * V + v0 + q4;
+        const float* trow = tile + c * kRowPitch + q4;
+        if (fast) {
+          st_stream4(o, *reinterpret_cast<const float4*>(trow));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (v0 + q4 + i < V) st_stream(o + i, trow[i]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
 static int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -276,9 +439,9 @@ static int env_flag(const char* name, int dflt) {
 
 template <int KCH>
 static int launch_fwd(const float* depth, const float* feat, const int32_t* rd,
-                      const int32_t* rf, const int32_t* rb, const int32_t* tile_start, int B,
-                      int C, int64_t V, bool feat_rows_fit_32bit, float* out,
-                      cudaStream_t stream) {
+                      const int32_t* rf, const int32_t* rb, const int32_t* tile_start,
+                      const int32_t* heavy, int64_t heavy_ints, int B, int C, int64_t V,
+                      bool feat_rows_fit_32bit, float* out, cudaStream_t stream) {
   constexpr int CC = 32 * KCH;
   const size_t smem = sizeof(float) * kFwdWarps * (CC * kRowPitch + kRingSlots * kSlotInts);
   static int ctas_per_sm = 0;
@@ -298,9 +461,54 @@ static int launch_fwd(const float* depth, const float* feat, const int32_t* rd,
   int64_t blocks = ceil_div64(n_tiles * n_chunks, kFwdWarps);
   const int64_t resident = (int64_t)ctas_per_sm * sm_count();  // persistent grid
   if (blocks > resident) blocks = resident;
+  // the heavy-tile kernel stages feature rows with 16-byte copies
+  if (heavy && ((C & 3) != 0 || ((uintptr_t)feat & 15) != 0)) heavy = nullptr;
+  if (heavy) {
+    const size_t hsmem = sizeof(float) * (kHeavyChunk * CC + CC * kRowPitch + 2 * kHeavyChunk + 128);
+    static int heavy_ctas_per_sm = 0;
+    if (heavy_ctas_per_sm == 0) {
+      VEON_CUDA_TRY(cudaFuncSetAttribute(k_pool_fwd_heavy<KCH>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem));
+      VEON_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+          &heavy_ctas_per_sm, k_pool_fwd_heavy<KCH>, kHeavyThreads, hsmem));
+      if (heavy_ctas_per_sm < 1) heavy_ctas_per_sm = 1;
+    }
+    const int heavy_cap = (int)(heavy_ints - 2);
+    // a short-lived grid (a few tiles per CTA): the main kernel's persistent CTAs move in
+    // beside and behind it (measured: 2..5 CTAs/SM within noise, see profiles/README.md)
+    const int per_sm = min(heavy_ctas_per_sm, max(1, env_flag("VEON_FWD_HEAVY_CTAS", 4)));
+    int64_t hblocks = (int64_t)heavy_cap * n_chunks;
+    if (hblocks > (int64_t)per_sm * sm_count()) hblocks = (int64_t)per_sm * sm_count();
+    if (hblocks > 0) {
+      k_pool_fwd_heavy<KCH><<<(unsigned)hblocks, kHeavyThreads, hsmem, stream>>>(
+          depth, feat, rd, rf, rb, tile_start, heavy, heavy_cap, (uint32_t)tps, V, C,
+          (uint32_t)n_chunks, vec_ok, out);
+      VEON_LAUNCH_CHECK();
+    } else {
+      heavy = nullptr;
+    }
+  }
+  if (heavy && env_flag("VEON_FWD_PDL", 1)) {
+    // programmatic dependent launch: start as soon as every heavy-tile CTA is running
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)blocks);
+    cfg.blockDim = dim3(kFwdWarps * 32);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    VEON_CUDA_TRY(cudaLaunchKernelEx(&cfg, k_pool_fwd<KCH>, depth, feat, rd, rf, rb, tile_start,
+                                     heavy, (uint32_t)(n_tiles * n_chunks), (uint32_t)tps, V, C,
+                                     (uint32_t)n_chunks, vec_ok, out));
+    VEON_LAUNCH_CHECK();
+    return 0;
+  }
   k_pool_fwd<KCH><<<(unsigned)blocks, kFwdWarps * 32, smem, stream>>>(
-      depth, feat, rd, rf, rb, tile_start, (uint32_t)(n_tiles * n_chunks), (uint32_t)tps, V, C,
-      (uint32_t)n_chunks, vec_ok, out);
+      depth, feat, rd, rf, rb, tile_start, heavy, (uint32_t)(n_tiles * n_chunks), (uint32_t)tps,
+      V, C, (uint32_t)n_chunks, vec_ok, out);
   VEON_LAUNCH_CHECK();
   return 0;
 }
@@ -323,19 +531,21 @@ extern "C" int veon_bev_pool_v2_fwd_planar(const float* depth, const float* feat
                                            const int32_t* ranks_depth,
                                            const int32_t* ranks_feat,
                                            const int32_t* ranks_bev,
-                                           const int32_t* tile_start, int B, int C, int64_t V,
-                                           int64_t n_feat_rows, float* out, void* stream_) {
+                                           const int32_t* tile_start,
+                                           const int32_t* tile_heavy, int64_t tile_heavy_ints,
+                                           int B, int C, int64_t V, int64_t n_feat_rows,
+                                           float* out, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!depth || !feat || !ranks_depth || !ranks_feat || !ranks_bev || !tile_start || !out ||
-      B <= 0 || C <= 0 || V <= 0 || n_feat_rows <= 0)
+      B <= 0 || C <= 0 || V <= 0 || n_feat_rows <= 0 || (tile_heavy && tile_heavy_ints < 2))
     return VEON_E_BADARG;
   const bool fit32 = n_feat_rows * (int64_t)C <= 0xffffffffLL;
   int kch = fwd_kch_override();
   if (kch == 0) kch = (C <= 32) ? 1 : 2;
   switch (kch) {
-    case 1: return launch_fwd<1>(depth, feat, ranks_depth, ranks_feat, ranks_bev, tile_start, B, C, V, fit32, out, stream);
-    case 2: return launch_fwd<2>(depth, feat, ranks_depth, ranks_feat, ranks_bev, tile_start, B, C, V, fit32, out, stream);
-    case 4: return launch_fwd<4>(depth, feat, ranks_depth, ranks_feat, ranks_bev, tile_start, B, C, V, fit32, out, stream);
+    case 1: return launch_fwd<1>(depth, feat, ranks_depth, ranks_feat, ranks_bev, tile_start, tile_heavy, tile_heavy_ints, B, C, V, fit32, out, stream);
+    case 2: return launch_fwd<2>(depth, feat, ranks_depth, ranks_feat, ranks_bev, tile_start, tile_heavy, tile_heavy_ints, B, C, V, fit32, out, stream);
+    case 4: return launch_fwd<4>(depth, feat, ranks_depth, ranks_feat, ranks_bev, tile_start, tile_heavy, tile_heavy_ints, B, C, V, fit32, out, stream);
     default: return VEON_E_BADARG;
   }
 }

@@ -316,6 +316,29 @@ __global__ void k_tiles(const int32_t* __restrict__ count, const int32_t* __rest
   tile_occ[t] = m;
 }
 
+// -------------------------------------------------------------- k_heavy_list
+// heavy[0] = number of listed tiles (zeroed by the caller), heavy[1] = threshold,
+// heavy[2..] = tile ids in arbitrary order (the order only affects scheduling)
+__global__ void k_heavy_list(const int32_t* __restrict__ tile_start, int64_t n_tiles, int thr,
+                             int cap, int32_t* __restrict__ heavy) {
+  const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t == 0) heavy[1] = thr;
+  if (t >= n_tiles) return;
+  if (tile_start[t + 1] - tile_start[t] >= thr) {
+    const int i = atomicAdd(heavy, 1);
+    if (i < cap) heavy[2 + i] = (int32_t)t;
+  }
+}
+
+static int build_heavy_list(const int32_t* tile_start, int64_t n_tiles, int64_t n_points_cap,
+                            int32_t* heavy, cudaStream_t stream) {
+  VEON_CUDA_TRY(cudaMemsetAsync(heavy, 0, 2 * sizeof(int32_t), stream));
+  k_heavy_list<<<(unsigned)ceil_div64(n_tiles, 256), 256, 0, stream>>>(
+      tile_start, n_tiles, heavy_threshold(), (int)heavy_capacity(n_points_cap, n_tiles), heavy);
+  VEON_LAUNCH_CHECK();
+  return 0;
+}
+
 // ----------------------------------------------------------------- k_scatter
 __global__ void __launch_bounds__(256)
 k_scatter(const int32_t* __restrict__ key, const int32_t* __restrict__ slot,
@@ -510,6 +533,11 @@ extern "C" int64_t veon_pool_num_tiles(int B, int64_t V) {
   return (int64_t)B * ceil_div64(V, kTileVoxels);
 }
 
+extern "C" int64_t veon_pool_heavy_list_ints(int64_t n_points, int64_t n_tiles) {
+  if (n_points < 0 || n_tiles < 0) return 0;
+  return 2 + heavy_capacity(n_points, n_tiles);
+}
+
 static int check_dims(int B, int N, int D, int H, int W, int64_t* P) {
   if (B <= 0 || N <= 0 || D <= 0 || H <= 0 || W <= 0) return VEON_E_BADARG;
   int64_t p = (int64_t)B * N * D * H * W;
@@ -540,7 +568,8 @@ extern "C" int veon_prepare_v2(const float* coor, int B, int N, int D, int H, in
                                int32_t* ranks_depth, int32_t* ranks_feat,
                                int32_t* interval_starts, int32_t* interval_lengths,
                                int64_t* counts, int32_t* tile_start, int32_t* tile_istart,
-                               uint32_t* tile_occ, int32_t* point_interval, void* workspace,
+                               uint32_t* tile_occ, int32_t* tile_heavy,
+                               int32_t* point_interval, void* workspace,
                                size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   int64_t P;
@@ -579,6 +608,10 @@ extern "C" int veon_prepare_v2(const float* coor, int B, int N, int D, int H, in
         w.count, w.offset, w.iidx, n_tiles, tps, V, tile_start, tile_istart, tile_occ);
     VEON_LAUNCH_CHECK();
   }
+  if (want_tiles && tile_heavy) {
+    rc = build_heavy_list(tile_start, n_tiles, P, tile_heavy, stream);
+    if (rc) return rc;
+  }
   k_scatter<<<pblocks, 256, 0, stream>>>(w.key, w.slot, w.offset, P, w.tmp, ranks_bev);
   VEON_LAUNCH_CHECK();
   PointDims dims{D, H * W, D * H * W};
@@ -597,8 +630,8 @@ extern "C" int veon_pool_plan_build(const int32_t* ranks_depth, const int32_t* r
                                     const int32_t* interval_lengths, int64_t n_points,
                                     int64_t n_intervals, int B, int N, int D, int H, int W,
                                     int64_t V, int32_t* tile_start, int32_t* tile_istart,
-                                    uint32_t* tile_occ, int32_t* point_interval, int32_t* flags,
-                                    void* stream_) {
+                                    uint32_t* tile_occ, int32_t* tile_heavy,
+                                    int32_t* point_interval, int32_t* flags, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   int64_t P;
   int rc = check_dims(B, N, D, H, W, &P);
@@ -625,5 +658,6 @@ extern "C" int veon_pool_plan_build(const int32_t* ranks_depth, const int32_t* r
       ranks_bev, n_points, interval_starts, n_intervals, n_tiles, tps, V, tile_start,
       tile_istart, tile_occ);
   VEON_LAUNCH_CHECK();
+  if (tile_heavy) return build_heavy_list(tile_start, n_tiles, n_points, tile_heavy, stream);
   return 0;
 }
