@@ -108,6 +108,109 @@ k_bwd_rows(const float* __restrict__ out_grad, const int32_t* __restrict__ tile_
                  tiles_per_sample, V, C, vec_ok, rows);
 }
 
+
+// Persistent variant of the row pass (aligned volumes): every warp strides over the
+// (tile, channel chunk) items, keeps the NEXT occupied tile's 8 KB of out_grad in flight
+// (16-byte cp.async into the second half of a double-buffered shared tile, no registers
+// held) while it extracts the rows of the current one, and reads the plan's occupancy /
+// first-interval words 32 items at a time, one table ahead -- so neither the plan lookup
+// nor the transposition/row write sits between two tiles' loads.
+constexpr int kRowPitchP = kTileVoxels + 4;  // 16-byte aligned rows for cp.async
+
+__device__ __forceinline__ void cp_async16_cg(void* smem_dst, const void* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+
+template <int KCH>
+__global__ void __launch_bounds__(kRowWarps * 32)
+k_bwd_rows_persistent(const float* __restrict__ out_grad, const int32_t* __restrict__ tile_istart,
+                      const uint32_t* __restrict__ tile_occ, int64_t n_items,
+                      int64_t tiles_per_sample, int64_t V, int C, int n_chunks,
+                      float* __restrict__ rows) {
+  constexpr int CC = 32 * KCH;
+  constexpr int kBuf = CC * kRowPitchP;
+  extern __shared__ __align__(16) float smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  float* buf = smem + warp * 2 * kBuf;
+  const int64_t TW = (int64_t)gridDim.x * kRowWarps;
+  const int64_t first = (int64_t)blockIdx.x * kRowWarps + warp;
+  if (first >= n_items) return;
+  const int64_t mine = (n_items - first + TW - 1) / TW;
+  const int q4 = (lane & 7) * 4, r = lane >> 3;
+
+  auto load_table = [&](int64_t k0, uint32_t& occ, int32_t& i0) {
+    const int64_t k = k0 + lane;
+    occ = 0u;
+    i0 = 0;
+    if (k < mine) {
+      const int64_t t = (first + k * TW) / n_chunks;
+      occ = __ldg(tile_occ + t);
+      i0 = __ldg(tile_istart + t);
+    }
+  };
+  // rows of the tile sitting in `tile`: j-th occupied voxel -> interval i0 + j
+  auto extract = [&](const float* tile, uint32_t occ, int32_t i0, int cbase) {
+    const int cmax = min(CC, C - cbase);
+    float* row = rows + (int64_t)i0 * C + cbase + lane;
+    uint32_t rest = occ;
+    while (rest) {
+      const int vj = __ffs(rest) - 1;
+      rest &= rest - 1;
+#pragma unroll
+      for (int k = 0; k < KCH; ++k)
+        if (lane + 32 * k < cmax) row[32 * k] = tile[(lane + 32 * k) * kRowPitchP + vj];
+      row += C;
+    }
+  };
+
+  uint32_t occ_tab, occ_nxt = 0u, p_occ = 0u;
+  int32_t i0_tab, i0_nxt = 0, p_i0 = 0;
+  int p_cbase = 0, cur = 0;
+  load_table(0, occ_tab, i0_tab);
+  for (int64_t k0 = 0; k0 < mine; k0 += 32) {
+    if (k0 + 32 < mine) load_table(k0 + 32, occ_nxt, i0_nxt);
+    const int nj = (int)min((int64_t)32, mine - k0);
+    for (int j = 0; j < nj; ++j) {
+      const uint32_t occ = __shfl_sync(0xffffffffu, occ_tab, j);
+      if (occ == 0u) continue;  // empty tile: nothing read (warp-uniform)
+      const int32_t i0 = __shfl_sync(0xffffffffu, i0_tab, j);
+      const int64_t item = first + (k0 + j) * TW;
+      const int64_t t = item / n_chunks;
+      const int cbase = (int)(item - t * n_chunks) * CC;
+      const int64_t b = t / tiles_per_sample;
+      const int64_t v0 = (t - b * tiles_per_sample) * kTileVoxels;
+      const int cmax = min(CC, C - cbase);
+      // only the 32-byte sectors (8 voxels) that contain an occupied voxel
+      if (((occ >> (q4 & 24)) & 0xffu) != 0u) {
+        const float* g = out_grad + ((int64_t)b * C + cbase + r) * V + v0 + q4;
+        float* dst = buf + cur * kBuf + r * kRowPitchP + q4;
+#pragma unroll
+        for (int it = 0; it < CC / 4; ++it)
+          if (4 * it + r < cmax) cp_async16_cg(dst + it * 4 * kRowPitchP, g + (int64_t)it * 4 * V);
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      if (p_occ) {
+        asm volatile("cp.async.wait_group 1;" ::: "memory");
+        __syncwarp();
+        extract(buf + (cur ^ 1) * kBuf, p_occ, p_i0, p_cbase);
+        __syncwarp();  // the other half is refilled next
+      }
+      p_occ = occ;
+      p_i0 = i0;
+      p_cbase = cbase;
+      cur ^= 1;
+    }
+    occ_tab = occ_nxt;
+    i0_tab = i0_nxt;
+  }
+  if (p_occ) {
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncwarp();
+    extract(buf + (cur ^ 1) * kBuf, p_occ, p_i0, p_cbase);
+  }
+}
+
 // Sum U per-lane partials over the warp, for U values at once: after log2(U) exchange
 // steps every lane holds ONE value (the one selected by its upper lane bits), which is
 // then reduced over the remaining lane bits.  U + log2(32/U) - 1 shuffles instead of 5*U.
@@ -400,6 +503,33 @@ static int launch_rows(const float* out_grad, const int32_t* tile_istart, const 
   }
   const int n_chunks = (C + CC - 1) / CC;
   const int vec_ok = ((V & 3) == 0) && (((uintptr_t)out_grad & 15) == 0);
+  static int persist = -1;
+  if (persist < 0) {
+    const char* e = getenv("VEON_BWD_ROWS_PERSISTENT");
+    persist = e ? atoi(e) : 1;
+  }
+  if (persist && vec_ok && (V % kTileVoxels) == 0 && tile_begin == 0) {
+    const size_t psmem = sizeof(float) * kRowWarps * 2 * CC * kRowPitchP;
+    static int ctas_per_sm = 0;
+    if (ctas_per_sm == 0) {
+      VEON_CUDA_TRY(cudaFuncSetAttribute(k_bwd_rows_persistent<KCH>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+      VEON_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+          &ctas_per_sm, k_bwd_rows_persistent<KCH>, kRowWarps * 32, psmem));
+      if (ctas_per_sm < 1) ctas_per_sm = 1;
+    }
+    const int64_t n_items = tile_end * n_chunks;
+    if (n_items <= 0) return 0;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int64_t pblocks = (int64_t)ctas_per_sm * sms;
+    if (pblocks > ceil_div64(n_items, kRowWarps)) pblocks = ceil_div64(n_items, kRowWarps);
+    k_bwd_rows_persistent<KCH><<<(unsigned)pblocks, kRowWarps * 32, psmem, stream>>>(
+        out_grad, tile_istart, tile_occ, n_items, tps, V, C, n_chunks, rows);
+    VEON_LAUNCH_CHECK();
+    return 0;
+  }
   const int64_t blocks = ceil_div64(tile_end - tile_begin, kRowWarps) * n_chunks;
   if (blocks <= 0) return 0;
   if (blocks > 0x7fffffffLL) return VEON_E_RANGE;
