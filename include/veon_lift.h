@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define VEON_ABI_VERSION 2
+#define VEON_ABI_VERSION 3
 
 #define VEON_E_BADARG    (-1)  /* NULL pointer / non-positive dimension          */
 #define VEON_E_WORKSPACE (-2)  /* workspace smaller than *_workspace_bytes()     */
@@ -127,6 +127,10 @@ int veon_lidar_coor(const float* frustum, const float* sensor2ego, const float* 
  *      ranks_bev, ranks_depth, ranks_feat   first n_kept entries valid
  *      interval_starts, interval_lengths    first n_int  entries valid
  *  counts          device int64[2] = {n_kept, n_int}
+ *  counts_host     optional PINNED HOST int64[2] (device-accessible, e.g. cudaHostAlloc):
+ *                  the scan kernel stores the same two numbers there, so the host can
+ *                  read them after an event on `stream` without queueing a copy behind
+ *                  the caller's bulk transfers; NULL to skip
  *  Order: points sorted by ranks_bev; inside one voxel by ascending
  *  ranks_depth (the reference's argsort is unstable, so its in-voxel order is
  *  arbitrary; ours is the canonical stable one).
@@ -157,7 +161,7 @@ int veon_prepare_v2(const float* coor, int B, int N, int D, int H, int W,
                     const float* grid_size,
                     int32_t* ranks_bev, int32_t* ranks_depth, int32_t* ranks_feat,
                     int32_t* interval_starts, int32_t* interval_lengths,
-                    int64_t* counts,
+                    int64_t* counts, int64_t* counts_host,
                     int32_t* tile_start, int32_t* tile_istart, uint32_t* tile_occ,
                     int32_t* tile_heavy, int32_t* point_interval,
                     void* workspace, size_t workspace_bytes, void* stream);

@@ -18,6 +18,7 @@ in one pass (no memset, no permute copy), the backward needs no argsort, and a
 tensors.  Everything runs in CUDA through the C ABI; there is no CPU path.
 """
 import collections
+import weakref
 import ctypes
 
 import torch
@@ -104,7 +105,8 @@ def lidar_coor(frustum, sensor2ego, cam2imgs, post_rots, post_trans, bda):
 
 class PoolPlan:
     """By-products of the index preparation used by the planar kernels."""
-    __slots__ = ("tile_start", "tile_istart", "tile_occ", "tile_heavy", "point_interval", "dims", "V",
+    __slots__ = ("__weakref__", "tile_start", "tile_istart", "tile_occ", "tile_heavy",
+                 "point_interval", "dims", "V",
                  "flags", "_n_intervals", "_n_points", "counts_dev", "counts_host",
                  "counts_event", "keepalive")
 
@@ -143,6 +145,32 @@ class PreparedRanks:
                  "interval_lengths", "plan", "shape")
 
 
+# Pinned host slots the scan kernel writes {n_kept, n_int} into.  A ring owned by this
+# module (never returned to torch's host allocator while a kernel may still write to it);
+# a slot is reused only after the event of its previous prepare call has completed.
+_COUNTS_RING = {}
+_GEOMETRY_CACHE = {}   # per (shape, grid objects): float3 arrays, sizes (host-side only)
+_COUNTS_SLOTS = 64
+
+
+def _counts_slot(dev):
+    ring = _COUNTS_RING.get(dev.index)
+    if ring is None:
+        ring = [torch.zeros((_COUNTS_SLOTS, 2), dtype=torch.int64).pin_memory(),
+                [None] * _COUNTS_SLOTS, 0]
+        _COUNTS_RING[dev.index] = ring
+    buf, owners, nxt = ring
+    ring[2] = (nxt + 1) % _COUNTS_SLOTS
+    if owners[nxt] is not None:
+        ev, plan_ref = owners[nxt]
+        old = plan_ref()
+        if old is not None:
+            old._resolve()          # a plan that is still alive keeps its numbers
+        else:
+            ev.synchronize()        # the kernel that wrote the slot has finished
+    return buf[nxt], nxt
+
+
 def prepare_ranks(coor, grid_lower_bound, grid_interval, grid_size):
     """Launch the GPU index preparation; returns without a host sync.
 
@@ -157,21 +185,33 @@ def prepare_ranks(coor, grid_lower_bound, grid_interval, grid_size):
     B, N, D, H, W, _ = coor.shape
     P = B * N * D * H * W
     dev = coor.device
-    lower = [float(v) for v in grid_lower_bound]
-    interval = [float(v) for v in grid_interval]
-    size = [float(v) for v in grid_size]
-    V = int(size[0]) * int(size[1]) * int(size[2])
-    c_size = _lib.float3(size)
-    ws_bytes = lib.veon_prepare_v2_workspace_bytes(B, N, D, H, W, c_size)
-    if ws_bytes == 0:
-        raise _lib.VeonError(-3, "veon_prepare_v2_workspace_bytes")
-    n_tiles = lib.veon_pool_num_tiles(B, V)
+    key = (B, N, D, H, W, id(grid_lower_bound), id(grid_interval), id(grid_size),
+           getattr(grid_lower_bound, "_version", 0), getattr(grid_interval, "_version", 0),
+           getattr(grid_size, "_version", 0))
+    geo = _GEOMETRY_CACHE.get(key)
+    if geo is None or geo[0] is not grid_size:
+        lower = [float(v) for v in grid_lower_bound]
+        interval = [float(v) for v in grid_interval]
+        size = [float(v) for v in grid_size]
+        V = int(size[0]) * int(size[1]) * int(size[2])
+        c_size = _lib.float3(size)
+        ws_bytes = lib.veon_prepare_v2_workspace_bytes(B, N, D, H, W, c_size)
+        if ws_bytes == 0:
+            raise _lib.VeonError(-3, "veon_prepare_v2_workspace_bytes")
+        n_tiles = lib.veon_pool_num_tiles(B, V)
+        if len(_GEOMETRY_CACHE) > 64:
+            _GEOMETRY_CACHE.clear()
+        # (the grid objects are kept alive by the entry, so their ids stay unique)
+        geo = (grid_size, grid_lower_bound, grid_interval, _lib.float3(lower),
+               _lib.float3(interval), c_size, V, ws_bytes, n_tiles,
+               lib.veon_pool_heavy_list_ints(P, n_tiles))
+        _GEOMETRY_CACHE[key] = geo
+    _, _, _, c_lower, c_interval, c_size, V, ws_bytes, n_tiles, nh = geo
     with torch.cuda.device(dev):
         # one allocation for every int32 output + the kernel workspace (fewer allocator
         # round-trips per call); the pieces below are views of it
         nt1 = (n_tiles + 1 + 3) // 4 * 4
         ws_ints = (ws_bytes + 3) // 4
-        nh = lib.veon_pool_heavy_list_ints(P, n_tiles)
         nh4 = (nh + 3) // 4 * 4
         pool = torch.empty(6 * P + 3 * nt1 + nh4 + 4 + ws_ints + 64, dtype=torch.int32,
                            device=dev)
@@ -185,16 +225,17 @@ def prepare_ranks(coor, grid_lower_bound, grid_interval, grid_size):
         counts = pool[o:o + 4].view(torch.int64)
         o = (o + 4 + 63) // 64 * 64           # 256-byte aligned workspace
         ws = pool[o:o + ws_ints]
+        # The two counts come back through pinned host memory the scan kernel writes
+        # directly (no D2H copy that could queue behind the caller's bulk transfers on
+        # the copy engine); they are valid once `ev` has completed.
+        counts_host, slot = _counts_slot(dev)
         with _timed("prepare_v2", dev):
             rc = lib.veon_prepare_v2(
-                _ptr(coor), B, N, D, H, W, _lib.float3(lower), _lib.float3(interval), c_size,
+                _ptr(coor), B, N, D, H, W, c_lower, c_interval, c_size,
                 _ptr(ranks[0]), _ptr(ranks[1]), _ptr(ranks[2]), _ptr(ranks[3]), _ptr(ranks[4]),
-                _ptr(counts), _ptr(tiles[0]), _ptr(tiles[1]), _ptr(tiles[2]), _ptr(heavy),
-                _ptr(point_interval), _ptr(ws), ws_bytes, _stream_ptr(dev))
+                _ptr(counts), _ptr(counts_host), _ptr(tiles[0]), _ptr(tiles[1]), _ptr(tiles[2]),
+                _ptr(heavy), _ptr(point_interval), _ptr(ws), ws_bytes, _stream_ptr(dev))
         _lib.check(rc, "veon_prepare_v2")
-        # pinned read-back buffer: torch's caching host allocator makes this cheap
-        counts_host = torch.empty(2, dtype=torch.int64, pin_memory=True)
-        counts_host.copy_(counts, non_blocking=True)
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(dev))
     plan = PoolPlan()
@@ -204,6 +245,7 @@ def prepare_ranks(coor, grid_lower_bound, grid_interval, grid_size):
     plan.dims = (B, N, D, H, W)
     plan.V = V
     plan.counts_dev, plan.counts_host, plan.counts_event = counts, counts_host, ev
+    _COUNTS_RING[dev.index][1][slot] = (ev, weakref.ref(plan))
     out = PreparedRanks()
     out.ranks_bev, out.ranks_depth, out.ranks_feat = ranks[0], ranks[1], ranks[2]
     out.interval_starts, out.interval_lengths = ranks[3], ranks[4]

@@ -22,20 +22,33 @@
 #include "common.cuh"
 
 #ifndef VEON_FWD_WARPS
-#define VEON_FWD_WARPS 7
+#define VEON_FWD_WARPS 8
 #endif
 
 namespace veon {
 
-constexpr int kFwdWarps = VEON_FWD_WARPS;     // x 2 CTAs/SM (8 warps/SM run as fast as 16: the
-                                             // store path is the shared bottleneck)
+// timing experiments only (profiles/README.md): -DVEON_FWD_EXPERIMENT + env VEON_FWD_DBG
+//   1 no zero-fill  4 no global stores  8 no feature-row loads
+#ifdef VEON_FWD_EXPERIMENT
+#define VEON_DBG(bit) (dbg & (bit))
+#else
+#define VEON_DBG(bit) false
+#endif
+
+// x 2 CTAs/SM.  Keep it at 8: the 8 consecutive tiles of a CTA then cover an aligned 1 KB
+// of every channel plane; 7-warp CTAs (896 B) write the same volume 19 % slower
+// (tools/micro/store_pattern.cu: 266 vs 224 us).
+constexpr int kFwdWarps = VEON_FWD_WARPS;
 constexpr int kRowPitch = kTileVoxels + 4;   // 36 floats: rows stay 16-byte aligned
 
 // ---- per-warp prefetch ring in shared memory (cp.async, no registers held) ----
 // slot (ints): [0]=s [1]=e [2]=tile [3]=cbase, then one int4 per point (lane j):
 //   landing   {ranks_bev, ranks_feat, ranks_depth, depth}
 //   fixed up  {ranks_bev, row offset (floats), voxel | first<<8, depth}
-constexpr int kDist = 2;                     // prefetch distance in items per stage
+#ifndef VEON_FWD_DIST
+#define VEON_FWD_DIST 2
+#endif
+constexpr int kDist = VEON_FWD_DIST;         // prefetch distance in items per stage
 constexpr int kRingSlots = 4 * kDist;        // bounds run 3*kDist ahead
 constexpr int kSlotInts = 4 + 4 * 32;
 
@@ -55,22 +68,27 @@ __device__ __forceinline__ void cp_async_wait_dist() {
 //    items ahead as 4-byte cp.async copies into a per-warp ring (no registers held;
 //    `wait_group kDist-1` leaves the youngest group in flight, so short items do not
 //    expose the latency); a lanes=points fix-up turns the landed ranks into
-//    (row offset, voxel | first-of-voxel) so that the gather loop needs ONE
-//    broadcast LDS.128 per point;
-//  * gather: lanes = channels, 8 points' rows in flight, per-voxel sums in registers
+//    (row byte offset, voxel | first-of-voxel) so that the gather loop needs ONE
+//    broadcast LDS.128 per point.  The (tile, chunk, sample) of the next item is kept
+//    as running counters: no integer division in the loop;
+//  * gather: lanes = channels, up to 16 points' rows in flight (issued in groups of 4,
+//    groups past the tile's last point are skipped), per-voxel sums in registers
 //    (fma(feat, depth, acc) in rank order), one store per occupied voxel into the
 //    zero-filled [c][36] shared tile;
 //  * write-out: lanes = voxels, LDS.128 + one 16-byte streaming store covers
 //    4 channel planes x 128 B per instruction.
 // (A TMA tensor-store write-out was measured slower here: ~17 B/clk/SM for boxes
 //  of 128-byte rows vs ~23 B/clk/SM for st.global.v4; see profiles/README.md.)
-template <int KCH>
+// Slot header: [0]=s [1]=e [2]=g0 (global voxel index of the tile's first voxel)
+//              [3]=sample<<16 | chunk
+// FULLC: C is a multiple of the chunk width, so no channel predicate anywhere.
+template <int KCH, bool FULLC>
 __global__ void __launch_bounds__(kFwdWarps * 32)
 k_pool_fwd(const float* __restrict__ depth, const float* __restrict__ feat,
            const int32_t* __restrict__ ranks_depth, const int32_t* __restrict__ ranks_feat,
            const int32_t* __restrict__ ranks_bev, const int32_t* __restrict__ tile_start,
            const int32_t* __restrict__ heavy, uint32_t n_items, uint32_t tiles_per_sample,
-           int64_t V, int C, uint32_t n_chunks, int vec_ok, float* __restrict__ out) {
+           int64_t V, int C, uint32_t n_chunks, int vec_ok, float* __restrict__ out, int dbg) {
   constexpr int CC = 32 * KCH;
   constexpr int U = (KCH <= 2) ? 16 : 8;  // feature rows in flight per warp
   constexpr int kTileFloats = CC * kRowPitch;
@@ -85,29 +103,47 @@ k_pool_fwd(const float* __restrict__ depth, const float* __restrict__ feat,
   const uint32_t my_items = (n_items - first_item + TW - 1) / TW;
   // tiles with at least this many points belong to k_pool_fwd_heavy
   const int32_t heavy_thr = heavy ? __ldg(heavy + 1) : 0x7fffffff;
+  const uint32_t Vu = (uint32_t)V;                    // B*V < 2^31 (checked by the launcher)
+  const bool whole_tiles = (Vu % kTileVoxels) == 0;   // no ragged tile at a sample's end
+
+  // running decode of the next item to enter the ring (advanced by TW items per call)
+  uint32_t nx_t = first_item / n_chunks;
+  uint32_t nx_chunk = first_item - nx_t * n_chunks;
+  uint32_t nx_b = nx_t / tiles_per_sample;
+  uint32_t nx_vt = nx_t - nx_b * tiles_per_sample;
+  const uint32_t step_t = TW / n_chunks, step_c = TW - step_t * n_chunks;
 
   auto slot_of = [&](uint32_t m) { return ring + (m & (kRingSlots - 1)) * kSlotInts; };
-  auto issue_bounds = [&](uint32_t m) {  // tile_start[t], tile_start[t+1] -> slot[0..1]
+  auto issue_bounds = [&](uint32_t m) {  // header of item m; must be called for m = 0, 1, 2, ...
     int32_t* sl = slot_of(m);
-    if (lane < 2) {
-      if (m < my_items) {
-        const uint32_t item = first_item + m * TW;
-        const uint32_t t = (n_chunks == 1) ? item : item / n_chunks;
-        cp_async4(sl + lane, tile_start + t + lane);
-        if (lane == 0) {
-          sl[2] = (int32_t)t;
-          sl[3] = (int32_t)(item - t * n_chunks) * CC;
-        }
-      } else {
-        sl[lane] = 0;
+    if (m < my_items) {
+      if (lane < 2) cp_async4(sl + lane, tile_start + nx_t + lane);
+      if (lane == 0) {
+        const int32_t g0 = (int32_t)(nx_b * Vu + nx_vt * kTileVoxels);
+        *reinterpret_cast<int2*>(sl + 2) = make_int2(g0, (int)((nx_b << 16) | nx_chunk));
       }
+      uint32_t dt = step_t;
+      nx_chunk += step_c;
+      if (nx_chunk >= n_chunks) {
+        nx_chunk -= n_chunks;
+        ++dt;
+      }
+      nx_t += dt;
+      nx_vt += dt;
+      while (nx_vt >= tiles_per_sample) {
+        nx_vt -= tiles_per_sample;
+        ++nx_b;
+      }
+    } else if (lane < 2) {
+      sl[lane] = 0;
     }
   };
   auto issue_ranks = [&](uint32_t m) {  // needs bounds(m)
     int32_t* sl = slot_of(m);
     int32_t* pt = sl + 4 + 4 * lane;
-    const int32_t i = sl[0] + lane;
-    if (i < sl[1]) {
+    const int2 se = *reinterpret_cast<const int2*>(sl);
+    const int32_t i = se.x + lane;
+    if (i < se.y) {
       cp_async4(pt + 0, ranks_bev + i);
       cp_async4(pt + 1, ranks_feat + i);
       cp_async4(pt + 2, ranks_depth + i);
@@ -122,12 +158,11 @@ k_pool_fwd(const float* __restrict__ depth, const float* __restrict__ feat,
     const int32_t rb = pt[0];
     if (rb >= 0) {
       cp_async4(pt + 3, depth + pt[2]);
-      const uint32_t t = (uint32_t)sl[2];
-      const uint32_t b = t / tiles_per_sample;
-      const int32_t g0 = (int32_t)((int64_t)b * V) + (int32_t)(t - b * tiles_per_sample) * kTileVoxels;
+      const int2 h = *reinterpret_cast<const int2*>(sl + 2);
       const int32_t up = lane ? pt[-4] : -1;
-      pt[1] = (int32_t)((uint32_t)pt[1] * (uint32_t)C);    // row offset in floats (< 2^32)
-      pt[2] = (rb - g0) | ((rb != up) ? 0x100 : 0);        // voxel | first-of-voxel
+      // byte offset of this channel chunk of the point's feature row (< 2^32, checked)
+      pt[1] = (int32_t)(((uint32_t)pt[1] * (uint32_t)C + (uint32_t)(h.y & 0xffff) * CC) * 4u);
+      pt[2] = (rb - h.x) | ((rb != up) ? 0x100 : 0);  // voxel | first-of-voxel
     }
   };
 
@@ -144,35 +179,41 @@ k_pool_fwd(const float* __restrict__ depth, const float* __restrict__ feat,
 
   const int q4 = (lane & 7) * 4, r = lane >> 3;  // write-out role of this lane
   float* const tlane = tile + lane * kRowPitch;   // flush base: channel = lane (+32k)
+  const char* const feat_lane = reinterpret_cast<const char*>(feat) + lane * 4;
+  const int64_t ostep = 4 * V;
 
+  const uint32_t last_first = blockIdx.x * kFwdWarps + kFwdWarps - 1;
+  const uint32_t common_items = last_first < n_items ? (n_items - last_first + TW - 1) / TW : 0;
   for (uint32_t m = 0; m < my_items; ++m) {
+    if (VEON_DBG(16) && m < common_items) __syncthreads();
     cp_async_wait_dist();
     __syncwarp();
     int32_t* sl = slot_of(m);
-    const int32_t s0 = sl[0], e0 = sl[1];
-    const uint32_t t = (uint32_t)sl[2];
-    const int cbase = sl[3];
+    const int4 h = *reinterpret_cast<const int4*>(sl);  // s, e, g0, sample<<16 | chunk
     issue_bounds(m + 3 * kDist);  // lands in the slot item m-kDist used
     issue_ranks(m + 2 * kDist);
     issue_depth(m + kDist);
     cp_async_commit();
+    const int32_t s0 = h.x, e0 = h.y, g0 = h.z;
     if (e0 - s0 >= heavy_thr) continue;
 
-    const uint32_t b = t / tiles_per_sample;
-    const int v0 = (int)(t - b * tiles_per_sample) * kTileVoxels;
-    const int cmax = min(CC, C - cbase);
-    float* o = out + ((int64_t)b * C + cbase + r) * V + v0 + q4;
-    const int64_t ostep = 4 * V;
-    const bool fast = vec_ok && (v0 + kTileVoxels <= V);
+    const uint32_t b = (uint32_t)h.w >> 16;
+    const int cbase = (h.w & 0xffff) * CC;
+    const int cmax = FULLC ? CC : min(CC, C - cbase);
+    // (b*C + cbase + r)*V + v0 + q4  with  v0 = g0 - b*V
+    float* o = out + (int64_t)(b * (uint32_t)(C - 1) + (uint32_t)(cbase + r)) * V + g0 + q4;
+    const bool fast = vec_ok && (whole_tiles || (uint32_t)g0 - b * Vu + kTileVoxels <= Vu);
 
     if (e0 <= s0 && fast) {  // empty tile
+      if (!VEON_DBG(4)) {
 #pragma unroll 4
-      for (int c = r; c < cmax; c += 4, o += ostep) st_stream4(o, make_float4(0.f, 0.f, 0.f, 0.f));
+        for (int c = r; c < cmax; c += 4, o += ostep) st_stream4(o, make_float4(0.f, 0.f, 0.f, 0.f));
+      }
       continue;
     }
 
     __syncwarp();
-    {  // zero the tile (empty voxels must read as 0)
+    if (!VEON_DBG(1)) {  // zero the tile (empty voxels must read as 0)
       float4* t4 = reinterpret_cast<float4*>(tile);
 #pragma unroll
       for (int i = 0; i < kTileFloats / 4 / 32; ++i) t4[lane + 32 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -181,13 +222,11 @@ k_pool_fwd(const float* __restrict__ depth, const float* __restrict__ feat,
 
     float acc[KCH];
     int acc_vl = -1;
-    const float* feat_lane = feat + cbase + lane;
-    const bool full_chunk = (cmax == CC);
+    const bool full_chunk = FULLC || (cmax == CC);
     for (int32_t base = s0; base < e0; base += 32) {
       const int cnt = min(32, e0 - base);
-      if (base != s0) {  // long tile: later chunks are fetched synchronously
+      if (base != s0) {  // tile with more than 32 points: later chunks are fetched synchronously
         const int32_t i = base + lane;
-        const int32_t g0 = (int32_t)((int64_t)b * V) + v0;
         __syncwarp();
         int32_t rb = -1, rf = 0;
         float d = 0.f;
@@ -199,7 +238,7 @@ k_pool_fwd(const float* __restrict__ depth, const float* __restrict__ feat,
         const int32_t up = __shfl_up_sync(0xffffffffu, rb, 1);
         const bool first = (lane > 0) && (rb != up);  // lane 0 continues or starts: see below
         int32_t* pt = sl + 4 + 4 * lane;
-        pt[1] = (int32_t)((uint32_t)rf * (uint32_t)C);
+        pt[1] = (int32_t)(((uint32_t)rf * (uint32_t)C + (uint32_t)cbase) * 4u);
         pt[2] = (rb - g0) | (first ? 0x100 : 0);
         pt[3] = __float_as_int(d);
         if (lane == 0) {  // first point of the chunk: new voxel iff it differs from the last one
@@ -215,28 +254,41 @@ k_pool_fwd(const float* __restrict__ depth, const float* __restrict__ feat,
         int4 p[U];
         float f[U][KCH];
 #pragma unroll
-        for (int u = 0; u < U; ++u) {  // U points' rows in flight
-          p[u] = pts[min(j0 + u, cnt - 1)];
-          const float* row = feat_lane + (uint32_t)p[u].y;
+        for (int g = 0; g < U / 4; ++g) {
+          if (j0 + 4 * g < cnt) {  // warp-uniform: skip the groups past the last point
 #pragma unroll
-          for (int k = 0; k < KCH; ++k)
-            f[u][k] = (full_chunk || lane + 32 * k < cmax) ? __ldg(row + 32 * k) : 0.f;
+            for (int uu = 0; uu < 4; ++uu) {
+              const int u = 4 * g + uu;
+              p[u] = pts[min(j0 + u, cnt - 1)];
+              const float* row = reinterpret_cast<const float*>(feat_lane + (uint32_t)p[u].y);
+#pragma unroll
+              for (int k = 0; k < KCH; ++k)
+                f[u][k] = VEON_DBG(8) ? (float)p[u].y
+                          : (FULLC || full_chunk || lane + 32 * k < cmax) ? __ldg(row + 32 * k) : 0.f;
+            }
+          }
         }
 #pragma unroll
-        for (int u = 0; u < U; ++u) {
-          if (j0 + u < cnt) {
-            const float dj = __int_as_float(p[u].w);
-            if (p[u].z & 0x100) {  // first point of its voxel (warp-uniform)
-              if (acc_vl >= 0) {
+        for (int g = 0; g < U / 4; ++g) {
+          if (j0 + 4 * g < cnt) {
 #pragma unroll
-                for (int k = 0; k < KCH; ++k) tlane[32 * k * kRowPitch + acc_vl] = acc[k];
+            for (int uu = 0; uu < 4; ++uu) {
+              const int u = 4 * g + uu;
+              if (j0 + u < cnt) {
+                const float dj = __int_as_float(p[u].w);
+                if (p[u].z & 0x100) {  // first point of its voxel (warp-uniform)
+                  if (acc_vl >= 0) {
+#pragma unroll
+                    for (int k = 0; k < KCH; ++k) tlane[32 * k * kRowPitch + acc_vl] = acc[k];
+                  }
+                  acc_vl = p[u].z & 0xff;
+#pragma unroll
+                  for (int k = 0; k < KCH; ++k) acc[k] = fmaf(f[u][k], dj, 0.f);
+                } else {
+#pragma unroll
+                  for (int k = 0; k < KCH; ++k) acc[k] = fmaf(f[u][k], dj, acc[k]);
+                }
               }
-              acc_vl = p[u].z & 0xff;
-#pragma unroll
-              for (int k = 0; k < KCH; ++k) acc[k] = fmaf(f[u][k], dj, 0.f);
-            } else {
-#pragma unroll
-              for (int k = 0; k < KCH; ++k) acc[k] = fmaf(f[u][k], dj, acc[k]);
             }
           }
         }
@@ -253,9 +305,12 @@ k_pool_fwd(const float* __restrict__ depth, const float* __restrict__ feat,
     const float* trow = tile + r * kRowPitch + q4;
     if (fast) {
 #pragma unroll 4
-      for (int c = r; c < cmax; c += 4, o += ostep, trow += 4 * kRowPitch)
-        st_stream4(o, *reinterpret_cast<const float4*>(trow));
+      for (int c = r; c < cmax; c += 4, o += ostep, trow += 4 * kRowPitch) {
+        const float4 v4 = *reinterpret_cast<const float4*>(trow);
+        if (!VEON_DBG(4) || v4.x == 123.456f) st_stream4(o, v4);
+      }
     } else {  // ragged volume edge / unaligned volume: scalar, bounds-checked
+      const int v0 = (int)((uint32_t)g0 - b * Vu);
       for (int c = r; c < cmax; c += 4, o += ostep, trow += 4 * kRowPitch)
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -265,7 +320,6 @@ k_pool_fwd(const float* __restrict__ depth, const float* __restrict__ feat,
   }
   cp_async_wait_all();
 }
-
 
 // ---- heavy tiles -------------------------------------------------------------
 // A tile with hundreds of points (voxels next to the cameras collect a whole
@@ -437,8 +491,8 @@ static int env_flag(const char* name, int dflt) {
   return e ? atoi(e) : dflt;
 }
 
-template <int KCH>
-static int launch_fwd(const float* depth, const float* feat, const int32_t* rd,
+template <int KCH, bool FULLC>
+static int launch_fwd_impl(const float* depth, const float* feat, const int32_t* rd,
                       const int32_t* rf, const int32_t* rb, const int32_t* tile_start,
                       const int32_t* heavy, int64_t heavy_ints, int B, int C, int64_t V,
                       bool feat_rows_fit_32bit, float* out, cudaStream_t stream) {
@@ -446,11 +500,12 @@ static int launch_fwd(const float* depth, const float* feat, const int32_t* rd,
   const size_t smem = sizeof(float) * kFwdWarps * (CC * kRowPitch + kRingSlots * kSlotInts);
   static int ctas_per_sm = 0;
   if (ctas_per_sm == 0) {
-    VEON_CUDA_TRY(cudaFuncSetAttribute(k_pool_fwd<KCH>,
+    VEON_CUDA_TRY(cudaFuncSetAttribute(k_pool_fwd<KCH, FULLC>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    VEON_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_pool_fwd<KCH>,
+    VEON_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_pool_fwd<KCH, FULLC>,
                                                                 kFwdWarps * 32, smem));
     if (ctas_per_sm < 1) ctas_per_sm = 1;
+    if (env_flag("VEON_FWD_CTAS", 0) > 0 && env_flag("VEON_FWD_CTAS", 0) < ctas_per_sm) ctas_per_sm = env_flag("VEON_FWD_CTAS", 0);
   }
   const int64_t tps = ceil_div64(V, kTileVoxels), n_tiles = (int64_t)B * tps;
   const int n_chunks = (C + CC - 1) / CC;
@@ -500,17 +555,29 @@ static int launch_fwd(const float* depth, const float* feat, const int32_t* rd,
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    VEON_CUDA_TRY(cudaLaunchKernelEx(&cfg, k_pool_fwd<KCH>, depth, feat, rd, rf, rb, tile_start,
+    VEON_CUDA_TRY(cudaLaunchKernelEx(&cfg, k_pool_fwd<KCH, FULLC>, depth, feat, rd, rf, rb, tile_start,
                                      heavy, (uint32_t)(n_tiles * n_chunks), (uint32_t)tps, V, C,
-                                     (uint32_t)n_chunks, vec_ok, out));
+                                     (uint32_t)n_chunks, vec_ok, out, env_flag("VEON_FWD_DBG", 0)));
     VEON_LAUNCH_CHECK();
     return 0;
   }
-  k_pool_fwd<KCH><<<(unsigned)blocks, kFwdWarps * 32, smem, stream>>>(
+  k_pool_fwd<KCH, FULLC><<<(unsigned)blocks, kFwdWarps * 32, smem, stream>>>(
       depth, feat, rd, rf, rb, tile_start, heavy, (uint32_t)(n_tiles * n_chunks), (uint32_t)tps,
-      V, C, (uint32_t)n_chunks, vec_ok, out);
+      V, C, (uint32_t)n_chunks, vec_ok, out, env_flag("VEON_FWD_DBG", 0));
   VEON_LAUNCH_CHECK();
   return 0;
+}
+
+template <int KCH>
+static int launch_fwd(const float* depth, const float* feat, const int32_t* rd,
+                      const int32_t* rf, const int32_t* rb, const int32_t* tile_start,
+                      const int32_t* heavy, int64_t heavy_ints, int B, int C, int64_t V,
+                      bool feat_rows_fit_32bit, float* out, cudaStream_t stream) {
+  if (C % (32 * KCH) == 0)
+    return launch_fwd_impl<KCH, true>(depth, feat, rd, rf, rb, tile_start, heavy, heavy_ints, B, C,
+                                      V, feat_rows_fit_32bit, out, stream);
+  return launch_fwd_impl<KCH, false>(depth, feat, rd, rf, rb, tile_start, heavy, heavy_ints, B, C,
+                                     V, feat_rows_fit_32bit, out, stream);
 }
 
 }  // namespace veon
@@ -539,7 +606,10 @@ extern "C" int veon_bev_pool_v2_fwd_planar(const float* depth, const float* feat
   if (!depth || !feat || !ranks_depth || !ranks_feat || !ranks_bev || !tile_start || !out ||
       B <= 0 || C <= 0 || V <= 0 || n_feat_rows <= 0 || (tile_heavy && tile_heavy_ints < 2))
     return VEON_E_BADARG;
-  const bool fit32 = n_feat_rows * (int64_t)C <= 0xffffffffLL;
+  // the gather addresses feature rows with 32-bit BYTE offsets; the ring header packs
+  // sample<<16 | chunk
+  const bool fit32 = n_feat_rows * (int64_t)C <= 0x3fffffffLL && B < 65536 &&
+                     (int64_t)C <= 65535LL * 32;
   int kch = fwd_kch_override();
   if (kch == 0) kch = (C <= 32) ? 1 : 2;
   switch (kch) {

@@ -184,7 +184,8 @@ __global__ void __launch_bounds__(kScanThreads)
 k_scan(const int32_t* __restrict__ count, int32_t* __restrict__ offset,
        int32_t* __restrict__ iidx, int32_t* __restrict__ istarts,
        int32_t* __restrict__ ilens, unsigned long long* desc, uint32_t* ctrl,
-       int32_t* __restrict__ long_list, int long_cap, int64_t* counts_out, int num_tiles,
+       int32_t* __restrict__ long_list, int long_cap, int64_t* counts_out,
+       int64_t* counts_mirror, int num_tiles,
        int32_t* __restrict__ tile_start, int32_t* __restrict__ tile_istart,
        uint32_t* __restrict__ tile_occ, int64_t n_pool_tiles) {
   __shared__ uint32_t s_tile;
@@ -294,6 +295,11 @@ k_scan(const int32_t* __restrict__ count, int32_t* __restrict__ offset,
   if ((int)tile == num_tiles - 1 && tid == kScanThreads - 1) {
     counts_out[0] = (int64_t)(run & 0x7fffffffull);
     counts_out[1] = (int64_t)((run >> 31) & 0x7fffffffull);
+    if (counts_mirror) {  // pinned host memory: the host reads it after an event, no copy queued
+      counts_mirror[0] = counts_out[0];
+      counts_mirror[1] = counts_out[1];
+      __threadfence_system();
+    }
   }
 }
 
@@ -316,8 +322,52 @@ __global__ void k_tiles(const int32_t* __restrict__ count, const int32_t* __rest
   tile_occ[t] = m;
 }
 
+// -------------------------------------------------------------------- k_fill
+// Clears the scratch regions with a kernel instead of cudaMemsetAsync: memsets and the
+// caller's bulk host<->device copies share the copy engines, and a step's first launch
+// must not queue behind a 20 MB transfer of the previous step's results.
+struct FillJob {
+  uint32_t* p;
+  int64_t n;   // 32-bit words
+  uint32_t v;
+};
+struct FillJobs {
+  FillJob j[3];
+};
+__global__ void __launch_bounds__(256) k_fill(FillJobs jobs) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    uint32_t* p = jobs.j[q].p;
+    const int64_t n = jobs.j[q].n;
+    const uint32_t v = jobs.j[q].v;
+    if (n <= 0) continue;
+    // 16-byte stores over the aligned middle, scalar head and tail
+    const int64_t head = min(n, (int64_t)((16 - ((uintptr_t)p & 15)) & 15) / 4);
+    const int64_t n4 = (n - head) / 4;
+    uint4* p4 = reinterpret_cast<uint4*>(p + head);
+    for (int64_t i = t0; i < n4; i += stride) p4[i] = make_uint4(v, v, v, v);
+    if (t0 < head) p[t0] = v;
+    const int64_t tail0 = head + 4 * n4;
+    if (t0 < n - tail0) p[tail0 + t0] = v;
+  }
+}
+
+static int launch_fill(const FillJobs& jobs, cudaStream_t stream) {
+  int64_t words = 0;
+  for (int q = 0; q < 3; ++q) words += jobs.j[q].n > 0 ? jobs.j[q].n : 0;
+  if (words == 0) return 0;
+  int64_t blocks = ceil_div64(ceil_div64(words, 4), 256 * 4);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  k_fill<<<(unsigned)blocks, 256, 0, stream>>>(jobs);
+  VEON_LAUNCH_CHECK();
+  return 0;
+}
+
 // -------------------------------------------------------------- k_heavy_list
-// heavy[0] = number of listed tiles (zeroed by the caller), heavy[1] = threshold,
+// heavy[0] = number of listed tiles (zeroed by the caller's k_fill), heavy[1] = threshold,
 // heavy[2..] = tile ids in arbitrary order (the order only affects scheduling)
 __global__ void k_heavy_list(const int32_t* __restrict__ tile_start, int64_t n_tiles, int thr,
                              int cap, int32_t* __restrict__ heavy) {
@@ -332,7 +382,7 @@ __global__ void k_heavy_list(const int32_t* __restrict__ tile_start, int64_t n_t
 
 static int build_heavy_list(const int32_t* tile_start, int64_t n_tiles, int64_t n_points_cap,
                             int32_t* heavy, cudaStream_t stream) {
-  VEON_CUDA_TRY(cudaMemsetAsync(heavy, 0, 2 * sizeof(int32_t), stream));
+  // heavy[0] was cleared by the caller's k_fill
   k_heavy_list<<<(unsigned)ceil_div64(n_tiles, 256), 256, 0, stream>>>(
       tile_start, n_tiles, heavy_threshold(), (int)heavy_capacity(n_points_cap, n_tiles), heavy);
   VEON_LAUNCH_CHECK();
@@ -567,8 +617,8 @@ extern "C" int veon_prepare_v2(const float* coor, int B, int N, int D, int H, in
                                const float* grid_size, int32_t* ranks_bev,
                                int32_t* ranks_depth, int32_t* ranks_feat,
                                int32_t* interval_starts, int32_t* interval_lengths,
-                               int64_t* counts, int32_t* tile_start, int32_t* tile_istart,
-                               uint32_t* tile_occ, int32_t* tile_heavy,
+                               int64_t* counts, int64_t* counts_host, int32_t* tile_start,
+                               int32_t* tile_istart, uint32_t* tile_occ, int32_t* tile_heavy,
                                int32_t* point_interval, void* workspace,
                                size_t workspace_bytes, void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -586,9 +636,16 @@ extern "C" int veon_prepare_v2(const float* coor, int B, int N, int D, int H, in
   if (workspace_bytes < w.total) return VEON_E_WORKSPACE;
   if (((uintptr_t)workspace & 15) != 0) return VEON_E_BADARG;
 
-  VEON_CUDA_TRY(cudaMemsetAsync((char*)workspace + w.zero_begin, 0, w.zero_bytes, stream));
-  if (point_interval)
-    VEON_CUDA_TRY(cudaMemsetAsync(point_interval, 0xff, sizeof(int32_t) * P, stream));
+  {
+    FillJobs jobs = {};
+    jobs.j[0] = {reinterpret_cast<uint32_t*>((char*)workspace + w.zero_begin),
+                 (int64_t)(w.zero_bytes / 4), 0u};
+    if (point_interval) jobs.j[1] = {reinterpret_cast<uint32_t*>(point_interval), P, 0xffffffffu};
+    if (tile_start && tile_istart && tile_occ && tile_heavy)
+      jobs.j[2] = {reinterpret_cast<uint32_t*>(tile_heavy), 2, 0u};
+    rc = launch_fill(jobs, stream);
+    if (rc) return rc;
+  }
 
   const int64_t pts_per_sample = (int64_t)N * D * H * W;
   const unsigned pblocks = (unsigned)ceil_div64(P, 256);
@@ -600,7 +657,7 @@ extern "C" int veon_prepare_v2(const float* coor, int B, int N, int D, int H, in
   const bool fused_tiles = want_tiles && (V % kTileVoxels == 0);
   k_scan<<<(unsigned)w.scan_tiles, kScanThreads, 0, stream>>>(
       w.count, w.offset, w.iidx, interval_starts, interval_lengths, w.desc, w.ctrl,
-      w.long_list, (int)w.long_cap, counts, (int)w.scan_tiles,
+      w.long_list, (int)w.long_cap, counts, counts_host, (int)w.scan_tiles,
       fused_tiles ? tile_start : nullptr, tile_istart, tile_occ, n_tiles);
   VEON_LAUNCH_CHECK();
   if (want_tiles && !fused_tiles) {
@@ -642,8 +699,14 @@ extern "C" int veon_pool_plan_build(const int32_t* ranks_depth, const int32_t* r
       n_intervals <= 0)
     return VEON_E_BADARG;
   if ((int64_t)B * V > 0x7fffffffLL) return VEON_E_RANGE;
-  VEON_CUDA_TRY(cudaMemsetAsync(flags, 0, sizeof(int32_t), stream));
-  VEON_CUDA_TRY(cudaMemsetAsync(point_interval, 0xff, sizeof(int32_t) * P, stream));
+  {
+    FillJobs jobs = {};
+    jobs.j[0] = {reinterpret_cast<uint32_t*>(flags), 1, 0u};
+    jobs.j[1] = {reinterpret_cast<uint32_t*>(point_interval), P, 0xffffffffu};
+    if (tile_heavy) jobs.j[2] = {reinterpret_cast<uint32_t*>(tile_heavy), 2, 0u};
+    rc = launch_fill(jobs, stream);
+    if (rc) return rc;
+  }
   PointDims dims{D, H * W, D * H * W};
   k_plan_points<<<(unsigned)ceil_div64(n_points, 256), 256, 0, stream>>>(
       ranks_depth, ranks_feat, ranks_bev, n_points, P, (int64_t)B * N * H * W, (int64_t)B * V,

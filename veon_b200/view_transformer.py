@@ -131,8 +131,11 @@ class LSSViewTransformer(nn.Module):
         self.interval_lengths = interval_lengths.int().contiguous()
 
     def _bev_shape(self, depth, channels):
-        gs = self.grid_size
-        return (depth.shape[0], int(gs[2]), int(gs[1]), int(gs[0]), channels)  # B,Z,Y,X,C
+        zyx = self.__dict__.get("_zyx")
+        if zyx is None or zyx[0] is not self.grid_size:   # cached: three .item() calls
+            gs = self.grid_size
+            zyx = self.__dict__["_zyx"] = (gs, int(gs[2]), int(gs[1]), int(gs[0]))
+        return (depth.shape[0], zyx[1], zyx[2], zyx[3], channels)  # B,Z,Y,X,C
 
     # -- a4 ------------------------------------------------------------------
     def voxel_pooling_v2(self, coor, depth, feat):
