@@ -272,38 +272,68 @@ def run_ours(args):
                torch.empty((B * N, D, H, W), dtype=torch.float32, device=dev),
                torch.empty((B * N, C, H, W), dtype=torch.float32, device=dev)) for _ in range(2)]
 
-    def e2e_prefetch(i):
+    def e2e_h2d(i, gate=None):
         slot = i % 2
         with torch.cuda.stream(copy_stream):
             copy_stream.wait_event(consumed[slot])          # the slot's previous user is done
+            if gate is not None:
+                copy_stream.wait_event(gate)
             for dst, src in zip(dev_in[slot], e2e_host[i % n_sets]):
                 dst.copy_(src, non_blocking=True)
             ready[slot].record(copy_stream)
 
+    def e2e_d2h(slot, dgrad, fgrad, gate):
+        with torch.cuda.stream(d2h_stream):
+            d2h_stream.wait_event(consumed[slot])
+            d2h_stream.wait_event(gate)
+            dgrad.record_stream(d2h_stream)
+            fgrad.record_stream(d2h_stream)
+            dg_host[slot].copy_(dgrad, non_blocking=True)
+            fg_host[slot].copy_(fgrad, non_blocking=True)
+
     def run_e2e(steps):
+        """Every step copies its inputs in and its gradients out.  The copies are queued from
+        the neck's `prepared_hook`: H2D of step i+1 and D2H of step i-1 are released when the
+        index preparation of step i is done, so they overlap the two long pooling kernels
+        instead of the dozen short launches before them (those are measurably slower while
+        PCIe is saturated; tools/e2e_timeline.py)."""
         main = torch.cuda.current_stream(dev)
         for ev in consumed:
             ev.record(main)
-        e2e_prefetch(0)
-        for i in range(steps):
-            slot = i % 2
-            if i + 1 < steps:
-                e2e_prefetch(i + 1)
-            main.wait_event(ready[slot])
-            packed_dev, depth, feat = dev_in[slot]
-            metas = unpack_metas(packed_dev)
-            depth = depth.detach().requires_grad_()
-            feat = feat.detach().requires_grad_()
-            bev, _ = neck.view_transform([img_shape] + metas, depth, feat)
-            bev.backward(out_grad)
-            consumed[slot].record(main)
-            dgrad, fgrad = depth.grad, feat.grad
-            with torch.cuda.stream(d2h_stream):
-                d2h_stream.wait_event(consumed[slot])
-                dgrad.record_stream(d2h_stream)
-                fgrad.record_stream(d2h_stream)
-                dg_host[slot].copy_(dgrad, non_blocking=True)
-                fg_host[slot].copy_(fgrad, non_blocking=True)
+        gate = torch.cuda.Event()
+        state = {"i": 0, "pending": None}
+        done = [torch.cuda.Event() for _ in range(4)]   # bounds the host's run-ahead to 2 steps
+
+        def hook():
+            gate.record(main)
+            if state["i"] + 1 < steps:
+                e2e_h2d(state["i"] + 1, gate)
+            if state["pending"] is not None:
+                e2e_d2h(*state["pending"], gate)
+                state["pending"] = None
+
+        neck.prepared_hook = hook
+        try:
+            e2e_h2d(0)
+            for i in range(steps):
+                slot = i % 2
+                state["i"] = i
+                if i >= 2:
+                    done[(i - 2) % 4].synchronize()
+                main.wait_event(ready[slot])
+                packed_dev, depth, feat = dev_in[slot]
+                metas = unpack_metas(packed_dev)
+                depth = depth.detach().requires_grad_()
+                feat = feat.detach().requires_grad_()
+                bev, _ = neck.view_transform([img_shape] + metas, depth, feat)
+                bev.backward(out_grad)
+                consumed[slot].record(main)
+                done[i % 4].record(main)
+                state["pending"] = (slot, depth.grad, feat.grad)
+        finally:
+            neck.prepared_hook = None
+        gate.record(main)
+        e2e_d2h(*state["pending"], gate)
         main.wait_stream(d2h_stream)
 
     def barrier():

@@ -82,6 +82,27 @@ def test_view_transform_matches_cpu_lift(sync_free):
     assert rel(bev.cpu().numpy(), want.numpy()) <= 1e-5
 
 
+def test_sync_free_backward_equals_faithful_backward():
+    """sync_free sizes the backward scratch by an upper bound instead of reading the
+    interval count back; gradients must be the same bits as on the faithful path."""
+    from veon_b200.view_transformer import LSSViewTransformer
+    cfg = S.CONFIGS["small"]
+    B, C = 2, 32
+    img, metas, depth, feat = inputs(cfg, B, C, seed=2)
+    og = torch.randn(B, C, 16, 200, 200, generator=torch.Generator().manual_seed(9)).cuda()
+    grads = []
+    for sync_free in (False, True):
+        neck = LSSViewTransformer(cfg.grid_config, cfg.input_size, cfg.downsample, 8, C,
+                                  collapse_z=False, sync_free=sync_free)
+        d = depth.detach().clone().requires_grad_()
+        f = feat.detach().clone().requires_grad_()
+        bev, _ = neck.view_transform([img] + metas, d, f)
+        bev.backward(og)
+        grads.append((bev.detach(), d.grad, f.grad))
+    for a, b in zip(*grads):
+        assert torch.equal(a, b)
+
+
 def test_accelerate_equals_non_accelerate():
     """the idea of the reference's own neck test (tests/test_models/test_necks/test_necks.py:137-195)"""
     from veon_b200.view_transformer import LSSViewTransformer

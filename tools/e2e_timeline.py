@@ -27,7 +27,7 @@ def unpack(p):
 copy_s, d2h_s = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
 ready = [torch.cuda.Event(), torch.cuda.Event()]; consumed = [torch.cuda.Event(), torch.cuda.Event()]
 dgh = [torch.empty((B*N, D, H, W)).pin_memory() for _ in range(2)]; fgh = [torch.empty((B*N, C, H, W)).pin_memory() for _ in range(2)]
-dev_in = [tuple(torch.empty_like(x, device=dev) for x in host) for _ in range(2)]
+dev_in = [tuple(x.to(dev) for x in host) for _ in range(2)]
 T = lambda: torch.cuda.Event(enable_timing=True)
 log = []
 def prefetch(i, rec):
@@ -35,11 +35,15 @@ def prefetch(i, rec):
     with torch.cuda.stream(copy_s):
         copy_s.wait_event(consumed[slot])
         a = T(); a.record(copy_s)
-        for dst, src in zip(dev_in[slot], host): dst.copy_(src, non_blocking=True)
+        if "--no-h2d" not in sys.argv:
+            for dst, src in zip(dev_in[slot], host): dst.copy_(src, non_blocking=True)
         b = T(); b.record(copy_s)
         ready[slot].record(copy_s)
     if rec: log.append(("h2d", i, a, b))
+gated = "--gated" in sys.argv
 def run(steps, rec=False):
+    if gated:
+        return run_gated(steps, rec)
     main = torch.cuda.current_stream(dev)
     for ev in consumed: ev.record(main)
     t0 = T(); t0.record(main)
@@ -63,7 +67,8 @@ def run(steps, rec=False):
             d2h_s.wait_event(consumed[slot])
             dg.record_stream(d2h_s); fg.record_stream(d2h_s)
             x = T(); x.record(d2h_s)
-            dgh[slot].copy_(dg, non_blocking=True); fgh[slot].copy_(fg, non_blocking=True)
+            if "--no-d2h" not in sys.argv:
+                dgh[slot].copy_(dg, non_blocking=True); fgh[slot].copy_(fg, non_blocking=True)
             y = T(); y.record(d2h_s)
         cpu.append(time.perf_counter() - c0)
         if rec: log.append(("fwd", i, a, m)); log.append(("bwd", i, m, b)); log.append(("d2h", i, x, y))
@@ -71,6 +76,63 @@ def run(steps, rec=False):
     t1 = T(); t1.record(main)
     torch.cuda.synchronize()
     return t0, t0.elapsed_time(t1) / steps, sum(cpu) / len(cpu) * 1e3
+def run_gated(steps, rec=False):
+    """copies are released from the neck's prepared_hook: H2D of step i+1 and D2H of step
+    i-1 start when prepare(i) is done and overlap the pooling kernels only"""
+    main = torch.cuda.current_stream(dev)
+    for ev in consumed: ev.record(main)
+    t0 = T(); t0.record(main)
+    state = {"i": 0, "pending": None}
+    gate = torch.cuda.Event()
+    def issue_d2h(pending):
+        slot, dg, fg, i = pending
+        with torch.cuda.stream(d2h_s):
+            d2h_s.wait_event(consumed[slot]); d2h_s.wait_event(gate)
+            dg.record_stream(d2h_s); fg.record_stream(d2h_s)
+            x = T(); x.record(d2h_s)
+            dgh[slot].copy_(dg, non_blocking=True); fgh[slot].copy_(fg, non_blocking=True)
+            y = T(); y.record(d2h_s)
+        if rec: log.append(("d2h", i, x, y))
+    def hook():
+        gate.record(main)
+        i = state["i"]
+        if i + 1 < steps:
+            slot = (i + 1) % 2
+            with torch.cuda.stream(copy_s):
+                copy_s.wait_event(consumed[slot]); copy_s.wait_event(gate)
+                a = T(); a.record(copy_s)
+                for dst, src in zip(dev_in[slot], host): dst.copy_(src, non_blocking=True)
+                b = T(); b.record(copy_s)
+                ready[slot].record(copy_s)
+            if rec: log.append(("h2d", i + 1, a, b))
+        if state["pending"] is not None:
+            issue_d2h(state["pending"]); state["pending"] = None
+    neck.prepared_hook = hook
+    cpu = []
+    prefetch(0, rec)
+    for i in range(steps):
+        c0 = time.perf_counter()
+        slot = i % 2; state["i"] = i
+        main.wait_event(ready[slot])
+        p, depth, feat = dev_in[slot]
+        a = T(); a.record(main)
+        depth = depth.detach().requires_grad_(); feat = feat.detach().requires_grad_()
+        bev, _ = neck.view_transform([img] + unpack(p), depth, feat)
+        m = T(); m.record(main)
+        bev.backward(og)
+        b = T(); b.record(main)
+        consumed[slot].record(main)
+        state["pending"] = (slot, depth.grad, feat.grad, i)
+        cpu.append(time.perf_counter() - c0)
+        if rec: log.append(("fwd", i, a, m)); log.append(("bwd", i, m, b))
+    neck.prepared_hook = None
+    gate.record(main)
+    issue_d2h(state["pending"])
+    main.wait_stream(d2h_s)
+    t1 = T(); t1.record(main)
+    torch.cuda.synchronize()
+    return t0, t0.elapsed_time(t1) / steps, sum(cpu) / len(cpu) * 1e3
+
 run(5)
 _, ms, cpu = run(30); print(f"e2e {ms:.3f} ms/step, host loop {cpu:.3f} ms/step (sync_free={sync_free})")
 t0, ms, cpu = run(8, rec=True)
@@ -102,3 +164,13 @@ if "--trace" in sys.argv:
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     prof.export_chrome_trace(os.path.join(ROOT, "gpurun_out", "e2e_trace.json"))
     print("trace written")
+if "--cpu" in sys.argv:
+    blocked = [0.0]
+    orig = torch.cuda.Event.synchronize
+    def timed_sync(self):
+        t = time.perf_counter(); orig(self); blocked[0] += time.perf_counter() - t
+    torch.cuda.Event.synchronize = timed_sync
+    run(5); blocked[0] = 0.0
+    t = time.perf_counter(); run(50); torch.cuda.synchronize(); wall = time.perf_counter() - t
+    print(f"wall {wall/50*1e3:.3f} ms/step, blocked in Event.synchronize {blocked[0]/50*1e3:.3f} ms/step, "
+          f"host busy {(wall-blocked[0])/50*1e3:.3f} ms/step")

@@ -108,7 +108,7 @@ class PoolPlan:
     __slots__ = ("__weakref__", "tile_start", "tile_istart", "tile_occ", "tile_heavy",
                  "point_interval", "dims", "V",
                  "flags", "_n_intervals", "_n_points", "counts_dev", "counts_host",
-                 "counts_event", "keepalive")
+                 "counts_event", "keepalive", "sync_free")
 
     def __init__(self):
         self.flags = 0
@@ -116,6 +116,7 @@ class PoolPlan:
         self._n_points = None
         self.counts_dev = self.counts_host = self.counts_event = None
         self.keepalive = None
+        self.sync_free = False
 
     def _resolve(self):
         if self._n_intervals is None:
@@ -136,6 +137,16 @@ class PoolPlan:
     @property
     def ok(self):
         return self.flags == 0
+
+    def interval_capacity(self):
+        """Rows the backward scratch needs.  Exact when the counts are known (or have
+        already arrived); a `sync_free` plan whose counts are still in flight answers
+        with the upper bound (every point its own interval) instead of blocking."""
+        if (self._n_intervals is None and self.sync_free and self.counts_event is not None
+                and not self.counts_event.query()):
+            B, N, D, H, W = self.dims
+            return B * N * D * H * W
+        return self.n_intervals
 
 
 class PreparedRanks:
@@ -344,7 +355,7 @@ def _bwd_planar(grad_planar, depth, feat, rb, ist, plan, C):
     lib = _lib.load()
     dev = feat.device
     B, N, D, H, W = plan.dims
-    n_int = plan.n_intervals
+    n_int = plan.interval_capacity()
     with torch.cuda.device(dev):
         depth_grad = torch.empty_like(depth)
         feat_grad = torch.empty_like(feat)

@@ -52,6 +52,13 @@ class LSSViewTransformer(nn.Module):
         self.initial_flag = True
         self.collapse_z = collapse_z
         self.sync_free = sync_free
+        # Optional callable (not in the reference), invoked on the host right after the
+        # index-preparation kernels of a call have been queued and before the pooling
+        # kernels.  A pipelined caller uses it to release its bulk host<->device copies
+        # there: the dozen short launches before this point are latency-bound and measurably
+        # slower while PCIe is saturated (command fetch shares the link), the long pooling
+        # kernels after it are not (bench.py, tools/e2e_timeline.py).
+        self.prepared_hook = None
 
     # -- a1 ------------------------------------------------------------------
     def create_grid_infos(self, x, y, z, **kwargs):
@@ -150,6 +157,9 @@ class LSSViewTransformer(nn.Module):
         # boolean-mask indexing) overlaps the forward kernel instead of draining
         # the GPU; it only decides about the reference's empty-input result.
         prep = _bp.prepare_ranks(coor, self.grid_lower_bound, self.grid_interval, self.grid_size)
+        prep.plan.sync_free = self.sync_free   # the backward then sizes its scratch by a bound
+        if self.prepared_hook is not None:
+            self.prepared_hook()               # see __init__: lets a caller time its transfers
         bev_feat = _bp.pool_prepared(depth, feat_last, prep, shape)
         if not self.sync_free and prep.plan.n_intervals == 0:
             return self._no_points_dummy(feat)
