@@ -24,6 +24,37 @@ extern "C" void veon_count_launch(void);
 
 namespace veon {
 
+// ---- programmatic dependent launch --------------------------------------------------
+// Chains of short kernels (the index preparation is seven of them) lose ~4-6 us per link
+// to launch latency.  A kernel launched with launch_pdl() may be scheduled as soon as every
+// CTA of its predecessor has executed pdl_launch_dependents(); it must call pdl_wait()
+// before touching anything the predecessor (or, transitively, anything earlier in the
+// stream) produced.  Both are no-ops for a normally launched grid.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+// every kernel of a chain starts with this
+__device__ __forceinline__ void pdl_prologue() {
+  pdl_wait();
+  pdl_launch_dependents();
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 constexpr int kTileVoxels = 32;  // one warp-wide x-run of the output volume
 
 // A tile holding at least this many points is "heavy": one warp would serialise

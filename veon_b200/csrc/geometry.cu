@@ -41,6 +41,7 @@ __global__ void k_cam_xforms(const float* __restrict__ sensor2ego,
                              const float* __restrict__ post_trans,
                              const float* __restrict__ bda, int B, int N,
                              CamXform* __restrict__ out) {
+  pdl_launch_dependents();  // k_lidar_coor may be scheduled behind this grid (common.cuh)
   const int bn = blockIdx.x * blockDim.x + threadIdx.x;
   if (bn >= B * N) return;
   double pr[9], k[9], ipr[9], ik[9];
@@ -71,6 +72,7 @@ __device__ __forceinline__ float dot3(const float* m, float x, float y, float z)
 __global__ void __launch_bounds__(256)
 k_lidar_coor(const float* __restrict__ frustum, const CamXform* __restrict__ xf, int64_t DHW,
              int64_t total, float* __restrict__ coor) {
+  pdl_wait();
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= total) return;
   const int64_t bn = p / DHW, f = p - bn * DHW;
@@ -114,7 +116,8 @@ extern "C" int veon_lidar_coor(const float* frustum, const float* sensor2ego,
                                                      bda, B, N, xf);
   VEON_LAUNCH_CHECK();
   const int64_t DHW = (int64_t)D * H * W, total = DHW * B * N;
-  k_lidar_coor<<<(unsigned)ceil_div64(total, 256), 256, 0, stream>>>(frustum, xf, DHW, total, coor);
+  VEON_CUDA_TRY(launch_pdl(k_lidar_coor, dim3((unsigned)ceil_div64(total, 256)), dim3(256), 0, stream,
+                           frustum, (const CamXform*)xf, DHW, total, coor));
   VEON_LAUNCH_CHECK();
   return 0;
 }

@@ -136,6 +136,7 @@ __global__ void __launch_bounds__(256)
 k_classify(const float* __restrict__ coor, int64_t P, int64_t pts_per_sample, GridF g,
            int64_t nbins, int32_t* __restrict__ key, int32_t* __restrict__ slot,
            int32_t* __restrict__ count) {
+  pdl_prologue();
   int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P) return;
   const float* c = coor + 3 * p;
@@ -188,6 +189,7 @@ k_scan(const int32_t* __restrict__ count, int32_t* __restrict__ offset,
        int64_t* counts_mirror, int num_tiles,
        int32_t* __restrict__ tile_start, int32_t* __restrict__ tile_istart,
        uint32_t* __restrict__ tile_occ, int64_t n_pool_tiles) {
+  pdl_prologue();
   __shared__ uint32_t s_tile;
   __shared__ unsigned long long s_warp[kScanThreads / 32];
   __shared__ unsigned long long s_excl;
@@ -309,6 +311,7 @@ __global__ void k_tiles(const int32_t* __restrict__ count, const int32_t* __rest
                         const int32_t* __restrict__ iidx, int64_t n_tiles,
                         int64_t tiles_per_sample, int64_t V, int32_t* __restrict__ tile_start,
                         int32_t* __restrict__ tile_istart, uint32_t* __restrict__ tile_occ) {
+  pdl_prologue();
   int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t > n_tiles) return;
   int64_t b = t / tiles_per_sample, vt = t % tiles_per_sample;
@@ -335,6 +338,7 @@ struct FillJobs {
   FillJob j[3];
 };
 __global__ void __launch_bounds__(256) k_fill(FillJobs jobs) {
+  pdl_launch_dependents();
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
 #pragma unroll
@@ -371,6 +375,7 @@ static int launch_fill(const FillJobs& jobs, cudaStream_t stream) {
 // heavy[2..] = tile ids in arbitrary order (the order only affects scheduling)
 __global__ void k_heavy_list(const int32_t* __restrict__ tile_start, int64_t n_tiles, int thr,
                              int cap, int32_t* __restrict__ heavy) {
+  pdl_prologue();
   const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (t == 0) heavy[1] = thr;
   if (t >= n_tiles) return;
@@ -383,8 +388,9 @@ __global__ void k_heavy_list(const int32_t* __restrict__ tile_start, int64_t n_t
 static int build_heavy_list(const int32_t* tile_start, int64_t n_tiles, int64_t n_points_cap,
                             int32_t* heavy, cudaStream_t stream) {
   // heavy[0] was cleared by the caller's k_fill
-  k_heavy_list<<<(unsigned)ceil_div64(n_tiles, 256), 256, 0, stream>>>(
-      tile_start, n_tiles, heavy_threshold(), (int)heavy_capacity(n_points_cap, n_tiles), heavy);
+  VEON_CUDA_TRY(launch_pdl(k_heavy_list, dim3((unsigned)ceil_div64(n_tiles, 256)), dim3(256), 0, stream,
+                           tile_start, n_tiles, heavy_threshold(),
+                           (int)heavy_capacity(n_points_cap, n_tiles), heavy));
   VEON_LAUNCH_CHECK();
   return 0;
 }
@@ -394,6 +400,7 @@ __global__ void __launch_bounds__(256)
 k_scatter(const int32_t* __restrict__ key, const int32_t* __restrict__ slot,
           const int32_t* __restrict__ offset, int64_t P, int32_t* __restrict__ tmp,
           int32_t* __restrict__ ranks_bev) {
+  pdl_prologue();
   int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P) return;
   int32_t k = key[p];
@@ -423,6 +430,7 @@ k_rank(const int32_t* __restrict__ tmp, const int32_t* __restrict__ ranks_bev,
        const int64_t* __restrict__ counts, PointDims dims,
        int32_t* __restrict__ ranks_depth, int32_t* __restrict__ ranks_feat,
        int32_t* __restrict__ point_interval) {
+  pdl_prologue();
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= counts[0]) return;
   const int32_t v = ranks_bev[i];
@@ -447,6 +455,7 @@ k_sort_long(int32_t* tmp, const int32_t* __restrict__ offset, const int32_t* __r
             const int32_t* __restrict__ long_list, const uint32_t* __restrict__ ctrl,
             int long_cap, PointDims dims, int32_t* __restrict__ ranks_depth,
             int32_t* __restrict__ ranks_feat, int32_t* __restrict__ point_interval) {
+  pdl_prologue();
   uint32_t n_long = ctrl[1];
   if ((int)n_long > long_cap) n_long = long_cap;
   for (uint32_t q = blockIdx.x; q < n_long; q += gridDim.x) {
@@ -649,35 +658,39 @@ extern "C" int veon_prepare_v2(const float* coor, int B, int N, int D, int H, in
 
   const int64_t pts_per_sample = (int64_t)N * D * H * W;
   const unsigned pblocks = (unsigned)ceil_div64(P, 256);
-  k_classify<<<pblocks, 256, 0, stream>>>(coor, P, pts_per_sample, g, nbins, w.key, w.slot,
-                                          w.count);
+  // from here on every kernel is a programmatic dependent of the one before (common.cuh)
+  VEON_CUDA_TRY(launch_pdl(k_classify, dim3(pblocks), dim3(256), 0, stream, coor, P,
+                           pts_per_sample, g, nbins, w.key, w.slot, w.count));
   VEON_LAUNCH_CHECK();
   const bool want_tiles = tile_start && tile_istart && tile_occ;
   const int64_t tps = ceil_div64(V, kTileVoxels), n_tiles = (int64_t)B * tps;
   const bool fused_tiles = want_tiles && (V % kTileVoxels == 0);
-  k_scan<<<(unsigned)w.scan_tiles, kScanThreads, 0, stream>>>(
-      w.count, w.offset, w.iidx, interval_starts, interval_lengths, w.desc, w.ctrl,
-      w.long_list, (int)w.long_cap, counts, counts_host, (int)w.scan_tiles,
-      fused_tiles ? tile_start : nullptr, tile_istart, tile_occ, n_tiles);
+  VEON_CUDA_TRY(launch_pdl(k_scan, dim3((unsigned)w.scan_tiles), dim3(kScanThreads), 0, stream,
+                           w.count, w.offset, w.iidx, interval_starts, interval_lengths, w.desc,
+                           w.ctrl, w.long_list, (int)w.long_cap, counts, counts_host,
+                           (int)w.scan_tiles, fused_tiles ? tile_start : nullptr, tile_istart,
+                           tile_occ, n_tiles));
   VEON_LAUNCH_CHECK();
   if (want_tiles && !fused_tiles) {
-    k_tiles<<<(unsigned)ceil_div64(n_tiles + 1, 256), 256, 0, stream>>>(
-        w.count, w.offset, w.iidx, n_tiles, tps, V, tile_start, tile_istart, tile_occ);
+    VEON_CUDA_TRY(launch_pdl(k_tiles, dim3((unsigned)ceil_div64(n_tiles + 1, 256)), dim3(256), 0,
+                             stream, w.count, w.offset, w.iidx, n_tiles, tps, V, tile_start,
+                             tile_istart, tile_occ));
     VEON_LAUNCH_CHECK();
   }
   if (want_tiles && tile_heavy) {
     rc = build_heavy_list(tile_start, n_tiles, P, tile_heavy, stream);
     if (rc) return rc;
   }
-  k_scatter<<<pblocks, 256, 0, stream>>>(w.key, w.slot, w.offset, P, w.tmp, ranks_bev);
+  VEON_CUDA_TRY(launch_pdl(k_scatter, dim3(pblocks), dim3(256), 0, stream, w.key, w.slot, w.offset,
+                           P, w.tmp, ranks_bev));
   VEON_LAUNCH_CHECK();
   PointDims dims{D, H * W, D * H * W};
-  k_rank<<<pblocks, 256, 0, stream>>>(w.tmp, ranks_bev, w.offset, w.iidx, counts, dims,
-                                      ranks_depth, ranks_feat, point_interval);
+  VEON_CUDA_TRY(launch_pdl(k_rank, dim3(pblocks), dim3(256), 0, stream, w.tmp, ranks_bev, w.offset,
+                           w.iidx, counts, dims, ranks_depth, ranks_feat, point_interval));
   VEON_LAUNCH_CHECK();
-  k_sort_long<<<64, 1024, 0, stream>>>(w.tmp, w.offset, w.iidx, w.long_list, w.ctrl,
-                                       (int)w.long_cap, dims, ranks_depth, ranks_feat,
-                                       point_interval);
+  VEON_CUDA_TRY(launch_pdl(k_sort_long, dim3(64), dim3(1024), 0, stream, w.tmp, w.offset, w.iidx,
+                           w.long_list, w.ctrl, (int)w.long_cap, dims, ranks_depth, ranks_feat,
+                           point_interval));
   VEON_LAUNCH_CHECK();
   return 0;
 }
