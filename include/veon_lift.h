@@ -181,6 +181,12 @@ int veon_pool_plan_build(const int32_t* ranks_depth, const int32_t* ranks_feat,
                          int32_t* tile_heavy /* sized for n_points; may be NULL */,
                          int32_t* point_interval, int32_t* flags, void* stream);
 
+/* Batched transpose [batch][R][S] -> [batch][S][R] (float32, contiguous).  Replaces the
+ * `feat.permute(0,1,3,4,2)` + `.contiguous()` copy (view_transformer.py:279, bev_pool.py:88)
+ * on the way in and its inverse on feat_grad on the way out. */
+int veon_transpose_batched(const float* src, int64_t batch, int R, int S, float* dst,
+                           void* stream);
+
 /* ------------------------------------------------------------------------
  * (3) Fast pooling path: bev_pool_v2() INCLUDING its transpose
  *     (bev_pool.py:86-92 = QuickCumsumCuda.forward :17-41 + permute :91).

@@ -34,6 +34,7 @@ _SIGNATURES = {
     "veon_lidar_coor_workspace_bytes": (c_size_t, [c_int, c_int]),
     "veon_lidar_coor": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P, _P,
                                 c_size_t, _P]),
+    "veon_transpose_batched": (c_int, [_P, c_int64, c_int, c_int, _P, _P]),
     "veon_prepare_v2_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int, _P]),
     "veon_pool_num_tiles": (c_int64, [c_int, c_int64]),
     "veon_pool_heavy_list_ints": (c_int64, [c_int64, c_int64]),

@@ -337,6 +337,17 @@ def voxel_pooling_prepare_v2(coor, grid_lower_bound, grid_interval, grid_size):
 
 
 # ------------------------------------------------------------------ pooling
+def _transpose_batched(src, batch, R, S, out_shape):
+    """[batch][R][S] -> [batch][S][R] of a contiguous float32 tensor, returned as `out_shape`."""
+    lib = _lib.load()
+    dev = src.device
+    with torch.cuda.device(dev):
+        dst = torch.empty(out_shape, dtype=torch.float32, device=dev)
+        rc = lib.veon_transpose_batched(_ptr(src), batch, R, S, _ptr(dst), _stream_ptr(dev))
+    _lib.check(rc, "veon_transpose_batched")
+    return dst
+
+
 def _fwd_planar(depth, feat, rd, rf, rb, plan, B, C, V, shape5):
     lib = _lib.load()
     dev = feat.device
@@ -389,7 +400,16 @@ class QuickCumsumCuda(torch.autograd.Function):
             raise ValueError("depth must be [B,N,D,H,W] and feat [B,N,H,W,C]")
         ranks_bev = ranks_bev.int().contiguous()
         depth = depth.contiguous().float()
-        feat = feat.contiguous().float()
+        # the neck hands over a channels-last VIEW of channels-first maps: transpose it
+        # with our own kernel (and feat_grad back the same way) instead of a strided copy
+        ctx.feat_channels_first = (feat.dtype == torch.float32 and not feat.is_contiguous()
+                                   and feat.permute(0, 1, 4, 2, 3).is_contiguous())
+        if ctx.feat_channels_first:
+            feat = _transpose_batched(feat.permute(0, 1, 4, 2, 3), feat.shape[0] * feat.shape[1],
+                                      feat.shape[4], feat.shape[2] * feat.shape[3],
+                                      tuple(feat.shape))
+        else:
+            feat = feat.contiguous().float()
         ranks_depth = ranks_depth.contiguous().int()
         ranks_feat = ranks_feat.contiguous().int()
         interval_lengths = interval_lengths.contiguous().int()
@@ -441,6 +461,10 @@ class QuickCumsumCuda(torch.autograd.Function):
                     _ptr(feat), _ptr(ranks_depth), _ptr(ranks_feat), _ptr(ranks_bev),
                     _ptr(depth_grad), _ptr(feat_grad), _stream_ptr(feat.device))
             _lib.check(rc, "veon_bev_pool_v2_grad_generic")
+        if ctx.feat_channels_first:
+            Bf, Nf, Hf, Wf, Cf = feat_grad.shape
+            feat_grad = _transpose_batched(feat_grad, Bf * Nf, Hf * Wf, Cf,
+                                           (Bf, Nf, Cf, Hf, Wf)).permute(0, 1, 3, 4, 2)
         return (depth_grad, feat_grad, None, None, None, None, None, None) + (None,) * ctx.n_extra
 
 

@@ -93,6 +93,32 @@ k_lidar_coor(const float* __restrict__ frustum, const CamXform* __restrict__ xf,
   o[2] = dot3(x.bda + 6, ex, ey, ez);
 }
 
+
+// ---------------------------------------------------------------- layout change
+// feat arrives as [B*N, C, H*W] (the network's channels-first maps,
+// view_transformer.py:279-285 views + permutes it) and the pooling kernels gather
+// channel-contiguous rows; the reference lets `.contiguous()` do the copy
+// (bev_pool.py:88).  Batched tiled transpose [batch][R][S] -> [batch][S][R], used in
+// both directions (feat forward, feat_grad backward).
+__global__ void __launch_bounds__(256)
+k_transpose(const float* __restrict__ src, int R, int S, float* __restrict__ dst) {
+  __shared__ float t[32][33];
+  const int64_t base = (int64_t)blockIdx.z * R * S;
+  const int s0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = r0 + ty + 8 * i, c = s0 + tx;
+    if (r < R && c < S) t[ty + 8 * i][tx] = __ldg(src + base + (int64_t)r * S + c);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int c = s0 + ty + 8 * i, r = r0 + tx;
+    if (r < R && c < S) dst[base + (int64_t)c * R + r] = t[tx][ty + 8 * i];
+  }
+}
+
 }  // namespace veon
 
 using namespace veon;
@@ -118,6 +144,17 @@ extern "C" int veon_lidar_coor(const float* frustum, const float* sensor2ego,
   const int64_t DHW = (int64_t)D * H * W, total = DHW * B * N;
   VEON_CUDA_TRY(launch_pdl(k_lidar_coor, dim3((unsigned)ceil_div64(total, 256)), dim3(256), 0, stream,
                            frustum, (const CamXform*)xf, DHW, total, coor));
+  VEON_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int veon_transpose_batched(const float* src, int64_t batch, int R, int S, float* dst,
+                                      void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!src || !dst || batch <= 0 || R <= 0 || S <= 0) return VEON_E_BADARG;
+  if (batch > 65535) return VEON_E_RANGE;
+  const dim3 grid((unsigned)((S + 31) / 32), (unsigned)((R + 31) / 32), (unsigned)batch);
+  k_transpose<<<grid, 256, 0, stream>>>(src, R, S, dst);
   VEON_LAUNCH_CHECK();
   return 0;
 }
