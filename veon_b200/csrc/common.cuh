@@ -62,7 +62,7 @@ constexpr int kTileVoxels = 32;  // one warp-wide x-run of the output volume
 // and the forward hands each of them to a whole CTA (pool_fwd.cu).  The list
 // capacity assumes the threshold never goes below kHeavyMinThreshold.
 constexpr int kHeavyMinThreshold = 32;
-constexpr int kHeavyDefaultThreshold = 128;
+constexpr int kHeavyDefaultThreshold = 96;
 inline int heavy_threshold() {
   static int v = 0;
   if (v == 0) {

@@ -94,6 +94,7 @@ k_pool_fwd(const float* __restrict__ depth, const float* __restrict__ feat,
   constexpr int kTileFloats = CC * kRowPitch;
   constexpr int kWarpFloats = kTileFloats + kRingSlots * kSlotInts;
   extern __shared__ __align__(16) float smem[];
+  pdl_launch_dependents();  // the heavy-tile grid may be queued behind this one
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* tile = smem + warp * kWarpFloats;
   int32_t* ring = reinterpret_cast<int32_t*>(tile + kTileFloats);
@@ -356,9 +357,9 @@ k_pool_fwd_heavy(const float* __restrict__ depth, const float* __restrict__ feat
   uint32_t* off = reinterpret_cast<uint32_t*>(dep + kHeavyChunk);  // [kHeavyChunk]
   int32_t* bounds = reinterpret_cast<int32_t*>(off + kHeavyChunk); // [2][start 32 | end 32]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // let the main kernel (launched with programmatic stream serialization) start now:
-  // it writes a disjoint set of tiles, and this grid is small enough to share the SMs
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  // no griddepcontrol.wait: this grid and k_pool_fwd write disjoint tiles and read only
+  // what earlier, normally launched work produced (see launch_fwd_impl)
+  pdl_launch_dependents();
   const uint32_t n_heavy = (uint32_t)min(__ldg(heavy), heavy_cap);
   const uint32_t n_work = n_heavy * n_chunks;
 
@@ -518,6 +519,7 @@ static int launch_fwd_impl(const float* depth, const float* feat, const int32_t*
   if (blocks > resident) blocks = resident;
   // the heavy-tile kernel stages feature rows with 16-byte copies
   if (heavy && ((C & 3) != 0 || ((uintptr_t)feat & 15) != 0)) heavy = nullptr;
+  const int dbg = env_flag("VEON_FWD_DBG", 0);
   if (heavy) {
     const size_t hsmem = sizeof(float) * (kHeavyChunk * CC + CC * kRowPitch + 2 * kHeavyChunk + 128);
     static int heavy_ctas_per_sm = 0;
@@ -529,41 +531,42 @@ static int launch_fwd_impl(const float* depth, const float* feat, const int32_t*
       if (heavy_ctas_per_sm < 1) heavy_ctas_per_sm = 1;
     }
     const int heavy_cap = (int)(heavy_ints - 2);
-    // a short-lived grid (a few tiles per CTA): the main kernel's persistent CTAs move in
-    // beside and behind it (measured: 2..5 CTAs/SM within noise, see profiles/README.md)
-    const int per_sm = min(heavy_ctas_per_sm, max(1, env_flag("VEON_FWD_HEAVY_CTAS", 4)));
+    const int per_sm = min(heavy_ctas_per_sm, max(1, env_flag("VEON_FWD_HEAVY_CTAS", 8)));
     int64_t hblocks = (int64_t)heavy_cap * n_chunks;
     if (hblocks > (int64_t)per_sm * sm_count()) hblocks = (int64_t)per_sm * sm_count();
     if (hblocks > 0) {
+      // The two grids write disjoint tiles and neither waits for the other: the second is a
+      // programmatic dependent of the first (both trigger at their first instruction), so
+      // its CTAs are scheduled as soon as SM resources free up instead of after the drain.
+      // Heavy-tile CTAs last: they fill the SMs as the persistent CTAs of the main grid
+      // finish one by one (VEON_FWD_ORDER=0 runs them first instead).
+      if (env_flag("VEON_FWD_ORDER", 1) == 1) {
+        k_pool_fwd<KCH, FULLC><<<(unsigned)blocks, kFwdWarps * 32, smem, stream>>>(
+            depth, feat, rd, rf, rb, tile_start, heavy, (uint32_t)(n_tiles * n_chunks),
+            (uint32_t)tps, V, C, (uint32_t)n_chunks, vec_ok, out, dbg);
+        VEON_LAUNCH_CHECK();
+        VEON_CUDA_TRY(launch_pdl(k_pool_fwd_heavy<KCH>, dim3((unsigned)hblocks), dim3(kHeavyThreads),
+                                 hsmem, stream, depth, feat, rd, rf, rb, tile_start, heavy,
+                                 heavy_cap, (uint32_t)tps, V, C, (uint32_t)n_chunks, vec_ok, out));
+        VEON_LAUNCH_CHECK();
+        return 0;
+      }
       k_pool_fwd_heavy<KCH><<<(unsigned)hblocks, kHeavyThreads, hsmem, stream>>>(
           depth, feat, rd, rf, rb, tile_start, heavy, heavy_cap, (uint32_t)tps, V, C,
           (uint32_t)n_chunks, vec_ok, out);
       VEON_LAUNCH_CHECK();
-    } else {
-      heavy = nullptr;
+      VEON_CUDA_TRY(launch_pdl(k_pool_fwd<KCH, FULLC>, dim3((unsigned)blocks), dim3(kFwdWarps * 32),
+                               smem, stream, depth, feat, rd, rf, rb, tile_start, heavy,
+                               (uint32_t)(n_tiles * n_chunks), (uint32_t)tps, V, C,
+                               (uint32_t)n_chunks, vec_ok, out, dbg));
+      VEON_LAUNCH_CHECK();
+      return 0;
     }
-  }
-  if (heavy && env_flag("VEON_FWD_PDL", 1)) {
-    // programmatic dependent launch: start as soon as every heavy-tile CTA is running
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)blocks);
-    cfg.blockDim = dim3(kFwdWarps * 32);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    VEON_CUDA_TRY(cudaLaunchKernelEx(&cfg, k_pool_fwd<KCH, FULLC>, depth, feat, rd, rf, rb, tile_start,
-                                     heavy, (uint32_t)(n_tiles * n_chunks), (uint32_t)tps, V, C,
-                                     (uint32_t)n_chunks, vec_ok, out, env_flag("VEON_FWD_DBG", 0)));
-    VEON_LAUNCH_CHECK();
-    return 0;
+    heavy = nullptr;
   }
   k_pool_fwd<KCH, FULLC><<<(unsigned)blocks, kFwdWarps * 32, smem, stream>>>(
       depth, feat, rd, rf, rb, tile_start, heavy, (uint32_t)(n_tiles * n_chunks), (uint32_t)tps,
-      V, C, (uint32_t)n_chunks, vec_ok, out, env_flag("VEON_FWD_DBG", 0));
+      V, C, (uint32_t)n_chunks, vec_ok, out, dbg);
   VEON_LAUNCH_CHECK();
   return 0;
 }
