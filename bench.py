@@ -450,7 +450,7 @@ def run_ours(args):
                 "what": "pinned host calibration+depth+feat -> LSSViewTransformer.view_transform "
                         "(get_lidar_coor + prepare_v2 + bev_pool_v2) -> backward -> depth_grad + "
                         "feat_grad to pinned host; copies on side streams, double-buffered"},
-        "roofline": {"bound": "hbm", "kernel": "k_pool_fwd (veon_bev_pool_v2_fwd_planar)",
+        "roofline": {"bound": "hbm", "kernel": "k_pool_fwd + k_pool_fwd_heavy (one veon_bev_pool_v2_fwd_planar call; the heavy-tile grid runs in the tail of the main grid)",
                      "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                      "frac": (achieved / peak_gbs) if achieved else None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg["pool_fwd"],
