@@ -476,6 +476,249 @@ k_pool_fwd_heavy(const float* __restrict__ depth, const float* __restrict__ feat
   }
 }
 
+
+// ---- tile-group kernel (experimental: VEON_FWD_GROUP=1) -------------------------------
+// A CTA takes 8 consecutive tiles (256 voxels = one aligned 1 KB run of every channel plane)
+// at a time: the index records of the group's points are prefetched one group ahead in
+// registers (thread per point), ALL their feature rows are gathered by 16-byte cp.async into
+// shared memory at once, warp w then runs the rank-ordered fma chains of tile w's voxels out
+// of shared memory into a [c][260] staging tile, and the whole CTA writes the 64 x 1 KB rows
+// together.  Compared with the warp-per-tile kernel: no per-point address arithmetic in the
+// gather, no exposed row-load latency per 16 points, and the store stream leaves the SM in
+// aligned 1 KB runs.  Heavy tiles are skipped exactly as in k_pool_fwd.
+#ifndef VEON_GROUP_ROUND
+#define VEON_GROUP_ROUND 64
+#endif
+#ifndef VEON_GROUP_TILES
+#define VEON_GROUP_TILES 4
+#endif
+constexpr int kGroupTiles = VEON_GROUP_TILES;    // 4 or 8: one warp per tile
+constexpr int kGroupVoxels = kGroupTiles * kTileVoxels;
+constexpr int kGroupThreads = 32 * kGroupTiles;
+constexpr int kGroupRound = VEON_GROUP_ROUND;    // points staged per round (thread per point)
+constexpr int kStagePitch = kGroupVoxels + 4;    // floats; rows stay 16-byte aligned
+
+template <int KCH>
+__global__ void __launch_bounds__(kGroupThreads)
+k_pool_fwd_group(const float* __restrict__ depth, const float* __restrict__ feat,
+                 const int32_t* __restrict__ ranks_depth, const int32_t* __restrict__ ranks_feat,
+                 const int32_t* __restrict__ ranks_bev, const int32_t* __restrict__ tile_start,
+                 const int32_t* __restrict__ heavy, uint32_t n_items, uint32_t n_chunks,
+                 uint32_t groups_per_sample, int64_t V, int C, float* __restrict__ out) {
+  constexpr int CC = 32 * KCH;
+  constexpr int kSegs = CC / 4;
+  extern __shared__ __align__(16) float gsm[];
+  float* rows = gsm;                                                 // [kGroupRound][CC]
+  float* stage = rows + kGroupRound * CC;                            // [CC][kStagePitch]
+  float* dep = stage + CC * kStagePitch;                             // [kGroupRound]
+  uint32_t* off = reinterpret_cast<uint32_t*>(dep + kGroupRound);    // [kGroupRound]
+  int32_t* bounds = reinterpret_cast<int32_t*>(off + kGroupRound);   // [2][start 256 | end 256]
+  int32_t* hdrs = bounds + 4 * kGroupVoxels;                         // [2][12]: tile_start[0..8]
+  pdl_launch_dependents();
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (blockIdx.x >= n_items) return;
+  const uint32_t my_items = (n_items - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  const int32_t heavy_thr = heavy ? __ldg(heavy + 1) : 0x7fffffff;
+
+  auto item_group = [&](uint32_t k, uint32_t& g, uint32_t& chunk) {
+    const uint32_t item = blockIdx.x + k * gridDim.x;
+    g = item / n_chunks;
+    chunk = item - g * n_chunks;
+  };
+  auto load_hdr = [&](uint32_t k) -> int32_t {   // thread j < 9: tile_start[8g + j] of item k
+    if (tid <= kGroupTiles && k < my_items) {
+      uint32_t g, chunk;
+      item_group(k, g, chunk);
+      return __ldg(tile_start + (int64_t)g * kGroupTiles + tid);
+    }
+    return 0;
+  };
+  // compacted position q of a group (heavy tiles left out) -> point index, index of the
+  // previous compacted point (-1 for q == 0); returns the group's number of points
+  auto locate = [&](const int32_t* hdr, int q, int32_t& i, int32_t& iprev) -> int {
+    int acc = 0;
+    int32_t last = -1;
+    i = -1;
+    iprev = -1;
+#pragma unroll
+    for (int j = 0; j < kGroupTiles; ++j) {
+      const int32_t s = hdr[j];
+      int n = hdr[j + 1] - s;
+      if (n >= heavy_thr) n = 0;
+      if (i < 0 && q < acc + n) {
+        i = s + (q - acc);
+        iprev = (q == acc) ? last : i - 1;
+      }
+      if (n > 0) last = s + n - 1;
+      acc += n;
+    }
+    return acc;
+  };
+  // index records of one point (thread tid < kGroupRound): stage A loads the ranks, stage B
+  // the depth value
+  struct Rec { int32_t rb, rp, rf, rd; float d; };
+  auto stage_a = [&](const int32_t* hdr, int q, Rec& r) {
+    r.rb = -1;
+    r.rp = -1;
+    if (tid < kGroupRound) {
+      int32_t i, ip;
+      locate(hdr, q, i, ip);
+      if (i >= 0) {
+        r.rb = __ldg(ranks_bev + i);
+        r.rf = __ldg(ranks_feat + i);
+        r.rd = __ldg(ranks_depth + i);
+        if (ip >= 0) r.rp = __ldg(ranks_bev + ip);
+      }
+    }
+  };
+  auto stage_b = [&](Rec& r) {
+    r.d = 0.f;
+    if (r.rb >= 0) r.d = __ldg(depth + r.rd);
+  };
+  // records -> shared memory + [start, end) of every voxel inside the round
+  auto publish = [&](const Rec& r, int cnt, int32_t g0, uint32_t chunk, int parity) {
+    int32_t* cstart = bounds + parity * 2 * kGroupVoxels;
+    int32_t* cend = cstart + kGroupVoxels;
+    if (r.rb >= 0) {
+      const int vox = r.rb - g0;
+      off[tid] = ((uint32_t)r.rf * (uint32_t)C + chunk * CC) * 4u;
+      dep[tid] = r.d;
+      const bool starts = (tid == 0) || (r.rb != r.rp);
+      if (starts) cstart[vox] = tid;
+      if (tid > 0 && r.rb != r.rp) cend[r.rp - g0] = tid;
+      if (tid == cnt - 1) cend[vox] = cnt;
+    }
+  };
+  auto gather_rows = [&](int cnt) {   // every feature row of the round in flight at once
+    const char* fbase = reinterpret_cast<const char*>(feat);
+#pragma unroll
+    for (int i = 0; i < kGroupRound * kSegs / kGroupThreads; ++i) {
+      const int idx = tid + kGroupThreads * i;
+      const int r = idx / kSegs, seg = (idx % kSegs) * 4;
+      if (r < cnt) cp_async16(rows + r * CC + seg, fbase + off[r] + seg * 4);
+    }
+    cp_async_commit();
+  };
+  auto accumulate = [&](int parity) {  // warp w: the voxels of tile w, lanes = channels
+    const int32_t* cstart = bounds + parity * 2 * kGroupVoxels;
+    const int32_t* cend = cstart + kGroupVoxels;
+    const int a_l = cstart[kTileVoxels * warp + lane], e_l = cend[kTileVoxels * warp + lane];
+    uint32_t m = __ballot_sync(0xffffffffu, e_l > a_l);
+    while (m) {
+      const int v = __ffs(m) - 1;
+      m &= m - 1;
+      const int a = __shfl_sync(0xffffffffu, a_l, v), e = __shfl_sync(0xffffffffu, e_l, v);
+      float* sp = stage + lane * kStagePitch + kTileVoxels * warp + v;
+      float acc[KCH];
+#pragma unroll
+      for (int c = 0; c < KCH; ++c) acc[c] = sp[32 * c * kStagePitch];
+#pragma unroll 4
+      for (int j = a; j < e; ++j) {
+        const float dj = dep[j];
+#pragma unroll
+        for (int c = 0; c < KCH; ++c) acc[c] = fmaf(rows[j * CC + lane + 32 * c], dj, acc[c]);
+      }
+#pragma unroll
+      for (int c = 0; c < KCH; ++c) sp[32 * c * kStagePitch] = acc[c];
+    }
+  };
+
+  // ---- prologue: headers of items 0 and 1, records of item 0
+  int32_t hreg = load_hdr(0);
+  if (tid <= kGroupTiles) hdrs[tid] = hreg;
+  hreg = load_hdr(1);
+  for (int i = tid; i < 4 * kGroupVoxels; i += kGroupThreads) bounds[i] = 0;
+  __syncthreads();
+  Rec nxt;
+  stage_a(hdrs, tid, nxt);
+  stage_b(nxt);
+  int parity = 0;
+
+  for (uint32_t k = 0; k < my_items; ++k) {
+    const int32_t* hdr = hdrs + (k & 1) * 12;
+    int32_t* hdr_next = hdrs + ((k + 1) & 1) * 12;
+    uint32_t g, chunk;
+    item_group(k, g, chunk);
+    const uint32_t b = g / groups_per_sample;
+    const int32_t g0 = (int32_t)(g * kGroupVoxels);     // global voxel index (V % 32 == 0)
+    const int cbase = (int)chunk * CC;
+    int32_t dummy_i, dummy_p;
+    const int total = locate(hdr, 0x7fffffff, dummy_i, dummy_p);
+    uint32_t heavy_mask = 0;                             // tiles left to k_pool_fwd_heavy
+#pragma unroll
+    for (int j = 0; j < kGroupTiles; ++j)
+      if (hdr[j + 1] - hdr[j] >= heavy_thr) heavy_mask |= 1u << j;
+
+    // T0: publish round 0 (prefetched), the next item's header; fetch the header after it
+    publish(nxt, min(total, kGroupRound), g0, chunk, parity);
+    if (tid <= kGroupTiles) hdr_next[tid] = hreg;
+    hreg = load_hdr(k + 2);
+    __syncthreads();
+
+    // T1: rows of round 0 in flight; meanwhile the next item's ranks, the staging tile
+    if (total > 0) gather_rows(min(total, kGroupRound));
+    Rec cur_next;
+    stage_a(hdr_next, tid, cur_next);                    // records of item k+1, round 0
+    if (total > 0) {
+      float4* s4 = reinterpret_cast<float4*>(stage);
+      for (int i = tid; i < CC * kStagePitch / 4; i += kGroupThreads)
+        s4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int i = tid; i < 2 * kGroupVoxels; i += kGroupThreads)
+      bounds[(parity ^ 1) * 2 * kGroupVoxels + i] = 0;
+    cp_async_wait_all();
+    __syncthreads();
+
+    // T2: fma chains; further rounds of a group with more than kGroupRound points are
+    // fetched synchronously.  The next item's depth values are requested first (their ranks
+    // have landed behind the row copies) and fly during the chains.
+    stage_b(cur_next);
+    if (total > 0) accumulate(parity);
+    parity ^= 1;
+    for (int base = kGroupRound; base < total; base += kGroupRound) {
+      const int cnt = min(kGroupRound, total - base);
+      Rec r;
+      stage_a(hdr, base + tid, r);
+      stage_b(r);
+      __syncthreads();                                   // previous round fully consumed
+      publish(r, cnt, g0, chunk, parity);
+      __syncthreads();
+      gather_rows(cnt);
+      for (int i = tid; i < 2 * kGroupVoxels; i += kGroupThreads)
+        bounds[(parity ^ 1) * 2 * kGroupVoxels + i] = 0;
+      cp_async_wait_all();
+      __syncthreads();
+      accumulate(parity);
+      parity ^= 1;
+    }
+    nxt = cur_next;
+    __syncthreads();
+
+    // T3: CC planes x (kGroupVoxels * 4) bytes; warp w takes planes w, w+W, ...; a lane's
+    // 16 bytes of half h lie in tile 4 h + lane / 8
+    {
+      constexpr int kHalves = kGroupVoxels / 128;
+      float* o = out + ((int64_t)b * C + cbase + warp) * V + (g0 - (int32_t)(b * (uint32_t)V)) +
+                 4 * lane;
+      const float* sp = stage + warp * kStagePitch + 4 * lane;
+      bool skip[kHalves];
+#pragma unroll
+      for (int h = 0; h < kHalves; ++h) skip[h] = (heavy_mask >> (4 * h + (lane >> 3))) & 1u;
+#pragma unroll 2
+      for (int c = warp; c < CC; c += kGroupThreads / 32, o += (int64_t)(kGroupThreads / 32) * V,
+               sp += (kGroupThreads / 32) * kStagePitch) {
+#pragma unroll
+        for (int h = 0; h < kHalves; ++h) {
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (total > 0) v = *reinterpret_cast<const float4*>(sp + 128 * h);
+          if (!skip[h]) st_stream4(o + 128 * h, v);
+        }
+      }
+    }
+    // (the staging tile is next written after two more barriers)
+  }
+}
+
 static int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -520,6 +763,48 @@ static int launch_fwd_impl(const float* depth, const float* feat, const int32_t*
   // the heavy-tile kernel stages feature rows with 16-byte copies
   if (heavy && ((C & 3) != 0 || ((uintptr_t)feat & 15) != 0)) heavy = nullptr;
   const int dbg = env_flag("VEON_FWD_DBG", 0);
+  const bool group_ok = FULLC && vec_ok && (V % kTileVoxels) == 0 && (tps % kGroupTiles) == 0 &&
+                        (C & 3) == 0 && ((uintptr_t)feat & 15) == 0;
+  if (group_ok && env_flag("VEON_FWD_GROUP", 0)) {
+    const size_t gsmem = sizeof(float) * (kGroupRound * CC + CC * kStagePitch + 2 * kGroupRound +
+                                          4 * kGroupVoxels + 24);
+    static int group_ctas_per_sm = 0;
+    if (group_ctas_per_sm == 0) {
+      VEON_CUDA_TRY(cudaFuncSetAttribute(k_pool_fwd_group<KCH>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
+      VEON_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+          &group_ctas_per_sm, k_pool_fwd_group<KCH>, kGroupThreads, gsmem));
+      if (group_ctas_per_sm < 1) group_ctas_per_sm = 1;
+    }
+    const int64_t n_gitems = n_tiles / kGroupTiles * n_chunks;
+    int64_t gblocks = (int64_t)group_ctas_per_sm * sm_count();
+    if (gblocks > n_gitems) gblocks = n_gitems;
+    k_pool_fwd_group<KCH><<<(unsigned)gblocks, kGroupThreads, gsmem, stream>>>(
+        depth, feat, rd, rf, rb, tile_start, heavy, (uint32_t)n_gitems, (uint32_t)n_chunks,
+        (uint32_t)(tps / kGroupTiles), V, C, out);
+    VEON_LAUNCH_CHECK();
+    if (heavy) {
+      const size_t hsmem2 = sizeof(float) * (kHeavyChunk * CC + CC * kRowPitch + 2 * kHeavyChunk + 128);
+      static int hc = 0;
+      if (hc == 0) {
+        VEON_CUDA_TRY(cudaFuncSetAttribute(k_pool_fwd_heavy<KCH>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem2));
+        VEON_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&hc, k_pool_fwd_heavy<KCH>,
+                                                                    kHeavyThreads, hsmem2));
+        if (hc < 1) hc = 1;
+      }
+      const int heavy_cap = (int)(heavy_ints - 2);
+      int64_t hblocks = (int64_t)heavy_cap * n_chunks;
+      if (hblocks > (int64_t)hc * sm_count()) hblocks = (int64_t)hc * sm_count();
+      if (hblocks > 0) {
+        VEON_CUDA_TRY(launch_pdl(k_pool_fwd_heavy<KCH>, dim3((unsigned)hblocks), dim3(kHeavyThreads),
+                                 hsmem2, stream, depth, feat, rd, rf, rb, tile_start, heavy,
+                                 heavy_cap, (uint32_t)tps, V, C, (uint32_t)n_chunks, vec_ok, out));
+        VEON_LAUNCH_CHECK();
+      }
+    }
+    return 0;
+  }
   if (heavy) {
     const size_t hsmem = sizeof(float) * (kHeavyChunk * CC + CC * kRowPitch + 2 * kHeavyChunk + 128);
     static int heavy_ctas_per_sm = 0;
