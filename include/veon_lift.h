@@ -153,6 +153,11 @@ int veon_lidar_coor(const float* frustum, const float* sensor2ego, const float* 
 size_t veon_prepare_v2_workspace_bytes(int B, int N, int D, int H, int W,
                                        const float* grid_size /*[host]*/);
 int64_t veon_pool_num_tiles(int B, int64_t voxels_per_sample);
+/* Byte offset, inside the veon_prepare_v2 workspace, of `voxel_start`: int32[B*V + 1], first
+ * point of every voxel (an exclusive prefix of the per-voxel point counts, valid after the call
+ * for B*V < 2^24).  Consumed by veon_bev_pool_v2_ds_fwd.  (size_t)-1 on bad arguments. */
+size_t veon_prepare_v2_voxel_start_offset(int B, int N, int D, int H, int W,
+                                          const float* grid_size /*[host]*/);
 /* int32 elements a tile_heavy buffer needs for a plan over at most n_points points */
 int64_t veon_pool_heavy_list_ints(int64_t n_points, int64_t n_tiles);
 
@@ -203,6 +208,24 @@ int veon_bev_pool_v2_fwd_planar(const float* depth, const float* feat,
                                 int B, int C, int64_t voxels_per_sample,
                                 int64_t n_feat_rows /* B*N*H*W rows of feat */,
                                 float* out, void* stream);
+
+/* Pooling fused with the 2x2x2 max-downsample VEON's neck applies next
+ * (view_transformer_raw.py:549-553), forward only: out is [B, C, Z/2, Y/2, X/2], bit-identical
+ * to amax over the volume veon_bev_pool_v2_fwd_planar would write, which is never materialised.
+ * Needs even Z, Y, X, C % 64 == 0 and the `voxel_start` array of the prepare workspace. */
+int veon_bev_pool_v2_ds_fwd(const float* depth, const float* feat,
+                            const int32_t* ranks_depth, const int32_t* ranks_feat,
+                            const int32_t* ranks_bev, const int32_t* voxel_start,
+                            int B, int C, int Z, int Y, int X, int64_t n_feat_rows,
+                            float* out, void* stream);
+
+/* The neck's 2x2x2 max-downsample on its own (view_transformer_raw.py:549-553: an 8-D
+ * `.amax` in the reference) and its gradient (ATen's amax backward: grad * (in == out) /
+ * count(in == out)).  in / grad_in [BC,Z,Y,X], out / grad_out [BC,Z/2,Y/2,X/2], float32,
+ * contiguous; Z, Y even and X % 4 == 0, else VEON_E_UNSUPPORTED. */
+int veon_maxdown2_fwd(const float* in, int64_t BC, int Z, int Y, int X, float* out, void* stream);
+int veon_maxdown2_bwd(const float* in, const float* out, const float* grad_out,
+                      int64_t BC, int Z, int Y, int X, float* grad_in, void* stream);
 
 /* QuickCumsumCuda.backward (bev_pool.py:43-83) for a [B,C,Z,Y,X] out_grad.
  *   rows_ws      float[n_intervals * C] scratch (compacted gradient rows)

@@ -191,3 +191,82 @@ def test_reference_neck_runs_unchanged_on_our_operators():
     neck2.accelerate = True                                  # reference's cache path on our ranks
     got3, _ = neck2.view_transform([img.cuda()] + [m.cuda() for m in metas], depth.cuda(), feat.cuda())
     assert _t.equal(got3.unsqueeze(2) if got3.dim() == 4 else got3, got) or rel(got3.cpu().numpy().reshape(got.shape), got.cpu().numpy()) == 0.0
+
+
+@pytest.mark.parametrize("C", [64, 128])
+def test_raw_neck_fused_downsample_is_bit_identical(C):
+    """the no-grad Raw neck pools and max-reduces 2x2x2 in one kernel; the result
+    must equal pool (bit-exact forward) + amax exactly, and the gradient route must be untouched."""
+    from veon_b200.view_transformer import LSSViewTransformerRaw
+    cfg = S.CONFIGS["small"]
+    B = 2
+    neck = LSSViewTransformerRaw(cfg.grid_config, cfg.input_size, cfg.downsample, 8, C, fuse_ds=True)
+    img, metas, depth, feat = inputs(cfg, B, C, seed=4)
+    H, W = cfg.feat_hw
+    feat5 = feat.view(B, cfg.n_cams, C, H, W)
+    depth5 = depth.view(B, cfg.n_cams, cfg.D, H, W)
+    from veon_b200 import bev_pool as BP
+    BP.enable_kernel_timing(True)
+    with torch.no_grad():
+        fused = neck([feat5] + metas, depth5)
+    used = BP.kernel_timings_ms()
+    BP.enable_kernel_timing(False)
+    assert "pool_ds_fwd" in used and "pool_fwd" not in used      # the fused kernel really ran
+    assert fused.shape == (B, C, 8, 100, 100)
+    f = feat5.detach().clone().requires_grad_()                   # gradient wanted -> plain route
+    plain = neck([f] + metas, depth5)
+    assert torch.equal(fused, plain.detach())
+    plain.sum().backward()
+    assert f.grad is not None and torch.isfinite(f.grad).all()
+
+
+def test_maxdown2x2x2_matches_aten_amax_forward_and_backward():
+    """own 2x2x2 max-downsample kernels vs the reference's expression
+    (view_transformer_raw.py:549-553) incl. ATen's tie-sharing gradient"""
+    from veon_b200.bev_pool import MaxDown2x2x2
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(2, 5, 6, 10, 24, generator=g).cuda()
+    x[x.abs() < 0.6] = 0.0                      # plenty of ties at zero, like an occupancy volume
+    x[0, 0, 0, 0, 0] = float("nan")
+    assert MaxDown2x2x2.supports(x)
+    a = x.clone().requires_grad_()
+    b = x.clone().requires_grad_()
+    out = MaxDown2x2x2.apply(a)
+    B, C, Z, Y, X = x.shape
+    want = b.view(B, C, Z // 2, 2, Y // 2, 2, X // 2, 2).amax(dim=(3, 5, 7))
+    assert torch.equal(torch.nan_to_num(out, nan=-7.0), torch.nan_to_num(want, nan=-7.0))
+    go = torch.randn(out.shape, generator=g).cuda()
+    out.backward(go)
+    want.backward(go)
+    ok = ~torch.isnan(b.grad) & ~torch.isnan(a.grad)        # the NaN cell's block is undefined
+    assert ok.float().mean() > 0.99
+    assert torch.equal(a.grad[ok], b.grad[ok])
+
+
+def test_raw_neck_training_route_uses_own_downsample_and_matches_amax():
+    from veon_b200.view_transformer import LSSViewTransformerRaw
+    from veon_b200 import bev_pool as BP
+    cfg = S.CONFIGS["small"]
+    B, C = 1, 64
+    img, metas, depth, feat = inputs(cfg, B, C, seed=6)
+    H, W = cfg.feat_hw
+    feat5 = feat.view(B, cfg.n_cams, C, H, W)
+    depth5 = depth.view(B, cfg.n_cams, cfg.D, H, W)
+    neck = LSSViewTransformerRaw(cfg.grid_config, cfg.input_size, cfg.downsample, 8, C)
+    f1 = feat5.detach().clone().requires_grad_()
+    BP.enable_kernel_timing(True)
+    out = neck([f1] + metas, depth5)
+    go = torch.randn(out.shape, generator=torch.Generator().manual_seed(3)).cuda()
+    out.backward(go)
+    used = BP.kernel_timings_ms()
+    BP.enable_kernel_timing(False)
+    assert "maxdown_fwd" in used and "maxdown_bwd" in used
+    # the reference's expression on the same pooled volume
+    f2 = feat5.detach().clone().requires_grad_()
+    bev, _ = neck.view_transform([f2] + metas, depth5.reshape(B * cfg.n_cams, cfg.D, H, W),
+                                 f2.reshape(B * cfg.n_cams, C, H, W))
+    b, c, z, y, x = bev.shape
+    want = bev.view(b, c, z // 2, 2, y // 2, 2, x // 2, 2).amax(dim=(3, 5, 7))
+    want.backward(go)
+    assert torch.equal(out, want)
+    assert torch.equal(f1.grad, f2.grad)

@@ -105,7 +105,7 @@ def lidar_coor(frustum, sensor2ego, cam2imgs, post_rots, post_trans, bda):
 
 class PoolPlan:
     """By-products of the index preparation used by the planar kernels."""
-    __slots__ = ("__weakref__", "tile_start", "tile_istart", "tile_occ", "tile_heavy",
+    __slots__ = ("__weakref__", "tile_start", "tile_istart", "tile_occ", "tile_heavy", "voxel_start",
                  "point_interval", "dims", "V",
                  "flags", "_n_intervals", "_n_points", "counts_dev", "counts_host",
                  "counts_event", "keepalive", "sync_free")
@@ -117,6 +117,7 @@ class PoolPlan:
         self.counts_dev = self.counts_host = self.counts_event = None
         self.keepalive = None
         self.sync_free = False
+        self.voxel_start = None
 
     def _resolve(self):
         if self._n_intervals is None:
@@ -215,9 +216,10 @@ def prepare_ranks(coor, grid_lower_bound, grid_interval, grid_size):
         # (the grid objects are kept alive by the entry, so their ids stay unique)
         geo = (grid_size, grid_lower_bound, grid_interval, _lib.float3(lower),
                _lib.float3(interval), c_size, V, ws_bytes, n_tiles,
-               lib.veon_pool_heavy_list_ints(P, n_tiles))
+               lib.veon_pool_heavy_list_ints(P, n_tiles),
+               lib.veon_prepare_v2_voxel_start_offset(B, N, D, H, W, c_size))
         _GEOMETRY_CACHE[key] = geo
-    _, _, _, c_lower, c_interval, c_size, V, ws_bytes, n_tiles, nh = geo
+    _, _, _, c_lower, c_interval, c_size, V, ws_bytes, n_tiles, nh, vs_off = geo
     with torch.cuda.device(dev):
         # one allocation for every int32 output + the kernel workspace (fewer allocator
         # round-trips per call); the pieces below are views of it
@@ -252,6 +254,9 @@ def prepare_ranks(coor, grid_lower_bound, grid_interval, grid_size):
     plan = PoolPlan()
     plan.tile_start, plan.tile_istart, plan.tile_occ = tiles[0], tiles[1], tiles[2]
     plan.tile_heavy = heavy
+    # first point of every voxel: lives in the preparation workspace (kept alive by this view)
+    if B * V < (1 << 24) and vs_off % 4 == 0:
+        plan.voxel_start = ws[vs_off // 4: vs_off // 4 + B * V + 1]
     plan.point_interval = point_interval
     plan.dims = (B, N, D, H, W)
     plan.V = V
@@ -316,6 +321,77 @@ def _plan_for(rd, rf, rb, ist, iln, dims, V):
     plan._n_points, plan._n_intervals = rd.numel(), ist.numel()
     _remember_plan(key, plan, (rd, rf, rb, ist, iln))
     return plan
+
+
+def pool_prepared_downsampled(depth, feat, prep, bev_feat_shape):
+    """bev_pool_v2 fused with the neck's 2x2x2 max-downsample (view_transformer_raw.py:549-553),
+    forward only: returns [B, C, Z/2, Y/2, X/2] without materialising the full volume, or None
+    when the shape is outside what the fused kernel takes (the caller then pools and reduces).
+
+    depth [B,N,D,H,W]; feat [B,N,H,W,C] (a permuted view of channels-first maps is fine);
+    prep from `prepare_ranks` (its workspace holds the per-voxel point prefix)."""
+    B, Z, Y, X, C = (int(v) for v in bev_feat_shape)
+    vs = prep.plan.voxel_start
+    if vs is None or (Z | Y | X) & 1 or C % 64 != 0:
+        return None
+    _require_cuda(depth, feat)
+    lib = _lib.load()
+    dev = feat.device
+    depth = depth.detach().contiguous().float()
+    feat = feat.detach()
+    if (feat.dtype == torch.float32 and not feat.is_contiguous()
+            and feat.permute(0, 1, 4, 2, 3).is_contiguous()):
+        feat = _transpose_batched(feat.permute(0, 1, 4, 2, 3), feat.shape[0] * feat.shape[1],
+                                  feat.shape[4], feat.shape[2] * feat.shape[3], tuple(feat.shape))
+    else:
+        feat = feat.contiguous().float()
+    with torch.cuda.device(dev):
+        out = torch.empty((B, C, Z // 2, Y // 2, X // 2), dtype=torch.float32, device=dev)
+        with _timed("pool_ds_fwd", dev):
+            rc = lib.veon_bev_pool_v2_ds_fwd(
+                _ptr(depth), _ptr(feat), _ptr(prep.ranks_depth), _ptr(prep.ranks_feat),
+                _ptr(prep.ranks_bev), _ptr(vs), B, C, Z, Y, X, feat.numel() // C, _ptr(out),
+                _stream_ptr(dev))
+    if rc == -4:        # VEON_E_UNSUPPORTED: shape outside the fused kernel
+        return None
+    _lib.check(rc, "veon_bev_pool_v2_ds_fwd")
+    return out
+
+
+class MaxDown2x2x2(torch.autograd.Function):
+    """`x.view(b,c,z/2,2,y/2,2,x/2,2).amax(dim=(3,5,7))` (view_transformer_raw.py:549-553) and
+    ATen's amax gradient (ties share equally) as two streaming kernels."""
+
+    @staticmethod
+    def supports(x):
+        return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 5 and x.is_contiguous()
+                and x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0 and x.shape[4] % 4 == 0)
+
+    @staticmethod
+    def forward(ctx, x):
+        lib = _lib.load()
+        B, C, Z, Y, X = x.shape
+        with torch.cuda.device(x.device):
+            out = torch.empty((B, C, Z // 2, Y // 2, X // 2), dtype=torch.float32, device=x.device)
+            with _timed("maxdown_fwd", x.device):
+                rc = lib.veon_maxdown2_fwd(_ptr(x), B * C, Z, Y, X, _ptr(out), _stream_ptr(x.device))
+        _lib.check(rc, "veon_maxdown2_fwd")
+        ctx.save_for_backward(x, out)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x, out = ctx.saved_tensors
+        lib = _lib.load()
+        B, C, Z, Y, X = x.shape
+        g = grad_out.contiguous().float()
+        with torch.cuda.device(x.device):
+            grad_in = torch.empty_like(x)
+            with _timed("maxdown_bwd", x.device):
+                rc = lib.veon_maxdown2_bwd(_ptr(x), _ptr(out), _ptr(g), B * C, Z, Y, X,
+                                           _ptr(grad_in), _stream_ptr(x.device))
+        _lib.check(rc, "veon_maxdown2_bwd")
+        return grad_in
 
 
 def voxel_pooling_prepare_v2(coor, grid_lower_bound, grid_interval, grid_size):
