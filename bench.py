@@ -492,6 +492,31 @@ def run_ours(args):
                         "frac_of_hbm_peak": bytes_t / (ms_t * 1e-3) / 1e9 / peak_gbs,
                         "tf32_tflops_issued": 3 * 2.0 * Bt * 640000 * Ct * 32 / (ms_t * 1e-3) / 1e12}
         del feat_occ, bin_occ
+        # ---- secondary: the neck's 2x2x2 max-downsample of the pooled volume
+        vol = out_grad.detach().clone().requires_grad_()
+        go_ds = torch.randn(B, C, 8, 100, 100, device=dev, generator=gt)
+
+        def ev_ms(fn, n=10):
+            for _ in range(2):
+                fn()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(n):
+                fn()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / n
+        with torch.no_grad():
+            ms_df = ev_ms(lambda: BP.MaxDown2x2x2.apply(vol))
+        ms_dfb = ev_ms(lambda: torch.autograd.grad(BP.MaxDown2x2x2.apply(vol), vol, go_ds))
+        vb = 4.0 * vol.numel()
+        line["downsample"] = {
+            "what": "2x2x2 max-downsample of the [B,C,16,200,200] volume "
+                    "(view_transformer_raw.py:549-553) and ATen-exact gradient, own kernels",
+            "fwd_ms": ms_df, "fwd_gbs": 1.125 * vb / (ms_df * 1e-3) / 1e9,
+            "bwd_ms": ms_dfb - ms_df, "bwd_gbs": 2.25 * vb / ((ms_dfb - ms_df) * 1e-3) / 1e9,
+            "frac_of_hbm_peak_fwd": 1.125 * vb / (ms_df * 1e-3) / 1e9 / peak_gbs}
+        del vol, go_ds
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         c1 = S.CONFIGS["C1"] if args.workload == "C2" else cfg
         v, cores, desc, _, _ = time_cpu_port(c1, args.cpu_seconds)
