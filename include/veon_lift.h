@@ -219,6 +219,15 @@ int veon_bev_pool_v2_ds_fwd(const float* depth, const float* feat,
                             int B, int C, int Z, int Y, int X, int64_t n_feat_rows,
                             float* out, void* stream);
 
+/* Depth-distribution producer in front of the path: LSSViewTransformerRaw.downsample_depth +
+ * get_two_hot_depth (view_transformer_raw.py:393-429).  depths [BN, H_out*s, W_out*s] metric
+ * depth (0 = no measurement), s = downsample (<= 1: none); out [BN, D, H_out, W_out]:
+ * softmax over the D+1 bin centres of max(-|d - c_k| * gamma, -16) with the last bin dropped.
+ * Forward only. */
+int veon_two_hot_depth(const float* depths, int64_t BN, int H_out, int W_out, int downsample,
+                       int D, float depth_lo, float depth_step, float gamma, float* out,
+                       void* stream);
+
 /* The neck's 2x2x2 max-downsample on its own (view_transformer_raw.py:549-553: an 8-D
  * `.amax` in the reference) and its gradient (ATen's amax backward: grad * (in == out) /
  * count(in == out)).  in / grad_in [BC,Z,Y,X], out / grad_out [BC,Z/2,Y/2,X/2], float32,

@@ -265,3 +265,34 @@ def torch_cpu_lift(coor, depth, feat, grid_lower_bound, grid_interval, grid_size
         return bev, None, None
     bev.backward(out_grad)
     return bev.detach(), depth.grad, feat.grad
+
+
+# ---------------------------------------------------------------- depth producer (8f-2)
+def downsample_depth(depths, downsample):
+    """LSSViewTransformerRaw.downsample_depth (view_transformer_raw.py:393-404): minimum over
+    every downsample x downsample block, a zero (= no measurement) counting as 1e5."""
+    d = np.asarray(depths, dtype=_f32)
+    B, N, H, W = d.shape
+    s = int(downsample)
+    blk = d.reshape(B, N, H // s, s, W // s, s)
+    blk = np.where(blk == 0.0, _f32(1e5), blk)
+    return blk.min(axis=(3, 5)).astype(_f32)
+
+
+def two_hot_depth(depths, depth_cfg, gamma=4, downsample=0):
+    """LSSViewTransformerRaw.get_two_hot_depth (view_transformer_raw.py:406-429):
+    softmax over D+1 bin centres of -|depth - centre| * gamma clamped at -16, last bin dropped;
+    returns [B,N,D,H,W] float32.  `downsample` > 0 applies downsample_depth first (:413-414)."""
+    d = np.asarray(depths, dtype=_f32)
+    if downsample:
+        d = downsample_depth(d, downsample)
+    lo, hi, st = (float(v) for v in depth_cfg)
+    D = int(np.arange(lo, hi, st, dtype=np.float32).shape[0])
+    # torch.arange(D+1) * step + (lo + step/2): int64 * python float -> float32 tensor
+    centers = np.arange(D + 1).astype(_f32) * _f32(st) + _f32(lo + st / 2)
+    gap = -np.abs(d[..., None] - centers) * _f32(gamma)
+    gap = np.where(gap >= _f32(-16), gap, _f32(-16)).astype(_f32)
+    m = gap.max(axis=-1, keepdims=True)
+    e = np.exp(gap - m, dtype=_f32)
+    dist = (e / e.sum(axis=-1, keepdims=True, dtype=_f32)).astype(_f32)
+    return np.ascontiguousarray(np.moveaxis(dist[..., :D], -1, 2))

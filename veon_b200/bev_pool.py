@@ -358,6 +358,28 @@ def pool_prepared_downsampled(depth, feat, prep, bev_feat_shape):
     return out
 
 
+def two_hot_depth(depths, depth_cfg, D, gamma=4.0, downsample=0):
+    """LSSViewTransformerRaw.get_two_hot_depth (+ downsample_depth), forward only
+    (view_transformer_raw.py:393-429): depths [B,N,H,W] metric depth on CUDA ->
+    [B,N,D,H/s,W/s] float32 (contiguous; the reference returns a permuted view of the same
+    values)."""
+    _require_cuda(depths)
+    lib = _lib.load()
+    d = depths.detach().contiguous().float()
+    B, N, H, W = d.shape
+    s = int(downsample) if downsample else 1
+    if H % s or W % s:
+        raise ValueError("depth map size must be a multiple of the downsample factor")
+    with torch.cuda.device(d.device):
+        out = torch.empty((B, N, D, H // s, W // s), dtype=torch.float32, device=d.device)
+        with _timed("two_hot_depth", d.device):
+            rc = lib.veon_two_hot_depth(_ptr(d), B * N, H // s, W // s, s, int(D),
+                                        float(depth_cfg[0]), float(depth_cfg[2]), float(gamma),
+                                        _ptr(out), _stream_ptr(d.device))
+    _lib.check(rc, "veon_two_hot_depth")
+    return out
+
+
 class MaxDown2x2x2(torch.autograd.Function):
     """`x.view(b,c,z/2,2,y/2,2,x/2,2).amax(dim=(3,5,7))` (view_transformer_raw.py:549-553) and
     ATen's amax gradient (ties share equally) as two streaming kernels."""

@@ -230,6 +230,32 @@ class LSSViewTransformerRaw(LSSViewTransformer):
         # our streaming 2x2x2 kernel (784 vs 705 us at C2), so it is opt-in.
         self.fuse_ds = fuse_ds
 
+    # -- depth-distribution producer ------------------------------
+    def downsample_depth(self, depths, downsample):
+        """reference view_transformer_raw.py:393-404 (plain torch: it is only a helper of the
+        autograd route below; the CUDA route fuses it)"""
+        B, N, H, W = depths.shape
+        d = depths.view(B * N, H // downsample, downsample, W // downsample, downsample)
+        d = torch.where(d == 0.0, torch.full_like(d, 1e5), d)
+        return d.amin(dim=(2, 4)).view(B, N, H // downsample, W // downsample)
+
+    def get_two_hot_depth(self, depths, gamma=4, downsample=False):
+        """reference view_transformer_raw.py:406-429: [B,N,H,W] metric depth -> [B,N,D,h,w]
+        distribution.  One CUDA kernel when no gradient is wanted (`veon_two_hot_depth`);
+        otherwise the reference's own expression, so that autograd sees the same graph."""
+        if depths.is_cuda and not (torch.is_grad_enabled() and depths.requires_grad):
+            return _bp.two_hot_depth(depths, self.grid_config["depth"], self.D, gamma,
+                                     self.downsample if downsample else 0)
+        if downsample:
+            depths = self.downsample_depth(depths, self.downsample)
+        B, N, H, W = depths.shape
+        cfg = self.grid_config["depth"]
+        centers = torch.arange(self.D + 1, device=depths.device) * cfg[2] + (cfg[0] + cfg[2] / 2)
+        gap = -torch.abs(depths.reshape(B * N, H, W, 1) - centers) * gamma
+        gap = torch.where(gap >= -16, gap, gap + (-16 - gap.detach()))
+        dist = torch.softmax(gap, dim=-1)[..., :-1]
+        return dist.view(B, N, H, W, self.D).permute(0, 1, 4, 2, 3)
+
     def forward(self, input, depth, stereo_metas=None):
         tran_feat = input[0]
         B, N, C, H, W = tran_feat.shape
