@@ -171,6 +171,22 @@ int veon_prepare_v2(const float* coor, int B, int N, int D, int H, int W,
                     int32_t* tile_heavy, int32_t* point_interval,
                     void* workspace, size_t workspace_bytes, void* stream);
 
+/* The same with get_lidar_coor fused in (view_transformer.py:114-152 + :202-260): takes the
+ * frustum and the calibration tensors of veon_lidar_coor instead of `coor`; the coordinate tensor
+ * is never materialised.  The ranks are bit-identical to veon_lidar_coor + veon_prepare_v2.
+ * xform_workspace: veon_lidar_coor_workspace_bytes(B, N) bytes. */
+int veon_prepare_v2_calib(const float* frustum, const float* sensor2ego, const float* cam2imgs,
+                          const float* post_rots, const float* post_trans, const float* bda,
+                          int B, int N, int D, int H, int W,
+                          const float* lower, const float* interval, const float* grid_size,
+                          int32_t* ranks_bev, int32_t* ranks_depth, int32_t* ranks_feat,
+                          int32_t* interval_starts, int32_t* interval_lengths,
+                          int64_t* counts, int64_t* counts_host,
+                          int32_t* tile_start, int32_t* tile_istart, uint32_t* tile_occ,
+                          int32_t* tile_heavy, int32_t* point_interval,
+                          void* xform_workspace, size_t xform_workspace_bytes,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
 /* Build the same plan from rank arrays the caller already holds (the
  * `accelerate=True` cache, view_transformer.py:154-173, or any user input) and
  * validate them.  *flags (device int32) receives an OR of VEON_PLAN_* bits; the

@@ -270,3 +270,31 @@ def test_raw_neck_training_route_uses_own_downsample_and_matches_amax():
     want.backward(go)
     assert torch.equal(out, want)
     assert torch.equal(f1.grad, f2.grad)
+
+
+def test_fused_geometry_gives_the_same_ranks_and_volume():
+    """get_lidar_coor folded into the preparation kernel = the two-step route"""
+    from veon_b200 import bev_pool as BP
+    from veon_b200.view_transformer import LSSViewTransformer
+    cfg = S.CONFIGS["small"]
+    B, C = 2, 64
+    neck = LSSViewTransformer(cfg.grid_config, cfg.input_size, cfg.downsample, 8, C, collapse_z=False)
+    img, metas, depth, feat = inputs(cfg, B, C, seed=8)
+    # non-trivial augmentation so that every matrix matters
+    metas[3] = metas[3] + 0.01 * torch.randn(metas[3].shape, generator=torch.Generator().manual_seed(1)).cuda()
+    metas[4] = metas[4] + torch.tensor([3.0, -2.0, 0.0]).cuda()
+    coor = neck.get_lidar_coor(*metas)
+    a = BP.prepare_ranks(coor, neck.grid_lower_bound, neck.grid_interval, neck.grid_size)
+    b = BP.prepare_ranks_calib(neck._frustum_on(coor.device), metas[0], metas[2], metas[3], metas[4],
+                               metas[5], neck.grid_lower_bound, neck.grid_interval, neck.grid_size)
+    n, m = a.plan.n_points, a.plan.n_intervals
+    assert (n, m) == (b.plan.n_points, b.plan.n_intervals) and n > 0
+    for x, y in ((a.ranks_bev, b.ranks_bev), (a.ranks_depth, b.ranks_depth),
+                 (a.ranks_feat, b.ranks_feat)):
+        assert torch.equal(x[:n], y[:n])
+    assert torch.equal(a.interval_starts[:m], b.interval_starts[:m])
+    assert torch.equal(a.plan.tile_start, b.plan.tile_start)
+    fused, _ = neck.view_transform([img] + metas, depth, feat)
+    neck.fuse_geometry = False
+    plain, _ = neck.view_transform([img] + metas, depth, feat)
+    assert torch.equal(fused, plain)

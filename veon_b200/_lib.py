@@ -47,6 +47,9 @@ _SIGNATURES = {
     "veon_pool_heavy_list_ints": (c_int64, [c_int64, c_int64]),
     "veon_prepare_v2": (c_int, [_P, c_int, c_int, c_int, c_int, c_int, _P, _P, _P,
                                 _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_size_t, _P]),
+    "veon_prepare_v2_calib": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int,
+                                      _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                                      _P, c_size_t, _P, c_size_t, _P]),
     "veon_pool_plan_build": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64,
                                      c_int, c_int, c_int, c_int, c_int, c_int64,
                                      _P, _P, _P, _P, _P, _P, _P]),

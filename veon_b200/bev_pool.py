@@ -183,6 +183,20 @@ def _counts_slot(dev):
     return buf[nxt], nxt
 
 
+def prepare_ranks_calib(frustum, sensor2ego, cam2imgs, post_rots, post_trans, bda,
+                        grid_lower_bound, grid_interval, grid_size):
+    """`prepare_ranks(lidar_coor(...))` in one call with the geometry fused into the
+    classification kernel: the [B,N,D,H,W,3] coordinate tensor is never written.
+    Same ranks, bit for bit."""
+    _require_cuda(frustum, sensor2ego, cam2imgs, post_rots, post_trans, bda)
+    calib = [t.detach().contiguous().float() for t in
+             (frustum, sensor2ego, cam2imgs, post_rots, post_trans, bda)]
+    B, N = sensor2ego.shape[:2]
+    D, H, W, _ = frustum.shape
+    return _prepare(None, calib, (B, N, D, H, W), sensor2ego.device, grid_lower_bound,
+                    grid_interval, grid_size)
+
+
 def prepare_ranks(coor, grid_lower_bound, grid_interval, grid_size):
     """Launch the GPU index preparation; returns without a host sync.
 
@@ -192,11 +206,15 @@ def prepare_ranks(coor, grid_lower_bound, grid_interval, grid_size):
     _require_cuda(coor)
     if coor.dim() != 6 or coor.shape[-1] != 3:
         raise ValueError(f"coor must be [B,N,D,H,W,3], got {tuple(coor.shape)}")
-    lib = _lib.load()
     coor = coor.detach().contiguous().float()
-    B, N, D, H, W, _ = coor.shape
+    return _prepare(coor, None, tuple(coor.shape[:5]), coor.device, grid_lower_bound,
+                    grid_interval, grid_size)
+
+
+def _prepare(coor, calib, dims, dev, grid_lower_bound, grid_interval, grid_size):
+    lib = _lib.load()
+    B, N, D, H, W = (int(v) for v in dims)
     P = B * N * D * H * W
-    dev = coor.device
     key = (B, N, D, H, W, id(grid_lower_bound), id(grid_interval), id(grid_size),
            getattr(grid_lower_bound, "_version", 0), getattr(grid_interval, "_version", 0),
            getattr(grid_size, "_version", 0))
@@ -242,12 +260,19 @@ def prepare_ranks(coor, grid_lower_bound, grid_interval, grid_size):
         # directly (no D2H copy that could queue behind the caller's bulk transfers on
         # the copy engine); they are valid once `ev` has completed.
         counts_host, slot = _counts_slot(dev)
-        with _timed("prepare_v2", dev):
-            rc = lib.veon_prepare_v2(
-                _ptr(coor), B, N, D, H, W, c_lower, c_interval, c_size,
-                _ptr(ranks[0]), _ptr(ranks[1]), _ptr(ranks[2]), _ptr(ranks[3]), _ptr(ranks[4]),
+        outs = (_ptr(ranks[0]), _ptr(ranks[1]), _ptr(ranks[2]), _ptr(ranks[3]), _ptr(ranks[4]),
                 _ptr(counts), _ptr(counts_host), _ptr(tiles[0]), _ptr(tiles[1]), _ptr(tiles[2]),
-                _ptr(heavy), _ptr(point_interval), _ptr(ws), ws_bytes, _stream_ptr(dev))
+                _ptr(heavy), _ptr(point_interval))
+        with _timed("prepare_v2", dev):
+            if calib is None:
+                rc = lib.veon_prepare_v2(_ptr(coor), B, N, D, H, W, c_lower, c_interval, c_size,
+                                         *outs, _ptr(ws), ws_bytes, _stream_ptr(dev))
+            else:
+                xbytes = lib.veon_lidar_coor_workspace_bytes(B, N)
+                xws = torch.empty(xbytes, dtype=torch.uint8, device=dev)
+                rc = lib.veon_prepare_v2_calib(*[_ptr(a) for a in calib], B, N, D, H, W, c_lower,
+                                               c_interval, c_size, *outs, _ptr(xws), xbytes,
+                                               _ptr(ws), ws_bytes, _stream_ptr(dev))
         _lib.check(rc, "veon_prepare_v2")
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(dev))

@@ -12,17 +12,9 @@
 // Float results agree with the reference to rounding (it is upstream of the
 // bit-exact op boundary; the ranks are defined on whatever `coor` is passed to
 // voxel_pooling_prepare_v2).
-#include "common.cuh"
+#include "geometry.cuh"
 
 namespace veon {
-
-struct CamXform {
-  float undo[9];   // inverse(post_rots)
-  float c2e[9];    // sensor2ego[:3,:3] @ inverse(cam2imgs)
-  float pt[3];     // post_trans
-  float t[3];      // sensor2ego[:3,3]
-  float bda[9];
-};
 
 __device__ inline void inv3(const double* m, double* o) {
   const double a = m[0], b = m[1], c = m[2], d = m[3], e = m[4], f = m[5], g = m[6], h = m[7],
@@ -65,10 +57,6 @@ __global__ void k_cam_xforms(const float* __restrict__ sensor2ego,
   out[bn] = x;
 }
 
-__device__ __forceinline__ float dot3(const float* m, float x, float y, float z) {
-  return fmaf(m[2], z, fmaf(m[1], y, m[0] * x));
-}
-
 __global__ void __launch_bounds__(256)
 k_lidar_coor(const float* __restrict__ frustum, const CamXform* __restrict__ xf, int64_t DHW,
              int64_t total, float* __restrict__ coor) {
@@ -76,23 +64,18 @@ k_lidar_coor(const float* __restrict__ frustum, const CamXform* __restrict__ xf,
   const int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= total) return;
   const int64_t bn = p / DHW, f = p - bn * DHW;
-  const CamXform& x = xf[bn];
-  const float fx = __ldg(frustum + 3 * f) - x.pt[0];
-  const float fy = __ldg(frustum + 3 * f + 1) - x.pt[1];
-  const float fz = __ldg(frustum + 3 * f + 2) - x.pt[2];
-  float qx = dot3(x.undo, fx, fy, fz), qy = dot3(x.undo + 3, fx, fy, fz);
-  const float qz = dot3(x.undo + 6, fx, fy, fz);
-  qx *= qz;
-  qy *= qz;
-  const float ex = dot3(x.c2e, qx, qy, qz) + x.t[0];
-  const float ey = dot3(x.c2e + 3, qx, qy, qz) + x.t[1];
-  const float ez = dot3(x.c2e + 6, qx, qy, qz) + x.t[2];
   float* o = coor + 3 * p;
-  o[0] = dot3(x.bda, ex, ey, ez);
-  o[1] = dot3(x.bda + 3, ex, ey, ez);
-  o[2] = dot3(x.bda + 6, ex, ey, ez);
+  lidar_point(frustum + 3 * f, xf[bn], o[0], o[1], o[2]);
 }
 
+int launch_cam_xforms(const float* sensor2ego, const float* cam2imgs, const float* post_rots,
+                      const float* post_trans, const float* bda, int B, int N, CamXform* xf,
+                      cudaStream_t stream) {
+  k_cam_xforms<<<(B * N + 63) / 64, 64, 0, stream>>>(sensor2ego, cam2imgs, post_rots, post_trans,
+                                                     bda, B, N, xf);
+  VEON_LAUNCH_CHECK();
+  return 0;
+}
 
 // ---------------------------------------------------------------- layout change
 // feat arrives as [B*N, C, H*W] (the network's channels-first maps,
@@ -138,9 +121,8 @@ extern "C" int veon_lidar_coor(const float* frustum, const float* sensor2ego,
     return VEON_E_BADARG;
   if (workspace_bytes < sizeof(CamXform) * (size_t)B * N) return VEON_E_WORKSPACE;
   CamXform* xf = (CamXform*)workspace;
-  k_cam_xforms<<<(B * N + 63) / 64, 64, 0, stream>>>(sensor2ego, cam2imgs, post_rots, post_trans,
-                                                     bda, B, N, xf);
-  VEON_LAUNCH_CHECK();
+  int rc = launch_cam_xforms(sensor2ego, cam2imgs, post_rots, post_trans, bda, B, N, xf, stream);
+  if (rc) return rc;
   const int64_t DHW = (int64_t)D * H * W, total = DHW * B * N;
   VEON_CUDA_TRY(launch_pdl(k_lidar_coor, dim3((unsigned)ceil_div64(total, 256)), dim3(256), 0, stream,
                            frustum, (const CamXform*)xf, DHW, total, coor));

@@ -21,7 +21,7 @@
 //
 // The dense histogram doubles as the voxel->points map the pooling kernels
 // need, so no separate pass builds it.
-#include "common.cuh"
+#include "geometry.cuh"
 
 namespace veon {
 
@@ -132,17 +132,30 @@ static PrepWs carve(void* base, int64_t P, int64_t nbins, int64_t BV) {
 // One thread per frustum point.  (coor - lower) / interval with IEEE sub/div
 // (no contraction), truncation toward zero like `.long()` (:227), bounds test
 // against the FLOAT grid_size (:233-235), float32 rank (:241-244).
+// FUSED: the coordinates are not read but computed from the frustum and the per-camera
+// transforms (the formula of k_lidar_coor, geometry.cuh): `coor` never exists in memory.
+template <bool FUSED>
 __global__ void __launch_bounds__(256)
-k_classify(const float* __restrict__ coor, int64_t P, int64_t pts_per_sample, GridF g,
-           int64_t nbins, int32_t* __restrict__ key, int32_t* __restrict__ slot,
+k_classify(const float* __restrict__ coor, const float* __restrict__ frustum,
+           const CamXform* __restrict__ xf, int64_t DHW, int64_t P, int64_t pts_per_sample,
+           GridF g, int64_t nbins, int32_t* __restrict__ key, int32_t* __restrict__ slot,
            int32_t* __restrict__ count) {
   pdl_prologue();
   int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P) return;
-  const float* c = coor + 3 * p;
-  float fx = __fdiv_rn(__fsub_rn(__ldg(c + 0), g.lo[0]), g.iv[0]);
-  float fy = __fdiv_rn(__fsub_rn(__ldg(c + 1), g.lo[1]), g.iv[1]);
-  float fz = __fdiv_rn(__fsub_rn(__ldg(c + 2), g.lo[2]), g.iv[2]);
+  float cx, cy, cz;
+  if (FUSED) {
+    const int64_t bn = p / DHW;
+    lidar_point(frustum + 3 * (p - bn * DHW), xf[bn], cx, cy, cz);
+  } else {
+    const float* c = coor + 3 * p;
+    cx = __ldg(c + 0);
+    cy = __ldg(c + 1);
+    cz = __ldg(c + 2);
+  }
+  float fx = __fdiv_rn(__fsub_rn(cx, g.lo[0]), g.iv[0]);
+  float fy = __fdiv_rn(__fsub_rn(cy, g.lo[1]), g.iv[1]);
+  float fz = __fdiv_rn(__fsub_rn(cz, g.lo[2]), g.iv[2]);
   float tx = truncf(fx), ty = truncf(fy), tz = truncf(fz);
   // NaN compares false everywhere -> dropped (the CPU reference drops it too:
   // cvttss2si yields INT64_MIN).  (-1,0) truncates to -0.0 which IS kept.
@@ -633,8 +646,8 @@ extern "C" size_t veon_prepare_v2_voxel_start_offset(int B, int N, int D, int H,
   return (size_t)((char*)w.offset - (char*)nullptr);
 }
 
-extern "C" int veon_prepare_v2(const float* coor, int B, int N, int D, int H, int W,
-                               const float* lower, const float* interval,
+static int prepare_impl(const float* coor, const float* frustum, const CamXform* xf, int B, int N,
+                        int D, int H, int W, const float* lower, const float* interval,
                                const float* grid_size, int32_t* ranks_bev,
                                int32_t* ranks_depth, int32_t* ranks_feat,
                                int32_t* interval_starts, int32_t* interval_lengths,
@@ -646,8 +659,8 @@ extern "C" int veon_prepare_v2(const float* coor, int B, int N, int D, int H, in
   int64_t P;
   int rc = check_dims(B, N, D, H, W, &P);
   if (rc) return rc;
-  if (!coor || !lower || !interval || !grid_size || !ranks_bev || !ranks_depth ||
-      !ranks_feat || !interval_starts || !interval_lengths || !counts || !workspace)
+  if ((!coor && !(frustum && xf)) || !lower || !interval || !grid_size || !ranks_bev ||
+      !ranks_depth || !ranks_feat || !interval_starts || !interval_lengths || !counts || !workspace)
     return VEON_E_BADARG;
   GridF g = make_grid(lower, interval, grid_size);
   const int64_t nbins = num_bins(B, g);
@@ -671,8 +684,16 @@ extern "C" int veon_prepare_v2(const float* coor, int B, int N, int D, int H, in
   const int64_t pts_per_sample = (int64_t)N * D * H * W;
   const unsigned pblocks = (unsigned)ceil_div64(P, 256);
   // from here on every kernel is a programmatic dependent of the one before (common.cuh)
-  VEON_CUDA_TRY(launch_pdl(k_classify, dim3(pblocks), dim3(256), 0, stream, coor, P,
-                           pts_per_sample, g, nbins, w.key, w.slot, w.count));
+  const int64_t DHW = (int64_t)D * H * W;
+  if (coor) {
+    VEON_CUDA_TRY(launch_pdl(k_classify<false>, dim3(pblocks), dim3(256), 0, stream, coor,
+                             (const float*)nullptr, (const CamXform*)nullptr, DHW, P,
+                             pts_per_sample, g, nbins, w.key, w.slot, w.count));
+  } else {
+    VEON_CUDA_TRY(launch_pdl(k_classify<true>, dim3(pblocks), dim3(256), 0, stream,
+                             (const float*)nullptr, frustum, xf, DHW, P, pts_per_sample, g, nbins,
+                             w.key, w.slot, w.count));
+  }
   VEON_LAUNCH_CHECK();
   const bool want_tiles = tile_start && tile_istart && tile_occ;
   const int64_t tps = ceil_div64(V, kTileVoxels), n_tiles = (int64_t)B * tps;
@@ -705,6 +726,51 @@ extern "C" int veon_prepare_v2(const float* coor, int B, int N, int D, int H, in
                            point_interval));
   VEON_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int veon_prepare_v2(const float* coor, int B, int N, int D, int H, int W,
+                               const float* lower, const float* interval,
+                               const float* grid_size, int32_t* ranks_bev,
+                               int32_t* ranks_depth, int32_t* ranks_feat,
+                               int32_t* interval_starts, int32_t* interval_lengths,
+                               int64_t* counts, int64_t* counts_host, int32_t* tile_start,
+                               int32_t* tile_istart, uint32_t* tile_occ, int32_t* tile_heavy,
+                               int32_t* point_interval, void* workspace,
+                               size_t workspace_bytes, void* stream_) {
+  if (!coor) return VEON_E_BADARG;
+  return prepare_impl(coor, nullptr, nullptr, B, N, D, H, W, lower, interval, grid_size, ranks_bev,
+                      ranks_depth, ranks_feat, interval_starts, interval_lengths, counts,
+                      counts_host, tile_start, tile_istart, tile_occ, tile_heavy, point_interval,
+                      workspace, workspace_bytes, stream_);
+}
+
+// get_lidar_coor fused into the preparation: same ranks as
+// veon_lidar_coor + veon_prepare_v2, without the [B,N,D,H,W,3] coordinate tensor.
+extern "C" int veon_prepare_v2_calib(const float* frustum, const float* sensor2ego,
+                                     const float* cam2imgs, const float* post_rots,
+                                     const float* post_trans, const float* bda, int B, int N,
+                                     int D, int H, int W, const float* lower,
+                                     const float* interval, const float* grid_size,
+                                     int32_t* ranks_bev, int32_t* ranks_depth,
+                                     int32_t* ranks_feat, int32_t* interval_starts,
+                                     int32_t* interval_lengths, int64_t* counts,
+                                     int64_t* counts_host, int32_t* tile_start,
+                                     int32_t* tile_istart, uint32_t* tile_occ,
+                                     int32_t* tile_heavy, int32_t* point_interval,
+                                     void* xform_workspace, size_t xform_workspace_bytes,
+                                     void* workspace, size_t workspace_bytes, void* stream_) {
+  if (!frustum || !sensor2ego || !cam2imgs || !post_rots || !post_trans || !bda ||
+      !xform_workspace || B <= 0 || N <= 0)
+    return VEON_E_BADARG;
+  if (xform_workspace_bytes < sizeof(CamXform) * (size_t)B * N) return VEON_E_WORKSPACE;
+  CamXform* xf = (CamXform*)xform_workspace;
+  int rc = launch_cam_xforms(sensor2ego, cam2imgs, post_rots, post_trans, bda, B, N, xf,
+                             (cudaStream_t)stream_);
+  if (rc) return rc;
+  return prepare_impl(nullptr, frustum, xf, B, N, D, H, W, lower, interval, grid_size, ranks_bev,
+                      ranks_depth, ranks_feat, interval_starts, interval_lengths, counts,
+                      counts_host, tile_start, tile_istart, tile_occ, tile_heavy, point_interval,
+                      workspace, workspace_bytes, stream_);
 }
 
 extern "C" int veon_pool_plan_build(const int32_t* ranks_depth, const int32_t* ranks_feat,

@@ -59,6 +59,10 @@ class LSSViewTransformer(nn.Module):
         # slower while PCIe is saturated (command fetch shares the link), the long pooling
         # kernels after it are not (bench.py, tools/e2e_timeline.py).
         self.prepared_hook = None
+        # Extra (not in the reference): fold get_lidar_coor into the index preparation inside
+        # view_transform.  Same float operations in the same order, so the pooled
+        # volume is the same bits; set False to run the two steps separately.
+        self.fuse_geometry = True
 
     # -- a1 ------------------------------------------------------------------
     def create_grid_infos(self, x, y, z, **kwargs):
@@ -148,15 +152,27 @@ class LSSViewTransformer(nn.Module):
     def voxel_pooling_v2(self, coor, depth, feat):
         """coor [B,N,D,H,W,3], depth [B,N,D,H,W], feat [B,N,C,H,W] ->
         [B,C,Z,Y,X] (or [B,C*Z,Y,X] with collapse_z) -- reference :175-200."""
-        feat_last = feat.permute(0, 1, 3, 4, 2)
-        shape = self._bev_shape(depth, feat_last.shape[-1])
         if coor.numel() == 0:
             return self._no_points_dummy(feat)
+        prep = _bp.prepare_ranks(coor, self.grid_lower_bound, self.grid_interval, self.grid_size)
+        return self._pool_prepared(prep, depth, feat)
+
+    def _voxel_pooling_calib(self, calib, depth, feat):
+        """voxel_pooling_v2 with get_lidar_coor folded into the index preparation:
+        `calib` = the six tensors get_lidar_coor takes; no coordinate tensor is written."""
+        sensor2ego, _ego2global, cam2imgs, post_rots, post_trans, bda = calib
+        prep = _bp.prepare_ranks_calib(self._frustum_on(sensor2ego.device), sensor2ego, cam2imgs,
+                                       post_rots, post_trans, bda, self.grid_lower_bound,
+                                       self.grid_interval, self.grid_size)
+        return self._pool_prepared(prep, depth, feat)
+
+    def _pool_prepared(self, prep, depth, feat):
+        feat_last = feat.permute(0, 1, 3, 4, 2)
+        shape = self._bev_shape(depth, feat_last.shape[-1])
         # The pooling is queued BEFORE the point / interval counts are read back, so
         # the host read-back (the reference syncs at the same place in its
         # boolean-mask indexing) overlaps the forward kernel instead of draining
         # the GPU; it only decides about the reference's empty-input result.
-        prep = _bp.prepare_ranks(coor, self.grid_lower_bound, self.grid_interval, self.grid_size)
         prep.plan.sync_free = self.sync_free   # the backward then sizes its scratch by a bound
         if self.prepared_hook is not None:
             self.prepared_hook()               # see __init__: lets a caller time its transfers
@@ -192,6 +208,10 @@ class LSSViewTransformer(nn.Module):
                                        self.ranks_bev, self._bev_shape(depth, feat.shape[-1]),
                                        self.interval_starts, self.interval_lengths)
             bev_feat = bev_feat.squeeze(2)
+        elif self.fuse_geometry and input[1].is_cuda:
+            # get_lidar_coor folded into the index preparation: same ranks, no coor tensor
+            bev_feat = self._voxel_pooling_calib(input[1:7], depth.view(B, N, self.D, H, W),
+                                                 tran_feat.view(B, N, self.out_channels, H, W))
         else:
             coor = self.get_lidar_coor(*input[1:7])
             bev_feat = self.voxel_pooling_v2(coor, depth.view(B, N, self.D, H, W),
