@@ -448,8 +448,9 @@ def run_ours(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / K,
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "what": "pinned host calibration+depth+feat -> LSSViewTransformer.view_transform "
-                        "(get_lidar_coor + prepare_v2 + bev_pool_v2) -> backward -> depth_grad + "
-                        "feat_grad to pinned host; copies on side streams, double-buffered"},
+                        "(get_lidar_coor fused into prepare_v2, bev_pool_v2) -> backward -> depth_grad "
+                        "+ feat_grad to pinned host; copies on side streams, double-buffered, "
+                        "released from the neck's prepared_hook"},
         "roofline": {"bound": "hbm", "kernel": "k_pool_fwd + k_pool_fwd_heavy (one veon_bev_pool_v2_fwd_planar call; the heavy-tile grid runs in the tail of the main grid)",
                      "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                      "frac": (achieved / peak_gbs) if achieved else None, "peak_source": peak_src,
