@@ -26,8 +26,8 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"libveonlift.so does not export {n}"
     assert set(names) == set(_lib.EXPORTED_SYMBOLS), "ctypes table and header disagree"
-    import re
-    declared = int(re.search(r"#define\s+VEON_ABI_VERSION\s+(\d+)", open(HEADER).read()).group(1))
+    header = open(os.path.join(ROOT, "include", "veon_lift.h")).read()
+    declared = int(re.search(r"#define\s+VEON_ABI_VERSION\s+(\d+)", header).group(1))
     assert lib.veon_abi_version() == declared >= 3
     assert b"bad argument" in lib.veon_error_string(-1)
 
