@@ -28,7 +28,10 @@
 namespace veon {
 
 constexpr int kBwdWarps = 8;   // pixel pass: 8 consecutive pixels per CTA
-constexpr int kRowWarps = 4;   // row pass
+#ifndef VEON_ROW_WARPS
+#define VEON_ROW_WARPS 4
+#endif
+constexpr int kRowWarps = VEON_ROW_WARPS;   // row pass
 constexpr int kPitch = kTileVoxels + 1;
 
 // one warp: tile t, channel chunk starting at cbase -> compact rows
