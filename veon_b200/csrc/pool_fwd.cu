@@ -494,7 +494,10 @@ k_pool_fwd_heavy(const float* __restrict__ depth, const float* __restrict__ feat
 #endif
 constexpr int kGroupTiles = VEON_GROUP_TILES;    // 4 or 8: one warp per tile
 constexpr int kGroupVoxels = kGroupTiles * kTileVoxels;
-constexpr int kGroupThreads = 32 * kGroupTiles;
+#ifndef VEON_GROUP_THREADS
+#define VEON_GROUP_THREADS (32 * VEON_GROUP_TILES)
+#endif
+constexpr int kGroupThreads = VEON_GROUP_THREADS;  // >= kGroupRound (thread per point)
 constexpr int kGroupRound = VEON_GROUP_ROUND;    // points staged per round (thread per point)
 constexpr int kStagePitch = kGroupVoxels + 4;    // floats; rows stay 16-byte aligned
 
@@ -507,13 +510,15 @@ k_pool_fwd_group(const float* __restrict__ depth, const float* __restrict__ feat
                  uint32_t groups_per_sample, int64_t V, int C, float* __restrict__ out) {
   constexpr int CC = 32 * KCH;
   constexpr int kSegs = CC / 4;
+  constexpr int kW = kGroupThreads / 32;
   extern __shared__ __align__(16) float gsm[];
-  float* rows = gsm;                                                 // [kGroupRound][CC]
-  float* stage = rows + kGroupRound * CC;                            // [CC][kStagePitch]
-  float* dep = stage + CC * kStagePitch;                             // [kGroupRound]
-  uint32_t* off = reinterpret_cast<uint32_t*>(dep + kGroupRound);    // [kGroupRound]
-  int32_t* bounds = reinterpret_cast<int32_t*>(off + kGroupRound);   // [2][start 256 | end 256]
-  int32_t* hdrs = bounds + 4 * kGroupVoxels;                         // [2][12]: tile_start[0..8]
+  float* rows = gsm;                                                 // [2][kGroupRound][CC]
+  float* stage = rows + 2 * kGroupRound * CC;                        // [CC][kStagePitch]
+  float* dep = stage + CC * kStagePitch;                             // [2][kGroupRound]
+  uint32_t* off = reinterpret_cast<uint32_t*>(dep + 2 * kGroupRound);  // [2][kGroupRound]
+  int32_t* b0 = reinterpret_cast<int32_t*>(off + 2 * kGroupRound);   // [3][start | end] round 0
+  int32_t* bx = b0 + 6 * kGroupVoxels;                               // [start | end] extra rounds
+  int32_t* hdrs = bx + 2 * kGroupVoxels;                             // [4][12]: tile_start[0..T]
   pdl_launch_dependents();
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   if (blockIdx.x >= n_items) return;
@@ -525,7 +530,7 @@ k_pool_fwd_group(const float* __restrict__ depth, const float* __restrict__ feat
     g = item / n_chunks;
     chunk = item - g * n_chunks;
   };
-  auto load_hdr = [&](uint32_t k) -> int32_t {   // thread j < 9: tile_start[8g + j] of item k
+  auto load_hdr = [&](uint32_t k) -> int32_t {   // thread j <= T: tile_start[T g + j] of item k
     if (tid <= kGroupTiles && k < my_items) {
       uint32_t g, chunk;
       item_group(k, g, chunk);
@@ -533,6 +538,7 @@ k_pool_fwd_group(const float* __restrict__ depth, const float* __restrict__ feat
     }
     return 0;
   };
+  auto hdr_of = [&](uint32_t k) { return hdrs + (k & 3) * 12; };
   // compacted position q of a group (heavy tiles left out) -> point index, index of the
   // previous compacted point (-1 for q == 0); returns the group's number of points
   auto locate = [&](const int32_t* hdr, int q, int32_t& i, int32_t& iprev) -> int {
@@ -554,12 +560,11 @@ k_pool_fwd_group(const float* __restrict__ depth, const float* __restrict__ feat
     }
     return acc;
   };
-  // index records of one point (thread tid < kGroupRound): stage A loads the ranks, stage B
-  // the depth value
   struct Rec { int32_t rb, rp, rf, rd; float d; };
   auto stage_a = [&](const int32_t* hdr, int q, Rec& r) {
     r.rb = -1;
     r.rp = -1;
+    r.rd = 0;
     if (tid < kGroupRound) {
       int32_t i, ip;
       locate(hdr, q, i, ip);
@@ -575,123 +580,162 @@ k_pool_fwd_group(const float* __restrict__ depth, const float* __restrict__ feat
     r.d = 0.f;
     if (r.rb >= 0) r.d = __ldg(depth + r.rd);
   };
-  // records -> shared memory + [start, end) of every voxel inside the round
-  auto publish = [&](const Rec& r, int cnt, int32_t g0, uint32_t chunk, int parity) {
-    int32_t* cstart = bounds + parity * 2 * kGroupVoxels;
+  auto publish = [&](const Rec& r, int cnt, int32_t g0, uint32_t chunk, int slot,
+                     int32_t* cstart) {
     int32_t* cend = cstart + kGroupVoxels;
     if (r.rb >= 0) {
       const int vox = r.rb - g0;
-      off[tid] = ((uint32_t)r.rf * (uint32_t)C + chunk * CC) * 4u;
-      dep[tid] = r.d;
+      off[slot * kGroupRound + tid] = ((uint32_t)r.rf * (uint32_t)C + chunk * CC) * 4u;
+      dep[slot * kGroupRound + tid] = r.d;
       const bool starts = (tid == 0) || (r.rb != r.rp);
       if (starts) cstart[vox] = tid;
       if (tid > 0 && r.rb != r.rp) cend[r.rp - g0] = tid;
       if (tid == cnt - 1) cend[vox] = cnt;
     }
   };
-  auto gather_rows = [&](int cnt) {   // every feature row of the round in flight at once
+  auto gather_rows = [&](int cnt, int slot) {   // every feature row of the round at once
     const char* fbase = reinterpret_cast<const char*>(feat);
+    float* dst = rows + slot * kGroupRound * CC;
+    const uint32_t* o = off + slot * kGroupRound;
 #pragma unroll
     for (int i = 0; i < kGroupRound * kSegs / kGroupThreads; ++i) {
       const int idx = tid + kGroupThreads * i;
       const int r = idx / kSegs, seg = (idx % kSegs) * 4;
-      if (r < cnt) cp_async16(rows + r * CC + seg, fbase + off[r] + seg * 4);
+      if (r < cnt) cp_async16(dst + r * CC + seg, fbase + o[r] + seg * 4);
     }
     cp_async_commit();
   };
-  auto accumulate = [&](int parity) {  // warp w: the voxels of tile w, lanes = channels
-    const int32_t* cstart = bounds + parity * 2 * kGroupVoxels;
+  // warp w takes voxels w, w + W, ...: a tile's points spread over all warps; lanes = channels
+  auto accumulate = [&](const int32_t* cstart, int slot) {
     const int32_t* cend = cstart + kGroupVoxels;
-    const int a_l = cstart[kTileVoxels * warp + lane], e_l = cend[kTileVoxels * warp + lane];
+    const float* rw = rows + slot * kGroupRound * CC;
+    const float* dp = dep + slot * kGroupRound;
+    const int mine = kW * lane + warp;
+    const bool has = mine < kGroupVoxels;
+    const int a_l = has ? cstart[mine] : 0, e_l = has ? cend[mine] : 0;
     uint32_t m = __ballot_sync(0xffffffffu, e_l > a_l);
     while (m) {
-      const int v = __ffs(m) - 1;
+      const int l = __ffs(m) - 1;
       m &= m - 1;
-      const int a = __shfl_sync(0xffffffffu, a_l, v), e = __shfl_sync(0xffffffffu, e_l, v);
-      float* sp = stage + lane * kStagePitch + kTileVoxels * warp + v;
+      const int a = __shfl_sync(0xffffffffu, a_l, l), e = __shfl_sync(0xffffffffu, e_l, l);
+      float* sp = stage + lane * kStagePitch + kW * l + warp;
       float acc[KCH];
 #pragma unroll
       for (int c = 0; c < KCH; ++c) acc[c] = sp[32 * c * kStagePitch];
-#pragma unroll 4
+#pragma unroll 2
       for (int j = a; j < e; ++j) {
-        const float dj = dep[j];
+        const float dj = dp[j];
 #pragma unroll
-        for (int c = 0; c < KCH; ++c) acc[c] = fmaf(rows[j * CC + lane + 32 * c], dj, acc[c]);
+        for (int c = 0; c < KCH; ++c) acc[c] = fmaf(rw[j * CC + lane + 32 * c], dj, acc[c]);
       }
 #pragma unroll
       for (int c = 0; c < KCH; ++c) sp[32 * c * kStagePitch] = acc[c];
     }
   };
+  auto group_total = [&](const int32_t* hdr) {
+    int32_t i, ip;
+    return locate(hdr, 0x7fffffff, i, ip);
+  };
 
-  // ---- prologue: headers of items 0 and 1, records of item 0
-  int32_t hreg = load_hdr(0);
-  if (tid <= kGroupTiles) hdrs[tid] = hreg;
-  hreg = load_hdr(1);
-  for (int i = tid; i < 4 * kGroupVoxels; i += kGroupThreads) bounds[i] = 0;
+  // ---- prologue: headers 0..2 published, rows of item 0 in flight, records of item 1
+  // complete, ranks of item 2 requested
+  {
+    const int32_t h0 = load_hdr(0), h1 = load_hdr(1), h2 = load_hdr(2);
+    if (tid <= kGroupTiles) {
+      hdr_of(0)[tid] = h0;
+      hdr_of(1)[tid] = h1;
+      hdr_of(2)[tid] = h2;
+    }
+    for (int i = tid; i < 8 * kGroupVoxels; i += kGroupThreads) b0[i] = 0;   // b0 and bx
+  }
+  int32_t hreg = load_hdr(3);
   __syncthreads();
-  Rec nxt;
-  stage_a(hdrs, tid, nxt);
-  stage_b(nxt);
-  int parity = 0;
+  Rec r1, r2, r3;
+  {
+    uint32_t g, chunk;
+    item_group(0, g, chunk);
+    Rec r0;
+    stage_a(hdr_of(0), tid, r0);
+    stage_b(r0);
+    const int total0 = group_total(hdr_of(0));
+    publish(r0, min(total0, kGroupRound), (int32_t)(g * kGroupVoxels), chunk, 0, b0);
+    __syncthreads();
+    gather_rows(min(total0, kGroupRound), 0);
+  }
+  stage_a(hdr_of(1), tid, r1);
+  stage_b(r1);
+  stage_a(hdr_of(2), tid, r2);
+
+  // per-item scalars are computed once, one item ahead: (group, chunk), point total, heavy mask
+  auto describe = [&](uint32_t k, uint32_t& g, uint32_t& chunk, int& total, uint32_t& hmask) {
+    g = chunk = 0;
+    total = 0;
+    hmask = 0;
+    if (k >= my_items) return;
+    item_group(k, g, chunk);
+    const int32_t* hdr = hdr_of(k);
+#pragma unroll
+    for (int j = 0; j < kGroupTiles; ++j) {
+      const int n = hdr[j + 1] - hdr[j];
+      if (n >= heavy_thr) hmask |= 1u << j; else total += n;
+    }
+  };
+  uint32_t g, chunk, g1, chunk1, heavy_mask, heavy_mask1;
+  int total, total1;
+  describe(0, g, chunk, total, heavy_mask);
+  int t0 = 0, t1 = 1, t2 = 2;                           // round-0 tables of items k, k+1, k+2
 
   for (uint32_t k = 0; k < my_items; ++k) {
-    const int32_t* hdr = hdrs + (k & 1) * 12;
-    int32_t* hdr_next = hdrs + ((k + 1) & 1) * 12;
-    uint32_t g, chunk;
-    item_group(k, g, chunk);
+    const int32_t* hdr = hdr_of(k);
     const uint32_t b = g / groups_per_sample;
     const int32_t g0 = (int32_t)(g * kGroupVoxels);     // global voxel index (V % 32 == 0)
     const int cbase = (int)chunk * CC;
-    int32_t dummy_i, dummy_p;
-    const int total = locate(hdr, 0x7fffffff, dummy_i, dummy_p);
-    uint32_t heavy_mask = 0;                             // tiles left to k_pool_fwd_heavy
-#pragma unroll
-    for (int j = 0; j < kGroupTiles; ++j)
-      if (hdr[j + 1] - hdr[j] >= heavy_thr) heavy_mask |= 1u << j;
+    const int cur = k & 1, nxt = cur ^ 1;
 
-    // T0: publish round 0 (prefetched), the next item's header; fetch the header after it
-    publish(nxt, min(total, kGroupRound), g0, chunk, parity);
-    if (tid <= kGroupTiles) hdr_next[tid] = hreg;
-    hreg = load_hdr(k + 2);
+    // T0: publish the records of item k+1 (prefetched), the header of item k+3
+    describe(k + 1, g1, chunk1, total1, heavy_mask1);
+    if (k + 1 < my_items)
+      publish(r1, min(total1, kGroupRound), (int32_t)(g1 * kGroupVoxels), chunk1, nxt,
+              b0 + t1 * 2 * kGroupVoxels);
+    if (tid <= kGroupTiles) hdr_of(k + 3)[tid] = hreg;
+    hreg = load_hdr(k + 4);
     __syncthreads();
 
-    // T1: rows of round 0 in flight; meanwhile the next item's ranks, the staging tile
-    if (total > 0) gather_rows(min(total, kGroupRound));
-    Rec cur_next;
-    stage_a(hdr_next, tid, cur_next);                    // records of item k+1, round 0
+    // T1: rows of item k+1 go in flight (consumed one iteration later), ranks of item k+3 and
+    // depths of item k+2 are requested, the staging tile is cleared; then wait for the rows of
+    // item k, which were requested one iteration ago
+    gather_rows(min(total1, kGroupRound), nxt);
+    stage_a(hdr_of(k + 3), tid, r3);
+    stage_b(r2);
     if (total > 0) {
       float4* s4 = reinterpret_cast<float4*>(stage);
-      for (int i = tid; i < CC * kStagePitch / 4; i += kGroupThreads)
-        s4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int i = 0; i < (CC * kStagePitch / 4 + kGroupThreads - 1) / kGroupThreads; ++i)
+        if (tid + i * kGroupThreads < CC * kStagePitch / 4)
+          s4[tid + i * kGroupThreads] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    for (int i = tid; i < 2 * kGroupVoxels; i += kGroupThreads)
-      bounds[(parity ^ 1) * 2 * kGroupVoxels + i] = 0;
-    cp_async_wait_all();
+    // the round-0 table item k-1 used is free: clear it for item k+2
+    for (int i = tid; i < 2 * kGroupVoxels; i += kGroupThreads) b0[t2 * 2 * kGroupVoxels + i] = 0;
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
     __syncthreads();
 
-    // T2: fma chains; further rounds of a group with more than kGroupRound points are
-    // fetched synchronously.  The next item's depth values are requested first (their ranks
-    // have landed behind the row copies) and fly during the chains.
-    stage_b(cur_next);
-    if (total > 0) accumulate(parity);
-    parity ^= 1;
+    // T2: fma chains of item k; rounds beyond the first are fetched synchronously
+    if (total > 0) accumulate(b0 + t0 * 2 * kGroupVoxels, cur);
     for (int base = kGroupRound; base < total; base += kGroupRound) {
       const int cnt = min(kGroupRound, total - base);
       Rec r;
       stage_a(hdr, base + tid, r);
       stage_b(r);
       __syncthreads();                                   // previous round fully consumed
-      publish(r, cnt, g0, chunk, parity);
+      publish(r, cnt, g0, chunk, cur, bx);
       __syncthreads();
-      gather_rows(cnt);
-      for (int i = tid; i < 2 * kGroupVoxels; i += kGroupThreads)
-        bounds[(parity ^ 1) * 2 * kGroupVoxels + i] = 0;
+      gather_rows(cnt, cur);
       cp_async_wait_all();
       __syncthreads();
-      accumulate(parity);
-      parity ^= 1;
+      accumulate(bx, cur);
+      __syncthreads();
+      for (int i = tid; i < 2 * kGroupVoxels; i += kGroupThreads) bx[i] = 0;
     }
-    nxt = cur_next;
     __syncthreads();
 
     // T3: CC planes x (kGroupVoxels * 4) bytes; warp w takes planes w, w+W, ...; a lane's
@@ -700,25 +744,37 @@ k_pool_fwd_group(const float* __restrict__ depth, const float* __restrict__ feat
       constexpr int kHalves = kGroupVoxels / 128;
       float* o = out + ((int64_t)b * C + cbase + warp) * V + (g0 - (int32_t)(b * (uint32_t)V)) +
                  4 * lane;
+      const int64_t ostep = (int64_t)kW * V;
       const float* sp = stage + warp * kStagePitch + 4 * lane;
       bool skip[kHalves];
 #pragma unroll
       for (int h = 0; h < kHalves; ++h) skip[h] = (heavy_mask >> (4 * h + (lane >> 3))) & 1u;
-#pragma unroll 2
-      for (int c = warp; c < CC; c += kGroupThreads / 32, o += (int64_t)(kGroupThreads / 32) * V,
-               sp += (kGroupThreads / 32) * kStagePitch) {
+      if (total > 0) {
+#pragma unroll 4
+        for (int c = 0; c < CC / kW; ++c, o += ostep) {
 #pragma unroll
-        for (int h = 0; h < kHalves; ++h) {
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (total > 0) v = *reinterpret_cast<const float4*>(sp + 128 * h);
-          if (!skip[h]) st_stream4(o + 128 * h, v);
+          for (int h = 0; h < kHalves; ++h)
+            if (!skip[h])
+              st_stream4(o + 128 * h,
+                         *reinterpret_cast<const float4*>(sp + c * kW * kStagePitch + 128 * h));
+        }
+      } else {
+        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+        for (int c = 0; c < CC / kW; ++c, o += ostep) {
+#pragma unroll
+          for (int h = 0; h < kHalves; ++h)
+            if (!skip[h]) st_stream4(o + 128 * h, z);
         }
       }
     }
-    // (the staging tile is next written after two more barriers)
+    r1 = r2;
+    r2 = r3;
+    g = g1; chunk = chunk1; total = total1; heavy_mask = heavy_mask1;
+    { const int t = t0; t0 = t1; t1 = t2; t2 = t; }
   }
+  cp_async_wait_all();
 }
-
 
 // ---- fused pooling + 2x2x2 max-downsample, forward ------------------------
 // VEON's neck reduces the pooled volume 8x right away (view_transformer_raw.py:549-553:
@@ -950,8 +1006,8 @@ static int launch_fwd_impl(const float* depth, const float* feat, const int32_t*
   const bool group_ok = FULLC && vec_ok && (V % kTileVoxels) == 0 && (tps % kGroupTiles) == 0 &&
                         (C & 3) == 0 && ((uintptr_t)feat & 15) == 0;
   if (group_ok && env_flag("VEON_FWD_GROUP", 0)) {
-    const size_t gsmem = sizeof(float) * (kGroupRound * CC + CC * kStagePitch + 2 * kGroupRound +
-                                          4 * kGroupVoxels + 24);
+    const size_t gsmem = sizeof(float) * (2 * kGroupRound * CC + CC * kStagePitch +
+                                          4 * kGroupRound + 8 * kGroupVoxels + 48);
     static int group_ctas_per_sm = 0;
     if (group_ctas_per_sm == 0) {
       VEON_CUDA_TRY(cudaFuncSetAttribute(k_pool_fwd_group<KCH>,
