@@ -15,4 +15,12 @@ Parity status (see DESIGN.md "Oracle"):
     has no test or fixture for it and its modules need detectron2/open_clip to
     import; it restates san_in_veon_temporal.py:257-259,
     san_in_veon_entry_temporal.py:273-297 and veon_temporal.py:223-229,240.
+  * depth-distribution producer (`lift_oracle.downsample_depth`,
+    `lift_oracle.two_hot_depth`)        -- PINNED: checked against the output of
+    the reference's own downsample_depth / get_two_hot_depth
+    (view_transformer_raw.py:393-429) executed from /root/reference
+    (tests/golden/make_golden_depth.py -> tests/golden/two_hot_depth.npz).
+  * 2x2x2 max-downsample and its gradient: the checker is the reference's own
+    expression evaluated by ATen (`view(...).amax(dim=(3,5,7))`,
+    view_transformer_raw.py:549-553), in tests/test_neck_gpu.py.
 """
