@@ -249,6 +249,10 @@ int veon_two_hot_depth(const float* depths, int64_t BN, int H_out, int W_out, in
  * count(in == out)).  in / grad_in [BC,Z,Y,X], out / grad_out [BC,Z/2,Y/2,X/2], float32,
  * contiguous; Z, Y even and X % 4 == 0, else VEON_E_UNSUPPORTED. */
 int veon_maxdown2_fwd(const float* in, int64_t BC, int Z, int Y, int X, float* out, void* stream);
+/* Forward that also emits, per output, the 8-bit mask of inputs equal to the maximum
+ * (bit (dz*2+dy)*2+dx) -- all veon_bev_pool_v2_bwd_planar_ds needs. */
+int veon_maxdown2_fwd_mask(const float* in, int64_t BC, int Z, int Y, int X, float* out,
+                           uint8_t* mask, void* stream);
 int veon_maxdown2_bwd(const float* in, const float* out, const float* grad_out,
                       int64_t BC, int Z, int Y, int X, float* grad_in, void* stream);
 
@@ -270,6 +274,18 @@ int veon_bev_pool_v2_bwd_planar(const float* out_grad,
                                 float* rows_ws, int32_t* ctrl_ws,
                                 float* depth_grad, float* feat_grad,
                                 void* stream);
+
+/* QuickCumsumCuda.backward for a gradient that arrives BEHIND the 2x2x2 max-downsample:
+ * grad_ds [B,C,Z/2,Y/2,X/2] and the mask of veon_maxdown2_fwd_mask replace out_grad; the
+ * full-resolution gradient is never formed (ATen amax gradient semantics: ties share equally).
+ * rows_ws as in veon_bev_pool_v2_bwd_planar; even Z, Y, X. */
+int veon_bev_pool_v2_bwd_planar_ds(const float* grad_ds, const uint8_t* mask,
+                                   const float* depth, const float* feat,
+                                   const int32_t* tile_istart, const uint32_t* tile_occ,
+                                   const int32_t* point_interval, int64_t n_intervals,
+                                   int B, int N, int D, int H, int W, int C, int Z, int Y, int X,
+                                   float* rows_ws, float* depth_grad, float* feat_grad,
+                                   void* stream);
 
 /* ------------------------------------------------------------------------
  * (4) Open-vocabulary tail: voxel-feature x text-embedding logits, per-class

@@ -260,16 +260,28 @@ def test_raw_neck_training_route_uses_own_downsample_and_matches_amax():
     out.backward(go)
     used = BP.kernel_timings_ms()
     BP.enable_kernel_timing(False)
-    assert "maxdown_fwd" in used and "maxdown_bwd" in used
+    # one autograd node: the backward goes from grad_ds + mask straight to the gradient rows
+    assert "maxdown_fwd" in used and "pool_bwd_ds" in used
+    assert "maxdown_bwd" not in used and "pool_bwd" not in used
     # the reference's expression on the same pooled volume
     f2 = feat5.detach().clone().requires_grad_()
     bev, _ = neck.view_transform([f2] + metas, depth5.reshape(B * cfg.n_cams, cfg.D, H, W),
                                  f2.reshape(B * cfg.n_cams, C, H, W))
     b, c, z, y, x = bev.shape
     want = bev.view(b, c, z // 2, 2, y // 2, 2, x // 2, 2).amax(dim=(3, 5, 7))
-    want.backward(go)
-    assert torch.equal(out, want)
+    d2 = depth5.detach().clone().requires_grad_()
+    bev2, _ = neck.view_transform([f2] + metas, d2.reshape(B * cfg.n_cams, cfg.D, H, W),
+                                  f2.reshape(B * cfg.n_cams, C, H, W))
+    want2 = bev2.view(b, c, z // 2, 2, y // 2, 2, x // 2, 2).amax(dim=(3, 5, 7))
+    f2.grad = None
+    want2.backward(go)
+    assert torch.equal(out, want) and torch.equal(out, want2)
     assert torch.equal(f1.grad, f2.grad)
+    # depth gradient through the fused node as well
+    d1 = depth5.detach().clone().requires_grad_()
+    f3 = feat5.detach().clone().requires_grad_()
+    neck([f3] + metas, d1).backward(go)
+    assert torch.equal(d1.grad, d2.grad) and torch.equal(f3.grad, f2.grad)
 
 
 def test_fused_geometry_gives_the_same_ranks_and_volume():

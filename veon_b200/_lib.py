@@ -40,6 +40,10 @@ _SIGNATURES = {
     "veon_two_hot_depth": (c_int, [_P, c_int64, c_int, c_int, c_int, c_int, ctypes.c_float,
                                    ctypes.c_float, ctypes.c_float, _P, _P]),
     "veon_maxdown2_fwd": (c_int, [_P, c_int64, c_int, c_int, c_int, _P, _P]),
+    "veon_maxdown2_fwd_mask": (c_int, [_P, c_int64, c_int, c_int, c_int, _P, _P, _P]),
+    "veon_bev_pool_v2_bwd_planar_ds": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64,
+                                               c_int, c_int, c_int, c_int, c_int, c_int,
+                                               c_int, c_int, c_int, _P, _P, _P, _P]),
     "veon_maxdown2_bwd": (c_int, [_P, _P, _P, c_int64, c_int, c_int, c_int, _P, _P]),
     "veon_prepare_v2_voxel_start_offset": (c_size_t, [c_int, c_int, c_int, c_int, c_int, _P]),
     "veon_bev_pool_v2_ds_fwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int,

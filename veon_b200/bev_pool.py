@@ -441,6 +441,80 @@ class MaxDown2x2x2(torch.autograd.Function):
         return grad_in
 
 
+class PoolMaxDown(torch.autograd.Function):
+    """bev_pool_v2 followed by the neck's 2x2x2 max-downsample as ONE autograd node
+    (view_transformer.py:175-200 + view_transformer_raw.py:549-553).  Forward: the two kernels
+    of the plain route, plus an 8-bit mask per output (which inputs equal the maximum).
+    Backward: the gradient rows of the occupied voxels come straight from grad_ds and the mask
+    (ATen's amax gradient: ties share equally), so neither the 1.31 GB full-resolution gradient
+    nor the volume is kept or touched."""
+
+    @staticmethod
+    def forward(ctx, depth, feat, prep, bev_feat_shape):
+        lib = _lib.load()
+        B, Z, Y, X, C = (int(v) for v in bev_feat_shape)
+        plan = prep.plan
+        depth = depth.contiguous().float()
+        ctx.feat_channels_first = (feat.dtype == torch.float32 and not feat.is_contiguous()
+                                   and feat.permute(0, 1, 4, 2, 3).is_contiguous())
+        if ctx.feat_channels_first:
+            feat = _transpose_batched(feat.permute(0, 1, 4, 2, 3), feat.shape[0] * feat.shape[1],
+                                      feat.shape[4], feat.shape[2] * feat.shape[3],
+                                      tuple(feat.shape))
+        else:
+            feat = feat.contiguous().float()
+        vol = _fwd_planar(depth, feat, prep.ranks_depth, prep.ranks_feat, prep.ranks_bev, plan,
+                          B, C, Z * Y * X, (B, C, Z, Y, X))
+        dev = vol.device
+        with torch.cuda.device(dev):
+            out = torch.empty((B, C, Z // 2, Y // 2, X // 2), dtype=torch.float32, device=dev)
+            mask = torch.empty(out.shape, dtype=torch.uint8, device=dev)
+            with _timed("maxdown_fwd", dev):
+                rc = lib.veon_maxdown2_fwd_mask(_ptr(vol), B * C, Z, Y, X, _ptr(out), _ptr(mask),
+                                                _stream_ptr(dev))
+        _lib.check(rc, "veon_maxdown2_fwd_mask")
+        ctx.save_for_backward(depth, feat, mask)
+        ctx.plan, ctx.grid = plan, (Z, Y, X)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_ds):
+        depth, feat, mask = ctx.saved_tensors
+        lib = _lib.load()
+        plan = ctx.plan
+        Z, Y, X = ctx.grid
+        B, N, D, H, W = plan.dims
+        C = feat.shape[-1]
+        dev = feat.device
+        g = grad_ds.contiguous().float()
+        n_int = plan.interval_capacity()
+        with torch.cuda.device(dev):
+            depth_grad = torch.empty_like(depth)
+            feat_grad = torch.empty_like(feat)
+            rows = torch.empty(max(n_int, 1) * C, dtype=torch.float32, device=dev)
+            with _timed("pool_bwd_ds", dev):
+                rc = lib.veon_bev_pool_v2_bwd_planar_ds(
+                    _ptr(g), _ptr(mask), _ptr(depth), _ptr(feat), _ptr(plan.tile_istart),
+                    _ptr(plan.tile_occ), _ptr(plan.point_interval), n_int, B, N, D, H, W, C,
+                    Z, Y, X, _ptr(rows), _ptr(depth_grad), _ptr(feat_grad), _stream_ptr(dev))
+        _lib.check(rc, "veon_bev_pool_v2_bwd_planar_ds")
+        if ctx.feat_channels_first:
+            Bf, Nf, Hf, Wf, Cf = feat_grad.shape
+            feat_grad = _transpose_batched(feat_grad, Bf * Nf, Hf * Wf, Cf,
+                                           (Bf, Nf, Cf, Hf, Wf)).permute(0, 1, 3, 4, 2)
+        return depth_grad, feat_grad, None, None
+
+
+def pool_prepared_maxdown(depth, feat, prep, bev_feat_shape):
+    """Pool + 2x2x2 max as one differentiable node (see PoolMaxDown); None when the grid is not
+    even / X % 4 != 0 or the plan is not a prepared one (the caller then takes the plain route)."""
+    B, Z, Y, X, C = (int(v) for v in bev_feat_shape)
+    if (Z | Y) & 1 or X & 3 or not prep.plan.ok:
+        return None
+    _require_cuda(depth, feat)
+    return PoolMaxDown.apply(depth, feat, prep, bev_feat_shape)
+
+
 def voxel_pooling_prepare_v2(coor, grid_lower_bound, grid_interval, grid_size):
     """Same contract as the reference method (view_transformer.py:202-260):
     returns (ranks_bev, ranks_depth, ranks_feat, interval_starts,

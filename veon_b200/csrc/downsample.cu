@@ -14,9 +14,12 @@ namespace veon {
 __device__ __forceinline__ float max_nan(float a, float b) { return (b > a || b != b) ? b : a; }
 
 // volumes: in [BC][Z][Y][X], out [BC][Z/2][Y/2][X/2]; X % 4 == 0, Z and Y even
+// MASK: also store, per output, which of its 8 inputs equal the maximum (bit (dz*2+dy)*2+dx):
+// all the backward needs (grad * bit / popcount), so the volume need not be kept for it.
+template <bool MASK>
 __global__ void __launch_bounds__(256)
 k_maxdown2_fwd(const float* __restrict__ in, int64_t n_quads, int Zh, int Yh, int X4, int Y, int X,
-               float* __restrict__ out) {
+               float* __restrict__ out, uint8_t* __restrict__ mask) {
   for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n_quads;
        q += (int64_t)gridDim.x * blockDim.x) {
     const int x4 = (int)(q % X4);
@@ -33,7 +36,15 @@ k_maxdown2_fwd(const float* __restrict__ in, int64_t n_quads, int Zh, int Yh, in
                   max_nan(max_nan(c.x, c.y), max_nan(d.x, d.y)));
     o.y = max_nan(max_nan(max_nan(a.z, a.w), max_nan(b.z, b.w)),
                   max_nan(max_nan(c.z, c.w), max_nan(d.z, d.w)));
-    *reinterpret_cast<float2*>(out + ((bc * Zh + zo) * Yh + yo) * (int64_t)(X / 2) + 2 * x4) = o;
+    const int64_t oi = ((bc * Zh + zo) * Yh + yo) * (int64_t)(X / 2) + 2 * x4;
+    *reinterpret_cast<float2*>(out + oi) = o;
+    if (MASK) {
+      const uint32_t m0 = (a.x == o.x) | (a.y == o.x) << 1 | (b.x == o.x) << 2 | (b.y == o.x) << 3 |
+                          (c.x == o.x) << 4 | (c.y == o.x) << 5 | (d.x == o.x) << 6 | (d.y == o.x) << 7;
+      const uint32_t m1 = (a.z == o.y) | (a.w == o.y) << 1 | (b.z == o.y) << 2 | (b.w == o.y) << 3 |
+                          (c.z == o.y) << 4 | (c.w == o.y) << 5 | (d.z == o.y) << 6 | (d.w == o.y) << 7;
+      *reinterpret_cast<uchar2*>(mask + oi) = make_uchar2((unsigned char)m0, (unsigned char)m1);
+    }
   }
 }
 
@@ -95,8 +106,23 @@ extern "C" int veon_maxdown2_fwd(const float* in, int64_t BC, int Z, int Y, int 
   const int64_t n_quads = BC * (Z / 2) * (Y / 2) * (X / 4);
   int64_t blocks = ceil_div64(n_quads, 256);
   if (blocks > 148 * 64) blocks = 148 * 64;
-  k_maxdown2_fwd<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(in, n_quads, Z / 2, Y / 2,
-                                                                      X / 4, Y, X, out);
+  k_maxdown2_fwd<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(
+      in, n_quads, Z / 2, Y / 2, X / 4, Y, X, out, nullptr);
+  VEON_LAUNCH_CHECK();
+  return 0;
+}
+
+extern "C" int veon_maxdown2_fwd_mask(const float* in, int64_t BC, int Z, int Y, int X, float* out,
+                                      uint8_t* mask, void* stream_) {
+  int rc = check(in, out, BC, Z, Y, X);
+  if (rc) return rc;
+  if (!mask) return VEON_E_BADARG;
+  if ((uintptr_t)mask & 1) return VEON_E_UNSUPPORTED;
+  const int64_t n_quads = BC * (Z / 2) * (Y / 2) * (X / 4);
+  int64_t blocks = ceil_div64(n_quads, 256);
+  if (blocks > 148 * 64) blocks = 148 * 64;
+  k_maxdown2_fwd<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream_>>>(
+      in, n_quads, Z / 2, Y / 2, X / 4, Y, X, out, mask);
   VEON_LAUNCH_CHECK();
   return 0;
 }

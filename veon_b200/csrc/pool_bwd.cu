@@ -214,6 +214,126 @@ k_bwd_rows_persistent(const float* __restrict__ out_grad, const int32_t* __restr
   }
 }
 
+
+// ---- row pass for a gradient that arrives behind the 2x2x2 max-downsample ---------------
+// (LSSViewTransformerRaw: pool -> amax, view_transformer_raw.py:549-553.)  ATen's amax
+// gradient is grad * (in == out) / count(in == out); the forward kept exactly that as an 8-bit
+// mask per output (k_maxdown2_fwd<true>), so the gradient row of an occupied voxel is
+//   rows[i, c] = bit(mask[c, block], pos) ? grad_ds[c, block] / popc(mask[c, block]) : 0
+// and neither the full-resolution gradient nor the volume itself is ever read: 0.2 GB instead
+// of 2.9 + 1.2 GB for the down-sample backward followed by the plain row pass.
+// One warp per occupied tile, lanes = channels, four voxels' loads in flight.
+__global__ void __launch_bounds__(256)
+k_bwd_rows_ds(const float* __restrict__ grad_ds, const uint8_t* __restrict__ mask,
+              const int32_t* __restrict__ tile_istart, const uint32_t* __restrict__ tile_occ,
+              int64_t n_tiles, int64_t tiles_per_sample, int Z, int Y, int X, int C,
+              float* __restrict__ rows) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int Zh = Z / 2, Yh = Y / 2, Xh = X / 2;
+  const int64_t plane = (int64_t)Zh * Yh * Xh;
+  for (int64_t t = warp0; t < n_tiles; t += n_warps) {
+    const uint32_t occ = __ldg(tile_occ + t);
+    if (occ == 0u) continue;
+    const int32_t i0 = __ldg(tile_istart + t);
+    const int64_t b = t / tiles_per_sample;
+    const int32_t v0 = (int32_t)(t - b * tiles_per_sample) * kTileVoxels;
+    uint32_t rest = occ;
+    int j = 0;                                   // j-th occupied voxel -> interval i0 + j
+    while (rest) {
+      int64_t blk[4];
+      int pos[4], nv = 0;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        blk[q] = 0;
+        pos[q] = 0;
+        if (rest) {
+          const int v = v0 + __ffs(rest) - 1;
+          rest &= rest - 1;
+          const int x = v % X, y = (v / X) % Y, z = v / (X * Y);
+          blk[q] = ((int64_t)(z >> 1) * Yh + (y >> 1)) * Xh + (x >> 1);
+          pos[q] = ((z & 1) * 2 + (y & 1)) * 2 + (x & 1);
+          nv = q + 1;
+        }
+      }
+      for (int c = lane; c < C; c += 32) {
+        const int64_t base = ((int64_t)b * C + c) * plane;
+        float g[4];
+        uint32_t m[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          g[q] = 0.f;
+          m[q] = 0u;
+          if (q < nv) {
+            g[q] = __ldg(grad_ds + base + blk[q]);
+            m[q] = __ldg(mask + base + blk[q]);
+          }
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          if (q < nv)
+            rows[(int64_t)(i0 + j + q) * C + c] =
+                ((m[q] >> pos[q]) & 1u) ? g[q] / (float)__popc(m[q]) : 0.f;
+      }
+      j += nv;
+    }
+  }
+}
+
+// Same result with full-sector accesses and no shared memory (X % 8 == 0): tile starts and row
+// lengths are then multiples of 8, so every aligned group of 8 voxels of a tile lies in one
+// x-row = 4 consecutive blocks of one (z/2, y/2) row of the down-sampled volume.  Lane
+// (cs = lane / 4, q = lane % 4) owns voxels 8q..8q+7 of the tile for channels cs, cs + 8, ...:
+// one 16-byte load of grad_ds and one 4-byte load of the mask per channel, then up to 8
+// predicated 4-byte row stores; the 8 lanes of a q write 32 consecutive bytes of a row.
+__global__ void __launch_bounds__(256)
+k_bwd_rows_ds_direct(const float* __restrict__ grad_ds, const uint8_t* __restrict__ mask,
+                     const int32_t* __restrict__ tile_istart,
+                     const uint32_t* __restrict__ tile_occ, int64_t n_tiles,
+                     int64_t tiles_per_sample, int Z, int Y, int X, int C,
+                     float* __restrict__ rows) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp0 = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  const int Zh = Z / 2, Yh = Y / 2, Xh = X / 2;
+  const int64_t plane = (int64_t)Zh * Yh * Xh;
+  const int cs = lane >> 2, q = lane & 3;
+  for (int64_t t = warp0; t < n_tiles; t += n_warps) {
+    const uint32_t occ = __ldg(tile_occ + t);
+    const uint32_t bits = (occ >> (8 * q)) & 0xffu;       // this lane's 8 voxels
+    if (occ == 0u) continue;
+    const int32_t i0 = __ldg(tile_istart + t);
+    if (bits == 0u) continue;
+    const int64_t b = t / tiles_per_sample;
+    const int32_t v = (int32_t)(t - b * tiles_per_sample) * kTileVoxels + 8 * q;  // first voxel
+    const int row = v / X, x = v - row * X;               // (x is a multiple of 8)
+    const int z = row / Y, y = row - z * Y;
+    const int64_t blk0 = ((int64_t)(z >> 1) * Yh + (y >> 1)) * Xh + (x >> 1);
+    const int pos0 = ((z & 1) * 2 + (y & 1)) * 2;
+    const int ibase = i0 + __popc(occ & ((1u << (8 * q)) - 1u));   // interval of the first set bit
+    for (int c = cs; c < C; c += 8) {
+      const int64_t src = ((int64_t)b * C + c) * plane + blk0;
+      const float4 g4 = __ldg(reinterpret_cast<const float4*>(grad_ds + src));
+      const uchar4 m4 = __ldg(reinterpret_cast<const uchar4*>(mask + src));
+      const float gv[4] = {g4.x, g4.y, g4.z, g4.w};
+      const uint32_t mv[4] = {m4.x, m4.y, m4.z, m4.w};
+      float* r = rows + (int64_t)ibase * C + c;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float share = gv[i] / (float)__popc(mv[i]);
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          if ((bits >> (2 * i + e)) & 1u) {
+            *r = ((mv[i] >> (pos0 + e)) & 1u) ? share : 0.f;
+            r += C;
+          }
+        }
+      }
+    }
+  }
+}
+
 // Sum U per-lane partials over the warp, for U values at once: after log2(U) exchange
 // steps every lane holds ONE value (the one selected by its upper lane bits), which is
 // then reduced over the remaining lane bits.  U + log2(32/U) - 1 shuffles instead of 5*U.
@@ -639,4 +759,46 @@ extern "C" int veon_bev_pool_v2_bwd_planar(
     if (rc) return rc;
   }
   return 0;
+}
+
+extern "C" int veon_bev_pool_v2_bwd_planar_ds(
+    const float* grad_ds, const uint8_t* mask, const float* depth, const float* feat,
+    const int32_t* tile_istart, const uint32_t* tile_occ, const int32_t* point_interval,
+    int64_t n_intervals, int B, int N, int D, int H, int W, int C, int Z, int Y, int X,
+    float* rows_ws, float* depth_grad, float* feat_grad, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!grad_ds || !mask || !depth || !feat || !tile_istart || !tile_occ || !point_interval ||
+      !rows_ws || !depth_grad || !feat_grad || B <= 0 || N <= 0 || D <= 0 || H <= 0 || W <= 0 ||
+      C <= 0 || Z <= 0 || Y <= 0 || X <= 0 || n_intervals < 0)
+    return VEON_E_BADARG;
+  if ((Z | Y | X) & 1) return VEON_E_UNSUPPORTED;
+  const int64_t V = (int64_t)Z * Y * X;
+  const int64_t tps = ceil_div64(V, kTileVoxels), n_tiles = (int64_t)B * tps;
+  if ((int64_t)B * V > 0x7fffffffLL) return VEON_E_RANGE;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int64_t plane = (int64_t)(Z / 2) * (Y / 2) * (X / 2);
+  const bool direct = (X % 8) == 0 && (plane % 4) == 0 && ((uintptr_t)grad_ds & 15) == 0 &&
+                      ((uintptr_t)mask & 3) == 0 && env_int("VEON_BWD_DS_DIRECT", 1);
+  int64_t blocks = ceil_div64(n_tiles, 8);
+  if (blocks > (int64_t)sms * 8) blocks = (int64_t)sms * 8;
+  if (direct)
+    k_bwd_rows_ds_direct<<<(unsigned)blocks, 256, 0, stream>>>(grad_ds, mask, tile_istart, tile_occ,
+                                                               n_tiles, tps, Z, Y, X, C, rows_ws);
+  else
+    k_bwd_rows_ds<<<(unsigned)blocks, 256, 0, stream>>>(grad_ds, mask, tile_istart, tile_occ,
+                                                        n_tiles, tps, Z, Y, X, C, rows_ws);
+  VEON_LAUNCH_CHECK();
+  const int HW = H * W;
+  const int64_t pixels = (int64_t)B * N * HW;
+  static int pix_kch = env_int("VEON_BWD_PIX_KCH", 0);
+  const int pk = pix_kch ? pix_kch : (C <= 32 ? 1 : (C <= 64 ? 2 : (C <= 256 ? 4 : 8)));
+  switch (pk) {
+    case 1: return launch_pixels<1>(rows_ws, depth, feat, point_interval, 0, pixels, D, HW, C, depth_grad, feat_grad, stream);
+    case 2: return launch_pixels<2>(rows_ws, depth, feat, point_interval, 0, pixels, D, HW, C, depth_grad, feat_grad, stream);
+    case 4: return launch_pixels<4>(rows_ws, depth, feat, point_interval, 0, pixels, D, HW, C, depth_grad, feat_grad, stream);
+    case 8: return launch_pixels<8>(rows_ws, depth, feat, point_interval, 0, pixels, D, HW, C, depth_grad, feat_grad, stream);
+    default: return VEON_E_BADARG;
+  }
 }

@@ -280,6 +280,8 @@ class LSSViewTransformerRaw(LSSViewTransformer):
         tran_feat = input[0]
         B, N, C, H, W = tran_feat.shape
         fused = self._forward_downsampled(input, depth)
+        if fused is None:
+            fused = self._forward_pool_maxdown(input, depth)
         if fused is not None:
             return fused
         tran_feat = tran_feat.reshape(B * N, C, H, W)
@@ -295,6 +297,29 @@ class LSSViewTransformerRaw(LSSViewTransformer):
                 bev_feat = bev_feat.view(b, c, z // dz, dz, y // dy, dy, x // dx, dx) \
                     .amax(dim=(3, 5, 7))
         return bev_feat
+
+    def _forward_pool_maxdown(self, input, depth):
+        """Training path: pooling and the 2x2x2 maximum as ONE autograd node whose backward never
+        forms the full-resolution gradient (bev_pool.PoolMaxDown).  None -> plain route."""
+        tran_feat = input[0]
+        if (not self.use_ds or self.ds != (2, 2, 2) or self.accelerate or self.collapse_z
+                or not tran_feat.is_cuda or not torch.is_grad_enabled()
+                or not (tran_feat.requires_grad or depth.requires_grad)):
+            return None
+        B, N, C, H, W = tran_feat.shape
+        sensor2ego, _e2g, cam2imgs, post_rots, post_trans, bda = input[1:7]
+        prep = _bp.prepare_ranks_calib(self._frustum_on(sensor2ego.device), sensor2ego, cam2imgs,
+                                       post_rots, post_trans, bda, self.grid_lower_bound,
+                                       self.grid_interval, self.grid_size)
+        prep.plan.sync_free = self.sync_free
+        if self.prepared_hook is not None:
+            self.prepared_hook()
+        feat_last = tran_feat.reshape(B, N, C, H, W).permute(0, 1, 3, 4, 2)
+        d5 = depth.reshape(B, N, self.D, H, W)
+        out = _bp.pool_prepared_maxdown(d5, feat_last, prep, self._bev_shape(d5, C))
+        if out is not None and not self.sync_free and prep.plan.n_intervals == 0:
+            return None     # let the plain route reproduce the reference's empty-input behaviour
+        return out
 
     def _forward_downsampled(self, input, depth):
         """Inference path: pooling and the 2x2x2 maximum in one kernel, the full-resolution
