@@ -1002,10 +1002,14 @@ static int launch_fwd_impl(const float* depth, const float* feat, const int32_t*
   if (blocks > resident) blocks = resident;
   // the heavy-tile kernel stages feature rows with 16-byte copies
   if (heavy && ((C & 3) != 0 || ((uintptr_t)feat & 15) != 0)) heavy = nullptr;
-  const int dbg = env_flag("VEON_FWD_DBG", 0);
+  // tuning knobs, read once per process
+  static const int dbg = env_flag("VEON_FWD_DBG", 0);
+  static const int knob_group = env_flag("VEON_FWD_GROUP", 0);
+  static const int knob_heavy_ctas = env_flag("VEON_FWD_HEAVY_CTAS", 8);
+  static const int knob_order = env_flag("VEON_FWD_ORDER", 1);
   const bool group_ok = FULLC && vec_ok && (V % kTileVoxels) == 0 && (tps % kGroupTiles) == 0 &&
                         (C & 3) == 0 && ((uintptr_t)feat & 15) == 0;
-  if (group_ok && env_flag("VEON_FWD_GROUP", 0)) {
+  if (group_ok && knob_group) {
     const size_t gsmem = sizeof(float) * (2 * kGroupRound * CC + CC * kStagePitch +
                                           4 * kGroupRound + 8 * kGroupVoxels + 48);
     static int group_ctas_per_sm = 0;
@@ -1056,7 +1060,7 @@ static int launch_fwd_impl(const float* depth, const float* feat, const int32_t*
       if (heavy_ctas_per_sm < 1) heavy_ctas_per_sm = 1;
     }
     const int heavy_cap = (int)(heavy_ints - 2);
-    const int per_sm = min(heavy_ctas_per_sm, max(1, env_flag("VEON_FWD_HEAVY_CTAS", 8)));
+    const int per_sm = min(heavy_ctas_per_sm, max(1, knob_heavy_ctas));
     int64_t hblocks = (int64_t)heavy_cap * n_chunks;
     if (hblocks > (int64_t)per_sm * sm_count()) hblocks = (int64_t)per_sm * sm_count();
     if (hblocks > 0) {
@@ -1065,7 +1069,7 @@ static int launch_fwd_impl(const float* depth, const float* feat, const int32_t*
       // its CTAs are scheduled as soon as SM resources free up instead of after the drain.
       // Heavy-tile CTAs last: they fill the SMs as the persistent CTAs of the main grid
       // finish one by one (VEON_FWD_ORDER=0 runs them first instead).
-      if (env_flag("VEON_FWD_ORDER", 1) == 1) {
+      if (knob_order == 1) {
         k_pool_fwd<KCH, FULLC><<<(unsigned)blocks, kFwdWarps * 32, smem, stream>>>(
             depth, feat, rd, rf, rb, tile_start, heavy, (uint32_t)(n_tiles * n_chunks),
             (uint32_t)tps, V, C, (uint32_t)n_chunks, vec_ok, out, dbg);
