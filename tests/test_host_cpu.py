@@ -43,6 +43,24 @@ def test_argument_errors_do_not_need_a_gpu():
     assert lib.veon_prepare_v2_workspace_bytes(0, 6, 88, 16, 44, gs) == 0
     assert lib.veon_pool_num_tiles(8, 640000) == 8 * 20000
     assert lib.veon_pool_num_tiles(2, 33) == 4
+    # the entry points added for the neck's other steps validate before touching CUDA as well
+    f1 = ctypes.c_float(1.0)
+    assert lib.veon_two_hot_depth(null, 1, 4, 4, 8, 88, f1, ctypes.c_float(0.5), f1, null, null) == -1
+    assert lib.veon_maxdown2_fwd(null, 1, 16, 200, 200, null, null) == -1
+    assert lib.veon_maxdown2_fwd_mask(null, 1, 16, 200, 200, null, null, null) == -1
+    assert lib.veon_maxdown2_bwd(null, null, null, 1, 16, 200, 200, null, null) == -1
+    assert lib.veon_transpose_batched(null, 1, 4, 4, null, null) == -1
+    assert lib.veon_bev_pool_v2_ds_fwd(null, null, null, null, null, null, 1, 64, 16, 200, 200, 10,
+                                       null, null) == -1
+    assert lib.veon_bev_pool_v2_bwd_planar_ds(null, null, null, null, null, null, null, 0, 1, 1, 2, 2,
+                                              2, 64, 16, 200, 200, null, null, null, null) == -1
+    assert lib.veon_pool_heavy_list_ints(1000, 10) == 12 and lib.veon_pool_heavy_list_ints(64, 10) == 4
+    assert lib.veon_prepare_v2_voxel_start_offset(8, 6, 88, 16, 44, gs) % 256 == 0
+    # a pooled volume that the fused / down-sample kernels do not take is refused, not mangled
+    buf = (ctypes.c_float * 16)()
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    assert lib.veon_maxdown2_fwd(p, 1, 3, 4, 8, p, null) == -4          # odd Z
+    assert lib.veon_maxdown2_fwd(p, 1, 2, 4, 6, p, null) == -4          # X % 4 != 0
 
 
 def test_cpu_tensors_are_refused_loudly():
