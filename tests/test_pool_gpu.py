@@ -401,3 +401,30 @@ def test_heavy_tile_with_thousands_of_points_in_one_voxel():
     want = O.bev_pool_v2(depth.numpy(), feat.numpy(), rd.numpy(), rf.numpy(), rb.numpy(),
                          (B, Z, Y, X, C), starts.numpy(), lengths.numpy())
     assert np.array_equal(out.cpu().numpy(), np.ascontiguousarray(want))
+
+
+def test_next_kernel_in_the_stream_sees_the_whole_volume():
+    """The forward is two grids, the second a programmatic dependent of the first that does not
+    wait for it.  Whatever is launched next on the stream must still find every tile written:
+    clone the volume with no synchronisation in between, many times, at full size."""
+    from veon_b200 import bev_pool as BP
+    cfg = S.CONFIGS["C2"]
+    B, C = 8, 64
+    lower, interval, size = S.grid_vectors(cfg.grid_config)
+    coor = torch.from_numpy(S.lidar_coor_np(cfg, batch=B)).cuda()
+    _, N, D, H, W, _ = coor.shape
+    g = torch.Generator(device="cuda").manual_seed(0)
+    depth = torch.softmax(torch.randn(B, N, D, H, W, device="cuda", generator=g) * 4, dim=2)
+    feat = torch.randn(B, N, H, W, C, device="cuda", generator=g)
+    prep = BP.prepare_ranks(coor, lower, interval, size)
+    assert int(prep.plan.tile_heavy[0]) > 0
+    shape = (B, 16, 200, 200, C)
+    ref = BP.pool_prepared(depth, feat, prep, shape).clone()
+    torch.cuda.synchronize()
+    scratch = torch.empty(64 << 20, device="cuda")
+    for i in range(12):
+        scratch.normal_()                               # unrelated work in front
+        vol = BP.pool_prepared(depth, feat, prep, shape)
+        copy = vol.clone()                              # the very next kernel reads the volume
+        torch.cuda.synchronize()
+        assert torch.equal(copy, ref), f"iteration {i}: a consumer ran before the volume was complete"
