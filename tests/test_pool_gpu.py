@@ -428,3 +428,33 @@ def test_next_kernel_in_the_stream_sees_the_whole_volume():
         copy = vol.clone()                              # the very next kernel reads the volume
         torch.cuda.synchronize()
         assert torch.equal(copy, ref), f"iteration {i}: a consumer ran before the volume was complete"
+
+
+def test_forward_inside_a_cuda_graph():
+    """Stream capture: the two forward grids and their programmatic edge go into a CUDA graph
+    (the heavy grid then joins the main grid before it completes); replays must reproduce the
+    eager volume, including through the node captured right behind them."""
+    from veon_b200 import bev_pool as BP
+    case = make_case("C1", 2, 64, seed=7)
+    rb, rd, rf, st, ln = gpu_ranks(case["ranks"])
+    B, Z, Y, X, C = case["shape"]
+    V = Z * Y * X
+    plan = BP._plan_for(rd, rf, rb, st, ln, case["dims"], V)
+    assert plan.ok and int(plan.tile_heavy[0]) > 0
+    depth, feat = case["depth"].cuda(), case["feat"].cuda()
+    eager = BP._fwd_planar(depth, feat, rd, rf, rb, plan, B, C, V, (B, C, Z, Y, X)).clone()
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        BP._fwd_planar(depth, feat, rd, rf, rb, plan, B, C, V, (B, C, Z, Y, X))   # warm-up
+    torch.cuda.current_stream().wait_stream(side)
+    with torch.cuda.graph(graph):
+        vol = BP._fwd_planar(depth, feat, rd, rf, rb, plan, B, C, V, (B, C, Z, Y, X))
+        copy = vol.clone()
+    for _ in range(5):
+        copy.zero_()
+        graph.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(copy, eager)

@@ -347,7 +347,8 @@ k_pool_fwd_heavy(const float* __restrict__ depth, const float* __restrict__ feat
                  const int32_t* __restrict__ ranks_depth, const int32_t* __restrict__ ranks_feat,
                  const int32_t* __restrict__ ranks_bev, const int32_t* __restrict__ tile_start,
                  const int32_t* __restrict__ heavy, int heavy_cap, uint32_t tiles_per_sample,
-                 int64_t V, int C, uint32_t n_chunks, int vec_ok, float* __restrict__ out) {
+                 int64_t V, int C, uint32_t n_chunks, int vec_ok, float* __restrict__ out,
+                 int join) {
   constexpr int CC = 32 * KCH;
   constexpr int kSegs = CC / 4;  // 16-byte segments per staged row
   extern __shared__ __align__(16) float hsm[];
@@ -474,6 +475,11 @@ k_pool_fwd_heavy(const float* __restrict__ depth, const float* __restrict__ feat
     }
     __syncthreads();
   }
+  // join != 0: do not COMPLETE before the grid this one is a programmatic dependent of.  Needed
+  // when the launches are captured into a CUDA graph, where the next node would depend on this
+  // grid only; on a plain stream the next launch waits for everything before it anyway, and the
+  // wait would put the main grid's memory flush on this grid's critical path (+17 us).
+  if (join) pdl_wait();
 }
 
 
@@ -1002,6 +1008,12 @@ static int launch_fwd_impl(const float* depth, const float* feat, const int32_t*
   if (blocks > resident) blocks = resident;
   // the heavy-tile kernel stages feature rows with 16-byte copies
   if (heavy && ((C & 3) != 0 || ((uintptr_t)feat & 15) != 0)) heavy = nullptr;
+  int capturing = 0;   // inside a stream capture the heavy grid joins the main grid explicitly
+  {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &st) == cudaSuccess && st != cudaStreamCaptureStatusNone)
+      capturing = 1;
+  }
   // tuning knobs, read once per process
   static const int dbg = env_flag("VEON_FWD_DBG", 0);
   static const int knob_group = env_flag("VEON_FWD_GROUP", 0);
@@ -1043,7 +1055,8 @@ static int launch_fwd_impl(const float* depth, const float* feat, const int32_t*
       if (hblocks > 0) {
         VEON_CUDA_TRY(launch_pdl(k_pool_fwd_heavy<KCH>, dim3((unsigned)hblocks), dim3(kHeavyThreads),
                                  hsmem2, stream, depth, feat, rd, rf, rb, tile_start, heavy,
-                                 heavy_cap, (uint32_t)tps, V, C, (uint32_t)n_chunks, vec_ok, out));
+                                 heavy_cap, (uint32_t)tps, V, C, (uint32_t)n_chunks, vec_ok, out,
+                                 capturing));
         VEON_LAUNCH_CHECK();
       }
     }
@@ -1076,13 +1089,14 @@ static int launch_fwd_impl(const float* depth, const float* feat, const int32_t*
         VEON_LAUNCH_CHECK();
         VEON_CUDA_TRY(launch_pdl(k_pool_fwd_heavy<KCH>, dim3((unsigned)hblocks), dim3(kHeavyThreads),
                                  hsmem, stream, depth, feat, rd, rf, rb, tile_start, heavy,
-                                 heavy_cap, (uint32_t)tps, V, C, (uint32_t)n_chunks, vec_ok, out));
+                                 heavy_cap, (uint32_t)tps, V, C, (uint32_t)n_chunks, vec_ok, out,
+                                 capturing));
         VEON_LAUNCH_CHECK();
         return 0;
       }
       k_pool_fwd_heavy<KCH><<<(unsigned)hblocks, kHeavyThreads, hsmem, stream>>>(
           depth, feat, rd, rf, rb, tile_start, heavy, heavy_cap, (uint32_t)tps, V, C,
-          (uint32_t)n_chunks, vec_ok, out);
+          (uint32_t)n_chunks, vec_ok, out, 0);
       VEON_LAUNCH_CHECK();
       VEON_CUDA_TRY(launch_pdl(k_pool_fwd<KCH, FULLC>, dim3((unsigned)blocks), dim3(kFwdWarps * 32),
                                smem, stream, depth, feat, rd, rf, rb, tile_start, heavy,
