@@ -13,12 +13,17 @@
 // CHANNELS while gathering (feature rows are read as full 128-byte lines, the
 // per-voxel sum lives in registers) and over VOXELS while storing (one 16-byte
 // store per lane = four full 128-byte lines of four channel planes per
-// instruction); a padded shared tile [c][33] does the transposition
-// conflict-free both ways.  Empty voxels are written as zeros from an
-// occupancy mask, so the volume is touched exactly once: no memset, no permute
-// pass, no atomics.  Accumulation order inside a voxel is the rank order,
-// fma(feat, depth, acc) starting from 0 -- the same sequence of roundings as
-// the reference kernel's `psum += feat * depth`.
+// instruction); a padded, zero-filled shared tile [c][36] does the transposition.
+// Empty voxels come out as zeros, so the volume is touched exactly once: no
+// memset, no permute pass, no atomics.  Accumulation order inside a voxel is the
+// rank order, fma(feat, depth, acc) starting from 0 -- the same sequence of
+// roundings as the reference kernel's `psum += feat * depth`.
+//
+// Kernels in this file:
+//   k_pool_fwd         the warp-per-tile kernel above (all tiles below the heavy threshold)
+//   k_pool_fwd_heavy   a CTA per heavy tile (rows staged by cp.async), queued behind it
+//   k_pool_fwd_group   opt-in experiment: a CTA per group of tiles, software-pipelined
+//   k_pool_ds_fwd      opt-in: pooling fused with the neck's 2x2x2 max-downsample
 #include "common.cuh"
 
 #ifndef VEON_FWD_WARPS
