@@ -137,6 +137,9 @@ struct Params {
   uint32_t tmem_cols;
 };
 
+// WP = float4 pieces of the W chunk a producer thread owns (1 for npad <= 64, else 2).
+// With WP == 1 three named register sets fit (three stages of A in flight per lane).
+template <int WP>
 __global__ void __launch_bounds__(kWarps * 32, 1) k_tail_tc(const Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -188,7 +191,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_tail_tc(const Params p) {
       a_off[i] = (uint32_t)(kg4 * 4 + ma) * 512u + (uint32_t)kin * 128u +
                  (uint32_t)(((j >> 1) ^ kin) << 5) + (uint32_t)((j & 1) << 4);
     }
-    constexpr int kWPieces = 2;  // npad * 8 float4 pieces over 512 threads (npad <= 128)
+    constexpr int kWPieces = WP;  // npad * 8 float4 pieces over 512 threads (npad <= 64 * WP)
     const float4* w_src[kWPieces];
     uint32_t w_hi_off[kWPieces], w_lo_off[kWPieces];
     bool w_has[kWPieces], w_real[kWPieces];
@@ -272,18 +275,35 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_tail_tc(const Params p) {
     };
     // Two named register sets, loop unrolled by two: the loads of stage k+1 are issued
     // before stage k is written, and no register is ever copied while its load is in flight
-    // (a rotating copy would wait for the load it copies; a third set spills at 672 threads).
+    // (a rotating copy would wait for the load it copies).  When the thread owns a single W
+    // piece (npad <= 64) a third set fits: three stages of A in flight per lane.
     const int64_t my_tiles = (n_tiles > (int64_t)blockIdx.x)
                                  ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     const int64_t n_stages_total = my_tiles * n_chunks;
-    float4 a0[2], a1[2], w0[kWPieces], w1[kWPieces];
-    if (n_stages_total > 0) load_stage(a0, w0);
-    for (int64_t k = 0; k < n_stages_total; k += 2) {
-      if (k + 1 < n_stages_total) load_stage(a1, w1);
-      store_stage(a0, w0);
-      if (k + 1 >= n_stages_total) break;
-      if (k + 2 < n_stages_total) load_stage(a0, w0);
-      store_stage(a1, w1);
+    if constexpr (WP == 1) {   // (a fourth set spills: 2 319 instead of 3 087 samples/s)
+      float4 a0[2], a1[2], a2[2], w0[1], w1[1], w2[1];
+      if (n_stages_total > 0) load_stage(a0, w0);
+      if (n_stages_total > 1) load_stage(a1, w1);
+      for (int64_t k = 0; k < n_stages_total; k += 3) {
+        if (k + 2 < n_stages_total) load_stage(a2, w2);
+        store_stage(a0, w0);
+        if (k + 1 >= n_stages_total) break;
+        if (k + 3 < n_stages_total) load_stage(a0, w0);
+        store_stage(a1, w1);
+        if (k + 2 >= n_stages_total) break;
+        if (k + 4 < n_stages_total) load_stage(a1, w1);
+        store_stage(a2, w2);
+      }
+    } else {
+      float4 a0[2], a1[2], w0[kWPieces], w1[kWPieces];
+      if (n_stages_total > 0) load_stage(a0, w0);
+      for (int64_t k = 0; k < n_stages_total; k += 2) {
+        if (k + 1 < n_stages_total) load_stage(a1, w1);
+        store_stage(a0, w0);
+        if (k + 1 >= n_stages_total) break;
+        if (k + 2 < n_stages_total) load_stage(a0, w0);
+        store_stage(a1, w1);
+      }
     }
   } else if (warp == kMmaWarp) {
     // ============================ MMA ISSUER ============================
@@ -399,11 +419,16 @@ int veon_tail_tc_launch(const float* feat_occ, const float* text_w, const int32_
   if (stages > tc::kMaxStages) stages = tc::kMaxStages;
   if (stages < 2) return VEON_E_UNSUPPORTED;
   const size_t smem = stages * stage_bytes + tail;
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) {
-    VEON_CUDA_TRY(cudaFuncSetAttribute(tc::k_tail_tc, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem));
-    attr_smem = smem;
+  const bool one_piece = npad <= 64;
+  static size_t attr_smem[2] = {0, 0};
+  if (smem > attr_smem[one_piece]) {
+    if (one_piece)
+      VEON_CUDA_TRY(cudaFuncSetAttribute(tc::k_tail_tc<1>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    else
+      VEON_CUDA_TRY(cudaFuncSetAttribute(tc::k_tail_tc<2>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem[one_piece] = smem;
   }
   uint32_t cols = 32;
   while (cols < (uint32_t)(4 * npad)) cols <<= 1;  // 2 accumulators x 2*npad columns
@@ -417,7 +442,10 @@ int veon_tail_tc_launch(const float* feat_occ, const float* text_w, const int32_
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t n_tiles = (int64_t)B * ((V + tc::TM - 1) / tc::TM);
   const unsigned grid = (unsigned)(n_tiles < sms ? n_tiles : sms);
-  tc::k_tail_tc<<<grid, tc::kWarps * 32, smem, stream>>>(p);
+  if (one_piece)
+    tc::k_tail_tc<1><<<grid, tc::kWarps * 32, smem, stream>>>(p);
+  else
+    tc::k_tail_tc<2><<<grid, tc::kWarps * 32, smem, stream>>>(p);
   VEON_LAUNCH_CHECK();
   return 0;
 }
