@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define VEON_ABI_VERSION 3
+#define VEON_ABI_VERSION 4
 
 #define VEON_E_BADARG    (-1)  /* NULL pointer / non-positive dimension          */
 #define VEON_E_WORKSPACE (-2)  /* workspace smaller than *_workspace_bytes()     */
@@ -301,6 +301,40 @@ int veon_voxel_text_argmax(const float* feat_occ, const float* text_w,
                            const int32_t* class_of_prompt, const float* bin_occ,
                            int B, int C, int Q, int Z, int Y, int X,
                            int free_label, uint8_t* labels, void* stream);
+
+/* semantic_inference_3d alone (san_in_veon_temporal.py:257-259, argument order of the
+ * reference method): sem_occ[b,q,z,y,x] = sum_c text_w[q,c] * feat_occ[b,c,z,y,x], fp32
+ * (3xTF32 on tcgen05 when C % 32 == 0, V % 4 == 0 and Q <= 128, else fp32 FFMA).
+ *   text_w [Q,C]; feat_occ [B,C,Z,Y,X]; sem_occ [B,Q,Z,Y,X] (written, not accumulated). */
+int veon_semantic_inference_3d(const float* text_w, const float* feat_occ,
+                               int B, int C, int Q, int Z, int Y, int X,
+                               float* sem_occ, void* stream);
+
+/* ------------------------------------------------------------------------
+ * (5) Tail at the decoder's resolution.  The reference
+ *     up-samples feat_occ and bin_occ to occ_size with
+ *     F.interpolate(mode="trilinear", align_corners=False)
+ *     (san_in_veon_temporal.py:196-207) and classifies the up-sampled volume.
+ *     Interpolation and classifier are linear, so the logits are computed on
+ *     the low-resolution volume and only Q + 2 channels are interpolated.
+ *
+ *   veon_upsample_classify: sem_occ_lr [B,Q,Zi,Yi,Xi] and bin_occ_lr
+ *     [B,2,Zi,Yi,Xi] -> trilinear (align_corners=False) to [Z,Y,X], class
+ *     merge, arg-max, gate -> labels uint8 [B,X,Y,Z].
+ *   veon_voxel_text_argmax_lowres: feat_occ_lr [B,C,Zi,Yi,Xi] -> the same
+ *     labels; `workspace` holds the low-resolution logits
+ *     (veon_voxel_text_argmax_lowres_workspace_bytes, VEON_E_WORKSPACE if short).
+ * ------------------------------------------------------------------------ */
+int veon_upsample_classify(const float* sem_occ_lr, const float* bin_occ_lr,
+                           const int32_t* class_of_prompt, int B, int Q,
+                           int Zi, int Yi, int Xi, int Z, int Y, int X,
+                           int free_label, uint8_t* labels, void* stream);
+size_t veon_voxel_text_argmax_lowres_workspace_bytes(int B, int Q, int Zi, int Yi, int Xi);
+int veon_voxel_text_argmax_lowres(const float* feat_occ_lr, const float* text_w,
+                                  const int32_t* class_of_prompt, const float* bin_occ_lr,
+                                  int B, int C, int Q, int Zi, int Yi, int Xi,
+                                  int Z, int Y, int X, int free_label, uint8_t* labels,
+                                  void* workspace, size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

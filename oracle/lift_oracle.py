@@ -226,6 +226,48 @@ def voxel_text_labels(feat_occ, text_w, class_of_prompt, bin_occ, free_label=17,
     return np.ascontiguousarray(lab.transpose(0, 3, 2, 1)).astype(np.uint8)
 
 
+def trilinear_upsample(x, size):
+    """F.interpolate(x, size=size, mode="trilinear", align_corners=False) for x [B,C,Zi,Yi,Xi]
+    (san_in_veon_temporal.py:196-207), float32, restated from ATen's upsample_trilinear3d:
+    src = max(scale*(dst+0.5)-0.5, 0) with scale = in/out, i0 = int(src), i1 = i0 + (i0 < in-1),
+    l1 = src - i0, l0 = 1 - l1;  value = lz0*(ly0*(lx0*a + lx1*b) + ly1*(lx0*c + lx1*d)) + lz1*(...).
+    Pinned against torch's own F.interpolate in tests/test_oracle_golden.py."""
+    x = np.asarray(x, dtype=np.float32)
+
+    def axis(n_in, n_out):
+        scale = np.float32(n_in) / np.float32(n_out)
+        src = scale * (np.arange(n_out, dtype=np.float32) + np.float32(0.5)) - np.float32(0.5)
+        src = np.maximum(src, np.float32(0)).astype(np.float32)
+        i0 = src.astype(np.int64)
+        i1 = i0 + (i0 < n_in - 1)
+        l1 = (src - i0.astype(np.float32)).astype(np.float32)
+        return i0, i1, (np.float32(1) - l1).astype(np.float32), l1
+
+    Z, Y, X = (int(v) for v in size)
+    z0, z1, lz0, lz1 = axis(x.shape[2], Z)
+    y0, y1, ly0, ly1 = axis(x.shape[3], Y)
+    x0, x1, lx0, lx1 = axis(x.shape[4], X)
+
+    def plane(zi):
+        p = x[:, :, zi]                                    # [B,C,Z,Yi,Xi]
+        r0, r1 = p[:, :, :, y0], p[:, :, :, y1]            # [B,C,Z,Y,Xi]
+        top = lx0 * r0[..., x0] + lx1 * r0[..., x1]
+        bot = lx0 * r1[..., x0] + lx1 * r1[..., x1]
+        return ly0[:, None] * top + ly1[:, None] * bot
+
+    out = lz0[:, None, None] * plane(z0) + lz1[:, None, None] * plane(z1)
+    return out.astype(np.float32)
+
+
+def voxel_text_labels_lowres(feat_occ_lr, text_w, class_of_prompt, bin_occ_lr, occ_size,
+                             free_label=17, dtype=np.float32):
+    """The reference's order of operations: up-sample the decoder's feat_occ and bin_occ
+    (san_in_veon_temporal.py:196-207), then classify the up-sampled volume."""
+    feat = trilinear_upsample(feat_occ_lr, occ_size)
+    gate = trilinear_upsample(bin_occ_lr, occ_size)
+    return voxel_text_labels(feat, text_w, class_of_prompt, gate, free_label, dtype)
+
+
 # --------------------------------------------------------------------------
 # BASELINE.json configs[0]: the reference's pure-PyTorch CPU lift (timed leg)
 # --------------------------------------------------------------------------

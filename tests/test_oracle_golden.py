@@ -161,3 +161,64 @@ def test_class_groups_and_tail_oracle():
                 merged = [logits[cls == k].max() for k in range(18)]
                 want = int(np.argmax(merged)) if bin_occ[0, 0, z, y, x] > bin_occ[0, 1, z, y, x] else 17
                 assert lab[0, x, y, z] == want
+
+
+# ---- tail at the decoder's resolution -------------------------------------
+@pytest.mark.parametrize("shape,size", [
+    ((2, 3, 8, 10, 12), (16, 20, 24)),      # the 2x case of the model
+    ((1, 2, 3, 5, 7), (7, 9, 20)),          # non-integer scales
+    ((1, 2, 6, 9, 9), (3, 4, 5)),           # down-sampling
+    ((1, 2, 4, 4, 4), (4, 4, 4)),           # identity
+    ((1, 1, 8, 100, 100), (16, 200, 200)),  # one channel at the real size
+])
+def test_trilinear_oracle_matches_torch_interpolate(shape, size):
+    """The reference calls F.interpolate(..., mode="trilinear", align_corners=False)
+    (san_in_veon_temporal.py:196-207); torch is that function, so it pins the restatement."""
+    import torch
+    import torch.nn.functional as F
+    x = torch.randn(*shape, generator=torch.Generator().manual_seed(sum(shape)))
+    want = F.interpolate(x, size=size, mode="trilinear", align_corners=False).numpy()
+    got = O.trilinear_upsample(x.numpy(), size)
+    assert got.shape == want.shape and got.dtype == np.float32
+    np.testing.assert_allclose(got, want, rtol=0, atol=2e-6)
+    if shape[2:] == tuple(size):
+        np.testing.assert_array_equal(got, x.numpy())
+
+
+def test_lowres_tail_oracle_follows_the_reference_expressions():
+    """interpolate -> einsum -> merge -> label rule, written with the reference's own torch
+    expressions (san_in_veon_temporal.py:196-208,257-259; san_in_veon_entry_temporal.py:273-297;
+    veon_temporal.py:223-229), against the numpy oracle."""
+    import torch
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(5)
+    refl = [0, 0, 1, 2, 2, 2, 3]
+    cls = O.class_groups(refl)
+    B, C, size = 2, 24, (6, 10, 14)
+    feat = torch.sigmoid(torch.randn(B, C, 3, 5, 7, generator=g)) - 0.5
+    gate = torch.randn(B, 2, 3, 5, 7, generator=g)
+    w = torch.randn(len(refl) + 1, C, generator=g)
+    feat_occ = F.interpolate(feat, size=size, mode="trilinear", align_corners=False)
+    bin_occ = F.interpolate(gate, size=size, mode="trilinear", align_corners=False)
+    sem = torch.einsum("qc,bczhw->bqzhw", w, feat_occ)
+    merged = torch.stack([sem[:, torch.from_numpy(np.where(cls == k)[0])].max(dim=1).values
+                          for k in range(int(cls.max()) + 1)], dim=1)
+    mx = torch.max(torch.softmax(merged, dim=1), dim=1)
+    sel = (mx.values > 0.0) & (torch.softmax(bin_occ, dim=1)[:, 0] > 0.5)
+    want = torch.where(sel, mx.indices, torch.ones_like(mx.indices) * 17)
+    want = want.permute(0, 3, 2, 1).contiguous().numpy().astype(np.uint8)
+    got = O.voxel_text_labels_lowres(feat.numpy(), w.numpy(), cls, gate.numpy(), size)
+    assert got.shape == want.shape == (B, size[2], size[1], size[0])
+    assert (got == want).mean() >= 0.999       # float near-ties only
+    assert 0.2 < (got == 17).mean() < 0.8
+
+
+def test_classifier_commutes_with_the_interpolation():
+    """the identity the low-resolution route rests on, in float64"""
+    rng = np.random.default_rng(0)
+    feat = rng.standard_normal((1, 6, 4, 5, 6))
+    w = rng.standard_normal((3, 6))
+    size = (8, 10, 12)
+    a = np.einsum("qc,bczyx->bqzyx", w, O.trilinear_upsample(feat, size).astype(np.float64))
+    b = O.trilinear_upsample(np.einsum("qc,bczyx->bqzyx", w, feat), size)
+    np.testing.assert_allclose(a, b, rtol=0, atol=1e-5)

@@ -71,3 +71,109 @@ def test_ties_take_first_class_and_nan_is_free():
     feat[0, 0, 0, 0, 0] = float("nan")
     got, _ = run(feat, w, refl, bin_occ)
     assert got[0, 0, 0, 0] == 17 and np.all(got.reshape(-1)[1:] == 0)
+
+
+# ---- semantic_inference_3d alone and the decoder-resolution route ---------
+@pytest.mark.parametrize("C,Q,vol", [
+    (512, 18, (4, 40, 50)),     # tcgen05 path, one W piece
+    (256, 67, (8, 25, 20)),     # tcgen05 path, two W pieces
+    (30, 6, (3, 5, 7)),         # FFMA path (C % 32 != 0, V % 4 != 0)
+])
+def test_semantic_inference_3d_matches_fp32_einsum(C, Q, vol):
+    """logits of san_in_veon_temporal.py:257-259; tolerance: max-abs error <= 1e-5 of the
+    largest logit (north_star allows 1e-3 relative for fp32 accumulation; 3xTF32 gives ~2^-21)."""
+    from veon_b200.tail import semantic_inference_3d
+    g = torch.Generator().manual_seed(C + Q)
+    feat = torch.sigmoid(torch.randn(2, C, *vol, generator=g)) - 0.5
+    w = torch.randn(Q, C, generator=g)
+    w = 100.0 * w / w.norm(dim=1, keepdim=True)
+    got = semantic_inference_3d(w.cuda(), feat.cuda())
+    torch.cuda.synchronize()
+    assert got.shape == (2, Q, *vol) and got.dtype == torch.float32
+    want = torch.einsum("qc,bczhw->bqzhw", w.double(), feat.double())
+    err = (got.cpu().double() - want).abs().max().item()
+    assert err <= 1e-5 * want.abs().max().item(), err
+
+
+def lowres_case(B, C, refl, lr, seed):
+    g = torch.Generator().manual_seed(seed)
+    feat = torch.sigmoid(torch.randn(B, C, *lr, generator=g)) - 0.5
+    w = torch.randn(len(refl) + 1, C, generator=g)
+    w = 100.0 * w / w.norm(dim=1, keepdim=True)
+    gate = torch.randn(B, 2, *lr, generator=g)
+    return feat, w, gate
+
+
+@pytest.mark.parametrize("C,refl,lr,size", [
+    (512, list(range(17)), (8, 20, 25), (16, 40, 50)),                                   # column kernel, Q=18
+    (256, [k for k, n in enumerate(SIZES) for _ in range(n)], (8, 12, 16), (16, 24, 32)),  # Q=67
+    (64, list(range(17)), (8, 10, 10), (16, 37, 23)),         # column kernel, non-integer x/y scales
+    (30, [0, 0, 1, 2, 2, 2], (3, 5, 7), (7, 9, 20)),          # generic kernel + FFMA logits
+    (32, [0, 1, 1, 2], (4, 6, 8), (4, 6, 8)),                 # identity sizes
+    (32, [0, 1, 1, 2], (6, 8, 12), (3, 4, 5)),                # down-sampling
+])
+def test_lowres_route_matches_oracle(C, refl, lr, size):
+    """classify-then-interpolate (ours) against interpolate-then-classify (the reference's order,
+    CPU oracle): labels agree on >= 99.99 % of voxels."""
+    from veon_b200.tail import class_of_prompt, voxel_text_argmax_lowres
+    feat, w, gate = lowres_case(2, C, refl, lr, seed=C + len(refl))
+    cls = class_of_prompt(refl)
+    got = voxel_text_argmax_lowres(feat.cuda(), w.cuda(), cls.cuda(), gate.cuda(), occ_size=size)
+    torch.cuda.synchronize()
+    got = got.cpu().numpy()
+    Z, Y, X = size
+    assert got.shape == (2, X, Y, Z) and got.dtype == np.uint8
+    want = O.voxel_text_labels_lowres(feat.numpy(), w.numpy(), cls.numpy(), gate.numpy(), size)
+    agree = float((got == want).mean())
+    n = want.size
+    assert agree >= 0.9999 or (n < 20000 and (got != want).sum() <= 1), agree
+    gate_hr = O.trilinear_upsample(gate.numpy(), size)
+    clear = np.abs(gate_hr[:, 0] - gate_hr[:, 1]) > 1e-4
+    free = np.transpose((gate_hr[:, 0] <= gate_hr[:, 1]) & clear, (0, 3, 2, 1))
+    assert np.all(got[free] == 17)
+    assert 0.2 < (got != 17).mean() < 0.8
+
+
+def test_lowres_route_full_volume_and_full_resolution_route_agree():
+    """8x100x100 -> 16x200x200 (the model's sizes), C=128: against the oracle and against our own
+    full-resolution kernel fed with torch's up-sampled volume."""
+    import torch.nn.functional as F
+    from veon_b200.tail import class_of_prompt, voxel_text_argmax, voxel_text_argmax_lowres
+    refl = list(range(17))
+    size = (16, 200, 200)
+    feat, w, gate = lowres_case(1, 128, refl, (8, 100, 100), seed=11)
+    cls = class_of_prompt(refl)
+    ws = torch.empty(18 * 80000, dtype=torch.float32, device="cuda")
+    got = voxel_text_argmax_lowres(feat.cuda(), w.cuda(), cls.cuda(), gate.cuda(), occ_size=size,
+                                   workspace=ws)
+    feat_hr = F.interpolate(feat.cuda(), size=size, mode="trilinear", align_corners=False)
+    gate_hr = F.interpolate(gate.cuda(), size=size, mode="trilinear", align_corners=False)
+    full = voxel_text_argmax(feat_hr, w.cuda(), cls.cuda(), gate_hr)
+    torch.cuda.synchronize()
+    assert got.shape == full.shape == (1, 200, 200, 16)
+    assert float((got == full).float().mean()) >= 0.9999
+    want = O.voxel_text_labels_lowres(feat.numpy(), w.numpy(), cls.numpy(), gate.numpy(), size)
+    assert float((got.cpu().numpy() == want).mean()) >= 0.9999
+
+
+def test_upsample_classify_on_given_logits_and_nan():
+    """exactly representable weights (2x up-sampling: 0.25 / 0.75) on integer logits: the label
+    map must equal the oracle's everywhere; a NaN logit frees every output it touches."""
+    from veon_b200.tail import upsample_classify
+    g = torch.Generator().manual_seed(2)
+    refl = [0, 1, 1, 2]
+    cls = torch.from_numpy(O.class_groups(refl))
+    for lr, size in (((8, 6, 9), (16, 12, 18)), ((2, 3, 4), (4, 6, 8))):
+        sem = torch.randint(-8, 9, (1, 5, *lr), generator=g).float() * 4.0 + torch.arange(5).view(1, 5, 1, 1, 1) * 0.125
+        gate = torch.randint(-3, 4, (1, 2, *lr), generator=g).float() * 4.0 + torch.tensor([0.0, 1.0]).view(1, 2, 1, 1, 1)
+        got = upsample_classify(sem.cuda(), gate.cuda(), cls.cuda(), size).cpu().numpy()
+        sem_hr = O.trilinear_upsample(sem.numpy(), size)
+        gate_hr = O.trilinear_upsample(gate.numpy(), size)
+        merged = np.stack([sem_hr[:, np.where(cls.numpy() == k)[0]].max(axis=1) for k in range(4)], 1)
+        want = np.where(gate_hr[:, 0] > gate_hr[:, 1], merged.argmax(1), 17)
+        np.testing.assert_array_equal(got, np.transpose(want, (0, 3, 2, 1)).astype(np.uint8))
+        sem[0, 2, 0, 0, 0] = float("nan")
+        got = upsample_classify(sem.cuda(), gate.cuda(), cls.cuda(), size).cpu().numpy()
+        touched = np.isnan(O.trilinear_upsample(sem.numpy(), size)).any(axis=1)
+        assert touched.sum() >= 1
+        assert np.all(got[np.transpose(touched, (0, 3, 2, 1))] == 17)

@@ -64,6 +64,13 @@ _SIGNATURES = {
                                             _P, _P, _P, _P, _P]),
     "veon_voxel_text_argmax": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int,
                                        c_int, _P, _P]),
+    "veon_semantic_inference_3d": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P]),
+    "veon_upsample_classify": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                       c_int, c_int, _P, _P]),
+    "veon_voxel_text_argmax_lowres_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
+    "veon_voxel_text_argmax_lowres": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int,
+                                              c_int, c_int, c_int, c_int, c_int, _P, _P, c_size_t,
+                                              _P]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

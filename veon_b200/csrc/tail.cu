@@ -20,11 +20,13 @@ namespace veon {
 constexpr int kTailThreads = 128;
 constexpr int kTailQT = 24;  // prompts held in registers per pass
 
+// LOGITS: store sem_occ [B,Q,V] (semantic_inference_3d alone) instead of the labels.
+template <bool LOGITS>
 __global__ void __launch_bounds__(kTailThreads)
 k_voxel_text_argmax(const float* __restrict__ feat_occ, const float* __restrict__ text_w,
                     const int32_t* __restrict__ class_of_prompt,
                     const float* __restrict__ bin_occ, int C, int Q, int Z, int Y, int X,
-                    int free_label, uint8_t* __restrict__ labels) {
+                    int free_label, uint8_t* __restrict__ labels, float* __restrict__ logits) {
   extern __shared__ float w_s[];  // [kTailQT][C] of the current prompt tile
   const int64_t V = (int64_t)Z * Y * X;
   const int b = blockIdx.y;
@@ -65,6 +67,12 @@ k_voxel_text_argmax(const float* __restrict__ feat_occ, const float* __restrict_
       for (int q = 0; q < kTailQT; ++q)
         if (q < nq) acc[q] = fmaf(w_s[q * C + c], f0, acc[q]);
     }
+    if constexpr (LOGITS) {
+#pragma unroll
+      for (int q = 0; q < kTailQT; ++q)
+        if (q < nq && live) logits[((int64_t)b * Q + q0 + q) * V + v] = acc[q];
+      continue;
+    }
     // group-max over prompts of one class, then first-index argmax over classes
 #pragma unroll
     for (int q = 0; q < kTailQT; ++q) {
@@ -82,6 +90,7 @@ k_voxel_text_argmax(const float* __restrict__ feat_occ, const float* __restrict_
       }
     }
   }
+  if constexpr (LOGITS) return;
   if (cur_cls >= 0 && (best_cls < 0 || cur > best)) { best = cur; best_cls = cur_cls; }
   if (!live) return;
   bad |= (best == -INFINITY);  // all logits -inf => softmax NaN
@@ -106,15 +115,13 @@ using namespace veon;
 // tensor-core path (tail_tc.cu); VEON_E_UNSUPPORTED when the shape does not fit it
 int veon_tail_tc_launch(const float* feat_occ, const float* text_w, const int32_t* cls,
                         const float* bin_occ, int B, int C, int Q, int Z, int Y, int X,
-                        int free_label, uint8_t* labels, cudaStream_t stream);
+                        int free_label, uint8_t* labels, float* logits, cudaStream_t stream);
 
-extern "C" int veon_voxel_text_argmax(const float* feat_occ, const float* text_w,
-                                      const int32_t* class_of_prompt, const float* bin_occ,
-                                      int B, int C, int Q, int Z, int Y, int X, int free_label,
-                                      uint8_t* labels, void* stream) {
-  if (!feat_occ || !text_w || !class_of_prompt || !bin_occ || !labels || B <= 0 || C <= 0 ||
-      Q <= 0 || Z <= 0 || Y <= 0 || X <= 0 || B > 65535)
-    return VEON_E_BADARG;
+// labels (logits == nullptr) or raw logits (labels == nullptr) of B volumes
+static int tail_dispatch(const float* feat_occ, const float* text_w,
+                         const int32_t* class_of_prompt, const float* bin_occ, int B, int C,
+                         int Q, int Z, int Y, int X, int free_label, uint8_t* labels,
+                         float* logits, cudaStream_t stream) {
   {  // tcgen05 path unless VEON_TAIL_IMPL=ffma or the shape does not fit (C % 32, V % 4, Q > 128)
     static int use_tc = -1;
     if (use_tc < 0) {
@@ -123,7 +130,7 @@ extern "C" int veon_voxel_text_argmax(const float* feat_occ, const float* text_w
     }
     if (use_tc) {
       const int rc = veon_tail_tc_launch(feat_occ, text_w, class_of_prompt, bin_occ, B, C, Q, Z, Y, X,
-                                         free_label, labels, (cudaStream_t)stream);
+                                         free_label, labels, logits, stream);
       if (rc != VEON_E_UNSUPPORTED) return rc;
     }
   }
@@ -131,14 +138,41 @@ extern "C" int veon_voxel_text_argmax(const float* feat_occ, const float* text_w
   if (smem > 200 * 1024) return VEON_E_UNSUPPORTED;
   static size_t attr_smem = 48 * 1024;
   if (smem > attr_smem) {
-    VEON_CUDA_TRY(cudaFuncSetAttribute(k_voxel_text_argmax,
+    VEON_CUDA_TRY(cudaFuncSetAttribute(k_voxel_text_argmax<false>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VEON_CUDA_TRY(cudaFuncSetAttribute(k_voxel_text_argmax<true>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_smem = smem;
   }
   const int64_t V = (int64_t)Z * Y * X;
   dim3 grid((unsigned)ceil_div64(V, kTailThreads), (unsigned)B);
-  k_voxel_text_argmax<<<grid, kTailThreads, smem, (cudaStream_t)stream>>>(
-      feat_occ, text_w, class_of_prompt, bin_occ, C, Q, Z, Y, X, free_label, labels);
+  if (logits)
+    k_voxel_text_argmax<true><<<grid, kTailThreads, smem, stream>>>(
+        feat_occ, text_w, class_of_prompt, bin_occ, C, Q, Z, Y, X, free_label, labels, logits);
+  else
+    k_voxel_text_argmax<false><<<grid, kTailThreads, smem, stream>>>(
+        feat_occ, text_w, class_of_prompt, bin_occ, C, Q, Z, Y, X, free_label, labels, logits);
   VEON_LAUNCH_CHECK();
   return 0;
+}
+
+extern "C" int veon_voxel_text_argmax(const float* feat_occ, const float* text_w,
+                                      const int32_t* class_of_prompt, const float* bin_occ,
+                                      int B, int C, int Q, int Z, int Y, int X, int free_label,
+                                      uint8_t* labels, void* stream) {
+  if (!feat_occ || !text_w || !class_of_prompt || !bin_occ || !labels || B <= 0 || C <= 0 ||
+      Q <= 0 || Z <= 0 || Y <= 0 || X <= 0 || B > 65535)
+    return VEON_E_BADARG;
+  return tail_dispatch(feat_occ, text_w, class_of_prompt, bin_occ, B, C, Q, Z, Y, X, free_label,
+                       labels, nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int veon_semantic_inference_3d(const float* text_w, const float* feat_occ, int B, int C,
+                                          int Q, int Z, int Y, int X, float* sem_occ,
+                                          void* stream) {
+  if (!feat_occ || !text_w || !sem_occ || B <= 0 || C <= 0 || Q <= 0 || Z <= 0 || Y <= 0 ||
+      X <= 0 || B > 65535)
+    return VEON_E_BADARG;
+  return tail_dispatch(feat_occ, text_w, nullptr, nullptr, B, C, Q, Z, Y, X, 0, nullptr, sem_occ,
+                       (cudaStream_t)stream);
 }

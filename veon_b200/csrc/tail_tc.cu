@@ -132,6 +132,7 @@ struct Params {
   const int32_t* cls;    // [Q]
   const float* bin_occ;  // [B,2,V]
   uint8_t* labels;       // [B,X,Y,Z]
+  float* logits;         // LOGITS variant: sem_occ [B,Q,V] instead of labels
   int B, C, Q, Z, Y, X, npad, stages, free_label;
   int64_t V;
   uint32_t tmem_cols;
@@ -139,7 +140,8 @@ struct Params {
 
 // WP = float4 pieces of the W chunk a producer thread owns (1 for npad <= 64, else 2).
 // With WP == 1 three named register sets fit (three stages of A in flight per lane).
-template <int WP>
+// LOGITS: the epilogue stores the raw logits (semantic_inference_3d alone) instead of labels.
+template <int WP, bool LOGITS>
 __global__ void __launch_bounds__(kWarps * 32, 1) k_tail_tc(const Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -347,6 +349,21 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_tail_tc(const Params p) {
       const int64_t b = tile / vtiles;
       const int64_t v = (tile - b * vtiles) * TM + 32 * quarter + lane;
       const uint32_t taddr = tmem_base + (uint32_t)(acc * 2 * npad) + ((uint32_t)(32 * quarter) << 16);
+      if constexpr (LOGITS) {
+        float* dst = p.logits + (int64_t)b * p.Q * p.V + v;  // lanes = consecutive voxels
+        for (int q0 = 0; q0 < npad; q0 += 16) {
+          float m[16], x[16];
+          tc_ld16(taddr + q0, m);
+          tc_ld16(taddr + npad + q0, x);
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (q0 + i < p.Q && v < p.V) dst[(int64_t)(q0 + i) * p.V] = m[i] + x[i];
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(acc_empty + acc);
+        continue;
+      }
       float best = 0.f, cur = 0.f;
       int best_cls = -1, cur_cls = -1;
       bool bad = false;
@@ -405,10 +422,24 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_tail_tc(const Params p) {
 
 using namespace veon;
 
-// returns 0 when launched, VEON_E_UNSUPPORTED when the shape does not fit this path
+// returns 0 when launched, VEON_E_UNSUPPORTED when the shape does not fit this path.
+// logits != nullptr: write sem_occ [B,Q,V] (cls / bin_occ / labels unused).
+template <int WP, bool LOGITS>
+static int launch_variant(const tc::Params& p, unsigned grid, size_t smem, cudaStream_t stream) {
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    VEON_CUDA_TRY(cudaFuncSetAttribute(tc::k_tail_tc<WP, LOGITS>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem = smem;
+  }
+  tc::k_tail_tc<WP, LOGITS><<<grid, tc::kWarps * 32, smem, stream>>>(p);
+  VEON_LAUNCH_CHECK();
+  return 0;
+}
+
 int veon_tail_tc_launch(const float* feat_occ, const float* text_w, const int32_t* cls,
                         const float* bin_occ, int B, int C, int Q, int Z, int Y, int X,
-                        int free_label, uint8_t* labels, cudaStream_t stream) {
+                        int free_label, uint8_t* labels, float* logits, cudaStream_t stream) {
   const int64_t V = (int64_t)Z * Y * X;
   const int npad = ((Q + 15) / 16) * 16;
   if (C % tc::KC != 0 || (V & 3) != 0 || npad > 128 || (((uintptr_t)feat_occ | (uintptr_t)text_w) & 15))
@@ -420,21 +451,12 @@ int veon_tail_tc_launch(const float* feat_occ, const float* text_w, const int32_
   if (stages < 2) return VEON_E_UNSUPPORTED;
   const size_t smem = stages * stage_bytes + tail;
   const bool one_piece = npad <= 64;
-  static size_t attr_smem[2] = {0, 0};
-  if (smem > attr_smem[one_piece]) {
-    if (one_piece)
-      VEON_CUDA_TRY(cudaFuncSetAttribute(tc::k_tail_tc<1>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    else
-      VEON_CUDA_TRY(cudaFuncSetAttribute(tc::k_tail_tc<2>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_smem[one_piece] = smem;
-  }
   uint32_t cols = 32;
   while (cols < (uint32_t)(4 * npad)) cols <<= 1;  // 2 accumulators x 2*npad columns
   if (cols > 512) return VEON_E_UNSUPPORTED;
   tc::Params p;
   p.feat = feat_occ; p.w = text_w; p.cls = cls; p.bin_occ = bin_occ; p.labels = labels;
+  p.logits = logits;
   p.B = B; p.C = C; p.Q = Q; p.Z = Z; p.Y = Y; p.X = X; p.npad = npad; p.stages = stages;
   p.free_label = free_label; p.V = V; p.tmem_cols = cols;
   int dev = 0, sms = 148;
@@ -442,10 +464,9 @@ int veon_tail_tc_launch(const float* feat_occ, const float* text_w, const int32_
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t n_tiles = (int64_t)B * ((V + tc::TM - 1) / tc::TM);
   const unsigned grid = (unsigned)(n_tiles < sms ? n_tiles : sms);
-  if (one_piece)
-    tc::k_tail_tc<1><<<grid, tc::kWarps * 32, smem, stream>>>(p);
-  else
-    tc::k_tail_tc<2><<<grid, tc::kWarps * 32, smem, stream>>>(p);
-  VEON_LAUNCH_CHECK();
-  return 0;
+  if (logits)
+    return one_piece ? launch_variant<1, true>(p, grid, smem, stream)
+                     : launch_variant<2, true>(p, grid, smem, stream);
+  return one_piece ? launch_variant<1, false>(p, grid, smem, stream)
+                   : launch_variant<2, false>(p, grid, smem, stream);
 }

@@ -5,6 +5,11 @@ Mirrors three reference sites as ONE fused call:
     semantic_inference_3d(ov_classifier_weight, feat_occ)   san_in_veon_temporal.py:257-259
     _merge_classes_prob(sem_occ, dim=1, ...)                san_in_veon_entry_temporal.py:273-297
     simple_test label rule                                  veon_temporal.py:223-229,240
+
+and, for the decoder-resolution route, the two up-samplings in front of them
+(san_in_veon_temporal.py:196-207): `voxel_text_argmax_lowres` classifies the low-resolution
+volume and interpolates the Q logit channels instead of the C feature channels.
+`semantic_inference_3d` is the reference method of that name on its own (logits out).
 """
 import ctypes
 
@@ -12,7 +17,8 @@ import torch
 
 from . import _lib
 
-__all__ = ["class_of_prompt", "voxel_text_argmax"]
+__all__ = ["class_of_prompt", "voxel_text_argmax", "semantic_inference_3d",
+           "upsample_classify", "voxel_text_argmax_lowres"]
 
 
 def class_of_prompt(class_reflection):
@@ -59,4 +65,93 @@ def voxel_text_argmax(feat_occ, ov_classifier_weight, prompt_class, bin_occ, fre
             B, C, Q, Z, Y, X, int(free_label), ctypes.c_void_p(labels.data_ptr()),
             ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
     _lib.check(rc, "veon_voxel_text_argmax")
+    return labels
+
+
+def _cuda_only(*tensors):
+    for t in tensors:
+        if not t.is_cuda:
+            raise RuntimeError("veon_b200 runs on CUDA tensors only (no CPU fallback)")
+
+
+def _stream(dev):
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def semantic_inference_3d(ov_classifier_weight, mask_pred):
+    """`SANInVeonTemporal.semantic_inference_3d` (san_in_veon_temporal.py:257-259):
+    einsum("qc,bczhw->bqzhw") of the [Q,C] classifier and a [B,C,Z,Y,X] volume -> [B,Q,Z,Y,X]
+    f32 (no gradient: the reference's weight is a detached constant and this entry serves the
+    inference route)."""
+    _cuda_only(ov_classifier_weight, mask_pred)
+    lib = _lib.load()
+    w = ov_classifier_weight.detach().contiguous().float()
+    feat = mask_pred.detach().contiguous().float()
+    B, C, Z, Y, X = feat.shape
+    Q = w.shape[0]
+    if w.shape[1] != C:
+        raise ValueError("inconsistent tail shapes")
+    dev = feat.device
+    with torch.cuda.device(dev):
+        sem = torch.empty((B, Q, Z, Y, X), dtype=torch.float32, device=dev)
+        rc = lib.veon_semantic_inference_3d(
+            ctypes.c_void_p(w.data_ptr()), ctypes.c_void_p(feat.data_ptr()), B, C, Q, Z, Y, X,
+            ctypes.c_void_p(sem.data_ptr()), _stream(dev))
+    _lib.check(rc, "veon_semantic_inference_3d")
+    return sem
+
+
+def upsample_classify(sem_occ_lr, bin_occ_lr, prompt_class, occ_size, free_label=17):
+    """Low-resolution logits [B,Q,Zi,Yi,Xi] and gate [B,2,Zi,Yi,Xi] -> trilinear
+    (align_corners=False) to `occ_size` = (Z,Y,X), class merge, arg-max, gate -> uint8 [B,X,Y,Z]."""
+    _cuda_only(sem_occ_lr, bin_occ_lr, prompt_class)
+    lib = _lib.load()
+    sem = sem_occ_lr.detach().contiguous().float()
+    gate = bin_occ_lr.detach().contiguous().float()
+    cls = prompt_class.contiguous().int()
+    B, Q, Zi, Yi, Xi = sem.shape
+    Z, Y, X = (int(v) for v in occ_size)
+    if tuple(gate.shape) != (B, 2, Zi, Yi, Xi) or cls.numel() != Q:
+        raise ValueError("inconsistent tail shapes")
+    dev = sem.device
+    with torch.cuda.device(dev):
+        labels = torch.empty((B, X, Y, Z), dtype=torch.uint8, device=dev)
+        rc = lib.veon_upsample_classify(
+            ctypes.c_void_p(sem.data_ptr()), ctypes.c_void_p(gate.data_ptr()),
+            ctypes.c_void_p(cls.data_ptr()), B, Q, Zi, Yi, Xi, Z, Y, X, int(free_label),
+            ctypes.c_void_p(labels.data_ptr()), _stream(dev))
+    _lib.check(rc, "veon_upsample_classify")
+    return labels
+
+
+def voxel_text_argmax_lowres(feat_occ_lr, ov_classifier_weight, prompt_class, bin_occ_lr,
+                             occ_size=(16, 200, 200), free_label=17, workspace=None):
+    """The whole inference tail from the decoder's outputs (san_in_veon_temporal.py:196-208 +
+    the merge and label rule): feat_occ_lr [B,C,Zi,Yi,Xi], bin_occ_lr [B,2,Zi,Yi,Xi] ->
+    uint8 labels [B,X,Y,Z] on the `occ_size` grid.  `workspace`: optional float32 CUDA tensor of
+    at least B*Q*Zi*Yi*Xi elements to hold the low-resolution logits (allocated if absent)."""
+    _cuda_only(feat_occ_lr, ov_classifier_weight, prompt_class, bin_occ_lr)
+    lib = _lib.load()
+    feat = feat_occ_lr.detach().contiguous().float()
+    w = ov_classifier_weight.detach().contiguous().float()
+    cls = prompt_class.contiguous().int()
+    gate = bin_occ_lr.detach().contiguous().float()
+    B, C, Zi, Yi, Xi = feat.shape
+    Q = w.shape[0]
+    Z, Y, X = (int(v) for v in occ_size)
+    if w.shape[1] != C or cls.numel() != Q or tuple(gate.shape) != (B, 2, Zi, Yi, Xi):
+        raise ValueError("inconsistent tail shapes")
+    dev = feat.device
+    need = lib.veon_voxel_text_argmax_lowres_workspace_bytes(B, Q, Zi, Yi, Xi)
+    with torch.cuda.device(dev):
+        if workspace is None:
+            workspace = torch.empty(need // 4, dtype=torch.float32, device=dev)
+        ws_bytes = workspace.numel() * workspace.element_size()
+        labels = torch.empty((B, X, Y, Z), dtype=torch.uint8, device=dev)
+        rc = lib.veon_voxel_text_argmax_lowres(
+            ctypes.c_void_p(feat.data_ptr()), ctypes.c_void_p(w.data_ptr()),
+            ctypes.c_void_p(cls.data_ptr()), ctypes.c_void_p(gate.data_ptr()),
+            B, C, Q, Zi, Yi, Xi, Z, Y, X, int(free_label), ctypes.c_void_p(labels.data_ptr()),
+            ctypes.c_void_p(workspace.data_ptr()), ws_bytes, _stream(dev))
+    _lib.check(rc, "veon_voxel_text_argmax_lowres")
     return labels
