@@ -329,6 +329,14 @@ int veon_upsample_classify(const float* sem_occ_lr, const float* bin_occ_lr,
                            const int32_t* class_of_prompt, int B, int Q,
                            int Zi, int Yi, int Xi, int Z, int Y, int X,
                            int free_label, uint8_t* labels, void* stream);
+/* _merge_classes_prob + the label rule alone (san_in_veon_entry_temporal.py:273-297,
+ * veon_temporal.py:223-229,240) on ready-made logits: sem_occ [B,Q,Z,Y,X], bin_occ [B,2,Z,Y,X]
+ * -> labels uint8 [B,X,Y,Z].  The batch strides (in floats) are free, so both inputs may be
+ * channel slices of one volume; everything inside a sample is contiguous. */
+int veon_classify_logits(const float* sem_occ, int64_t sem_batch_stride,
+                         const float* bin_occ, int64_t bin_batch_stride,
+                         const int32_t* class_of_prompt, int B, int Q, int Z, int Y, int X,
+                         int free_label, uint8_t* labels, void* stream);
 size_t veon_voxel_text_argmax_lowres_workspace_bytes(int B, int Q, int Zi, int Yi, int Xi);
 int veon_voxel_text_argmax_lowres(const float* feat_occ_lr, const float* text_w,
                                   const int32_t* class_of_prompt, const float* bin_occ_lr,

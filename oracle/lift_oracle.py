@@ -300,7 +300,7 @@ def torch_cpu_lift(coor, depth, feat, grid_lower_bound, grid_interval, grid_size
     depth = depth.detach().requires_grad_(out_grad is not None)
     feat = feat.detach().requires_grad_(out_grad is not None)
     rows = feat.permute(0, 1, 3, 4, 2).reshape(-1, C)
-    vol = torch.zeros(B * Z * Y * X, C).index_add_(
+    vol = torch.zeros(B * Z * Y * X, C, dtype=rows.dtype).index_add_(
         0, rb, depth.reshape(-1)[rd].unsqueeze(1) * rows[rf])
     bev = vol.view(B, Z, Y, X, C).permute(0, 4, 1, 2, 3).contiguous()
     if out_grad is None:

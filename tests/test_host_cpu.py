@@ -60,6 +60,7 @@ def test_argument_errors_do_not_need_a_gpu():
     assert lib.veon_semantic_inference_3d(null, null, 1, 64, 18, 8, 100, 100, null, null) == -1
     assert lib.veon_upsample_classify(null, null, null, 1, 18, 8, 100, 100, 16, 200, 200, 17,
                                       null, null) == -1
+    assert lib.veon_classify_logits(null, 0, null, 0, null, 1, 18, 16, 200, 200, 17, null, null) == -1
     assert lib.veon_voxel_text_argmax_lowres_workspace_bytes(2, 18, 8, 100, 100) == 2 * 18 * 80000 * 4
     assert lib.veon_voxel_text_argmax_lowres_workspace_bytes(0, 18, 8, 100, 100) == 0
     some = ctypes.cast((ctypes.c_float * 4)(), ctypes.c_void_p)

@@ -177,3 +177,77 @@ def test_upsample_classify_on_given_logits_and_nan():
         touched = np.isnan(O.trilinear_upsample(sem.numpy(), size)).any(axis=1)
         assert touched.sum() >= 1
         assert np.all(got[np.transpose(touched, (0, 3, 2, 1))] == 17)
+
+
+def test_classify_logits_on_channel_slices():
+    """merge + label rule on ready-made logits, given as slices of one volume (no copy), against
+    the oracle's rule; column kernel (Z=16) and the generic one"""
+    from veon_b200.tail import classify_logits
+    refl = [0, 0, 1, 2, 2, 2, 3]
+    cls = torch.from_numpy(O.class_groups(refl))
+    Q = len(refl) + 1
+    for vol in ((16, 9, 13), (5, 4, 7)):
+        g = torch.Generator().manual_seed(vol[0])
+        both = torch.randn(3, Q + 4, *vol, generator=g).cuda()
+        got = classify_logits(both[:, :Q], both[:, Q:Q + 2], cls.cuda()).cpu().numpy()
+        sem, gate = both[:, :Q].cpu().numpy(), both[:, Q:Q + 2].cpu().numpy()
+        merged = np.stack([sem[:, np.where(cls.numpy() == k)[0]].max(axis=1) for k in range(5)], 1)
+        want = np.where(gate[:, 0] > gate[:, 1], merged.argmax(1), 17)
+        np.testing.assert_array_equal(got, np.transpose(want, (0, 3, 2, 1)).astype(np.uint8))
+
+
+def test_lift_classify_in_logit_space_matches_feature_space_and_oracle():
+    """pooling the per-pixel logits (Q+2 channels) == classifying the pooled C-channel volume:
+    against our own feature-space route and against the CPU oracle (lift + tail)."""
+    from veon_b200 import synthetic as S
+    from veon_b200.pipeline import lift_classify, lift_then_classify
+    from veon_b200.tail import class_of_prompt
+    from veon_b200.view_transformer import LSSViewTransformer
+    cfg = S.CONFIGS["small"]
+    B, C = 2, 64
+    refl = list(range(17))
+    H, W = cfg.feat_hw
+    g = torch.Generator().manual_seed(4)
+    cal = S.calibration(cfg, batch=B)
+    metas = [torch.from_numpy(cal[k]).cuda() for k in
+             ("sensor2ego", "ego2global", "intrins", "post_rots", "post_trans", "bda")]
+    depth = torch.softmax(torch.randn(B * cfg.n_cams, cfg.D, H, W, generator=g) * 4, dim=1).cuda()
+    feat = (torch.randn(B * cfg.n_cams, C, H, W, generator=g) * 0.05).cuda()
+    w = torch.randn(len(refl) + 1, C, generator=g)
+    w = (100.0 * w / w.norm(dim=1, keepdim=True)).cuda()
+    gate_w = torch.randn(2, C, generator=g).cuda()
+    cls = class_of_prompt(refl).cuda()
+    img = torch.zeros(B, cfg.n_cams, 8, H, W, device="cuda")
+    neck = LSSViewTransformer(cfg.grid_config, cfg.input_size, cfg.downsample, 8, C, collapse_z=False)
+    got = lift_classify(neck, [img] + metas, depth, feat, w, cls, gate_w)
+    ref = lift_then_classify(neck, [img] + metas, depth, feat, w, cls, gate_w)
+    torch.cuda.synchronize()
+    assert got.shape == ref.shape == (B, 200, 200, 16) and got.dtype == torch.uint8
+    assert float((got == ref).float().mean()) >= 0.9999
+    # CPU oracle: the reference's lift (index_add_ order), then the tail's oracle.  The pooled
+    # fp32 features themselves depend on the summation order, so next to the agreement rate
+    # every disagreement must be a near-tie of the float64 evaluation (top-2 class margin or
+    # gate margin below 1e-4 of the voxel's largest logit / gate value, or an absolute gate
+    # difference below 1e-6: `softmax(bin_occ)[:,0] > 0.5` in fp32 cannot resolve less than
+    # ~1.2e-7 and what it returns there depends on the exp implementation), never a gross error.
+    coor = neck.get_lidar_coor(*metas).cpu()
+    d5, f5 = depth.view(B, cfg.n_cams, cfg.D, H, W).cpu(), feat.view(B, cfg.n_cams, C, H, W).cpu()
+    grid = (neck.grid_lower_bound, neck.grid_interval, neck.grid_size)
+    vol, _, _ = O.torch_cpu_lift(coor, d5, f5, *grid)
+    gate = torch.einsum("kc,bczyx->bkzyx", gate_w.cpu(), vol)
+    want = O.voxel_text_labels(vol.numpy(), w.cpu().numpy(), cls.cpu().numpy(), gate.numpy())
+    got_np = got.cpu().numpy()
+    assert float((got_np == want).mean()) >= 0.9995
+    vol64, _, _ = O.torch_cpu_lift(coor, d5.double(), f5.double(), *grid)
+    sem64 = torch.einsum("qc,bczyx->bqzyx", w.cpu().double(), vol64)     # one prompt per class
+    gate64 = torch.einsum("kc,bczyx->bkzyx", gate_w.cpu().double(), vol64)
+    top2 = sem64.topk(2, dim=1).values
+    cls_margin = (top2[:, 0] - top2[:, 1]) / sem64.abs().amax(dim=1).clamp_min(1e-300)
+    gate_margin = (gate64[:, 0] - gate64[:, 1]).abs() / gate64.abs().amax(dim=1).clamp_min(1e-300)
+    gate_abs = (gate64[:, 0] - gate64[:, 1]).abs()
+    near_tie = ((cls_margin < 1e-4) | (gate_margin < 1e-4) | (gate_abs < 1e-6)) \
+        .permute(0, 3, 2, 1).numpy()
+    want64 = O.voxel_text_labels(vol64.numpy(), w.cpu().numpy(), cls.cpu().numpy(), gate64.numpy(),
+                                 dtype=np.float64)
+    assert np.all(near_tie[got_np != want64]), int((~near_tie[got_np != want64]).sum())
+    assert 0.001 < float((got != 17).float().mean()) < 0.9

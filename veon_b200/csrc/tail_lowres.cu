@@ -63,6 +63,68 @@ struct ClassMerge {  // running per-class max over prompt rows + first-index arg
   }
 };
 
+// The same for the ZO outputs of one (x, y) column: the prompt's class is the same for all of
+// them, so the run bookkeeping is scalar and only the two maxima and the winner are per output.
+template <int ZO>
+struct ColumnMerge {
+  float best[ZO], cur[ZO];
+  int best_cls[ZO];
+  uint32_t bad = 0;  // bit z: NaN / +inf seen => the softmax score is NaN => free
+  int cur_cls = -1;
+  bool have_best = false;
+  __device__ __forceinline__ ColumnMerge() {
+#pragma unroll
+    for (int z = 0; z < ZO; ++z) { best[z] = 0.f; cur[z] = 0.f; best_cls[z] = -1; }
+  }
+  __device__ __forceinline__ void close_run() {
+    if (cur_cls < 0) return;
+#pragma unroll
+    for (int z = 0; z < ZO; ++z)
+      if (!have_best || cur[z] > best[z]) { best[z] = cur[z]; best_cls[z] = cur_cls; }
+    have_best = true;
+  }
+  __device__ __forceinline__ void push(int cls, const float* v) {
+    if (cls != cur_cls) {
+      close_run();
+      cur_cls = cls;
+#pragma unroll
+      for (int z = 0; z < ZO; ++z) cur[z] = v[z];
+    } else {
+#pragma unroll
+      for (int z = 0; z < ZO; ++z) cur[z] = fmaxf(cur[z], v[z]);
+    }
+#pragma unroll
+    for (int z = 0; z < ZO; ++z) bad |= (uint32_t)(!(v[z] < INFINITY)) << z;
+  }
+  // after the last push + close_run(): labels of the column, stored as [.., Z] bytes
+  __device__ __forceinline__ void store(const float* b0, const float* b1, int free_label,
+                                        uint8_t* dst) const {
+    auto label = [&](int z) -> uint32_t {
+      const bool is_bad = ((bad >> z) & 1u) || best[z] == -INFINITY;
+      const float mx = fmaxf(b0[z], b1[z]);  // softmax(bin_occ)[0] > 0.5 as torch.softmax does it
+      const float e0 = expf(b0[z] - mx), e1 = expf(b1[z] - mx);
+      const bool occupied = (e0 / (e0 + e1)) > 0.5f;
+      return (uint32_t)(uint8_t)((occupied && !is_bad) ? best_cls[z] : free_label);
+    };
+    if constexpr (ZO % 16 == 0) {
+#pragma unroll
+      for (int z0 = 0; z0 < ZO; z0 += 16) {
+        uint32_t w[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          w[k] = 0;
+#pragma unroll
+          for (int i = 0; i < 4; ++i) w[k] |= label(z0 + 4 * k + i) << (8 * i);
+        }
+        *reinterpret_cast<uint4*>(dst + z0) = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    } else {
+#pragma unroll
+      for (int z = 0; z < ZO; ++z) dst[z] = (uint8_t)label(z);
+    }
+  }
+};
+
 constexpr int kColThreads = 128;
 
 // Fast path: one thread per output (x, y) column, all ZO outputs of the column in registers.
@@ -101,67 +163,18 @@ k_upsample_classify_cols(const float* __restrict__ logits, const float* __restri
     }
   };
 
-  // class merge of the ZO outputs: the prompt's class is the same for all of them, so the
-  // run bookkeeping is scalar and only the two maxima and the winner are per output
-  float best[ZO], cur[ZO];
-  int best_cls[ZO];
-  uint32_t bad = 0;  // bit z: NaN / +inf seen => the softmax score is NaN => free
-  int cur_cls = -1;
-  bool have_best = false;
-#pragma unroll
-  for (int z = 0; z < ZO; ++z) { best[z] = 0.f; cur[z] = 0.f; best_cls[z] = -1; }
-  auto close_run = [&]() {
-    if (cur_cls < 0) return;
-#pragma unroll
-    for (int z = 0; z < ZO; ++z)
-      if (!have_best || cur[z] > best[z]) { best[z] = cur[z]; best_cls[z] = cur_cls; }
-    have_best = true;
-  };
+  ColumnMerge<ZO> m;
   const float* lg = logits + (int64_t)b * Q * Vi;
   for (int q = 0; q < Q; ++q) {
     float v[ZO];
     column(lg + (int64_t)q * Vi, v);
-    const int cls = __ldg(class_of_prompt + q);
-    if (cls != cur_cls) {
-      close_run();
-      cur_cls = cls;
-#pragma unroll
-      for (int z = 0; z < ZO; ++z) cur[z] = v[z];
-    } else {
-#pragma unroll
-      for (int z = 0; z < ZO; ++z) cur[z] = fmaxf(cur[z], v[z]);
-    }
-#pragma unroll
-    for (int z = 0; z < ZO; ++z) bad |= (uint32_t)(!(v[z] < INFINITY)) << z;
+    m.push(__ldg(class_of_prompt + q), v);
   }
-  close_run();
+  m.close_run();
   float b0[ZO], b1[ZO];
   column(bin_occ + ((int64_t)b * 2 + 0) * Vi, b0);
   column(bin_occ + ((int64_t)b * 2 + 1) * Vi, b1);
-  auto label = [&](int z) -> uint32_t {
-    const bool is_bad = ((bad >> z) & 1u) || best[z] == -INFINITY;
-    const float mx = fmaxf(b0[z], b1[z]);  // softmax(bin_occ)[0] > 0.5 as torch.softmax does it
-    const float e0 = expf(b0[z] - mx), e1 = expf(b1[z] - mx);
-    const bool occupied = (e0 / (e0 + e1)) > 0.5f;
-    return (uint32_t)(uint8_t)((occupied && !is_bad) ? best_cls[z] : free_label);
-  };
-  uint8_t* dst = labels + (((int64_t)b * X + x) * Y + y) * ZO;  // [B,X,Y,Z]
-  if constexpr (ZO % 16 == 0) {
-#pragma unroll
-    for (int z0 = 0; z0 < ZO; z0 += 16) {
-      uint32_t w[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        w[k] = 0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) w[k] |= label(z0 + 4 * k + i) << (8 * i);
-      }
-      *reinterpret_cast<uint4*>(dst + z0) = make_uint4(w[0], w[1], w[2], w[3]);
-    }
-  } else {
-#pragma unroll
-    for (int z = 0; z < ZO; ++z) dst[z] = (uint8_t)label(z);
-  }
+  m.store(b0, b1, free_label, labels + (((int64_t)b * X + x) * Y + y) * ZO);  // [B,X,Y,Z]
 }
 
 // Any other pair of sizes: one thread per output voxel, 8 neighbours per channel.
@@ -196,9 +209,85 @@ k_upsample_classify_any(const float* __restrict__ logits, const float* __restric
   labels[(((int64_t)b * X + x) * Y + y) * Z + z] = (uint8_t)m.label(b0, b1, free_label);
 }
 
+// ---- merge + arg-max + gate of ready-made logits (no interpolation) ---------------------------
+// _merge_classes_prob (san_in_veon_entry_temporal.py:273-297) + the label rule
+// (veon_temporal.py:223-229,240) on sem_occ [B,Q,Z,Y,X] / bin_occ [B,2,Z,Y,X]; the batch strides
+// are free so that both may be channel slices of one pooled volume (lift_classify).
+template <int ZO>
+__global__ void __launch_bounds__(kColThreads)
+k_classify_cols(const float* __restrict__ sem_occ, int64_t sem_bstride,
+                const float* __restrict__ bin_occ, int64_t bin_bstride,
+                const int32_t* __restrict__ class_of_prompt, int Q, int Y, int X, int free_label,
+                uint8_t* __restrict__ labels) {
+  const int b = blockIdx.y;
+  const int idx = blockIdx.x * kColThreads + threadIdx.x;
+  const int plane = X * Y;
+  if (idx >= plane) return;
+  const int x = idx % X, y = idx / X;
+  const int64_t V = (int64_t)plane * ZO;
+  auto column = [&](const float* __restrict__ src, float* out) {
+#pragma unroll
+    for (int z = 0; z < ZO; ++z) out[z] = ld_stream(src + (int64_t)z * plane + idx);
+  };
+  ColumnMerge<ZO> m;
+  const float* lg = sem_occ + (int64_t)b * sem_bstride;
+  for (int q = 0; q < Q; ++q) {
+    float v[ZO];
+    column(lg + (int64_t)q * V, v);
+    m.push(__ldg(class_of_prompt + q), v);
+  }
+  m.close_run();
+  float b0[ZO], b1[ZO];
+  column(bin_occ + (int64_t)b * bin_bstride, b0);
+  column(bin_occ + (int64_t)b * bin_bstride + V, b1);
+  m.store(b0, b1, free_label, labels + (((int64_t)b * X + x) * Y + y) * ZO);
+}
+
+__global__ void __launch_bounds__(kColThreads)
+k_classify_any(const float* __restrict__ sem_occ, int64_t sem_bstride,
+               const float* __restrict__ bin_occ, int64_t bin_bstride,
+               const int32_t* __restrict__ class_of_prompt, int Q, int Z, int Y, int X,
+               int free_label, uint8_t* __restrict__ labels) {
+  const int b = blockIdx.y;
+  const int64_t V = (int64_t)Z * Y * X;
+  const int64_t v = (int64_t)blockIdx.x * kColThreads + threadIdx.x;
+  if (v >= V) return;
+  ClassMerge m;
+  const float* lg = sem_occ + (int64_t)b * sem_bstride + v;
+  for (int q = 0; q < Q; ++q) m.push(__ldg(class_of_prompt + q), ld_stream(lg + (int64_t)q * V));
+  const float b0 = ld_stream(bin_occ + (int64_t)b * bin_bstride + v);
+  const float b1 = ld_stream(bin_occ + (int64_t)b * bin_bstride + V + v);
+  const int x = (int)(v % X), y = (int)((v / X) % Y), z = (int)(v / ((int64_t)X * Y));
+  labels[(((int64_t)b * X + x) * Y + y) * Z + z] = (uint8_t)m.label(b0, b1, free_label);
+}
+
 }  // namespace veon
 
 using namespace veon;
+
+extern "C" int veon_classify_logits(const float* sem_occ, int64_t sem_batch_stride,
+                                    const float* bin_occ, int64_t bin_batch_stride,
+                                    const int32_t* class_of_prompt, int B, int Q, int Z, int Y,
+                                    int X, int free_label, uint8_t* labels, void* stream) {
+  if (!sem_occ || !bin_occ || !class_of_prompt || !labels || B <= 0 || Q <= 0 || Z <= 0 ||
+      Y <= 0 || X <= 0 || B > 65535 || sem_batch_stride < 0 || bin_batch_stride < 0)
+    return VEON_E_BADARG;
+  if ((int64_t)X * Y > INT32_MAX) return VEON_E_RANGE;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (Z == 16 && (((uintptr_t)labels) & 15) == 0) {
+    dim3 grid((unsigned)ceil_div64((int64_t)X * Y, kColThreads), (unsigned)B);
+    k_classify_cols<16><<<grid, kColThreads, 0, st>>>(sem_occ, sem_batch_stride, bin_occ,
+                                                      bin_batch_stride, class_of_prompt, Q, Y, X,
+                                                      free_label, labels);
+  } else {
+    dim3 grid((unsigned)ceil_div64((int64_t)Z * Y * X, kColThreads), (unsigned)B);
+    k_classify_any<<<grid, kColThreads, 0, st>>>(sem_occ, sem_batch_stride, bin_occ,
+                                                 bin_batch_stride, class_of_prompt, Q, Z, Y, X,
+                                                 free_label, labels);
+  }
+  VEON_LAUNCH_CHECK();
+  return 0;
+}
 
 extern "C" int veon_upsample_classify(const float* sem_occ_lr, const float* bin_occ_lr,
                                       const int32_t* class_of_prompt, int B, int Q, int Zi, int Yi,

@@ -1,0 +1,71 @@
+"""Lift + classify as one pipeline (BASELINE.json configs[2]).
+
+When the classifier is applied to the pooled volume directly (north_star's "2D-to-3D lifting
+followed by the open-vocabulary voxel-text classification tail"), both steps are linear in the
+image features:
+
+    sem_occ[b,q,v] = sum_c W[q,c] * sum_{p in v} depth[p] * feat[pixel(p), c]
+                   = sum_{p in v} depth[p] * (sum_c W[q,c] * feat[pixel(p), c])
+
+so the classifier can run on the [B,N,C,H,W] image features (17 k pixels per sample instead of
+640 k voxels) and the pooling then moves Q + 2 channels instead of C = 512: the 1.31 GB/sample
+feature volume is never formed.  `lift_classify` does that with the same operators as the
+separate steps (`semantic_inference_3d` on tcgen05, `view_transform`'s index preparation and
+pooling kernels, `classify_logits`); `lift_then_classify` is the feature-space order of the
+reference (`view_transform` -> `voxel_text_argmax`) kept for comparison and for the tests.
+
+The occupancy gate is a linear head here (`gate_weight [2,C]`, bin_occ = gate_weight . volume):
+the reference's gate comes out of its 3D decoder, which sits between the two steps in the full
+model and is out of scope; with a non-linear decoder in between only
+`voxel_text_argmax_lowres` applies.
+"""
+import torch
+
+from . import tail as _tail
+
+__all__ = ["lift_classify", "lift_then_classify"]
+
+
+def _heads(ov_classifier_weight, gate_weight):
+    w = ov_classifier_weight.detach().float()
+    g = gate_weight.detach().float()
+    if g.shape != (2, w.shape[1]):
+        raise ValueError("gate_weight must be [2, C]")
+    rows = torch.cat((w, g), 0)
+    pad = (-rows.shape[0]) % 4          # the pooling kernels stage rows with 16-byte copies
+    if pad:
+        rows = torch.cat((rows, rows.new_zeros(pad, rows.shape[1])), 0)
+    return rows.contiguous()
+
+
+def lift_classify(neck, input, depth, tran_feat, ov_classifier_weight, prompt_class, gate_weight,
+                  free_label=17):
+    """neck: LSSViewTransformer; input = (img [B,N,*,H,W], sensor2ego, ego2global, cam2imgs,
+    post_rots, post_trans, bda); depth [B*N,D,H,W]; tran_feat [B*N,C,H,W];
+    ov_classifier_weight [Q,C]; prompt_class [Q]; gate_weight [2,C] -> uint8 [B,X,Y,Z]."""
+    B, N = input[0].shape[:2]
+    BN, C, H, W = tran_feat.shape
+    Q = ov_classifier_weight.shape[0]
+    rows = _heads(ov_classifier_weight, gate_weight)
+    with torch.no_grad():
+        # per-pixel logits: the classifier over each camera's feature map, [B*N, Q', 1, H, W]
+        px = _tail.semantic_inference_3d(rows, tran_feat.reshape(BN, C, 1, H, W))
+        d5 = depth.reshape(B, N, neck.D, H, W)
+        px5 = px.view(B, N, rows.shape[0], H, W)
+        if input[1].is_cuda and neck.fuse_geometry:
+            vol = neck._voxel_pooling_calib(input[1:7], d5, px5)
+        else:
+            vol = neck.voxel_pooling_v2(neck.get_lidar_coor(*input[1:7]), d5, px5)
+        if vol.dim() != 5:
+            raise RuntimeError("lift_classify needs collapse_z=False and points inside the grid")
+        return _tail.classify_logits(vol[:, :Q], vol[:, Q:Q + 2], prompt_class, free_label)
+
+
+def lift_then_classify(neck, input, depth, tran_feat, ov_classifier_weight, prompt_class,
+                       gate_weight, free_label=17):
+    """The same result in the reference's order: pool the C-channel features, then classify the
+    volume (einsum for the gate head: it is a stand-in for the decoder, not a path kernel)."""
+    with torch.no_grad():
+        vol, _ = neck.view_transform(input, depth, tran_feat)
+        gate = torch.einsum("kc,bczyx->bkzyx", gate_weight.float(), vol)
+        return _tail.voxel_text_argmax(vol, ov_classifier_weight, prompt_class, gate, free_label)

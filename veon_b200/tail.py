@@ -17,7 +17,7 @@ import torch
 
 from . import _lib
 
-__all__ = ["class_of_prompt", "voxel_text_argmax", "semantic_inference_3d",
+__all__ = ["class_of_prompt", "voxel_text_argmax", "semantic_inference_3d", "classify_logits",
            "upsample_classify", "voxel_text_argmax_lowres"]
 
 
@@ -99,6 +99,45 @@ def semantic_inference_3d(ov_classifier_weight, mask_pred):
             ctypes.c_void_p(sem.data_ptr()), _stream(dev))
     _lib.check(rc, "veon_semantic_inference_3d")
     return sem
+
+
+def _sample_contiguous(t):
+    """float32 view whose samples are contiguous blocks (any batch stride), else a copy"""
+    t = t.detach()
+    if t.dtype != torch.float32:
+        t = t.float()
+    inner = 1
+    for size, stride in zip(reversed(t.shape[1:]), reversed(t.stride()[1:])):
+        if size != 1 and stride != inner:
+            return t.contiguous()
+        inner *= size
+    if t.shape[0] > 1 and t.stride(0) < inner:
+        return t.contiguous()
+    return t
+
+
+def classify_logits(sem_occ, bin_occ, prompt_class, free_label=17):
+    """`_merge_classes_prob` + the label rule on ready-made logits
+    (san_in_veon_entry_temporal.py:273-297, veon_temporal.py:223-229,240): sem_occ [B,Q,Z,Y,X],
+    bin_occ [B,2,Z,Y,X] -> uint8 [B,X,Y,Z].  Channel slices of a larger volume are taken as
+    they are (no copy)."""
+    _cuda_only(sem_occ, bin_occ, prompt_class)
+    lib = _lib.load()
+    sem = _sample_contiguous(sem_occ)
+    gate = _sample_contiguous(bin_occ)
+    cls = prompt_class.contiguous().int()
+    B, Q, Z, Y, X = sem.shape
+    if tuple(gate.shape) != (B, 2, Z, Y, X) or cls.numel() != Q:
+        raise ValueError("inconsistent tail shapes")
+    dev = sem.device
+    with torch.cuda.device(dev):
+        labels = torch.empty((B, X, Y, Z), dtype=torch.uint8, device=dev)
+        rc = lib.veon_classify_logits(
+            ctypes.c_void_p(sem.data_ptr()), sem.stride(0), ctypes.c_void_p(gate.data_ptr()),
+            gate.stride(0), ctypes.c_void_p(cls.data_ptr()), B, Q, Z, Y, X, int(free_label),
+            ctypes.c_void_p(labels.data_ptr()), _stream(dev))
+    _lib.check(rc, "veon_classify_logits")
+    return labels
 
 
 def upsample_classify(sem_occ_lr, bin_occ_lr, prompt_class, occ_size, free_label=17):
