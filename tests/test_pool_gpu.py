@@ -80,7 +80,10 @@ def test_known_answer_test(golden_dir):
 
 
 @pytest.mark.parametrize("cfg_name,batch,C", [("tiny", 2, 32), ("tiny", 2, 7), ("small", 2, 64),
-                                              ("tiny", 1, 100), ("C1", 1, 64), ("small", 1, 256)])
+                                              ("tiny", 1, 100), ("C1", 1, 64), ("small", 1, 256),
+                                              # narrow rows: the lane-per-voxel kernel (C <= 32, C % 4 == 0)
+                                              ("tiny", 2, 20), ("small", 2, 4), ("small", 2, 20),
+                                              ("C1", 2, 28)])
 def test_forward_bit_exact_vs_oracle(cfg_name, batch, C):
     case = make_case(cfg_name, batch, C)
     rb, rd, rf, st, ln = case["ranks"]
@@ -350,11 +353,13 @@ def test_heavy_tile_list_matches_point_counts():
     assert (n2, thr2) == (n, thr) and np.array_equal(ids2, want)
 
 
-@pytest.mark.parametrize("C", [64, 80, 6, 200])
+@pytest.mark.parametrize("C", [64, 80, 6, 200, 20, 32])
 def test_heavy_tile_kernel_is_bit_identical_to_the_warp_path(C):
     """The CTA-per-tile kernel for heavy tiles only re-schedules the loads: with and
     without the heavy list the volume is the same bit for bit (C=80: ragged last
-    channel chunk; C=6: rows not 16-byte sized, the heavy list is ignored)."""
+    channel chunk; C=6: rows not 16-byte sized, the heavy list is ignored; C=20, 32: with the
+    list the main grid is the lane-per-voxel kernel for narrow rows, without it the
+    lane-per-channel one, so this also checks those two against each other)."""
     from veon_b200 import _lib, bev_pool as BP
     case = make_case("C1", 1, C, seed=3)
     rb, rd, rf, st, ln = gpu_ranks(case["ranks"])

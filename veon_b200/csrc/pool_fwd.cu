@@ -986,6 +986,101 @@ static int env_flag(const char* name, int dflt) {
   return e ? atoi(e) : dflt;
 }
 
+
+// ---- narrow rows (C <= 32): lane = voxel ---------------------------------------------------
+// With few channels a lane-per-channel warp leaves lanes idle and pays one row-load latency
+// per point (the logit-space lift pools Q + 2 = 20 channels over 4x the points of C2:
+// 437 us for 410 MB).  Here a warp still owns a 32-voxel tile, but a LANE owns a voxel: it
+// walks its own contiguous slice of the sorted points, two points per trip with all their
+// loads (ranks, depth, the 16-byte pieces of both rows) in flight together, and accumulates
+// every channel of its voxel in registers with the same fma(feat, depth, acc) chain in rank
+// order, so the result is the same bits as k_pool_fwd's.  The write-out needs no transposition:
+// for each channel plane the 32 lanes store one aligned 128-byte run (zeros for empty voxels).
+// Segment bounds come from ranks_bev itself (head flags over the tile's points, 32 at a time).
+constexpr int kNarrowWarps = 8;
+template <int NV>  // 16-byte pieces per feature row: C = 4 * NV
+__global__ void __launch_bounds__(kNarrowWarps * 32)
+k_pool_fwd_narrow(const float* __restrict__ depth, const float* __restrict__ feat,
+                  const int32_t* __restrict__ ranks_depth, const int32_t* __restrict__ ranks_feat,
+                  const int32_t* __restrict__ ranks_bev, const int32_t* __restrict__ tile_start,
+                  const int32_t* __restrict__ heavy, uint32_t n_tiles, uint32_t tiles_per_sample,
+                  int64_t V, float* __restrict__ out) {
+  constexpr int C = 4 * NV;
+  __shared__ int32_t seg_s[kNarrowWarps][32];
+  pdl_launch_dependents();  // the heavy-tile grid may be queued behind this one
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int32_t* seg = seg_s[warp];
+  const int32_t heavy_thr = heavy ? __ldg(heavy + 1) : 0x7fffffff;
+  const uint32_t TW = gridDim.x * kNarrowWarps;
+  for (uint32_t t = blockIdx.x * kNarrowWarps + warp; t < n_tiles; t += TW) {
+    const int32_t s0 = __ldg(tile_start + t), e0 = __ldg(tile_start + t + 1);
+    if (e0 - s0 >= heavy_thr) continue;  // k_pool_fwd_heavy's
+    const uint32_t b = t / tiles_per_sample;
+    const uint32_t v0 = (t - b * tiles_per_sample) * kTileVoxels;
+    const int32_t g0 = (int32_t)((int64_t)b * V) + (int32_t)v0;  // rank of the tile's first voxel
+    float acc[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) acc[c] = 0.f;
+    if (e0 > s0) {
+      // first point of every occupied voxel
+      seg[lane] = -1;
+      __syncwarp();
+      int32_t prev = -1;
+      for (int32_t p0 = s0; p0 < e0; p0 += 32) {
+        const int32_t i = p0 + lane;
+        const int32_t vox = (i < e0) ? __ldg(ranks_bev + i) - g0 : -2;
+        int32_t up = __shfl_up_sync(0xffffffffu, vox, 1);
+        if (lane == 0) up = prev;
+        if (i < e0 && vox != up && (uint32_t)vox < 32u) seg[vox] = i;
+        prev = __shfl_sync(0xffffffffu, vox, 31);
+      }
+      __syncwarp();
+      const int32_t st = seg[lane];
+      const uint32_t occ = __ballot_sync(0xffffffffu, st >= 0);
+      const uint32_t higher = (lane == 31) ? 0u : (occ >> (lane + 1));
+      const int nxt = higher ? lane + __ffs(higher) : 0;
+      const int32_t nst = __shfl_sync(0xffffffffu, st, nxt);
+      const int32_t en = higher ? nst : e0;
+      __syncwarp();  // seg is rewritten for the next tile
+      if (st >= 0) {
+        for (int32_t i = st; i < en; i += 2) {
+          const bool two = i + 1 < en;
+          const int32_t r0 = __ldg(ranks_depth + i), f0 = __ldg(ranks_feat + i);
+          const int32_t r1 = two ? __ldg(ranks_depth + i + 1) : r0;
+          const int32_t f1 = two ? __ldg(ranks_feat + i + 1) : f0;
+          const float d0 = __ldg(depth + r0), d1 = __ldg(depth + r1);
+          const float4* row0 = reinterpret_cast<const float4*>(feat + (int64_t)f0 * C);
+          const float4* row1 = reinterpret_cast<const float4*>(feat + (int64_t)f1 * C);
+          float4 a[NV], q[NV];
+#pragma unroll
+          for (int k = 0; k < NV; ++k) a[k] = __ldg(row0 + k);
+#pragma unroll
+          for (int k = 0; k < NV; ++k) q[k] = __ldg(row1 + k);
+#pragma unroll
+          for (int k = 0; k < NV; ++k) {
+            acc[4 * k + 0] = fmaf(a[k].x, d0, acc[4 * k + 0]);
+            acc[4 * k + 1] = fmaf(a[k].y, d0, acc[4 * k + 1]);
+            acc[4 * k + 2] = fmaf(a[k].z, d0, acc[4 * k + 2]);
+            acc[4 * k + 3] = fmaf(a[k].w, d0, acc[4 * k + 3]);
+          }
+          if (two) {
+#pragma unroll
+            for (int k = 0; k < NV; ++k) {
+              acc[4 * k + 0] = fmaf(q[k].x, d1, acc[4 * k + 0]);
+              acc[4 * k + 1] = fmaf(q[k].y, d1, acc[4 * k + 1]);
+              acc[4 * k + 2] = fmaf(q[k].z, d1, acc[4 * k + 2]);
+              acc[4 * k + 3] = fmaf(q[k].w, d1, acc[4 * k + 3]);
+            }
+          }
+        }
+      }
+    }
+    float* o = out + (int64_t)b * C * V + v0 + lane;
+#pragma unroll
+    for (int c = 0; c < C; ++c) st_stream(o + (int64_t)c * V, acc[c]);
+  }
+}
+
 template <int KCH, bool FULLC>
 static int launch_fwd_impl(const float* depth, const float* feat, const int32_t* rd,
                       const int32_t* rf, const int32_t* rb, const int32_t* tile_start,
@@ -1119,6 +1214,56 @@ static int launch_fwd_impl(const float* depth, const float* feat, const int32_t*
   return 0;
 }
 
+// main grid = k_pool_fwd_narrow, heavy tiles = k_pool_fwd_heavy<1> queued behind it (as in
+// launch_fwd_impl)
+template <int NV>
+static int launch_fwd_narrow(const float* depth, const float* feat, const int32_t* rd,
+                             const int32_t* rf, const int32_t* rb, const int32_t* tile_start,
+                             const int32_t* heavy, int64_t heavy_ints, int B, int64_t V,
+                             float* out, cudaStream_t stream) {
+  constexpr int C = 4 * NV;
+  const int64_t tps = V / kTileVoxels, n_tiles = (int64_t)B * tps;
+  static int ctas_per_sm = 0;
+  if (ctas_per_sm == 0) {
+    VEON_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_pool_fwd_narrow<NV>,
+                                                                kNarrowWarps * 32, 0));
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+  }
+  int64_t blocks = ceil_div64(n_tiles, kNarrowWarps);
+  if (blocks > (int64_t)ctas_per_sm * sm_count()) blocks = (int64_t)ctas_per_sm * sm_count();
+  int capturing = 0;
+  {
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &st) == cudaSuccess && st != cudaStreamCaptureStatusNone)
+      capturing = 1;
+  }
+  k_pool_fwd_narrow<NV><<<(unsigned)blocks, kNarrowWarps * 32, 0, stream>>>(
+      depth, feat, rd, rf, rb, tile_start, heavy, (uint32_t)n_tiles, (uint32_t)tps, V, out);
+  VEON_LAUNCH_CHECK();
+  if (heavy) {
+    const size_t hsmem = sizeof(float) * (kHeavyChunk * 32 + 32 * kRowPitch + 2 * kHeavyChunk + 128);
+    static int heavy_ctas_per_sm = 0;
+    if (heavy_ctas_per_sm == 0) {
+      VEON_CUDA_TRY(cudaFuncSetAttribute(k_pool_fwd_heavy<1>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem));
+      VEON_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+          &heavy_ctas_per_sm, k_pool_fwd_heavy<1>, kHeavyThreads, hsmem));
+      if (heavy_ctas_per_sm < 1) heavy_ctas_per_sm = 1;
+    }
+    const int heavy_cap = (int)(heavy_ints - 2);
+    const int per_sm = min(heavy_ctas_per_sm, 8);
+    int64_t hblocks = heavy_cap;
+    if (hblocks > (int64_t)per_sm * sm_count()) hblocks = (int64_t)per_sm * sm_count();
+    if (hblocks > 0) {
+      VEON_CUDA_TRY(launch_pdl(k_pool_fwd_heavy<1>, dim3((unsigned)hblocks), dim3(kHeavyThreads),
+                               hsmem, stream, depth, feat, rd, rf, rb, tile_start, heavy,
+                               heavy_cap, (uint32_t)tps, V, C, 1u, 1, out, capturing));
+      VEON_LAUNCH_CHECK();
+    }
+  }
+  return 0;
+}
+
 template <int KCH>
 static int launch_fwd(const float* depth, const float* feat, const int32_t* rd,
                       const int32_t* rf, const int32_t* rb, const int32_t* tile_start,
@@ -1162,6 +1307,23 @@ extern "C" int veon_bev_pool_v2_fwd_planar(const float* depth, const float* feat
   const bool fit32 = n_feat_rows * (int64_t)C <= 0x3fffffffLL && B < 65536 &&
                      (int64_t)C <= 65535LL * 32;
   int kch = fwd_kch_override();
+  {  // narrow rows: lane-per-voxel kernel (VEON_FWD_NARROW=0 keeps the lane-per-channel one)
+    static const int knob_narrow = env_flag("VEON_FWD_NARROW", 1);
+    // without a heavy list a single lane would walk arbitrarily long voxels; rank arithmetic
+    // is exact (no float32 merging of voxels) only while B*V <= 2^24
+    const bool ok = knob_narrow && kch == 0 && C <= 32 && (C & 3) == 0 && tile_heavy && fit32 &&
+                    V % kTileVoxels == 0 && (int64_t)B * V <= (1 << 24) &&
+                    (((uintptr_t)feat | (uintptr_t)out) & 15) == 0;
+    if (ok) {
+#define VEON_NARROW_CASE(NV_) case NV_: return launch_fwd_narrow<NV_>(depth, feat, ranks_depth, ranks_feat, ranks_bev, tile_start, tile_heavy, tile_heavy_ints, B, V, out, stream);
+      switch (C / 4) {
+        VEON_NARROW_CASE(1) VEON_NARROW_CASE(2) VEON_NARROW_CASE(3) VEON_NARROW_CASE(4)
+        VEON_NARROW_CASE(5) VEON_NARROW_CASE(6) VEON_NARROW_CASE(7) VEON_NARROW_CASE(8)
+        default: break;
+      }
+#undef VEON_NARROW_CASE
+    }
+  }
   if (kch == 0) kch = (C <= 32) ? 1 : 2;
   switch (kch) {
     case 1: return launch_fwd<1>(depth, feat, ranks_depth, ranks_feat, ranks_bev, tile_start, tile_heavy, tile_heavy_ints, B, C, V, fit32, out, stream);

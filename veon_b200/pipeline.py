@@ -26,27 +26,27 @@ from . import tail as _tail
 __all__ = ["lift_classify", "lift_then_classify"]
 
 
-def _heads(ov_classifier_weight, gate_weight):
+def _heads(ov_classifier_weight, gate_weight, channel_pad=4):
     w = ov_classifier_weight.detach().float()
     g = gate_weight.detach().float()
     if g.shape != (2, w.shape[1]):
         raise ValueError("gate_weight must be [2, C]")
     rows = torch.cat((w, g), 0)
-    pad = (-rows.shape[0]) % 4          # the pooling kernels stage rows with 16-byte copies
+    pad = (-rows.shape[0]) % channel_pad   # the pooling kernels stage rows with 16-byte copies
     if pad:
         rows = torch.cat((rows, rows.new_zeros(pad, rows.shape[1])), 0)
     return rows.contiguous()
 
 
 def lift_classify(neck, input, depth, tran_feat, ov_classifier_weight, prompt_class, gate_weight,
-                  free_label=17):
+                  free_label=17, channel_pad=4):
     """neck: LSSViewTransformer; input = (img [B,N,*,H,W], sensor2ego, ego2global, cam2imgs,
     post_rots, post_trans, bda); depth [B*N,D,H,W]; tran_feat [B*N,C,H,W];
     ov_classifier_weight [Q,C]; prompt_class [Q]; gate_weight [2,C] -> uint8 [B,X,Y,Z]."""
     B, N = input[0].shape[:2]
     BN, C, H, W = tran_feat.shape
     Q = ov_classifier_weight.shape[0]
-    rows = _heads(ov_classifier_weight, gate_weight)
+    rows = _heads(ov_classifier_weight, gate_weight, channel_pad)
     with torch.no_grad():
         # per-pixel logits: the classifier over each camera's feature map, [B*N, Q', 1, H, W]
         px = _tail.semantic_inference_3d(rows, tran_feat.reshape(BN, C, 1, H, W))
