@@ -353,7 +353,7 @@ k_pool_fwd_heavy(const float* __restrict__ depth, const float* __restrict__ feat
                  const int32_t* __restrict__ ranks_bev, const int32_t* __restrict__ tile_start,
                  const int32_t* __restrict__ heavy, int heavy_cap, uint32_t tiles_per_sample,
                  int64_t V, int C, uint32_t n_chunks, int vec_ok, float* __restrict__ out,
-                 int join) {
+                 int join, int min_points) {
   constexpr int CC = 32 * KCH;
   constexpr int kSegs = CC / 4;  // 16-byte segments per staged row
   extern __shared__ __align__(16) float hsm[];
@@ -375,6 +375,7 @@ k_pool_fwd_heavy(const float* __restrict__ depth, const float* __restrict__ feat
     const uint32_t t = (uint32_t)__ldg(heavy + 2 + hi);
     const int32_t s = __ldg(tile_start + t);
     const int32_t n = __ldg(tile_start + t + 1) - s;
+    if (n < min_points) continue;  // left to the main grid (k_pool_fwd_narrow takes more)
     const uint32_t b = t / tiles_per_sample;
     const int v0 = (int)(t - b * tiles_per_sample) * kTileVoxels;
     const int32_t g0 = (int32_t)((int64_t)b * V) + v0;
@@ -997,23 +998,49 @@ static int env_flag(const char* name, int dflt) {
 // order, so the result is the same bits as k_pool_fwd's.  The write-out needs no transposition:
 // for each channel plane the 32 lanes store one aligned 128-byte run (zeros for empty voxels).
 // Segment bounds come from ranks_bev itself (head flags over the tile's points, 32 at a time).
+// A lane walks two points per load latency, so this kernel keeps every tile below
+// kNarrowHeavyMin points (at C3 density the plan's threshold of 96 would hand half of all
+// points to the CTA-per-tile kernel: 252 us of a 437 us call); k_pool_fwd_heavy skips those.
 constexpr int kNarrowWarps = 8;
+constexpr int kNarrowHeavyMin = 512;
 template <int NV>  // 16-byte pieces per feature row: C = 4 * NV
-__global__ void __launch_bounds__(kNarrowWarps * 32)
+__global__ void __launch_bounds__(kNarrowWarps * 32, (NV <= 5) ? 3 : 2)
 k_pool_fwd_narrow(const float* __restrict__ depth, const float* __restrict__ feat,
                   const int32_t* __restrict__ ranks_depth, const int32_t* __restrict__ ranks_feat,
                   const int32_t* __restrict__ ranks_bev, const int32_t* __restrict__ tile_start,
                   const int32_t* __restrict__ heavy, uint32_t n_tiles, uint32_t tiles_per_sample,
-                  int64_t V, float* __restrict__ out) {
+                  int64_t V, float* __restrict__ out, uint32_t zero, int heavy_min) {
   constexpr int C = 4 * NV;
   __shared__ int32_t seg_s[kNarrowWarps][32];
   pdl_launch_dependents();  // the heavy-tile grid may be queued behind this one
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int32_t* seg = seg_s[warp];
-  const int32_t heavy_thr = heavy ? __ldg(heavy + 1) : 0x7fffffff;
+  const int32_t heavy_thr = heavy ? max(__ldg(heavy + 1), heavy_min) : 0x7fffffff;
   const uint32_t TW = gridDim.x * kNarrowWarps;
-  for (uint32_t t = blockIdx.x * kNarrowWarps + warp; t < n_tiles; t += TW) {
-    const int32_t s0 = __ldg(tile_start + t), e0 = __ldg(tile_start + t + 1);
+  // The per-tile chain (bounds -> ranks_bev -> segment table -> ranks -> rows -> stores) is a
+  // string of dependent load latencies, so the head of the chain runs ahead: bounds are read
+  // two tiles early, the first 32 ranks_bev of a tile one tile early.
+  const uint32_t first = blockIdx.x * kNarrowWarps + warp;
+  int32_t ns = 0, ne = 0, as = 0, ae = 0, nrb = 0;  // next tile, the one after; next tile's ranks
+  if (first < n_tiles) {
+    ns = __ldg(tile_start + first);
+    ne = __ldg(tile_start + first + 1);
+    if (ns + lane < ne) nrb = __ldg(ranks_bev + ns + lane);
+  }
+  if (first + TW < n_tiles) {
+    as = __ldg(tile_start + first + TW);
+    ae = __ldg(tile_start + first + TW + 1);
+  }
+  for (uint32_t t = first; t < n_tiles; t += TW) {
+    const int32_t s0 = ns, e0 = ne, rb_first = nrb;
+    ns = as;
+    ne = ae;
+    as = ae = 0;
+    if (t + 2 * TW < n_tiles) {
+      as = __ldg(tile_start + t + 2 * TW);
+      ae = __ldg(tile_start + t + 2 * TW + 1);
+    }
+    nrb = (ns + lane < ne) ? __ldg(ranks_bev + ns + lane) : 0;
     if (e0 - s0 >= heavy_thr) continue;  // k_pool_fwd_heavy's
     const uint32_t b = t / tiles_per_sample;
     const uint32_t v0 = (t - b * tiles_per_sample) * kTileVoxels;
@@ -1025,14 +1052,28 @@ k_pool_fwd_narrow(const float* __restrict__ depth, const float* __restrict__ fea
       // first point of every occupied voxel
       seg[lane] = -1;
       __syncwarp();
-      int32_t prev = -1;
-      for (int32_t p0 = s0; p0 < e0; p0 += 32) {
-        const int32_t i = p0 + lane;
-        const int32_t vox = (i < e0) ? __ldg(ranks_bev + i) - g0 : -2;
-        int32_t up = __shfl_up_sync(0xffffffffu, vox, 1);
-        if (lane == 0) up = prev;
-        if (i < e0 && vox != up && (uint32_t)vox < 32u) seg[vox] = i;
+      int32_t prev;
+      {
+        const int32_t vox = (s0 + lane < e0) ? rb_first - g0 : -2;
+        const int32_t up = __shfl_up_sync(0xffffffffu, vox, 1);
+        if (s0 + lane < e0 && (lane == 0 || vox != up) && (uint32_t)vox < 32u) seg[vox] = s0 + lane;
         prev = __shfl_sync(0xffffffffu, vox, 31);
+      }
+      for (int32_t p0 = s0 + 32; p0 < e0; p0 += 128) {  // four rounds' loads in flight together
+        int32_t vx[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int32_t i = p0 + 32 * r + lane;
+          vx[r] = (i < e0) ? __ldg(ranks_bev + i) - g0 : -2;
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          const int32_t i = p0 + 32 * r + lane;
+          int32_t up = __shfl_up_sync(0xffffffffu, vx[r], 1);
+          if (lane == 0) up = prev;
+          if (i < e0 && vx[r] != up && (uint32_t)vx[r] < 32u) seg[vx[r]] = i;
+          prev = __shfl_sync(0xffffffffu, vx[r], 31);
+        }
       }
       __syncwarp();
       const int32_t st = seg[lane];
@@ -1043,35 +1084,55 @@ k_pool_fwd_narrow(const float* __restrict__ depth, const float* __restrict__ fea
       const int32_t en = higher ? nst : e0;
       __syncwarp();  // seg is rewritten for the next tile
       if (st >= 0) {
-        for (int32_t i = st; i < en; i += 2) {
-          const bool two = i + 1 < en;
-          const int32_t r0 = __ldg(ranks_depth + i), f0 = __ldg(ranks_feat + i);
-          const int32_t r1 = two ? __ldg(ranks_depth + i + 1) : r0;
-          const int32_t f1 = two ? __ldg(ranks_feat + i + 1) : f0;
-          const float d0 = __ldg(depth + r0), d1 = __ldg(depth + r1);
+        int32_t i = st;
+        bool two = i + 1 < en;
+        int32_t r0 = __ldg(ranks_depth + i), f0 = __ldg(ranks_feat + i);
+        int32_t r1 = two ? __ldg(ranks_depth + i + 1) : r0;
+        int32_t f1 = two ? __ldg(ranks_feat + i + 1) : f0;
+        while (true) {
+          // A trip always runs both fma chains (no branch for the scheduler to sink the second
+          // point's loads into); a missing second point is (+0) * (-0): acc + (-0) == acc bit for
+          // bit, whatever acc is.
+          const float d0 = __ldg(depth + r0), d1 = two ? __ldg(depth + r1) : -0.f;
           const float4* row0 = reinterpret_cast<const float4*>(feat + (int64_t)f0 * C);
           const float4* row1 = reinterpret_cast<const float4*>(feat + (int64_t)f1 * C);
           float4 a[NV], q[NV];
 #pragma unroll
           for (int k = 0; k < NV; ++k) a[k] = __ldg(row0 + k);
 #pragma unroll
-          for (int k = 0; k < NV; ++k) q[k] = __ldg(row1 + k);
+          for (int k = 0; k < NV; ++k) q[k] = two ? __ldg(row1 + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+          // `zero` is a kernel argument that is always 0: making the first depth value depend
+          // on every piece of the second row keeps the assembler from re-using the first row's
+          // registers for the second row's loads (it otherwise issues them only after the first
+          // chain has consumed its operands: two exposed latencies per trip instead of one).
+          uint32_t tie = 0;
+#pragma unroll
+          for (int k = 0; k < NV; ++k) tie |= __float_as_uint(q[k].x);
+          const float d0t = __uint_as_float(__float_as_uint(d0) | (tie & zero));
+          i += 2;  // the next trip's ranks travel with this trip's rows
+          const bool more = i < en;
+          if (more) {
+            two = i + 1 < en;
+            r0 = __ldg(ranks_depth + i);
+            f0 = __ldg(ranks_feat + i);
+            r1 = two ? __ldg(ranks_depth + i + 1) : r0;
+            f1 = two ? __ldg(ranks_feat + i + 1) : f0;
+          }
 #pragma unroll
           for (int k = 0; k < NV; ++k) {
-            acc[4 * k + 0] = fmaf(a[k].x, d0, acc[4 * k + 0]);
-            acc[4 * k + 1] = fmaf(a[k].y, d0, acc[4 * k + 1]);
-            acc[4 * k + 2] = fmaf(a[k].z, d0, acc[4 * k + 2]);
-            acc[4 * k + 3] = fmaf(a[k].w, d0, acc[4 * k + 3]);
+            acc[4 * k + 0] = fmaf(a[k].x, d0t, acc[4 * k + 0]);
+            acc[4 * k + 1] = fmaf(a[k].y, d0t, acc[4 * k + 1]);
+            acc[4 * k + 2] = fmaf(a[k].z, d0t, acc[4 * k + 2]);
+            acc[4 * k + 3] = fmaf(a[k].w, d0t, acc[4 * k + 3]);
           }
-          if (two) {
 #pragma unroll
-            for (int k = 0; k < NV; ++k) {
-              acc[4 * k + 0] = fmaf(q[k].x, d1, acc[4 * k + 0]);
-              acc[4 * k + 1] = fmaf(q[k].y, d1, acc[4 * k + 1]);
-              acc[4 * k + 2] = fmaf(q[k].z, d1, acc[4 * k + 2]);
-              acc[4 * k + 3] = fmaf(q[k].w, d1, acc[4 * k + 3]);
-            }
+          for (int k = 0; k < NV; ++k) {
+            acc[4 * k + 0] = fmaf(q[k].x, d1, acc[4 * k + 0]);
+            acc[4 * k + 1] = fmaf(q[k].y, d1, acc[4 * k + 1]);
+            acc[4 * k + 2] = fmaf(q[k].z, d1, acc[4 * k + 2]);
+            acc[4 * k + 3] = fmaf(q[k].w, d1, acc[4 * k + 3]);
           }
+          if (!more) break;
         }
       }
     }
@@ -1156,7 +1217,7 @@ static int launch_fwd_impl(const float* depth, const float* feat, const int32_t*
         VEON_CUDA_TRY(launch_pdl(k_pool_fwd_heavy<KCH>, dim3((unsigned)hblocks), dim3(kHeavyThreads),
                                  hsmem2, stream, depth, feat, rd, rf, rb, tile_start, heavy,
                                  heavy_cap, (uint32_t)tps, V, C, (uint32_t)n_chunks, vec_ok, out,
-                                 capturing));
+                                 capturing, 0));
         VEON_LAUNCH_CHECK();
       }
     }
@@ -1190,13 +1251,13 @@ static int launch_fwd_impl(const float* depth, const float* feat, const int32_t*
         VEON_CUDA_TRY(launch_pdl(k_pool_fwd_heavy<KCH>, dim3((unsigned)hblocks), dim3(kHeavyThreads),
                                  hsmem, stream, depth, feat, rd, rf, rb, tile_start, heavy,
                                  heavy_cap, (uint32_t)tps, V, C, (uint32_t)n_chunks, vec_ok, out,
-                                 capturing));
+                                 capturing, 0));
         VEON_LAUNCH_CHECK();
         return 0;
       }
       k_pool_fwd_heavy<KCH><<<(unsigned)hblocks, kHeavyThreads, hsmem, stream>>>(
           depth, feat, rd, rf, rb, tile_start, heavy, heavy_cap, (uint32_t)tps, V, C,
-          (uint32_t)n_chunks, vec_ok, out, 0);
+          (uint32_t)n_chunks, vec_ok, out, 0, 0);
       VEON_LAUNCH_CHECK();
       VEON_CUDA_TRY(launch_pdl(k_pool_fwd<KCH, FULLC>, dim3((unsigned)blocks), dim3(kFwdWarps * 32),
                                smem, stream, depth, feat, rd, rf, rb, tile_start, heavy,
@@ -1231,6 +1292,7 @@ static int launch_fwd_narrow(const float* depth, const float* feat, const int32_
   }
   int64_t blocks = ceil_div64(n_tiles, kNarrowWarps);
   if (blocks > (int64_t)ctas_per_sm * sm_count()) blocks = (int64_t)ctas_per_sm * sm_count();
+  static const int heavy_min = env_flag("VEON_NARROW_HEAVY_MIN", kNarrowHeavyMin);  // tuning knob
   int capturing = 0;
   {
     cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
@@ -1238,7 +1300,8 @@ static int launch_fwd_narrow(const float* depth, const float* feat, const int32_
       capturing = 1;
   }
   k_pool_fwd_narrow<NV><<<(unsigned)blocks, kNarrowWarps * 32, 0, stream>>>(
-      depth, feat, rd, rf, rb, tile_start, heavy, (uint32_t)n_tiles, (uint32_t)tps, V, out);
+      depth, feat, rd, rf, rb, tile_start, heavy, (uint32_t)n_tiles, (uint32_t)tps, V, out, 0u,
+      heavy_min);
   VEON_LAUNCH_CHECK();
   if (heavy) {
     const size_t hsmem = sizeof(float) * (kHeavyChunk * 32 + 32 * kRowPitch + 2 * kHeavyChunk + 128);
@@ -1257,7 +1320,8 @@ static int launch_fwd_narrow(const float* depth, const float* feat, const int32_
     if (hblocks > 0) {
       VEON_CUDA_TRY(launch_pdl(k_pool_fwd_heavy<1>, dim3((unsigned)hblocks), dim3(kHeavyThreads),
                                hsmem, stream, depth, feat, rd, rf, rb, tile_start, heavy,
-                               heavy_cap, (uint32_t)tps, V, C, 1u, 1, out, capturing));
+                               heavy_cap, (uint32_t)tps, V, C, 1u, 1, out, capturing,
+                               heavy_min));
       VEON_LAUNCH_CHECK();
     }
   }
