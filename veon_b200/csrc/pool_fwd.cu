@@ -1299,12 +1299,13 @@ static int launch_fwd_narrow(const float* depth, const float* feat, const int32_
     if (cudaStreamIsCapturing(stream, &st) == cudaSuccess && st != cudaStreamCaptureStatusNone)
       capturing = 1;
   }
-  k_pool_fwd_narrow<NV><<<(unsigned)blocks, kNarrowWarps * 32, 0, stream>>>(
-      depth, feat, rd, rf, rb, tile_start, heavy, (uint32_t)n_tiles, (uint32_t)tps, V, out, 0u,
-      heavy_min);
-  VEON_LAUNCH_CHECK();
+  static const int knob_order = env_flag("VEON_NARROW_ORDER", 0);        // 0: heavy grid first (344 -> 295 us at C3 density)
+  static const int knob_heavy_ctas = env_flag("VEON_NARROW_HEAVY_CTAS", 8);
+  int64_t hblocks = 0;
+  size_t hsmem = 0;
+  int heavy_cap = 0;
   if (heavy) {
-    const size_t hsmem = sizeof(float) * (kHeavyChunk * 32 + 32 * kRowPitch + 2 * kHeavyChunk + 128);
+    hsmem = sizeof(float) * (kHeavyChunk * 32 + 32 * kRowPitch + 2 * kHeavyChunk + 128);
     static int heavy_ctas_per_sm = 0;
     if (heavy_ctas_per_sm == 0) {
       VEON_CUDA_TRY(cudaFuncSetAttribute(k_pool_fwd_heavy<1>,
@@ -1313,17 +1314,32 @@ static int launch_fwd_narrow(const float* depth, const float* feat, const int32_
           &heavy_ctas_per_sm, k_pool_fwd_heavy<1>, kHeavyThreads, hsmem));
       if (heavy_ctas_per_sm < 1) heavy_ctas_per_sm = 1;
     }
-    const int heavy_cap = (int)(heavy_ints - 2);
-    const int per_sm = min(heavy_ctas_per_sm, 8);
-    int64_t hblocks = heavy_cap;
+    heavy_cap = (int)(heavy_ints - 2);
+    const int per_sm = min(heavy_ctas_per_sm, max(1, knob_heavy_ctas));
+    hblocks = heavy_cap;
     if (hblocks > (int64_t)per_sm * sm_count()) hblocks = (int64_t)per_sm * sm_count();
-    if (hblocks > 0) {
-      VEON_CUDA_TRY(launch_pdl(k_pool_fwd_heavy<1>, dim3((unsigned)hblocks), dim3(kHeavyThreads),
-                               hsmem, stream, depth, feat, rd, rf, rb, tile_start, heavy,
-                               heavy_cap, (uint32_t)tps, V, C, 1u, 1, out, capturing,
-                               heavy_min));
-      VEON_LAUNCH_CHECK();
-    }
+  }
+  if (hblocks > 0 && knob_order == 0 && !capturing) {
+    // heavy tiles first (a normal launch), the main grid moves in beside it; neither waits
+    k_pool_fwd_heavy<1><<<(unsigned)hblocks, kHeavyThreads, hsmem, stream>>>(
+        depth, feat, rd, rf, rb, tile_start, heavy, heavy_cap, (uint32_t)tps, V, C, 1u, 1, out, 0,
+        heavy_min);
+    VEON_LAUNCH_CHECK();
+    VEON_CUDA_TRY(launch_pdl(k_pool_fwd_narrow<NV>, dim3((unsigned)blocks), dim3(kNarrowWarps * 32),
+                             0, stream, depth, feat, rd, rf, rb, tile_start, heavy,
+                             (uint32_t)n_tiles, (uint32_t)tps, V, out, 0u, heavy_min));
+    VEON_LAUNCH_CHECK();
+    return 0;
+  }
+  k_pool_fwd_narrow<NV><<<(unsigned)blocks, kNarrowWarps * 32, 0, stream>>>(
+      depth, feat, rd, rf, rb, tile_start, heavy, (uint32_t)n_tiles, (uint32_t)tps, V, out, 0u,
+      heavy_min);
+  VEON_LAUNCH_CHECK();
+  if (hblocks > 0) {
+    VEON_CUDA_TRY(launch_pdl(k_pool_fwd_heavy<1>, dim3((unsigned)hblocks), dim3(kHeavyThreads),
+                             hsmem, stream, depth, feat, rd, rf, rb, tile_start, heavy,
+                             heavy_cap, (uint32_t)tps, V, C, 1u, 1, out, capturing, heavy_min));
+    VEON_LAUNCH_CHECK();
   }
   return 0;
 }
