@@ -137,6 +137,34 @@ def test_tail_class_of_prompt_matches_oracle():
     assert class_of_prompt(list(range(17))).tolist() == list(range(18))
 
 
+def test_pipeline_heads_and_cpu_refusal():
+    """lift_classify stacks [W ; gate] and pads the row count for the 16-byte row copies of the
+    pooling kernels; like every operator it refuses CPU tensors."""
+    from veon_b200 import pipeline, tail
+    w, g = torch.randn(18, 64), torch.randn(2, 64)
+    rows = pipeline._heads(w, g)
+    assert rows.shape == (20, 64) and torch.equal(rows[:18], w) and torch.equal(rows[18:], g)
+    rows = pipeline._heads(torch.randn(67, 64), g)
+    assert rows.shape == (72, 64) and torch.all(rows[69:] == 0)
+    assert pipeline._heads(w, g, 32).shape == (32, 64)
+    with pytest.raises(ValueError):
+        pipeline._heads(w, torch.randn(3, 64))
+    for fn, args in ((tail.semantic_inference_3d, (w, torch.randn(1, 64, 2, 2, 4))),
+                     (tail.classify_logits, (torch.randn(1, 18, 2, 2, 4), torch.randn(1, 2, 2, 2, 4),
+                                             torch.arange(18, dtype=torch.int32))),
+                     (tail.voxel_text_argmax_lowres, (torch.randn(1, 64, 2, 2, 4), w,
+                                                      torch.arange(18, dtype=torch.int32),
+                                                      torch.randn(1, 2, 2, 2, 4)))):
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            fn(*args)
+    # channel slices of one volume are passed through without a copy, anything else is copied
+    vol = torch.randn(3, 12, 4, 5, 6)
+    assert tail._sample_contiguous(vol[:, :8]).data_ptr() == vol.data_ptr()
+    assert tail._sample_contiguous(vol[:, 8:10]).stride(0) == vol.stride(0)
+    assert tail._sample_contiguous(vol[:, :, ::2]).is_contiguous()
+    assert tail._sample_contiguous(vol[:1].expand(3, 12, 4, 5, 6)).data_ptr() != vol.data_ptr()
+
+
 def test_shard_samples():
     from veon_b200.dist import shard_samples
     for n, g in ((8, 1), (8, 2), (9, 4), (3, 8), (64, 8)):
