@@ -213,6 +213,9 @@ int veon_transpose_batched(const float* src, int64_t batch, int R, int S, float*
  *     (bev_pool.py:86-92 = QuickCumsumCuda.forward :17-41 + permute :91).
  *     `out` is [B,C,Z,Y,X]; every element is written exactly once (zeros for
  *     empty voxels), so the caller need not zero it.  Requires a valid plan.
+ *     The result is bit-identical to the reference kernel for every C; rows of
+ *     at most 32 channels (C % 4 == 0, tile_heavy given, B*V <= 2^24) take a
+ *     lane-per-voxel kernel, everything else the lane-per-channel one.
  * ------------------------------------------------------------------------ */
 int veon_bev_pool_v2_fwd_planar(const float* depth, const float* feat,
                                 const int32_t* ranks_depth,

@@ -22,6 +22,8 @@
 // Kernels in this file:
 //   k_pool_fwd         the warp-per-tile kernel above (all tiles below the heavy threshold)
 //   k_pool_fwd_heavy   a CTA per heavy tile (rows staged by cp.async), queued behind it
+//   k_pool_fwd_narrow  C <= 32 (C % 4 == 0): a LANE per voxel instead of a lane per channel, all
+//                      channels of the voxel in registers, same fma order; heavy grid first
 //   k_pool_fwd_group   opt-in experiment: a CTA per group of tiles, software-pipelined
 //   k_pool_ds_fwd      opt-in: pooling fused with the neck's 2x2x2 max-downsample
 #include "common.cuh"
