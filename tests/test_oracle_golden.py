@@ -222,3 +222,35 @@ def test_classifier_commutes_with_the_interpolation():
     a = np.einsum("qc,bczyx->bqzyx", w, O.trilinear_upsample(feat, size).astype(np.float64))
     b = O.trilinear_upsample(np.einsum("qc,bczyx->bqzyx", w, feat), size)
     np.testing.assert_allclose(a, b, rtol=0, atol=1e-5)
+
+
+# ---- tail: golden vectors from the reference's own functions (tests/golden/make_golden_tail.py)
+@pytest.fixture(scope="module")
+def tail_golden(golden_dir):
+    return np.load(os.path.join(golden_dir, "tail_reference.npz"))
+
+
+@pytest.mark.parametrize("voc", ["nuscenes_brief", "nuscenes_default"])
+def test_tail_oracle_matches_reference_functions(tail_golden, voc):
+    """class groups, logits, merged logits and labels against `_add_vocabulary_nuscenes`,
+    `semantic_inference_3d`, `_merge_classes_prob` (run from /root/reference) and the label rule
+    of veon_temporal.py:223-229,240 applied literally."""
+    from veon_b200.tail import class_of_prompt
+    t = tail_golden
+    refl = t[f"{voc}.class_reflection"]
+    cls = O.class_groups(refl)
+    assert cls.size == refl.size + 1 == t[f"{voc}.w"].shape[0]
+    assert class_of_prompt(refl.tolist()).numpy().tolist() == cls.tolist()   # the product's host logic
+    merged = t[f"{voc}.merged"]
+    assert int(cls.max()) + 1 == merged.shape[1] == 18
+    assert cls[-1] == 17 and (cls[:-1] == refl).all()       # background row is its own, last class
+    feat, w = t[f"{voc}.feat"], t[f"{voc}.w"]
+    sem = np.einsum("qc,bczyx->bqzyx", w, feat)
+    np.testing.assert_allclose(sem, t[f"{voc}.sem_occ"], rtol=0, atol=2e-5 * np.abs(sem).max())
+    ref_sem = t[f"{voc}.sem_occ"]
+    for k in range(18):                                      # the merge itself is exact
+        np.testing.assert_array_equal(ref_sem[:, cls == k].max(axis=1), merged[:, k])
+    got = O.voxel_text_labels(feat, w, cls, t[f"{voc}.bin_occ"])
+    np.testing.assert_array_equal(got, t[f"{voc}.labels"])
+    if voc == "nuscenes_brief":
+        assert np.bincount(refl).tolist() == [16, 1, 1, 1, 8, 1, 1, 3, 1, 1, 1, 1, 5, 3, 5, 13, 4]

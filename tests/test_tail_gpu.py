@@ -251,3 +251,25 @@ def test_lift_classify_in_logit_space_matches_feature_space_and_oracle():
                                  dtype=np.float64)
     assert np.all(near_tie[got_np != want64]), int((~near_tie[got_np != want64]).sum())
     assert 0.001 < float((got != 17).float().mean()) < 0.9
+
+
+@pytest.mark.parametrize("voc", ["nuscenes_brief", "nuscenes_default"])
+def test_tail_kernels_match_reference_golden(golden_dir, voc):
+    """the reference's own `semantic_inference_3d` / `_merge_classes_prob` outputs and the label
+    rule applied literally (tests/golden/make_golden_tail.py), real prompt groups"""
+    import os
+    from veon_b200.tail import (class_of_prompt, classify_logits, semantic_inference_3d,
+                                voxel_text_argmax)
+    t = np.load(os.path.join(golden_dir, "tail_reference.npz"))
+    cls = class_of_prompt(t[f"{voc}.class_reflection"].tolist()).cuda()
+    feat, w = torch.from_numpy(t[f"{voc}.feat"]).cuda(), torch.from_numpy(t[f"{voc}.w"]).cuda()
+    bin_occ = torch.from_numpy(t[f"{voc}.bin_occ"]).cuda()
+    want = t[f"{voc}.labels"]
+    got = voxel_text_argmax(feat, w, cls, bin_occ).cpu().numpy()
+    np.testing.assert_array_equal(got, want)
+    sem = semantic_inference_3d(w, feat)
+    ref_sem = t[f"{voc}.sem_occ"]
+    assert np.abs(sem.cpu().numpy() - ref_sem).max() <= 1e-5 * np.abs(ref_sem).max()
+    # merge + label rule on the reference's own logits: nothing left to round
+    got2 = classify_logits(torch.from_numpy(ref_sem).cuda(), bin_occ, cls).cpu().numpy()
+    np.testing.assert_array_equal(got2, want)
