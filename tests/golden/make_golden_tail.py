@@ -12,7 +12,7 @@ three functions above); the vocabulary tables are the reference's own files.  Th
 (veon_temporal.py:223-229,240) is inline code of `simple_test` and cannot be called on its own; the
 generator applies those lines literally to the merged logits.  Run in the build container only:
 
-    python tests/golden/make_golden_tail.py      ->  tests/golden/tail_reference.npz
+    python tests/golden/make_golden_tail.py [out.npz]   ->  tests/golden/tail_reference.npz
 """
 import importlib.util
 import os
@@ -132,7 +132,8 @@ def main():
         out[f"{voc}.labels"] = occ_pred_cls.numpy().astype(np.uint8)
         print(voc, "prompts", len(refl), "classes", merged.shape[1],
               "group sizes", np.bincount(np.asarray(refl)).tolist())
-    np.savez_compressed(os.path.join(HERE, "tail_reference.npz"), **out)
+    dst = sys.argv[1] if len(sys.argv) > 1 else os.path.join(HERE, "tail_reference.npz")
+    np.savez_compressed(dst, **out)
 
 
 if __name__ == "__main__":

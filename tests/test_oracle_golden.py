@@ -254,3 +254,19 @@ def test_tail_oracle_matches_reference_functions(tail_golden, voc):
     np.testing.assert_array_equal(got, t[f"{voc}.labels"])
     if voc == "nuscenes_brief":
         assert np.bincount(refl).tolist() == [16, 1, 1, 1, 8, 1, 1, 3, 1, 1, 1, 1, 5, 3, 5, 13, 4]
+
+
+@pytest.mark.needs_reference
+def test_tail_fixture_is_what_the_reference_functions_return_today(golden_dir, tmp_path):
+    """build container only: re-run the generator (its own process: it stubs detectron2 & co. in
+    sys.modules) and compare with the committed fixture"""
+    import subprocess
+    import sys
+    out = tmp_path / "tail.npz"
+    res = subprocess.run([sys.executable, os.path.join(golden_dir, "make_golden_tail.py"), str(out)],
+                         stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout[-2000:]
+    new, old = np.load(out), np.load(os.path.join(golden_dir, "tail_reference.npz"))
+    assert sorted(new.files) == sorted(old.files)
+    for k in old.files:
+        np.testing.assert_array_equal(new[k], old[k], err_msg=k)
