@@ -535,66 +535,68 @@ def run_ours(args):
                         "achieved_gbs_algorithmic": bytes_t / (ms_t * 1e-3) / 1e9,
                         "frac_of_hbm_peak": bytes_t / (ms_t * 1e-3) / 1e9 / peak_gbs,
                         "tf32_tflops_issued": 3 * 2.0 * Bt * 640000 * Ct * 32 / (ms_t * 1e-3) / 1e12}
-        # ---- secondary: the same tail from the decoder's resolution: the reference
-        # up-samples feat_occ [B,C,8,100,100] to 16x200x200 and classifies there; ours classifies
-        # the low-resolution volume (tcgen05) and interpolates the Q logit channels
-        from veon_b200.tail import voxel_text_argmax_lowres
-        Bl = 8
-        feat_lr = torch.sigmoid(torch.randn(Bl, Ct, 8, 100, 100, device=dev, generator=gt)) - 0.5
-        bin_lr = torch.randn(Bl, 2, 8, 100, 100, device=dev, generator=gt)
-        ws_lr = torch.empty(Bl * Qt * 80000, dtype=torch.float32, device=dev)
-        for _ in range(3):
-            voxel_text_argmax_lowres(feat_lr, wt, cls_t, bin_lr, workspace=ws_lr)
-        torch.cuda.synchronize()
-        t0.record()
-        for _ in range(nt):
-            voxel_text_argmax_lowres(feat_lr, wt, cls_t, bin_lr, workspace=ws_lr)
-        t1.record()
-        torch.cuda.synchronize()
-        ms_l = t0.elapsed_time(t1) / nt
-        bytes_l = Bl * (4 * 80000 * Ct + 8 * 80000 + 640000) + 4 * Qt * Ct
-        line["tail_lowres"] = {
-            "what": f"veon_voxel_text_argmax_lowres, C={Ct}, Q={Qt}, {Bl} samples/call, feat_occ "
-                    "[B,C,8,100,100] -> logits (tcgen05 3xTF32) -> trilinear up-sampling of the Q "
-                    "logits + class-max/argmax/gate -> uint8 [B,200,200,16]; equals the full-"
-                    "resolution route on >= 99.99 % of voxels (tests/test_tail_gpu.py)",
-            "samples_per_s_per_gpu": Bl / (ms_l * 1e-3), "ms_per_call": ms_l,
-            "achieved_gbs_algorithmic": bytes_l / (ms_l * 1e-3) / 1e9,
-            "frac_of_hbm_peak": bytes_l / (ms_l * 1e-3) / 1e9 / peak_gbs,
-            "speedup_vs_full_resolution_tail": (Bl / ms_l) / (Bt / ms_t)}
-        del feat_occ, bin_occ, feat_lr, bin_lr, ws_lr
-        # ---- secondary: BASELINE configs[2] as one pipeline, lift + classify (C=512, Q=18) with
-        # the classifier in front of the pooling (veon_b200.pipeline.lift_classify)
-        from veon_b200.pipeline import lift_classify
-        c3 = S.CONFIGS["C3"]
-        Bp, Np, Dp = 8, c3.n_cams, c3.D
-        Hp, Wp = c3.feat_hw
-        neck3 = LSSViewTransformer(c3.grid_config, c3.input_size, c3.downsample, 8, Ct,
-                                   collapse_z=False)
-        cal3 = S.calibration(c3, batch=Bp)
-        metas3 = [torch.from_numpy(cal3[k]).to(dev) for k in
-                  ("sensor2ego", "ego2global", "intrins", "post_rots", "post_trans", "bda")]
-        depth3 = torch.softmax(torch.randn(Bp * Np, Dp, Hp, Wp, device=dev, generator=gt) * 4, 1)
-        feat3 = torch.randn(Bp * Np, Ct, Hp, Wp, device=dev, generator=gt) * 0.05
-        gate_w = torch.randn(2, Ct, device=dev, generator=gt)
-        img3 = torch.zeros(Bp, Np, 1, Hp, Wp, device=dev)
-        for _ in range(3):
-            lift_classify(neck3, [img3] + metas3, depth3, feat3, wt, cls_t, gate_w)
-        torch.cuda.synchronize()
-        t0.record()
-        for _ in range(nt):
-            lift_classify(neck3, [img3] + metas3, depth3, feat3, wt, cls_t, gate_w)
-        t1.record()
-        torch.cuda.synchronize()
-        ms_p = t0.elapsed_time(t1) / nt
-        line["lift_classify"] = {
-            "what": f"C3 geometry (6 cams 32x88, D={Dp}), C={Ct} image features -> per-pixel logits "
-                    f"(tcgen05) -> get_lidar_coor + prepare_v2 + bev_pool_v2 forward of Q+2={Qt + 2} "
-                    "channels -> merge/argmax/gate -> uint8 [B,200,200,16]; equals pooling the C-channel "
-                    "features and classifying the volume on >= 99.99 % of voxels (tests/test_tail_gpu.py)",
-            "samples_per_call": Bp, "ms_per_call": ms_p,
-            "samples_per_s_per_gpu": Bp / (ms_p * 1e-3)}
-        del depth3, feat3, neck3
+        if world == 1:   # the two 8f-4 legs are single-GPU figures (every rank would repeat them)
+            # ---- secondary: the same tail from the decoder's resolution: the reference
+            # up-samples feat_occ [B,C,8,100,100] to 16x200x200 and classifies there; ours classifies
+            # the low-resolution volume (tcgen05) and interpolates the Q logit channels
+            from veon_b200.tail import voxel_text_argmax_lowres
+            Bl = 8
+            feat_lr = torch.sigmoid(torch.randn(Bl, Ct, 8, 100, 100, device=dev, generator=gt)) - 0.5
+            bin_lr = torch.randn(Bl, 2, 8, 100, 100, device=dev, generator=gt)
+            ws_lr = torch.empty(Bl * Qt * 80000, dtype=torch.float32, device=dev)
+            for _ in range(3):
+                voxel_text_argmax_lowres(feat_lr, wt, cls_t, bin_lr, workspace=ws_lr)
+            torch.cuda.synchronize()
+            t0.record()
+            for _ in range(nt):
+                voxel_text_argmax_lowres(feat_lr, wt, cls_t, bin_lr, workspace=ws_lr)
+            t1.record()
+            torch.cuda.synchronize()
+            ms_l = t0.elapsed_time(t1) / nt
+            bytes_l = Bl * (4 * 80000 * Ct + 8 * 80000 + 640000) + 4 * Qt * Ct
+            line["tail_lowres"] = {
+                "what": f"veon_voxel_text_argmax_lowres, C={Ct}, Q={Qt}, {Bl} samples/call, feat_occ "
+                        "[B,C,8,100,100] -> logits (tcgen05 3xTF32) -> trilinear up-sampling of the Q "
+                        "logits + class-max/argmax/gate -> uint8 [B,200,200,16]; equals the full-"
+                        "resolution route on >= 99.99 % of voxels (tests/test_tail_gpu.py)",
+                "samples_per_s_per_gpu": Bl / (ms_l * 1e-3), "ms_per_call": ms_l,
+                "achieved_gbs_algorithmic": bytes_l / (ms_l * 1e-3) / 1e9,
+                "frac_of_hbm_peak": bytes_l / (ms_l * 1e-3) / 1e9 / peak_gbs,
+                "speedup_vs_full_resolution_tail": (Bl / ms_l) / (Bt / ms_t)}
+            del feat_lr, bin_lr, ws_lr
+            # ---- secondary: BASELINE configs[2] as one pipeline, lift + classify (C=512, Q=18) with
+            # the classifier in front of the pooling (veon_b200.pipeline.lift_classify)
+            from veon_b200.pipeline import lift_classify
+            c3 = S.CONFIGS["C3"]
+            Bp, Np, Dp = 8, c3.n_cams, c3.D
+            Hp, Wp = c3.feat_hw
+            neck3 = LSSViewTransformer(c3.grid_config, c3.input_size, c3.downsample, 8, Ct,
+                                       collapse_z=False)
+            cal3 = S.calibration(c3, batch=Bp)
+            metas3 = [torch.from_numpy(cal3[k]).to(dev) for k in
+                      ("sensor2ego", "ego2global", "intrins", "post_rots", "post_trans", "bda")]
+            depth3 = torch.softmax(torch.randn(Bp * Np, Dp, Hp, Wp, device=dev, generator=gt) * 4, 1)
+            feat3 = torch.randn(Bp * Np, Ct, Hp, Wp, device=dev, generator=gt) * 0.05
+            gate_w = torch.randn(2, Ct, device=dev, generator=gt)
+            img3 = torch.zeros(Bp, Np, 1, Hp, Wp, device=dev)
+            for _ in range(3):
+                lift_classify(neck3, [img3] + metas3, depth3, feat3, wt, cls_t, gate_w)
+            torch.cuda.synchronize()
+            t0.record()
+            for _ in range(nt):
+                lift_classify(neck3, [img3] + metas3, depth3, feat3, wt, cls_t, gate_w)
+            t1.record()
+            torch.cuda.synchronize()
+            ms_p = t0.elapsed_time(t1) / nt
+            line["lift_classify"] = {
+                "what": f"C3 geometry (6 cams 32x88, D={Dp}), C={Ct} image features -> per-pixel logits "
+                        f"(tcgen05) -> get_lidar_coor + prepare_v2 + bev_pool_v2 forward of Q+2={Qt + 2} "
+                        "channels -> merge/argmax/gate -> uint8 [B,200,200,16]; equals pooling the C-channel "
+                        "features and classifying the volume on >= 99.99 % of voxels (tests/test_tail_gpu.py)",
+                "samples_per_call": Bp, "ms_per_call": ms_p,
+                "samples_per_s_per_gpu": Bp / (ms_p * 1e-3)}
+            del depth3, feat3, neck3
+        del feat_occ, bin_occ
         # ---- secondary: the neck's 2x2x2 max-downsample of the pooled volume
         vol = out_grad.detach().clone().requires_grad_()
         go_ds = torch.randn(B, C, 8, 100, 100, device=dev, generator=gt)
