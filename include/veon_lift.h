@@ -247,13 +247,15 @@ int veon_two_hot_depth(const float* depths, int64_t BN, int H_out, int W_out, in
                        int D, float depth_lo, float depth_step, float gamma, float* out,
                        void* stream);
 
-/* The neck's 2x2x2 max-downsample on its own (view_transformer_raw.py:549-553: an 8-D
- * `.amax` in the reference) and its gradient (ATen's amax backward: grad * (in == out) /
- * count(in == out)).  in / grad_in [BC,Z,Y,X], out / grad_out [BC,Z/2,Y/2,X/2], float32,
- * contiguous; Z, Y even and X % 4 == 0, else VEON_E_UNSUPPORTED. */
+/* The neck's 2x2x2 max-downsample on its own (view_transformer_raw.py:549-553: einops
+ * rearrange to a trailing (dz dh dw) axis + torch.max(dim=-1).values) and its gradient (the
+ * backward of max(dim): the whole gradient to the first arg-max of each block).  in / grad_in
+ * [BC,Z,Y,X], out / grad_out [BC,Z/2,Y/2,X/2], float32, contiguous; Z, Y even and X % 4 == 0,
+ * else VEON_E_UNSUPPORTED. */
 int veon_maxdown2_fwd(const float* in, int64_t BC, int Z, int Y, int X, float* out, void* stream);
-/* Forward that also emits, per output, the 8-bit mask of inputs equal to the maximum
- * (bit (dz*2+dy)*2+dx) -- all veon_bev_pool_v2_bwd_planar_ds needs. */
+/* Forward that also emits, per output, an 8-bit mask with ONE bit set: the arg-max input
+ * (bit (dz*2+dy)*2+dx, the first maximum on ties) -- all veon_bev_pool_v2_bwd_planar_ds
+ * needs. */
 int veon_maxdown2_fwd_mask(const float* in, int64_t BC, int Z, int Y, int X, float* out,
                            uint8_t* mask, void* stream);
 int veon_maxdown2_bwd(const float* in, const float* out, const float* grad_out,
@@ -280,7 +282,7 @@ int veon_bev_pool_v2_bwd_planar(const float* out_grad,
 
 /* QuickCumsumCuda.backward for a gradient that arrives BEHIND the 2x2x2 max-downsample:
  * grad_ds [B,C,Z/2,Y/2,X/2] and the mask of veon_maxdown2_fwd_mask replace out_grad; the
- * full-resolution gradient is never formed (ATen amax gradient semantics: ties share equally).
+ * full-resolution gradient is never formed (max(dim) gradient semantics: all to the arg-max).
  * rows_ws as in veon_bev_pool_v2_bwd_planar; even Z, Y, X. */
 int veon_bev_pool_v2_bwd_planar_ds(const float* grad_ds, const uint8_t* mask,
                                    const float* depth, const float* feat,

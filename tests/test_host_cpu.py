@@ -260,3 +260,51 @@ def test_operator_surface_matches_reference_call_sites():
     for attr in ("grid_lower_bound", "grid_interval", "grid_size", "frustum", "D", "accelerate",
                  "initial_flag", "collapse_z", "out_channels", "in_channels", "downsample", "sid"):
         assert hasattr(ours, attr) and hasattr(neck, attr)
+
+
+# ---- INTEGRATION route B plumbing (no GPU needed) -----------------------------------------------
+@pytest.mark.needs_reference
+def test_reference_operator_file_runs_on_a_substituted_ext(golden_dir):
+    """mmdet3d/ops/bev_pool_v2/bev_pool.py, unmodified, imports whatever module is registered
+    as `bev_pool_v2_ext` (bev_pool.py:6).  With an ext made of the C oracle it reproduces the
+    reference's known-answer test (bev_pool.py:145-176) on the CPU -- the same substitution
+    tests/test_dropin_reference.py makes with veon_b200.bev_pool_v2_ext on the GPU."""
+    import json
+    import types
+    import torch
+    from _ref_loader import load_reference_bev_pool
+    from oracle import lift_oracle as O
+
+    def fwd(depth, feat, out, rd, rf, rb, ln, st):
+        out.copy_(torch.from_numpy(O.bev_pool_v2_channels_last(
+            depth.numpy(), feat.numpy(), rd.numpy(), rf.numpy(), rb.numpy(), tuple(out.shape),
+            st.numpy(), ln.numpy())))
+
+    mod = load_reference_bev_pool(types.SimpleNamespace(bev_pool_v2_forward=fwd,
+                                                        bev_pool_v2_backward=None))
+    with open(os.path.join(golden_dir, "kat_bev_pool_v2.json")) as f:
+        k = json.load(f)
+    depth = torch.tensor(k["depth"]).float().view(*k["depth_shape"])
+    feat = torch.ones(size=k["feat_shape"])
+    rd, rf, rb = (torch.tensor(k[n]).int() for n in ("ranks_depth", "ranks_feat", "ranks_bev"))
+    bev = mod.bev_pool_v2(depth, feat, rd, rf, rb, tuple(k["bev_feat_shape"]),
+                          torch.tensor([0, 2]).int(), torch.tensor([2, 2]).int())
+    assert abs(float(bev.sum()) - k["loss"]) < 1e-6
+
+
+def test_ext_stand_in_has_the_pybind_surface_and_refuses_cpu_tensors():
+    """veon_b200.bev_pool_v2_ext mirrors bev_pool.cpp:106-111 (two functions, lengths before
+    starts) and has no CPU path."""
+    import inspect
+    import torch
+    from veon_b200 import bev_pool_v2_ext as ext
+    assert list(inspect.signature(ext.bev_pool_v2_forward).parameters) == [
+        "depth", "feat", "out", "ranks_depth", "ranks_feat", "ranks_bev", "interval_lengths",
+        "interval_starts"]
+    assert list(inspect.signature(ext.bev_pool_v2_backward).parameters) == [
+        "out_grad", "depth_grad", "feat_grad", "depth", "feat", "ranks_depth", "ranks_feat",
+        "ranks_bev", "interval_lengths", "interval_starts"]
+    t = torch.zeros(1, 1, 1, 1, 1)
+    i = torch.zeros(1, dtype=torch.int32)
+    with pytest.raises(RuntimeError):
+        ext.bev_pool_v2_forward(t, t, t, i, i, i, i, i)

@@ -94,12 +94,17 @@ def test_forward_bit_exact_vs_oracle(cfg_name, batch, C):
 
 
 @pytest.mark.parametrize("cfg_name,batch,C", [("tiny", 2, 32), ("tiny", 2, 7), ("small", 2, 64),
-                                              ("C1", 1, 64), ("small", 1, 160)])
+                                              ("C1", 1, 64), ("small", 1, 160),
+                                              # the widths VEON uses (its neck: 256; CLIP dims 512 / 768),
+                                              # several samples each: the multi-chunk, multi-sample backward
+                                              ("small", 2, 256), ("small", 3, 512), ("tiny", 2, 768),
+                                              ("C1", 2, 256), ("tiny", 3, 96), ("small", 2, 100)])
 def test_backward_vs_oracle(cfg_name, batch, C):
     case = make_case(cfg_name, batch, C, seed=1)
     rb, rd, rf, st, ln = case["ranks"]
     B, Z, Y, X, _ = case["shape"]
-    og = torch.randn(B, C, Z, Y, X, generator=torch.Generator().manual_seed(2))
+    og = torch.randn(B, C, Z, Y, X, generator=torch.Generator(device="cuda").manual_seed(2),
+                     device="cuda").cpu()
     dg_want, fg_want = O.bev_pool_v2_backward(og.numpy(), case["depth"].numpy(),
                                               case["feat"].numpy(), rd, rf, rb)
     _, dg, fg = run_gpu(case, og)
@@ -289,6 +294,35 @@ def test_full_size_properties_c2():
     assert abs(lhs - via_depth) <= 1e-6 * abs(lhs) + 1e-3
 
 
+def test_full_size_c2_backward_elementwise_per_sample():
+    """BASELINE configs[1] at full size (B=8, C=64): the gradients of the first, a middle and the
+    last sample against the C oracle run on that sample alone (every sample is independent:
+    the batch index is only the top digit of ranks_bev, view_transformer.py:241)."""
+    from veon_b200.bev_pool import bev_pool_v2, voxel_pooling_prepare_v2
+    cfg = S.CONFIGS["C2"]
+    coor_np = S.lidar_coor_np(cfg)
+    lower, interval, size = S.grid_vectors(cfg.grid_config)
+    coor = torch.from_numpy(coor_np).cuda()
+    rb, rd, rf, st, ln = voxel_pooling_prepare_v2(coor, lower, interval, size)
+    B, N, D, H, W, _ = coor_np.shape
+    C = cfg.channels
+    g = torch.Generator(device="cuda").manual_seed(21)
+    depth = torch.softmax(torch.randn(B, N, D, H, W, device="cuda", generator=g) * 4, dim=2).requires_grad_()
+    feat = torch.randn(B, N, H, W, C, device="cuda", generator=g).requires_grad_()
+    og = torch.randn(B, C, 16, 200, 200, device="cuda", generator=g)
+    out = bev_pool_v2(depth, feat, rd, rf, rb, (B, 16, 200, 200, C), st, ln)
+    out.backward(og)
+    for b in (0, 3, B - 1):
+        r1 = O.prepare_v2(coor_np[b:b + 1], lower, interval, size)
+        d1 = depth.detach()[b:b + 1].cpu().numpy()
+        f1 = feat.detach()[b:b + 1].cpu().numpy()
+        want = O.bev_pool_v2(d1, f1, r1[1], r1[2], r1[0], (1, 16, 200, 200, C), r1[3], r1[4])
+        np.testing.assert_array_equal(out.detach()[b:b + 1].cpu().numpy(), want)
+        dg, fg = O.bev_pool_v2_backward(og[b:b + 1].cpu().numpy(), d1, f1, r1[1], r1[2], r1[0])
+        assert rel_max_err(depth.grad[b:b + 1].cpu().numpy(), dg) <= 2e-5
+        assert rel_max_err(feat.grad[b:b + 1].cpu().numpy(), fg) <= 2e-5
+
+
 @pytest.mark.parametrize("name,batch", [("C3", 1), ("C4", 1)])
 def test_full_size_properties_wide_channels(name, batch):
     """BASELINE configs[2]/[3] shapes (32x88 feats, C=512 / D=118, C=768; one sample):
@@ -326,6 +360,12 @@ def test_full_size_properties_wide_channels(name, batch):
     via_depth = (depth.grad.double() * depth.detach().double()).sum().item()
     assert abs(lhs - via_feat) <= 1e-6 * abs(lhs) + 1e-2
     assert abs(lhs - via_depth) <= 1e-6 * abs(lhs) + 1e-2
+    # ... and element by element against the C oracle (bev_pool_cuda.cu:67-121 restated)
+    dg, fg = O.bev_pool_v2_backward(og.cpu().numpy(), depth.detach().cpu().numpy(),
+                                    feat.detach().cpu().numpy(), rd.cpu().numpy(),
+                                    rf.cpu().numpy(), rb.cpu().numpy())
+    assert rel_max_err(depth.grad.cpu().numpy(), dg) <= 2e-5
+    assert rel_max_err(feat.grad.cpu().numpy(), fg) <= 2e-5
 
 
 # ---------------------------------------------------------------- heavy tiles

@@ -273,3 +273,58 @@ def test_tail_kernels_match_reference_golden(golden_dir, voc):
     # merge + label rule on the reference's own logits: nothing left to round
     got2 = classify_logits(torch.from_numpy(ref_sem).cuda(), bin_occ, cls).cpu().numpy()
     np.testing.assert_array_equal(got2, want)
+
+
+# ---- adversarial near-ties and the full-size C=512 case -------------------
+@pytest.mark.parametrize("eps", [1e-6, 1e-5, 1e-4, 1e-3])
+@pytest.mark.parametrize("Q_per_class", [1, 3])
+def test_near_tie_labels(eps, Q_per_class):
+    """Classifier rows that differ from each other by a relative perturbation `eps`, so that the
+    two best classes of EVERY voxel are a near-tie with a logit gap of about eps x |logit|
+    (the 3xTF32 contraction has ~2^-21 relative error per product; plain TF32 would flip
+    classes up to eps ~ 1e-3).  Rule checked: wherever the float64 gap between the best and the
+    second-best merged class exceeds 2e-5 of the largest logit (twice the logit tolerance of
+    test_semantic_inference_3d_matches_fp32_einsum) the label is the float64 arg-max; below that
+    any class within the tolerance of the best one is acceptable."""
+    C, Z, Y, X, B = 512, 4, 40, 50, 2
+    n_cls = 6
+    g = torch.Generator().manual_seed(int(-np.log10(eps)) * 10 + Q_per_class)
+    base = torch.randn(1, C, generator=g)
+    rows = base + eps * base.norm() * torch.nn.functional.normalize(
+        torch.randn(n_cls * Q_per_class + 1, C, generator=g), dim=1)
+    w = (100.0 * rows / rows.norm(dim=1, keepdim=True)).float()
+    refl = [k for k in range(n_cls) for _ in range(Q_per_class)]
+    feat = torch.sigmoid(torch.randn(B, C, Z, Y, X, generator=g)) - 0.5
+    bin_occ = torch.zeros(B, 2, Z, Y, X)
+    bin_occ[:, 0] = 1.0                                    # everything occupied: classes decide
+    got, cls = run(feat, w, refl, bin_occ)
+    sem = torch.einsum("qc,bczyx->bqzyx", w.double(), feat.double())
+    merged = torch.stack([sem[:, torch.from_numpy(cls == k)].max(dim=1).values
+                          for k in range(int(cls.max()) + 1)], 1)          # [B,K,Z,Y,X]
+    top = merged.max(dim=1)
+    scale = sem.abs().amax()
+    got_t = torch.from_numpy(got.astype(np.int64)).permute(0, 3, 2, 1)     # [B,Z,Y,X]
+    assert int(got_t.max()) < merged.shape[1]                              # never "free" here
+    chosen = merged.gather(1, got_t.unsqueeze(1)).squeeze(1)
+    # the chosen class is the float64 best one up to the logit tolerance -- which pins it
+    # exactly wherever the runner-up is further away than that
+    assert float(((top.values - chosen) / scale).max()) <= 2e-5
+    second = merged.topk(2, dim=1).values[:, 1]
+    clear = (top.values - second) / scale > 2e-5
+    assert bool((got_t[clear] == top.indices[clear]).all())
+    if eps >= 1e-4:
+        assert float(clear.float().mean()) > 0.2        # the construction does decide many voxels
+
+
+def test_full_volume_c512_q18_and_q67():
+    """BASELINE configs[2] at full size: one Occ3D sample (16x200x200), C=512, the 18-row and the
+    real 67-row vocabulary; labels against the fp32 CPU oracle (>= 99.99 %) and, where they
+    differ, against float64 (near-ties only)."""
+    for refl in (list(range(17)), [k for k, n in enumerate(SIZES) for _ in range(n)]):
+        feat, w, bin_occ = synth(1, 512, refl, 16, 200, 200, seed=len(refl))
+        got, cls = run(feat, w, refl, bin_occ)
+        want = O.voxel_text_labels(feat.numpy(), w.numpy(), cls, bin_occ.numpy())
+        assert got.shape == (1, 200, 200, 16)
+        assert float((got == want).mean()) >= 0.9999
+        want64 = O.voxel_text_labels(feat.numpy(), w.numpy(), cls, bin_occ.numpy(), dtype=np.float64)
+        assert float((got == want64).mean()) >= 0.9999

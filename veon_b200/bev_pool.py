@@ -406,8 +406,9 @@ def two_hot_depth(depths, depth_cfg, D, gamma=4.0, downsample=0):
 
 
 class MaxDown2x2x2(torch.autograd.Function):
-    """`x.view(b,c,z/2,2,y/2,2,x/2,2).amax(dim=(3,5,7))` (view_transformer_raw.py:549-553) and
-    ATen's amax gradient (ties share equally) as two streaming kernels."""
+    """The neck's 2x2x2 reduction, `rearrange(... '(dz dh dw)') -> torch.max(dim=-1).values`
+    (view_transformer_raw.py:549-553), and its gradient (all of it to the first arg-max of a
+    block, as max(dim) does) as two streaming kernels."""
 
     @staticmethod
     def supports(x):
@@ -444,10 +445,10 @@ class MaxDown2x2x2(torch.autograd.Function):
 class PoolMaxDown(torch.autograd.Function):
     """bev_pool_v2 followed by the neck's 2x2x2 max-downsample as ONE autograd node
     (view_transformer.py:175-200 + view_transformer_raw.py:549-553).  Forward: the two kernels
-    of the plain route, plus an 8-bit mask per output (which inputs equal the maximum).
-    Backward: the gradient rows of the occupied voxels come straight from grad_ds and the mask
-    (ATen's amax gradient: ties share equally), so neither the 1.31 GB full-resolution gradient
-    nor the volume is kept or touched."""
+    of the plain route, plus an 8-bit mask per output (one bit: which input is the arg-max,
+    the first one on ties).  Backward: the gradient rows of the occupied voxels come straight
+    from grad_ds and the mask (the gradient of torch.max(dim): everything to the arg-max), so
+    neither the 1.31 GB full-resolution gradient nor the volume is kept or touched."""
 
     @staticmethod
     def forward(ctx, depth, feat, prep, bev_feat_shape):

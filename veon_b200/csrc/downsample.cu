@@ -1,12 +1,15 @@
 // 2x2x2 max-downsample of the pooled volume and its gradient.
 //
 // Reference: LSSViewTransformerRaw.forward (view_transformer_raw.py:549-553)
-//   bev_feat.view(b, c, z/2, 2, y/2, 2, x/2, 2).amax(dim=(3, 5, 7))
-// i.e. a strided 8-D reduction in ATen (2.8 ms for the 1.31 GB volume of C2 on B200) and, in
-// training, ATen's amax backward: grad * (in == out) / count(in == out), ties sharing equally.
-// Both are plain streaming passes here: a thread owns two neighbouring outputs = one 16-byte
-// load from each of the four input x-rows, so every access is a full coalesced line.
-// NaN propagates like torch.amax (a NaN input makes the output NaN).
+//   rearrange(bev_feat, 'b c (z dz) (h dh) (w dw) -> b c z h w (dz dh dw)', dz=2, dh=2, dw=2)
+//   torch.max(bev_feat, dim=-1).values
+// i.e. a strided gather + reduction in ATen (2.8 ms for the 1.31 GB volume of C2 on B200) and,
+// in training, the backward of max(dim): the WHOLE gradient goes to the one arg-max element,
+// the first one in (dz, dh, dw) order on ties.  (Ties are structural here: empty voxels are
+// exactly 0.0.)  Both are plain streaming passes: a thread owns two neighbouring outputs = one
+// 16-byte load from each of the four input x-rows, so every access is a full coalesced line.
+// NaN propagates like torch.max (a NaN input makes the output NaN; the first NaN takes the
+// gradient).
 #include "common.cuh"
 
 namespace veon {
@@ -14,8 +17,10 @@ namespace veon {
 __device__ __forceinline__ float max_nan(float a, float b) { return (b > a || b != b) ? b : a; }
 
 // volumes: in [BC][Z][Y][X], out [BC][Z/2][Y/2][X/2]; X % 4 == 0, Z and Y even
-// MASK: also store, per output, which of its 8 inputs equal the maximum (bit (dz*2+dy)*2+dx):
-// all the backward needs (grad * bit / popcount), so the volume need not be kept for it.
+// MASK: also store, per output, WHICH of its 8 inputs is the arg-max (one bit set, bit index
+// (dz*2+dy)*2+dx = the position in the reference's trailing (dz dh dw) axis, first maximum on
+// ties): all the backward needs, so the volume need not be kept for it.
+__device__ __forceinline__ bool is_max(float v, float m) { return v == m || (m != m && v != v); }
 template <bool MASK>
 __global__ void __launch_bounds__(256)
 k_maxdown2_fwd(const float* __restrict__ in, int64_t n_quads, int Zh, int Yh, int X4, int Y, int X,
@@ -39,10 +44,14 @@ k_maxdown2_fwd(const float* __restrict__ in, int64_t n_quads, int Zh, int Yh, in
     const int64_t oi = ((bc * Zh + zo) * Yh + yo) * (int64_t)(X / 2) + 2 * x4;
     *reinterpret_cast<float2*>(out + oi) = o;
     if (MASK) {
-      const uint32_t m0 = (a.x == o.x) | (a.y == o.x) << 1 | (b.x == o.x) << 2 | (b.y == o.x) << 3 |
-                          (c.x == o.x) << 4 | (c.y == o.x) << 5 | (d.x == o.x) << 6 | (d.y == o.x) << 7;
-      const uint32_t m1 = (a.z == o.y) | (a.w == o.y) << 1 | (b.z == o.y) << 2 | (b.w == o.y) << 3 |
-                          (c.z == o.y) << 4 | (c.w == o.y) << 5 | (d.z == o.y) << 6 | (d.w == o.y) << 7;
+      uint32_t m0 = is_max(a.x, o.x) | is_max(a.y, o.x) << 1 | is_max(b.x, o.x) << 2 |
+                    is_max(b.y, o.x) << 3 | is_max(c.x, o.x) << 4 | is_max(c.y, o.x) << 5 |
+                    is_max(d.x, o.x) << 6 | is_max(d.y, o.x) << 7;
+      uint32_t m1 = is_max(a.z, o.y) | is_max(a.w, o.y) << 1 | is_max(b.z, o.y) << 2 |
+                    is_max(b.w, o.y) << 3 | is_max(c.z, o.y) << 4 | is_max(c.w, o.y) << 5 |
+                    is_max(d.z, o.y) << 6 | is_max(d.w, o.y) << 7;
+      m0 &= 0u - m0;   // the first maximum only
+      m1 &= 0u - m1;
       *reinterpret_cast<uchar2*>(mask + oi) = make_uchar2((unsigned char)m0, (unsigned char)m1);
     }
   }
@@ -68,21 +77,20 @@ k_maxdown2_bwd(const float* __restrict__ in, const float* __restrict__ out,
     for (int k = 0; k < 4; ++k) v[k] = ld_stream4(in + ibase + step[k]);
     const float2 m = *reinterpret_cast<const float2*>(out + obase);
     const float2 g = *reinterpret_cast<const float2*>(grad_out + obase);
-    int n0 = 0, n1 = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      n0 += (v[k].x == m.x) + (v[k].y == m.x);
-      n1 += (v[k].z == m.y) + (v[k].w == m.y);
-    }
-    // grad * mask / count, exactly ATen's formula (count == 0 only if the output is NaN)
-    const float g0 = g.x / (float)n0, g1 = g.y / (float)n1;
+    // the whole gradient to the FIRST maximum in (dz, dy, dx) order = k-major, then x
+    // (the backward of torch.max(dim).values: index_put of the arg-max)
+    bool open0 = true, open1 = true;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       float4 w;
-      w.x = v[k].x == m.x ? g0 : 0.f;
-      w.y = v[k].y == m.x ? g0 : 0.f;
-      w.z = v[k].z == m.y ? g1 : 0.f;
-      w.w = v[k].w == m.y ? g1 : 0.f;
+      w.x = (open0 && is_max(v[k].x, m.x)) ? g.x : 0.f;
+      open0 = open0 && !is_max(v[k].x, m.x);
+      w.y = (open0 && is_max(v[k].y, m.x)) ? g.x : 0.f;
+      open0 = open0 && !is_max(v[k].y, m.x);
+      w.z = (open1 && is_max(v[k].z, m.y)) ? g.y : 0.f;
+      open1 = open1 && !is_max(v[k].z, m.y);
+      w.w = (open1 && is_max(v[k].w, m.y)) ? g.y : 0.f;
+      open1 = open1 && !is_max(v[k].w, m.y);
       st_stream4(grad_in + ibase + step[k], w);
     }
   }

@@ -293,9 +293,10 @@ class LSSViewTransformerRaw(LSSViewTransformer):
             b, c, z, y, x = bev_feat.shape
             if self.ds == (2, 2, 2) and _bp.MaxDown2x2x2.supports(bev_feat):
                 bev_feat = _bp.MaxDown2x2x2.apply(bev_feat)      # same values, own kernels
-            else:
+            else:   # other factors / odd grids: the reference's expression (:549-553)
                 bev_feat = bev_feat.view(b, c, z // dz, dz, y // dy, dy, x // dx, dx) \
-                    .amax(dim=(3, 5, 7))
+                    .permute(0, 1, 2, 4, 6, 3, 5, 7).reshape(b, c, z // dz, y // dy, x // dx, -1)
+                bev_feat = torch.max(bev_feat, dim=-1).values
         return bev_feat
 
     def _forward_pool_maxdown(self, input, depth):
