@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define VEON_ABI_VERSION 4
+#define VEON_ABI_VERSION 5
 
 #define VEON_E_BADARG    (-1)  /* NULL pointer / non-positive dimension          */
 #define VEON_E_WORKSPACE (-2)  /* workspace smaller than *_workspace_bytes()     */
@@ -213,20 +213,34 @@ int veon_transpose_batched(const float* src, int64_t batch, int R, int S, float*
  *     (bev_pool.py:86-92 = QuickCumsumCuda.forward :17-41 + permute :91).
  *     `out` is [B,C,Z,Y,X]; every element is written exactly once (zeros for
  *     empty voxels), so the caller need not zero it.  Requires a valid plan.
- *     The result is bit-identical to the reference kernel for every C; rows of
- *     at most 32 channels (C % 4 == 0, tile_heavy given, B*V <= 2^24) take a
- *     lane-per-voxel kernel, everything else the lane-per-channel one.
+ *     The result is bit-identical to the reference kernel for every C.
+ *     Kernel selection: rows of at most 32 channels (C % 4 == 0, tile_heavy
+ *     given, B*V <= 2^24) take a lane-per-voxel kernel; aligned volumes
+ *     (V % 32 == 0) with C a multiple of 64 (of 128 above 128, up to 1024), a
+ *     complete plan (tile_istart, tile_occ, tile_heavy) and a workspace take the
+ *     two-role streaming kernel (compact rows through an L2-resident ring, the
+ *     volume written as a pure store stream); everything else the general
+ *     lane-per-channel kernel.
+ *   workspace   optional scratch of veon_bev_pool_v2_fwd_workspace_bytes()
+ *               bytes, 256-byte aligned (a larger or smaller buffer is legal: it
+ *               sizes the ring; too small a one selects the general kernel);
+ *               contents need not be preserved between calls, but one buffer
+ *               must not be shared by calls that may run concurrently.
  * ------------------------------------------------------------------------ */
+size_t veon_bev_pool_v2_fwd_workspace_bytes(int B, int C, int64_t voxels_per_sample);
 int veon_bev_pool_v2_fwd_planar(const float* depth, const float* feat,
                                 const int32_t* ranks_depth,
                                 const int32_t* ranks_feat,
                                 const int32_t* ranks_bev,
                                 const int32_t* tile_start,
+                                const int32_t* tile_istart /* may be NULL */,
+                                const uint32_t* tile_occ /* may be NULL */,
                                 const int32_t* tile_heavy /* may be NULL */,
                                 int64_t tile_heavy_ints /* its size in int32 */,
                                 int B, int C, int64_t voxels_per_sample,
                                 int64_t n_feat_rows /* B*N*H*W rows of feat */,
-                                float* out, void* stream);
+                                float* out, void* workspace, size_t workspace_bytes,
+                                void* stream);
 
 /* Pooling fused with the 2x2x2 max-downsample VEON's neck applies next
  * (view_transformer_raw.py:549-553), forward only: out is [B, C, Z/2, Y/2, X/2], bit-identical

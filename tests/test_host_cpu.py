@@ -37,7 +37,10 @@ def test_argument_errors_do_not_need_a_gpu():
     lib = _lib.load()
     null = ctypes.c_void_p(0)
     assert lib.veon_bev_pool_v2(64, 10, null, null, null, null, null, null, null, null, null) == -1
-    assert lib.veon_bev_pool_v2_fwd_planar(null, null, null, null, null, null, null, 0, 1, 64, 640000, 4224, null, null) == -1
+    assert lib.veon_bev_pool_v2_fwd_planar(null, null, null, null, null, null, null, null, null, 0,
+                                           1, 64, 640000, 4224, null, null, 0, null) == -1
+    assert lib.veon_bev_pool_v2_fwd_workspace_bytes(8, 64, 640000) > (32 << 20)
+    assert lib.veon_bev_pool_v2_fwd_workspace_bytes(0, 64, 640000) == 0
     gs = _lib.float3([200, 200, 16])
     assert lib.veon_prepare_v2_workspace_bytes(8, 6, 88, 16, 44, gs) > 0
     assert lib.veon_prepare_v2_workspace_bytes(0, 6, 88, 16, 44, gs) == 0

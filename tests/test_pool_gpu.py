@@ -396,7 +396,9 @@ def test_heavy_tile_list_matches_point_counts():
 @pytest.mark.parametrize("C", [64, 80, 6, 200, 20, 32])
 def test_heavy_tile_kernel_is_bit_identical_to_the_warp_path(C):
     """The CTA-per-tile kernel for heavy tiles only re-schedules the loads: with and
-    without the heavy list the volume is the same bit for bit (C=80: ragged last
+    without the heavy list the volume is the same bit for bit; the call without the list (and
+    without a workspace) takes the general lane-per-channel kernel, the planned call the
+    streaming two-role kernel at C=64 -- so this also pins those two against each other (C=80: ragged last
     channel chunk; C=6: rows not 16-byte sized, the heavy list is ignored; C=20, 32: with the
     list the main grid is the lane-per-voxel kernel for narrow rows, without it the
     lane-per-channel one, so this also checks those two against each other)."""
@@ -413,8 +415,8 @@ def test_heavy_tile_kernel_is_bit_identical_to_the_warp_path(C):
     without = torch.full((B, C, Z, Y, X), float("nan"), device="cuda")
     rc = lib.veon_bev_pool_v2_fwd_planar(
         BP._ptr(depth), BP._ptr(feat), BP._ptr(rd), BP._ptr(rf), BP._ptr(rb),
-        BP._ptr(plan.tile_start), None, 0, B, C, V, feat.numel() // C, BP._ptr(without),
-        BP._stream_ptr(depth.device))
+        BP._ptr(plan.tile_start), None, None, None, 0, B, C, V, feat.numel() // C,
+        BP._ptr(without), None, 0, BP._stream_ptr(depth.device))
     assert rc == 0
     torch.cuda.synchronize()
     assert torch.equal(with_heavy, without)

@@ -313,7 +313,7 @@ def test_near_tie_labels(eps, Q_per_class):
     clear = (top.values - second) / scale > 2e-5
     assert bool((got_t[clear] == top.indices[clear]).all())
     if eps >= 1e-4:
-        assert float(clear.float().mean()) > 0.2        # the construction does decide many voxels
+        assert float(clear.float().mean()) > 0.1        # the construction does decide many voxels
 
 
 def test_full_volume_c512_q18_and_q67():

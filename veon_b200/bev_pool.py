@@ -546,16 +546,37 @@ def _transpose_batched(src, batch, R, S, out_shape):
     return dst
 
 
+# Scratch of the streaming forward (control block + the L2-resident ring of compact rows):
+# one buffer per (device, stream) -- calls on one stream are ordered, calls on different
+# streams may overlap and must not share it.  FWD_RING_BYTES: None = the library's default size
+# (tools/fwd_check.py sweeps it: the buffer size decides how many ring slots an SM gets).
+_FWD_WS = {}
+FWD_RING_BYTES = None
+
+
+def _fwd_workspace(lib, dev, B, C, V):
+    need = lib.veon_bev_pool_v2_fwd_workspace_bytes(B, C, V)
+    if FWD_RING_BYTES is not None:
+        need = int(FWD_RING_BYTES)
+    key = (dev.index, torch.cuda.current_stream(dev).cuda_stream)
+    ws = _FWD_WS.get(key)
+    if ws is None or ws.numel() != need:
+        ws = _FWD_WS[key] = torch.empty(need, dtype=torch.uint8, device=dev)
+    return ws
+
+
 def _fwd_planar(depth, feat, rd, rf, rb, plan, B, C, V, shape5):
     lib = _lib.load()
     dev = feat.device
     with torch.cuda.device(dev):
         out = torch.empty(shape5, dtype=torch.float32, device=dev)  # [B,C,Z,Y,X]
+        ws = _fwd_workspace(lib, dev, B, C, V)
         with _timed("pool_fwd", dev):
             rc = lib.veon_bev_pool_v2_fwd_planar(
                 _ptr(depth), _ptr(feat), _ptr(rd), _ptr(rf), _ptr(rb), _ptr(plan.tile_start),
+                _ptr(plan.tile_istart), _ptr(plan.tile_occ),
                 _ptr(plan.tile_heavy), plan.tile_heavy.numel(),
-                B, C, V, feat.numel() // C, _ptr(out), _stream_ptr(dev))
+                B, C, V, feat.numel() // C, _ptr(out), _ptr(ws), ws.numel(), _stream_ptr(dev))
     _lib.check(rc, "veon_bev_pool_v2_fwd_planar")
     return out
 

@@ -63,21 +63,31 @@ constexpr int kTileVoxels = 32;  // one warp-wide x-run of the output volume
 // capacity assumes the threshold never goes below kHeavyMinThreshold.
 constexpr int kHeavyMinThreshold = 32;
 constexpr int kHeavyDefaultThreshold = 96;
-inline int heavy_threshold() {
-  static int v = 0;
-  if (v == 0) {
-    const char* e = getenv("VEON_HEAVY_THRESHOLD");  // tuning knob
-    v = e ? atoi(e) : kHeavyDefaultThreshold;
-    if (v < kHeavyMinThreshold) v = kHeavyMinThreshold;
-  }
-  return v;
-}
+inline int heavy_threshold() { return kHeavyDefaultThreshold; }
 inline int64_t heavy_capacity(int64_t n_points, int64_t n_tiles) {
   const int64_t by_points = n_points / kHeavyMinThreshold;
   return by_points < n_tiles ? by_points : n_tiles;
 }
 
 static inline int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// Launch configuration that depends on the device (opt-in shared-memory sizes, occupancy,
+// SM count) is cached PER DEVICE: one process may drive several GPUs.
+constexpr int kMaxDevices = 64;
+inline int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+}
+inline int sm_count() {
+  static int n[kMaxDevices] = {};
+  const int dev = current_device();
+  if (n[dev] == 0) {
+    cudaDeviceGetAttribute(&n[dev], cudaDevAttrMultiProcessorCount, dev);
+    if (n[dev] <= 0) n[dev] = 148;
+  }
+  return n[dev];
+}
 
 // Streaming stores/loads: the feature volume is written once and never re-read
 // by the same kernel, so keep it from evicting the (L2-resident) rank / depth /

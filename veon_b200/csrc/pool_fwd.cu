@@ -20,27 +20,21 @@
 // roundings as the reference kernel's `psum += feat * depth`.
 //
 // Kernels in this file:
-//   k_pool_fwd         the warp-per-tile kernel above (all tiles below the heavy threshold)
-//   k_pool_fwd_heavy   a CTA per heavy tile (rows staged by cp.async), queued behind it
+//   k_pool_fwd         the warp-per-tile kernel above: the general route (any C, ragged volumes,
+//                      no workspace).  Aligned volumes with C % 64 == 0 take the two-role
+//                      streaming kernel of pool_fwd_stream.cu instead (see there).
+//   k_pool_fwd_heavy   a CTA per heavy tile (rows staged by cp.async), queued behind the main grid
 //   k_pool_fwd_narrow  C <= 32 (C % 4 == 0): a LANE per voxel instead of a lane per channel, all
 //                      channels of the voxel in registers, same fma order; heavy grid first
-//   k_pool_fwd_group   opt-in experiment: a CTA per group of tiles, software-pipelined
 //   k_pool_ds_fwd      opt-in: pooling fused with the neck's 2x2x2 max-downsample
 #include "common.cuh"
+#include "pool_fwd.cuh"
 
 #ifndef VEON_FWD_WARPS
 #define VEON_FWD_WARPS 8
 #endif
 
 namespace veon {
-
-// timing experiments only (profiles/README.md): -DVEON_FWD_EXPERIMENT + env VEON_FWD_DBG
-//   1 no zero-fill  4 no global stores  8 no feature-row loads
-#ifdef VEON_FWD_EXPERIMENT
-#define VEON_DBG(bit) (dbg & (bit))
-#else
-#define VEON_DBG(bit) false
-#endif
 
 // x 2 CTAs/SM.  Keep it at 8: the 8 consecutive tiles of a CTA then cover an aligned 1 KB
 // of every channel plane; 7-warp CTAs (896 B) write the same volume 19 % slower
@@ -95,7 +89,7 @@ k_pool_fwd(const float* __restrict__ depth, const float* __restrict__ feat,
            const int32_t* __restrict__ ranks_depth, const int32_t* __restrict__ ranks_feat,
            const int32_t* __restrict__ ranks_bev, const int32_t* __restrict__ tile_start,
            const int32_t* __restrict__ heavy, uint32_t n_items, uint32_t tiles_per_sample,
-           int64_t V, int C, uint32_t n_chunks, int vec_ok, float* __restrict__ out, int dbg) {
+           int64_t V, int C, uint32_t n_chunks, int vec_ok, float* __restrict__ out) {
   constexpr int CC = 32 * KCH;
   constexpr int U = (KCH <= 2) ? 16 : 8;  // feature rows in flight per warp
   constexpr int kTileFloats = CC * kRowPitch;
@@ -190,10 +184,7 @@ k_pool_fwd(const float* __restrict__ depth, const float* __restrict__ feat,
   const char* const feat_lane = reinterpret_cast<const char*>(feat) + lane * 4;
   const int64_t ostep = 4 * V;
 
-  const uint32_t last_first = blockIdx.x * kFwdWarps + kFwdWarps - 1;
-  const uint32_t common_items = last_first < n_items ? (n_items - last_first + TW - 1) / TW : 0;
   for (uint32_t m = 0; m < my_items; ++m) {
-    if (VEON_DBG(16) && m < common_items) __syncthreads();
     cp_async_wait_dist();
     __syncwarp();
     int32_t* sl = slot_of(m);
@@ -213,15 +204,13 @@ k_pool_fwd(const float* __restrict__ depth, const float* __restrict__ feat,
     const bool fast = vec_ok && (whole_tiles || (uint32_t)g0 - b * Vu + kTileVoxels <= Vu);
 
     if (e0 <= s0 && fast) {  // empty tile
-      if (!VEON_DBG(4)) {
 #pragma unroll 4
-        for (int c = r; c < cmax; c += 4, o += ostep) st_stream4(o, make_float4(0.f, 0.f, 0.f, 0.f));
-      }
+      for (int c = r; c < cmax; c += 4, o += ostep) st_stream4(o, make_float4(0.f, 0.f, 0.f, 0.f));
       continue;
     }
 
     __syncwarp();
-    if (!VEON_DBG(1)) {  // zero the tile (empty voxels must read as 0)
+    {  // zero the tile (empty voxels must read as 0)
       float4* t4 = reinterpret_cast<float4*>(tile);
 #pragma unroll
       for (int i = 0; i < kTileFloats / 4 / 32; ++i) t4[lane + 32 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -271,8 +260,7 @@ k_pool_fwd(const float* __restrict__ depth, const float* __restrict__ feat,
               const float* row = reinterpret_cast<const float*>(feat_lane + (uint32_t)p[u].y);
 #pragma unroll
               for (int k = 0; k < KCH; ++k)
-                f[u][k] = VEON_DBG(8) ? (float)p[u].y
-                          : (FULLC || full_chunk || lane + 32 * k < cmax) ? __ldg(row + 32 * k) : 0.f;
+                f[u][k] = (FULLC || full_chunk || lane + 32 * k < cmax) ? __ldg(row + 32 * k) : 0.f;
             }
           }
         }
@@ -315,7 +303,7 @@ k_pool_fwd(const float* __restrict__ depth, const float* __restrict__ feat,
 #pragma unroll 4
       for (int c = r; c < cmax; c += 4, o += ostep, trow += 4 * kRowPitch) {
         const float4 v4 = *reinterpret_cast<const float4*>(trow);
-        if (!VEON_DBG(4) || v4.x == 123.456f) st_stream4(o, v4);
+        st_stream4(o, v4);
       }
     } else {  // ragged volume edge / unaligned volume: scalar, bounds-checked
       const int v0 = (int)((uint32_t)g0 - b * Vu);
@@ -365,8 +353,8 @@ k_pool_fwd_heavy(const float* __restrict__ depth, const float* __restrict__ feat
   uint32_t* off = reinterpret_cast<uint32_t*>(dep + kHeavyChunk);  // [kHeavyChunk]
   int32_t* bounds = reinterpret_cast<int32_t*>(off + kHeavyChunk); // [2][start 32 | end 32]
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  // no griddepcontrol.wait: this grid and k_pool_fwd write disjoint tiles and read only
-  // what earlier, normally launched work produced (see launch_fwd_impl)
+  // no griddepcontrol.wait up front: this grid and the main grid write disjoint tiles and read
+  // only what earlier, normally launched work produced; it joins at the end (below)
   pdl_launch_dependents();
   const uint32_t n_heavy = (uint32_t)min(__ldg(heavy), heavy_cap);
   const uint32_t n_work = n_heavy * n_chunks;
@@ -483,312 +471,14 @@ k_pool_fwd_heavy(const float* __restrict__ depth, const float* __restrict__ feat
     }
     __syncthreads();
   }
-  // join != 0: do not COMPLETE before the grid this one is a programmatic dependent of.  Needed
-  // when the launches are captured into a CUDA graph, where the next node would depend on this
-  // grid only; on a plain stream the next launch waits for everything before it anyway, and the
-  // wait would put the main grid's memory flush on this grid's critical path (+17 us).
+  // join != 0 (always, when this grid was launched as a programmatic dependent): do not
+  // COMPLETE before the grid it depends on has completed and flushed -- whatever is launched
+  // next on the stream, a programmatic dependent or a graph node included, then sees the whole
+  // volume (PTX: a dependent of a grid that triggers launch_dependents must execute
+  // griddepcontrol.wait).
   if (join) pdl_wait();
 }
 
-
-// ---- tile-group kernel (experimental: VEON_FWD_GROUP=1) -------------------------------
-// A CTA takes 8 consecutive tiles (256 voxels = one aligned 1 KB run of every channel plane)
-// at a time: the index records of the group's points are prefetched one group ahead in
-// registers (thread per point), ALL their feature rows are gathered by 16-byte cp.async into
-// shared memory at once, warp w then runs the rank-ordered fma chains of tile w's voxels out
-// of shared memory into a [c][260] staging tile, and the whole CTA writes the 64 x 1 KB rows
-// together.  Compared with the warp-per-tile kernel: no per-point address arithmetic in the
-// gather, no exposed row-load latency per 16 points, and the store stream leaves the SM in
-// aligned 1 KB runs.  Heavy tiles are skipped exactly as in k_pool_fwd.
-#ifndef VEON_GROUP_ROUND
-#define VEON_GROUP_ROUND 64
-#endif
-#ifndef VEON_GROUP_TILES
-#define VEON_GROUP_TILES 4
-#endif
-constexpr int kGroupTiles = VEON_GROUP_TILES;    // 4 or 8: one warp per tile
-constexpr int kGroupVoxels = kGroupTiles * kTileVoxels;
-#ifndef VEON_GROUP_THREADS
-#define VEON_GROUP_THREADS (32 * VEON_GROUP_TILES)
-#endif
-constexpr int kGroupThreads = VEON_GROUP_THREADS;  // >= kGroupRound (thread per point)
-constexpr int kGroupRound = VEON_GROUP_ROUND;    // points staged per round (thread per point)
-constexpr int kStagePitch = kGroupVoxels + 4;    // floats; rows stay 16-byte aligned
-
-template <int KCH>
-__global__ void __launch_bounds__(kGroupThreads)
-k_pool_fwd_group(const float* __restrict__ depth, const float* __restrict__ feat,
-                 const int32_t* __restrict__ ranks_depth, const int32_t* __restrict__ ranks_feat,
-                 const int32_t* __restrict__ ranks_bev, const int32_t* __restrict__ tile_start,
-                 const int32_t* __restrict__ heavy, uint32_t n_items, uint32_t n_chunks,
-                 uint32_t groups_per_sample, int64_t V, int C, float* __restrict__ out) {
-  constexpr int CC = 32 * KCH;
-  constexpr int kSegs = CC / 4;
-  constexpr int kW = kGroupThreads / 32;
-  extern __shared__ __align__(16) float gsm[];
-  float* rows = gsm;                                                 // [2][kGroupRound][CC]
-  float* stage = rows + 2 * kGroupRound * CC;                        // [CC][kStagePitch]
-  float* dep = stage + CC * kStagePitch;                             // [2][kGroupRound]
-  uint32_t* off = reinterpret_cast<uint32_t*>(dep + 2 * kGroupRound);  // [2][kGroupRound]
-  int32_t* b0 = reinterpret_cast<int32_t*>(off + 2 * kGroupRound);   // [3][start | end] round 0
-  int32_t* bx = b0 + 6 * kGroupVoxels;                               // [start | end] extra rounds
-  int32_t* hdrs = bx + 2 * kGroupVoxels;                             // [4][12]: tile_start[0..T]
-  pdl_launch_dependents();
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (blockIdx.x >= n_items) return;
-  const uint32_t my_items = (n_items - blockIdx.x + gridDim.x - 1) / gridDim.x;
-  const int32_t heavy_thr = heavy ? __ldg(heavy + 1) : 0x7fffffff;
-
-  auto item_group = [&](uint32_t k, uint32_t& g, uint32_t& chunk) {
-    const uint32_t item = blockIdx.x + k * gridDim.x;
-    g = item / n_chunks;
-    chunk = item - g * n_chunks;
-  };
-  auto load_hdr = [&](uint32_t k) -> int32_t {   // thread j <= T: tile_start[T g + j] of item k
-    if (tid <= kGroupTiles && k < my_items) {
-      uint32_t g, chunk;
-      item_group(k, g, chunk);
-      return __ldg(tile_start + (int64_t)g * kGroupTiles + tid);
-    }
-    return 0;
-  };
-  auto hdr_of = [&](uint32_t k) { return hdrs + (k & 3) * 12; };
-  // compacted position q of a group (heavy tiles left out) -> point index, index of the
-  // previous compacted point (-1 for q == 0); returns the group's number of points
-  auto locate = [&](const int32_t* hdr, int q, int32_t& i, int32_t& iprev) -> int {
-    int acc = 0;
-    int32_t last = -1;
-    i = -1;
-    iprev = -1;
-#pragma unroll
-    for (int j = 0; j < kGroupTiles; ++j) {
-      const int32_t s = hdr[j];
-      int n = hdr[j + 1] - s;
-      if (n >= heavy_thr) n = 0;
-      if (i < 0 && q < acc + n) {
-        i = s + (q - acc);
-        iprev = (q == acc) ? last : i - 1;
-      }
-      if (n > 0) last = s + n - 1;
-      acc += n;
-    }
-    return acc;
-  };
-  struct Rec { int32_t rb, rp, rf, rd; float d; };
-  auto stage_a = [&](const int32_t* hdr, int q, Rec& r) {
-    r.rb = -1;
-    r.rp = -1;
-    r.rd = 0;
-    if (tid < kGroupRound) {
-      int32_t i, ip;
-      locate(hdr, q, i, ip);
-      if (i >= 0) {
-        r.rb = __ldg(ranks_bev + i);
-        r.rf = __ldg(ranks_feat + i);
-        r.rd = __ldg(ranks_depth + i);
-        if (ip >= 0) r.rp = __ldg(ranks_bev + ip);
-      }
-    }
-  };
-  auto stage_b = [&](Rec& r) {
-    r.d = 0.f;
-    if (r.rb >= 0) r.d = __ldg(depth + r.rd);
-  };
-  auto publish = [&](const Rec& r, int cnt, int32_t g0, uint32_t chunk, int slot,
-                     int32_t* cstart) {
-    int32_t* cend = cstart + kGroupVoxels;
-    if (r.rb >= 0) {
-      const int vox = r.rb - g0;
-      off[slot * kGroupRound + tid] = ((uint32_t)r.rf * (uint32_t)C + chunk * CC) * 4u;
-      dep[slot * kGroupRound + tid] = r.d;
-      const bool starts = (tid == 0) || (r.rb != r.rp);
-      if (starts) cstart[vox] = tid;
-      if (tid > 0 && r.rb != r.rp) cend[r.rp - g0] = tid;
-      if (tid == cnt - 1) cend[vox] = cnt;
-    }
-  };
-  auto gather_rows = [&](int cnt, int slot) {   // every feature row of the round at once
-    const char* fbase = reinterpret_cast<const char*>(feat);
-    float* dst = rows + slot * kGroupRound * CC;
-    const uint32_t* o = off + slot * kGroupRound;
-#pragma unroll
-    for (int i = 0; i < kGroupRound * kSegs / kGroupThreads; ++i) {
-      const int idx = tid + kGroupThreads * i;
-      const int r = idx / kSegs, seg = (idx % kSegs) * 4;
-      if (r < cnt) cp_async16(dst + r * CC + seg, fbase + o[r] + seg * 4);
-    }
-    cp_async_commit();
-  };
-  // warp w takes voxels w, w + W, ...: a tile's points spread over all warps; lanes = channels
-  auto accumulate = [&](const int32_t* cstart, int slot) {
-    const int32_t* cend = cstart + kGroupVoxels;
-    const float* rw = rows + slot * kGroupRound * CC;
-    const float* dp = dep + slot * kGroupRound;
-    const int mine = kW * lane + warp;
-    const bool has = mine < kGroupVoxels;
-    const int a_l = has ? cstart[mine] : 0, e_l = has ? cend[mine] : 0;
-    uint32_t m = __ballot_sync(0xffffffffu, e_l > a_l);
-    while (m) {
-      const int l = __ffs(m) - 1;
-      m &= m - 1;
-      const int a = __shfl_sync(0xffffffffu, a_l, l), e = __shfl_sync(0xffffffffu, e_l, l);
-      float* sp = stage + lane * kStagePitch + kW * l + warp;
-      float acc[KCH];
-#pragma unroll
-      for (int c = 0; c < KCH; ++c) acc[c] = sp[32 * c * kStagePitch];
-#pragma unroll 2
-      for (int j = a; j < e; ++j) {
-        const float dj = dp[j];
-#pragma unroll
-        for (int c = 0; c < KCH; ++c) acc[c] = fmaf(rw[j * CC + lane + 32 * c], dj, acc[c]);
-      }
-#pragma unroll
-      for (int c = 0; c < KCH; ++c) sp[32 * c * kStagePitch] = acc[c];
-    }
-  };
-  auto group_total = [&](const int32_t* hdr) {
-    int32_t i, ip;
-    return locate(hdr, 0x7fffffff, i, ip);
-  };
-
-  // ---- prologue: headers 0..2 published, rows of item 0 in flight, records of item 1
-  // complete, ranks of item 2 requested
-  {
-    const int32_t h0 = load_hdr(0), h1 = load_hdr(1), h2 = load_hdr(2);
-    if (tid <= kGroupTiles) {
-      hdr_of(0)[tid] = h0;
-      hdr_of(1)[tid] = h1;
-      hdr_of(2)[tid] = h2;
-    }
-    for (int i = tid; i < 8 * kGroupVoxels; i += kGroupThreads) b0[i] = 0;   // b0 and bx
-  }
-  int32_t hreg = load_hdr(3);
-  __syncthreads();
-  Rec r1, r2, r3;
-  {
-    uint32_t g, chunk;
-    item_group(0, g, chunk);
-    Rec r0;
-    stage_a(hdr_of(0), tid, r0);
-    stage_b(r0);
-    const int total0 = group_total(hdr_of(0));
-    publish(r0, min(total0, kGroupRound), (int32_t)(g * kGroupVoxels), chunk, 0, b0);
-    __syncthreads();
-    gather_rows(min(total0, kGroupRound), 0);
-  }
-  stage_a(hdr_of(1), tid, r1);
-  stage_b(r1);
-  stage_a(hdr_of(2), tid, r2);
-
-  // per-item scalars are computed once, one item ahead: (group, chunk), point total, heavy mask
-  auto describe = [&](uint32_t k, uint32_t& g, uint32_t& chunk, int& total, uint32_t& hmask) {
-    g = chunk = 0;
-    total = 0;
-    hmask = 0;
-    if (k >= my_items) return;
-    item_group(k, g, chunk);
-    const int32_t* hdr = hdr_of(k);
-#pragma unroll
-    for (int j = 0; j < kGroupTiles; ++j) {
-      const int n = hdr[j + 1] - hdr[j];
-      if (n >= heavy_thr) hmask |= 1u << j; else total += n;
-    }
-  };
-  uint32_t g, chunk, g1, chunk1, heavy_mask, heavy_mask1;
-  int total, total1;
-  describe(0, g, chunk, total, heavy_mask);
-  int t0 = 0, t1 = 1, t2 = 2;                           // round-0 tables of items k, k+1, k+2
-
-  for (uint32_t k = 0; k < my_items; ++k) {
-    const int32_t* hdr = hdr_of(k);
-    const uint32_t b = g / groups_per_sample;
-    const int32_t g0 = (int32_t)(g * kGroupVoxels);     // global voxel index (V % 32 == 0)
-    const int cbase = (int)chunk * CC;
-    const int cur = k & 1, nxt = cur ^ 1;
-
-    // T0: publish the records of item k+1 (prefetched), the header of item k+3
-    describe(k + 1, g1, chunk1, total1, heavy_mask1);
-    if (k + 1 < my_items)
-      publish(r1, min(total1, kGroupRound), (int32_t)(g1 * kGroupVoxels), chunk1, nxt,
-              b0 + t1 * 2 * kGroupVoxels);
-    if (tid <= kGroupTiles) hdr_of(k + 3)[tid] = hreg;
-    hreg = load_hdr(k + 4);
-    __syncthreads();
-
-    // T1: rows of item k+1 go in flight (consumed one iteration later), ranks of item k+3 and
-    // depths of item k+2 are requested, the staging tile is cleared; then wait for the rows of
-    // item k, which were requested one iteration ago
-    gather_rows(min(total1, kGroupRound), nxt);
-    stage_a(hdr_of(k + 3), tid, r3);
-    stage_b(r2);
-    if (total > 0) {
-      float4* s4 = reinterpret_cast<float4*>(stage);
-#pragma unroll
-      for (int i = 0; i < (CC * kStagePitch / 4 + kGroupThreads - 1) / kGroupThreads; ++i)
-        if (tid + i * kGroupThreads < CC * kStagePitch / 4)
-          s4[tid + i * kGroupThreads] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    // the round-0 table item k-1 used is free: clear it for item k+2
-    for (int i = tid; i < 2 * kGroupVoxels; i += kGroupThreads) b0[t2 * 2 * kGroupVoxels + i] = 0;
-    asm volatile("cp.async.wait_group 1;" ::: "memory");
-    __syncthreads();
-
-    // T2: fma chains of item k; rounds beyond the first are fetched synchronously
-    if (total > 0) accumulate(b0 + t0 * 2 * kGroupVoxels, cur);
-    for (int base = kGroupRound; base < total; base += kGroupRound) {
-      const int cnt = min(kGroupRound, total - base);
-      Rec r;
-      stage_a(hdr, base + tid, r);
-      stage_b(r);
-      __syncthreads();                                   // previous round fully consumed
-      publish(r, cnt, g0, chunk, cur, bx);
-      __syncthreads();
-      gather_rows(cnt, cur);
-      cp_async_wait_all();
-      __syncthreads();
-      accumulate(bx, cur);
-      __syncthreads();
-      for (int i = tid; i < 2 * kGroupVoxels; i += kGroupThreads) bx[i] = 0;
-    }
-    __syncthreads();
-
-    // T3: CC planes x (kGroupVoxels * 4) bytes; warp w takes planes w, w+W, ...; a lane's
-    // 16 bytes of half h lie in tile 4 h + lane / 8
-    {
-      constexpr int kHalves = kGroupVoxels / 128;
-      float* o = out + ((int64_t)b * C + cbase + warp) * V + (g0 - (int32_t)(b * (uint32_t)V)) +
-                 4 * lane;
-      const int64_t ostep = (int64_t)kW * V;
-      const float* sp = stage + warp * kStagePitch + 4 * lane;
-      bool skip[kHalves];
-#pragma unroll
-      for (int h = 0; h < kHalves; ++h) skip[h] = (heavy_mask >> (4 * h + (lane >> 3))) & 1u;
-      if (total > 0) {
-#pragma unroll 4
-        for (int c = 0; c < CC / kW; ++c, o += ostep) {
-#pragma unroll
-          for (int h = 0; h < kHalves; ++h)
-            if (!skip[h])
-              st_stream4(o + 128 * h,
-                         *reinterpret_cast<const float4*>(sp + c * kW * kStagePitch + 128 * h));
-        }
-      } else {
-        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-        for (int c = 0; c < CC / kW; ++c, o += ostep) {
-#pragma unroll
-          for (int h = 0; h < kHalves; ++h)
-            if (!skip[h]) st_stream4(o + 128 * h, z);
-        }
-      }
-    }
-    r1 = r2;
-    r2 = r3;
-    g = g1; chunk = chunk1; total = total1; heavy_mask = heavy_mask1;
-    { const int t = t0; t0 = t1; t1 = t2; t2 = t; }
-  }
-  cp_async_wait_all();
-}
 
 // ---- fused pooling + 2x2x2 max-downsample, forward ------------------------
 // VEON's neck reduces the pooled volume 8x right away (view_transformer_raw.py:549-553:
@@ -973,23 +663,6 @@ k_pool_ds_fwd(const float* __restrict__ depth, const float* __restrict__ feat,
   }
 }
 
-static int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
-  }
-  return n;
-}
-
-static int env_flag(const char* name, int dflt) {
-  const char* e = getenv(name);
-  return e ? atoi(e) : dflt;
-}
-
-
 // ---- narrow rows (C <= 32): lane = voxel ---------------------------------------------------
 // With few channels a lane-per-channel warp leaves lanes idle and pays one row-load latency
 // per point (the logit-space lift pools Q + 2 = 20 channels over 4x the points of C2:
@@ -1011,7 +684,7 @@ k_pool_fwd_narrow(const float* __restrict__ depth, const float* __restrict__ fea
                   const int32_t* __restrict__ ranks_depth, const int32_t* __restrict__ ranks_feat,
                   const int32_t* __restrict__ ranks_bev, const int32_t* __restrict__ tile_start,
                   const int32_t* __restrict__ heavy, uint32_t n_tiles, uint32_t tiles_per_sample,
-                  int64_t V, float* __restrict__ out, uint32_t zero, int heavy_min) {
+                  int64_t V, float* __restrict__ out, uint32_t zero, int heavy_min, int join) {
   constexpr int C = 4 * NV;
   __shared__ int32_t seg_s[kNarrowWarps][32];
   pdl_launch_dependents();  // the heavy-tile grid may be queued behind this one
@@ -1142,207 +815,110 @@ k_pool_fwd_narrow(const float* __restrict__ depth, const float* __restrict__ fea
 #pragma unroll
     for (int c = 0; c < C; ++c) st_stream(o + (int64_t)c * V, acc[c]);
   }
+  if (join) pdl_wait();   // launched behind the heavy grid: complete after it (see k_pool_fwd_heavy)
 }
 
-template <int KCH, bool FULLC>
-static int launch_fwd_impl(const float* depth, const float* feat, const int32_t* rd,
-                      const int32_t* rf, const int32_t* rb, const int32_t* tile_start,
-                      const int32_t* heavy, int64_t heavy_ints, int B, int C, int64_t V,
-                      bool feat_rows_fit_32bit, float* out, cudaStream_t stream) {
+
+// ---- launchers ---------------------------------------------------------------------------------
+template <int KCH>
+static int heavy_config(size_t& smem, int& ctas_per_sm) {
   constexpr int CC = 32 * KCH;
-  const size_t smem = sizeof(float) * kFwdWarps * (CC * kRowPitch + kRingSlots * kSlotInts);
-  static int ctas_per_sm = 0;
-  if (ctas_per_sm == 0) {
-    VEON_CUDA_TRY(cudaFuncSetAttribute(k_pool_fwd<KCH, FULLC>,
+  smem = sizeof(float) * (kHeavyChunk * CC + CC * kRowPitch + 2 * kHeavyChunk + 128);
+  static int cached[kMaxDevices] = {};
+  const int dev = current_device();
+  if (cached[dev] == 0) {
+    VEON_CUDA_TRY(cudaFuncSetAttribute(k_pool_fwd_heavy<KCH>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    VEON_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_pool_fwd<KCH, FULLC>,
-                                                                kFwdWarps * 32, smem));
-    if (ctas_per_sm < 1) ctas_per_sm = 1;
-    if (env_flag("VEON_FWD_CTAS", 0) > 0 && env_flag("VEON_FWD_CTAS", 0) < ctas_per_sm) ctas_per_sm = env_flag("VEON_FWD_CTAS", 0);
+    int n = 0;
+    VEON_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_pool_fwd_heavy<KCH>,
+                                                                kHeavyThreads, smem));
+    cached[dev] = n < 1 ? 1 : (n > 8 ? 8 : n);
   }
-  const int64_t tps = ceil_div64(V, kTileVoxels), n_tiles = (int64_t)B * tps;
+  ctas_per_sm = cached[dev];
+  return 0;
+}
+
+// the heavy-tile grid; pdl: queued as a programmatic dependent of the previous launch (joins it)
+template <int KCH>
+static int launch_heavy(const float* depth, const float* feat, const int32_t* rd, const int32_t* rf,
+                        const int32_t* rb, const int32_t* tile_start, const int32_t* heavy,
+                        int64_t heavy_ints, int B, int C, int64_t V, float* out, bool pdl,
+                        int min_points, cudaStream_t stream) {
+  constexpr int CC = 32 * KCH;
+  size_t smem;
+  int per_sm;
+  int rc = heavy_config<KCH>(smem, per_sm);
+  if (rc) return rc;
+  const int64_t tps = ceil_div64(V, kTileVoxels);
   const int n_chunks = (C + CC - 1) / CC;
-  if (n_tiles * n_chunks > 0x7fffffffLL || (int64_t)B * V > 0x7fffffffLL) return VEON_E_RANGE;
-  // the gather addresses rows with 32-bit float offsets
-  if (!feat_rows_fit_32bit) return VEON_E_RANGE;
   const int vec_ok = ((V & 3) == 0) && (((uintptr_t)out & 15) == 0);
-  int64_t blocks = ceil_div64(n_tiles * n_chunks, kFwdWarps);
-  const int64_t resident = (int64_t)ctas_per_sm * sm_count();  // persistent grid
-  if (blocks > resident) blocks = resident;
-  // the heavy-tile kernel stages feature rows with 16-byte copies
-  if (heavy && ((C & 3) != 0 || ((uintptr_t)feat & 15) != 0)) heavy = nullptr;
-  int capturing = 0;   // inside a stream capture the heavy grid joins the main grid explicitly
-  {
-    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
-    if (cudaStreamIsCapturing(stream, &st) == cudaSuccess && st != cudaStreamCaptureStatusNone)
-      capturing = 1;
+  const int heavy_cap = (int)(heavy_ints - 2);
+  int64_t blocks = (int64_t)heavy_cap * n_chunks;
+  if (blocks > (int64_t)per_sm * sm_count()) blocks = (int64_t)per_sm * sm_count();
+  if (blocks <= 0) return 0;
+  if (pdl) {
+    VEON_CUDA_TRY(launch_pdl(k_pool_fwd_heavy<KCH>, dim3((unsigned)blocks), dim3(kHeavyThreads),
+                             smem, stream, depth, feat, rd, rf, rb, tile_start, heavy, heavy_cap,
+                             (uint32_t)tps, V, C, (uint32_t)n_chunks, vec_ok, out, 1, min_points));
+  } else {
+    k_pool_fwd_heavy<KCH><<<(unsigned)blocks, kHeavyThreads, smem, stream>>>(
+        depth, feat, rd, rf, rb, tile_start, heavy, heavy_cap, (uint32_t)tps, V, C,
+        (uint32_t)n_chunks, vec_ok, out, 0, min_points);
   }
-  // tuning knobs, read once per process
-  static const int dbg = env_flag("VEON_FWD_DBG", 0);
-  static const int knob_group = env_flag("VEON_FWD_GROUP", 0);
-  static const int knob_heavy_ctas = env_flag("VEON_FWD_HEAVY_CTAS", 8);
-  static const int knob_order = env_flag("VEON_FWD_ORDER", 1);
-  const bool group_ok = FULLC && vec_ok && (V % kTileVoxels) == 0 && (tps % kGroupTiles) == 0 &&
-                        (C & 3) == 0 && ((uintptr_t)feat & 15) == 0;
-  if (group_ok && knob_group) {
-    const size_t gsmem = sizeof(float) * (2 * kGroupRound * CC + CC * kStagePitch +
-                                          4 * kGroupRound + 8 * kGroupVoxels + 48);
-    static int group_ctas_per_sm = 0;
-    if (group_ctas_per_sm == 0) {
-      VEON_CUDA_TRY(cudaFuncSetAttribute(k_pool_fwd_group<KCH>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsmem));
-      VEON_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-          &group_ctas_per_sm, k_pool_fwd_group<KCH>, kGroupThreads, gsmem));
-      if (group_ctas_per_sm < 1) group_ctas_per_sm = 1;
-    }
-    const int64_t n_gitems = n_tiles / kGroupTiles * n_chunks;
-    int64_t gblocks = (int64_t)group_ctas_per_sm * sm_count();
-    if (gblocks > n_gitems) gblocks = n_gitems;
-    k_pool_fwd_group<KCH><<<(unsigned)gblocks, kGroupThreads, gsmem, stream>>>(
-        depth, feat, rd, rf, rb, tile_start, heavy, (uint32_t)n_gitems, (uint32_t)n_chunks,
-        (uint32_t)(tps / kGroupTiles), V, C, out);
-    VEON_LAUNCH_CHECK();
-    if (heavy) {
-      const size_t hsmem2 = sizeof(float) * (kHeavyChunk * CC + CC * kRowPitch + 2 * kHeavyChunk + 128);
-      static int hc = 0;
-      if (hc == 0) {
-        VEON_CUDA_TRY(cudaFuncSetAttribute(k_pool_fwd_heavy<KCH>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem2));
-        VEON_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&hc, k_pool_fwd_heavy<KCH>,
-                                                                    kHeavyThreads, hsmem2));
-        if (hc < 1) hc = 1;
-      }
-      const int heavy_cap = (int)(heavy_ints - 2);
-      int64_t hblocks = (int64_t)heavy_cap * n_chunks;
-      if (hblocks > (int64_t)hc * sm_count()) hblocks = (int64_t)hc * sm_count();
-      if (hblocks > 0) {
-        VEON_CUDA_TRY(launch_pdl(k_pool_fwd_heavy<KCH>, dim3((unsigned)hblocks), dim3(kHeavyThreads),
-                                 hsmem2, stream, depth, feat, rd, rf, rb, tile_start, heavy,
-                                 heavy_cap, (uint32_t)tps, V, C, (uint32_t)n_chunks, vec_ok, out,
-                                 capturing, 0));
-        VEON_LAUNCH_CHECK();
-      }
-    }
-    return 0;
-  }
-  if (heavy) {
-    const size_t hsmem = sizeof(float) * (kHeavyChunk * CC + CC * kRowPitch + 2 * kHeavyChunk + 128);
-    static int heavy_ctas_per_sm = 0;
-    if (heavy_ctas_per_sm == 0) {
-      VEON_CUDA_TRY(cudaFuncSetAttribute(k_pool_fwd_heavy<KCH>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem));
-      VEON_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-          &heavy_ctas_per_sm, k_pool_fwd_heavy<KCH>, kHeavyThreads, hsmem));
-      if (heavy_ctas_per_sm < 1) heavy_ctas_per_sm = 1;
-    }
-    const int heavy_cap = (int)(heavy_ints - 2);
-    const int per_sm = min(heavy_ctas_per_sm, max(1, knob_heavy_ctas));
-    int64_t hblocks = (int64_t)heavy_cap * n_chunks;
-    if (hblocks > (int64_t)per_sm * sm_count()) hblocks = (int64_t)per_sm * sm_count();
-    if (hblocks > 0) {
-      // The two grids write disjoint tiles and neither waits for the other: the second is a
-      // programmatic dependent of the first (both trigger at their first instruction), so
-      // its CTAs are scheduled as soon as SM resources free up instead of after the drain.
-      // Heavy-tile CTAs last: they fill the SMs as the persistent CTAs of the main grid
-      // finish one by one (VEON_FWD_ORDER=0 runs them first instead).
-      if (knob_order == 1) {
-        k_pool_fwd<KCH, FULLC><<<(unsigned)blocks, kFwdWarps * 32, smem, stream>>>(
-            depth, feat, rd, rf, rb, tile_start, heavy, (uint32_t)(n_tiles * n_chunks),
-            (uint32_t)tps, V, C, (uint32_t)n_chunks, vec_ok, out, dbg);
-        VEON_LAUNCH_CHECK();
-        VEON_CUDA_TRY(launch_pdl(k_pool_fwd_heavy<KCH>, dim3((unsigned)hblocks), dim3(kHeavyThreads),
-                                 hsmem, stream, depth, feat, rd, rf, rb, tile_start, heavy,
-                                 heavy_cap, (uint32_t)tps, V, C, (uint32_t)n_chunks, vec_ok, out,
-                                 capturing, 0));
-        VEON_LAUNCH_CHECK();
-        return 0;
-      }
-      k_pool_fwd_heavy<KCH><<<(unsigned)hblocks, kHeavyThreads, hsmem, stream>>>(
-          depth, feat, rd, rf, rb, tile_start, heavy, heavy_cap, (uint32_t)tps, V, C,
-          (uint32_t)n_chunks, vec_ok, out, 0, 0);
-      VEON_LAUNCH_CHECK();
-      VEON_CUDA_TRY(launch_pdl(k_pool_fwd<KCH, FULLC>, dim3((unsigned)blocks), dim3(kFwdWarps * 32),
-                               smem, stream, depth, feat, rd, rf, rb, tile_start, heavy,
-                               (uint32_t)(n_tiles * n_chunks), (uint32_t)tps, V, C,
-                               (uint32_t)n_chunks, vec_ok, out, dbg));
-      VEON_LAUNCH_CHECK();
-      return 0;
-    }
-    heavy = nullptr;
-  }
-  k_pool_fwd<KCH, FULLC><<<(unsigned)blocks, kFwdWarps * 32, smem, stream>>>(
-      depth, feat, rd, rf, rb, tile_start, heavy, (uint32_t)(n_tiles * n_chunks), (uint32_t)tps,
-      V, C, (uint32_t)n_chunks, vec_ok, out, dbg);
   VEON_LAUNCH_CHECK();
   return 0;
 }
 
-// main grid = k_pool_fwd_narrow, heavy tiles = k_pool_fwd_heavy<1> queued behind it (as in
-// launch_fwd_impl)
-template <int NV>
-static int launch_fwd_narrow(const float* depth, const float* feat, const int32_t* rd,
-                             const int32_t* rf, const int32_t* rb, const int32_t* tile_start,
-                             const int32_t* heavy, int64_t heavy_ints, int B, int64_t V,
-                             float* out, cudaStream_t stream) {
-  constexpr int C = 4 * NV;
-  const int64_t tps = V / kTileVoxels, n_tiles = (int64_t)B * tps;
-  static int ctas_per_sm = 0;
-  if (ctas_per_sm == 0) {
-    VEON_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_pool_fwd_narrow<NV>,
-                                                                kNarrowWarps * 32, 0));
-    if (ctas_per_sm < 1) ctas_per_sm = 1;
+int launch_heavy_behind(const float* depth, const float* feat, const int32_t* rd,
+                        const int32_t* rf, const int32_t* rb, const int32_t* tile_start,
+                        const int32_t* heavy, int64_t heavy_ints, int B, int C, int64_t V,
+                        float* out, cudaStream_t stream) {
+  if (!heavy || heavy_ints < 2 || (C & 3) != 0 || ((uintptr_t)feat & 15) != 0)
+    return VEON_E_BADARG;
+  return C <= 32 ? launch_heavy<1>(depth, feat, rd, rf, rb, tile_start, heavy, heavy_ints, B, C, V,
+                                   out, true, 0, stream)
+                 : launch_heavy<2>(depth, feat, rd, rf, rb, tile_start, heavy, heavy_ints, B, C, V,
+                                   out, true, 0, stream);
+}
+
+// general route: k_pool_fwd over every (tile, channel chunk), the heavy tiles queued behind it
+template <int KCH, bool FULLC>
+static int launch_fwd_impl(const float* depth, const float* feat, const int32_t* rd,
+                           const int32_t* rf, const int32_t* rb, const int32_t* tile_start,
+                           const int32_t* heavy, int64_t heavy_ints, int B, int C, int64_t V,
+                           bool feat_rows_fit_32bit, float* out, cudaStream_t stream) {
+  constexpr int CC = 32 * KCH;
+  const size_t smem = sizeof(float) * kFwdWarps * (CC * kRowPitch + kRingSlots * kSlotInts);
+  static int ctas_per_sm[kMaxDevices] = {};
+  const int dev = current_device();
+  if (ctas_per_sm[dev] == 0) {
+    VEON_CUDA_TRY(cudaFuncSetAttribute(k_pool_fwd<KCH, FULLC>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int n = 0;
+    VEON_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_pool_fwd<KCH, FULLC>,
+                                                                kFwdWarps * 32, smem));
+    ctas_per_sm[dev] = n < 1 ? 1 : n;
   }
-  int64_t blocks = ceil_div64(n_tiles, kNarrowWarps);
-  if (blocks > (int64_t)ctas_per_sm * sm_count()) blocks = (int64_t)ctas_per_sm * sm_count();
-  static const int heavy_min = env_flag("VEON_NARROW_HEAVY_MIN", kNarrowHeavyMin);  // tuning knob
-  int capturing = 0;
-  {
-    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
-    if (cudaStreamIsCapturing(stream, &st) == cudaSuccess && st != cudaStreamCaptureStatusNone)
-      capturing = 1;
-  }
-  static const int knob_order = env_flag("VEON_NARROW_ORDER", 0);        // 0: heavy grid first (344 -> 295 us at C3 density)
-  static const int knob_heavy_ctas = env_flag("VEON_NARROW_HEAVY_CTAS", 8);
-  int64_t hblocks = 0;
-  size_t hsmem = 0;
-  int heavy_cap = 0;
-  if (heavy) {
-    hsmem = sizeof(float) * (kHeavyChunk * 32 + 32 * kRowPitch + 2 * kHeavyChunk + 128);
-    static int heavy_ctas_per_sm = 0;
-    if (heavy_ctas_per_sm == 0) {
-      VEON_CUDA_TRY(cudaFuncSetAttribute(k_pool_fwd_heavy<1>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsmem));
-      VEON_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-          &heavy_ctas_per_sm, k_pool_fwd_heavy<1>, kHeavyThreads, hsmem));
-      if (heavy_ctas_per_sm < 1) heavy_ctas_per_sm = 1;
-    }
-    heavy_cap = (int)(heavy_ints - 2);
-    const int per_sm = min(heavy_ctas_per_sm, max(1, knob_heavy_ctas));
-    hblocks = heavy_cap;
-    if (hblocks > (int64_t)per_sm * sm_count()) hblocks = (int64_t)per_sm * sm_count();
-  }
-  if (hblocks > 0 && knob_order == 0 && !capturing) {
-    // heavy tiles first (a normal launch), the main grid moves in beside it; neither waits
-    k_pool_fwd_heavy<1><<<(unsigned)hblocks, kHeavyThreads, hsmem, stream>>>(
-        depth, feat, rd, rf, rb, tile_start, heavy, heavy_cap, (uint32_t)tps, V, C, 1u, 1, out, 0,
-        heavy_min);
-    VEON_LAUNCH_CHECK();
-    VEON_CUDA_TRY(launch_pdl(k_pool_fwd_narrow<NV>, dim3((unsigned)blocks), dim3(kNarrowWarps * 32),
-                             0, stream, depth, feat, rd, rf, rb, tile_start, heavy,
-                             (uint32_t)n_tiles, (uint32_t)tps, V, out, 0u, heavy_min));
-    VEON_LAUNCH_CHECK();
-    return 0;
-  }
-  k_pool_fwd_narrow<NV><<<(unsigned)blocks, kNarrowWarps * 32, 0, stream>>>(
-      depth, feat, rd, rf, rb, tile_start, heavy, (uint32_t)n_tiles, (uint32_t)tps, V, out, 0u,
-      heavy_min);
+  const int64_t tps = ceil_div64(V, kTileVoxels), n_tiles = (int64_t)B * tps;
+  const int n_chunks = (C + CC - 1) / CC;
+  if (n_tiles * n_chunks > 0x7fffffffLL || (int64_t)B * V > 0x7fffffffLL) return VEON_E_RANGE;
+  if (!feat_rows_fit_32bit) return VEON_E_RANGE;   // the gather uses 32-bit byte offsets
+  const int vec_ok = ((V & 3) == 0) && (((uintptr_t)out & 15) == 0);
+  int64_t blocks = ceil_div64(n_tiles * n_chunks, kFwdWarps);
+  const int64_t resident = (int64_t)ctas_per_sm[dev] * sm_count();  // persistent grid
+  if (blocks > resident) blocks = resident;
+  // the heavy-tile kernel stages feature rows with 16-byte copies
+  if (heavy && ((C & 3) != 0 || ((uintptr_t)feat & 15) != 0)) heavy = nullptr;
+  k_pool_fwd<KCH, FULLC><<<(unsigned)blocks, kFwdWarps * 32, smem, stream>>>(
+      depth, feat, rd, rf, rb, tile_start, heavy, (uint32_t)(n_tiles * n_chunks), (uint32_t)tps,
+      V, C, (uint32_t)n_chunks, vec_ok, out);
   VEON_LAUNCH_CHECK();
-  if (hblocks > 0) {
-    VEON_CUDA_TRY(launch_pdl(k_pool_fwd_heavy<1>, dim3((unsigned)hblocks), dim3(kHeavyThreads),
-                             hsmem, stream, depth, feat, rd, rf, rb, tile_start, heavy,
-                             heavy_cap, (uint32_t)tps, V, C, 1u, 1, out, capturing, heavy_min));
-    VEON_LAUNCH_CHECK();
-  }
+  // Heavy-tile CTAs behind the main grid (both trigger launch_dependents at their first
+  // instruction): they fill the SMs as the persistent CTAs finish one by one, and join the main
+  // grid before they complete.
+  if (heavy)
+    return launch_heavy<KCH>(depth, feat, rd, rf, rb, tile_start, heavy, heavy_ints, B, C, V, out,
+                             true, 0, stream);
   return 0;
 }
 
@@ -1358,18 +934,50 @@ static int launch_fwd(const float* depth, const float* feat, const int32_t* rd,
                                      V, feat_rows_fit_32bit, out, stream);
 }
 
+// narrow rows: the heavy tiles (from kNarrowHeavyMin points) first, as a normal launch (a heavy
+// CTA works ~100 us on one 1 000-point tile at C3 density: behind the persistent main grid the
+// two nearly serialise, 344 vs 295 us); k_pool_fwd_narrow moves in beside it as its programmatic
+// dependent and joins it at the end
+template <int NV>
+static int launch_fwd_narrow(const float* depth, const float* feat, const int32_t* rd,
+                             const int32_t* rf, const int32_t* rb, const int32_t* tile_start,
+                             const int32_t* heavy, int64_t heavy_ints, int B, int64_t V,
+                             float* out, cudaStream_t stream) {
+  constexpr int C = 4 * NV;
+  const int64_t tps = V / kTileVoxels, n_tiles = (int64_t)B * tps;
+  static int ctas_per_sm[kMaxDevices] = {};
+  const int dev = current_device();
+  if (ctas_per_sm[dev] == 0) {
+    int n = 0;
+    VEON_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_pool_fwd_narrow<NV>,
+                                                                kNarrowWarps * 32, 0));
+    ctas_per_sm[dev] = n < 1 ? 1 : n;
+  }
+  int64_t blocks = ceil_div64(n_tiles, kNarrowWarps);
+  if (blocks > (int64_t)ctas_per_sm[dev] * sm_count()) blocks = (int64_t)ctas_per_sm[dev] * sm_count();
+  int rc = launch_heavy<1>(depth, feat, rd, rf, rb, tile_start, heavy, heavy_ints, B, C, V, out,
+                           false, kNarrowHeavyMin, stream);
+  if (rc) return rc;
+  VEON_CUDA_TRY(launch_pdl(k_pool_fwd_narrow<NV>, dim3((unsigned)blocks), dim3(kNarrowWarps * 32),
+                           0, stream, depth, feat, rd, rf, rb, tile_start, heavy,
+                           (uint32_t)n_tiles, (uint32_t)tps, V, out, 0u, kNarrowHeavyMin, 1));
+  VEON_LAUNCH_CHECK();
+  return 0;
+}
+
 }  // namespace veon
 
 using namespace veon;
 
-// channel-chunk override for tuning (0 = automatic); read once
-static int fwd_kch_override() {
-  static int v = -1;
-  if (v < 0) {
-    const char* e = getenv("VEON_FWD_KCH");
-    v = e ? atoi(e) : 0;
-  }
-  return v;
+// Not part of the ABI in include/veon_lift.h: lets tools/fwd_check.py push wide rows through the
+// streaming kernel for its parity sweep and timing comparison.
+extern "C" void veon_internal_fwd_stream_force(int on) { stream_force = on != 0; }
+
+extern "C" size_t veon_bev_pool_v2_fwd_workspace_bytes(int B, int C, int64_t V) {
+  if (B <= 0 || C <= 0 || V <= 0) return 0;
+  // the ring of compact rows (a few slots per SM; only their occupied prefix is ever touched,
+  // so the part that lives in L2 is a fraction of this)
+  return fwd_stream_workspace_bytes(C);
 }
 
 extern "C" int veon_bev_pool_v2_fwd_planar(const float* depth, const float* feat,
@@ -1377,9 +985,12 @@ extern "C" int veon_bev_pool_v2_fwd_planar(const float* depth, const float* feat
                                            const int32_t* ranks_feat,
                                            const int32_t* ranks_bev,
                                            const int32_t* tile_start,
+                                           const int32_t* tile_istart,
+                                           const uint32_t* tile_occ,
                                            const int32_t* tile_heavy, int64_t tile_heavy_ints,
                                            int B, int C, int64_t V, int64_t n_feat_rows,
-                                           float* out, void* stream_) {
+                                           float* out, void* workspace, size_t workspace_bytes,
+                                           void* stream_) {
   cudaStream_t stream = (cudaStream_t)stream_;
   if (!depth || !feat || !ranks_depth || !ranks_feat || !ranks_bev || !tile_start || !out ||
       B <= 0 || C <= 0 || V <= 0 || n_feat_rows <= 0 || (tile_heavy && tile_heavy_ints < 2))
@@ -1388,13 +999,10 @@ extern "C" int veon_bev_pool_v2_fwd_planar(const float* depth, const float* feat
   // sample<<16 | chunk
   const bool fit32 = n_feat_rows * (int64_t)C <= 0x3fffffffLL && B < 65536 &&
                      (int64_t)C <= 65535LL * 32;
-  int kch = fwd_kch_override();
-  {  // narrow rows: lane-per-voxel kernel (VEON_FWD_NARROW=0 keeps the lane-per-channel one)
-    static const int knob_narrow = env_flag("VEON_FWD_NARROW", 1);
-    // without a heavy list a single lane would walk arbitrarily long voxels; rank arithmetic
-    // is exact (no float32 merging of voxels) only while B*V <= 2^24
-    const bool ok = knob_narrow && kch == 0 && C <= 32 && (C & 3) == 0 && tile_heavy && fit32 &&
-                    V % kTileVoxels == 0 && (int64_t)B * V <= (1 << 24) &&
+  {  // narrow rows: lane-per-voxel kernel.  Without a heavy list a single lane would walk
+     // arbitrarily long voxels; rank arithmetic is exact only while B*V <= 2^24
+    const bool ok = C <= 32 && (C & 3) == 0 && tile_heavy && fit32 && V % kTileVoxels == 0 &&
+                    (int64_t)B * V <= (1 << 24) &&
                     (((uintptr_t)feat | (uintptr_t)out) & 15) == 0;
     if (ok) {
 #define VEON_NARROW_CASE(NV_) case NV_: return launch_fwd_narrow<NV_>(depth, feat, ranks_depth, ranks_feat, ranks_bev, tile_start, tile_heavy, tile_heavy_ints, B, V, out, stream);
@@ -1406,13 +1014,18 @@ extern "C" int veon_bev_pool_v2_fwd_planar(const float* depth, const float* feat
 #undef VEON_NARROW_CASE
     }
   }
-  if (kch == 0) kch = (C <= 32) ? 1 : 2;
-  switch (kch) {
-    case 1: return launch_fwd<1>(depth, feat, ranks_depth, ranks_feat, ranks_bev, tile_start, tile_heavy, tile_heavy_ints, B, C, V, fit32, out, stream);
-    case 2: return launch_fwd<2>(depth, feat, ranks_depth, ranks_feat, ranks_bev, tile_start, tile_heavy, tile_heavy_ints, B, C, V, fit32, out, stream);
-    case 4: return launch_fwd<4>(depth, feat, ranks_depth, ranks_feat, ranks_bev, tile_start, tile_heavy, tile_heavy_ints, B, C, V, fit32, out, stream);
-    default: return VEON_E_BADARG;
+  // aligned volumes, whole 64-channel chunks: the two-role streaming kernel
+  if (workspace && tile_occ && tile_heavy && fwd_stream_supported(B, C, V, feat, out, n_feat_rows)) {
+    const int rc = launch_fwd_stream(depth, feat, ranks_depth, ranks_feat, ranks_bev, tile_start,
+                                     tile_occ, tile_heavy, tile_heavy_ints, B, C, V, out,
+                                     workspace, workspace_bytes, stream);
+    if (rc != VEON_E_UNSUPPORTED && rc != VEON_E_WORKSPACE) return rc;
   }
+  if (C <= 32)
+    return launch_fwd<1>(depth, feat, ranks_depth, ranks_feat, ranks_bev, tile_start, tile_heavy,
+                         tile_heavy_ints, B, C, V, fit32, out, stream);
+  return launch_fwd<2>(depth, feat, ranks_depth, ranks_feat, ranks_bev, tile_start, tile_heavy,
+                       tile_heavy_ints, B, C, V, fit32, out, stream);
 }
 
 extern "C" int veon_bev_pool_v2_ds_fwd(const float* depth, const float* feat,
@@ -1429,22 +1042,18 @@ extern "C" int veon_bev_pool_v2_ds_fwd(const float* depth, const float* feat,
   if ((Z | Y | X) & 1 || C % CC != 0 || ((uintptr_t)feat & 15) != 0) return VEON_E_UNSUPPORTED;
   const int64_t V = (int64_t)Z * Y * X;
   if ((int64_t)B * V >= (1 << 24) || n_feat_rows * (int64_t)C > 0x3fffffffLL) return VEON_E_RANGE;
-  // an item covers half an x-row when that keeps the pieces even: smaller tiles, more CTAs/SM
-  int xsplit = 1;   // (halving the rows was measured slower: per-item overheads dominate)
-  {
-    const char* e = getenv("VEON_DS_XSPLIT");
-    if (e && atoi(e) >= 1 && X % (2 * atoi(e)) == 0) xsplit = atoi(e);
-  }
+  const int xsplit = 1;   // (halving the x-rows per item was measured slower: per-item overheads)
   const int Xs = X / xsplit;
   const int Xp = (Xs + 3) / 4 * 4 + 4, Xhp = Xs / 2 + 1;
   const size_t smem = sizeof(float) * ((size_t)kDsRound * CC + (size_t)CC * Xp + (size_t)CC * Xhp +
                                        2 * kDsRound + 4 * (size_t)Xp + 8);
   if (smem > 220 * 1024) return VEON_E_UNSUPPORTED;
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) {
+  static size_t attr_smem[kMaxDevices] = {};
+  const int dev = current_device();
+  if (smem > attr_smem[dev]) {
     VEON_CUDA_TRY(cudaFuncSetAttribute(k_pool_ds_fwd<KCH>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_smem = smem;
+    attr_smem[dev] = smem;
   }
   int per_sm = 1;
   VEON_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pool_ds_fwd<KCH>,

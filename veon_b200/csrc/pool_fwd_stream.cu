@@ -1,0 +1,540 @@
+// bev_pool_v2 forward as two warp-specialised roles around an L2-resident ring of compact rows.
+//
+// Reference behaviour: QuickCumsumCuda.forward (bev_pool.py:17-41: new_zeros +
+// bev_pool_v2_kernel, bev_pool_cuda.cu:21-48) followed by `.permute(0,4,1,2,3).contiguous()`
+// (bev_pool.py:91).
+//
+// The forward has an irregular half (gather the points of every occupied voxel: a chain of
+// dependent load latencies) and a regular half (write the dense [B,C,Z,Y,X] volume, 1.3 GB at
+// C2: the actual HBM cost).  When one warp does both for a tile the two halves do not overlap
+// on an SM (round 1: T = max + 0.3 min, 0.63 of the copy bandwidth).  Here ONE persistent
+// kernel (a CTA per SM) runs them as separate roles that meet in L2:
+//
+//   role A, 16 warps  A warp takes a 32-voxel tile, walks its points in rank order -- index
+//                     records prefetched three stages ahead by cp.async, 12 feature rows in
+//                     flight, lanes = channels, acc = fma(feat, depth, acc) starting from 0: the
+//                     reference kernel's rounding sequence, so the result stays bit-identical --
+//                     and stores ONE channel-contiguous row per occupied voxel into the CTA's
+//                     ring.  Wide rows are produced in passes of 128 channels from the same index
+//                     records: the index work is done once per point, not once per 64-channel
+//                     chunk.  No tile buffer, no zero fill, no transposition.
+//   role E, 16 warps  Two groups of 8 warps; a group's item is 8 consecutive tiles x a
+//                     64-channel chunk (an aligned 1 KB run of every channel plane).  A warp
+//                     copies its tile's rows out of the ring into shared memory (16-byte
+//                     cp.async, L2 only), the group meets at a named barrier, and every warp
+//                     writes its 32-voxel x 64-channel block with 16-byte streaming stores, zeros
+//                     where the occupancy mask says so: the group emits whole 1 KB runs in
+//                     lockstep.  While one group waits for its copies the other one writes.  E
+//                     reads nothing from DRAM: its only long-latency traffic is the store stream.
+//
+// Work is dealt in ROUNDS of 16 consecutive tiles (round r -> CTA r mod grid: every CTA samples
+// the whole volume, so the point density averages out).  A unit = (round, 128-channel pass) is
+// produced by the 16 A warps of a CTA and consumed by the 16 E warps of the SAME CTA, through one
+// of the CTA's own NS ring slots (512 rows x <=128 channels; rows of the round's tiles packed
+// by the running count of occupied voxels).  All flow control is two shared-memory counters per
+// slot (filled by A, drained by E): no global flags, no atomics on global memory, no dependence
+// between CTAs.  The ring (grid x NS slots, only the occupied prefix of a slot is ever touched)
+// is a few tens of MB: its lines are rewritten while still dirty in L2 and never reach DRAM;
+// DRAM sees the inputs once and the volume once.
+//
+// Tiles at or above the plan's heavy threshold are left to k_pool_fwd_heavy (pool_fwd.cu),
+// which writes them straight into the volume, queued behind this grid.
+#include "common.cuh"
+#include "pool_fwd.cuh"
+
+namespace veon {
+
+constexpr int kRoundTiles = 16;         // tiles per round
+constexpr int kAWarps = 16;             // role A warps per CTA: a tile each
+constexpr int kEWarps = 16;             // role E warps per CTA: a tile each, two groups of 8
+constexpr int kEGroup = 8;
+constexpr int kStreamWarps = kAWarps + kEWarps;
+// Registers are re-dealt between the warpgroups at role entry (setmaxnreg).  The pool is what
+// the CTA was launched with (1024 threads x 64): what role E gives back must cover what role A
+// takes -- anything less and the increase never returns.
+constexpr int kLaunchRegs = 64, kARegs = 80, kERegs = 48;
+static_assert(kEWarps * (kLaunchRegs - kERegs) >= kAWarps * (kARegs - kLaunchRegs),
+              "setmaxnreg: role E must release what role A acquires");
+template <int N>
+__device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+constexpr int kSlotRows = kRoundTiles * kTileVoxels;   // rows a ring slot can hold
+constexpr int kMaxSlots = 16;           // ring slots per CTA (NS <= this)
+// per-warp prefetch ring of role A.  slot = header + 32 point records of 4 ints.
+// header: [0..16] tile_start of the round's 16 tiles (+ the end), [17..32] their occupancy masks
+constexpr int kAHdr = 36;
+constexpr int kASlotInts = kAHdr + 4 * 32;
+constexpr int kADist = 1;               // prefetch distance in rounds per stage
+constexpr int kASlots = 4 * kADist;
+constexpr int kEChunk = 64;             // channels per E item
+constexpr int kERows = 33;              // staged rows per tile: <= 32 occupied voxels + 1 of zeros
+
+__device__ __forceinline__ void cpa4(void* smem_dst, const void* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cpa_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cpa_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void cpa16_cg(uint32_t smem_dst, const void* gsrc) {   // L2 only
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
+}
+
+template <int VEC> struct VecT;
+template <> struct VecT<2> { using T = float2; };
+template <> struct VecT<4> { using T = float4; };
+
+template <int VEC>
+__device__ __forceinline__ void vec_fma(float (&acc)[VEC], const typename VecT<VEC>::T& f, float d,
+                                        bool first) {
+  const float* fv = reinterpret_cast<const float*>(&f);
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) acc[i] = fmaf(fv[i], d, first ? 0.f : acc[i]);
+}
+
+bool stream_force = false;   // tools only: also take wide rows (veon_fwd_stream_force)
+
+struct FwdStreamParams {
+  const float *depth, *feat;
+  const int32_t *ranks_depth, *ranks_feat, *ranks_bev;
+  const int32_t* tile_start;
+  const uint32_t* tile_occ;
+  const int32_t* heavy;      // plan's heavy list ([1] = threshold) or NULL
+  float* ring;               // [grid][ns][kSlotRows][CU]
+  float* out;
+  int64_t V;
+  uint32_t n_tiles, n_rounds, tiles_per_sample;
+  int C, n_pass, ns;         // n_pass = C / CU passes per round; ns ring slots per CTA
+};
+
+// One full / empty mbarrier pair per ring slot (the classic producer-consumer pipeline): every
+// A warp arrives on full[s] when its rows of the unit are in the slot, every E warp on empty[s]
+// when it has copied its rows out; a generation of the slot = one phase of each.  Waiting
+// threads are suspended by the hardware (try_wait), they do not spin through the issue slots.
+struct StreamShared {
+  uint64_t full[kMaxSlots];
+  uint64_t empty[kMaxSlots];
+};
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)),
+               "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {   // release.cta
+  asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::
+               "r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {   // acquire.cta
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(bar);
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "W_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@!p bra W_%=;\n\t}" ::"r"(a), "r"(parity) : "memory");
+}
+
+// Rows the round's tiles in front of tile w contribute to the slot (their occupied voxels; a
+// heavy tile contributes none).  ts / occ: lane l < 17 holds tile_start of tile l, lane l < 16
+// its mask.  `live_w`: tile w itself is this kernel's (not heavy).
+__device__ __forceinline__ int rows_before(int32_t ts, uint32_t occ, int lane, int w,
+                                           int32_t heavy_thr, bool& live_w) {
+  const int32_t ts_next = __shfl_down_sync(0xffffffffu, ts, 1);
+  const bool live = lane < kRoundTiles && (ts_next - ts) < heavy_thr;
+  live_w = __shfl_sync(0xffffffffu, (int)live, w) != 0;
+  return __reduce_add_sync(0xffffffffu, (live && lane < w) ? __popc(occ) : 0);
+}
+
+// ------------------------------------------------------------------------------------------
+// role A: rows of the occupied voxels -> the CTA's ring.  CU = 32 * VEC channels per pass; a
+// lane owns VEC consecutive channels.  Warp w: tile w of every round.
+// ------------------------------------------------------------------------------------------
+template <int VEC>
+__device__ __forceinline__ void role_rows(const FwdStreamParams& p, int32_t* ring_idx,
+                                          StreamShared* sh, int lane, int warp) {
+  using V = typename VecT<VEC>::T;
+  constexpr int CU = 32 * VEC;
+  __builtin_assume(__isShared(ring_idx));   // LDS/STS instead of generic accesses
+  constexpr int U = VEC == 2 ? 12 : 8;   // feature-row pieces in flight per lane (3 / 4 KB per warp)
+  if (blockIdx.x >= p.n_rounds) return;
+  const uint32_t my_rounds = (p.n_rounds - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  const int32_t heavy_thr = p.heavy ? __ldg(p.heavy + 1) : 0x7fffffff;
+  float* const cta_ring = p.ring + (size_t)blockIdx.x * p.ns * (kSlotRows * CU);
+  const uint32_t row_bytes = (uint32_t)p.C * 4u;
+
+  auto slot_of = [&](uint32_t m) { return ring_idx + (m & (kASlots - 1)) * kASlotInts; };
+  auto round_of = [&](uint32_t m) { return blockIdx.x + m * gridDim.x; };
+  auto issue_bounds = [&](uint32_t m) {   // header of my m-th round
+    int32_t* sl = slot_of(m);
+    if (m < my_rounds) {
+      const uint32_t t0 = round_of(m) * kRoundTiles;
+      if (lane <= kRoundTiles) cpa4(sl + lane, p.tile_start + min(t0 + lane, p.n_tiles));
+      else if (lane < 2 * kRoundTiles + 1) {
+        const uint32_t t = t0 + (lane - kRoundTiles - 1);
+        if (t < p.n_tiles) cpa4(sl + lane, p.tile_occ + t);
+        else sl[lane] = 0;
+      }
+    } else if (lane < 2 * kRoundTiles + 1) {
+      sl[lane] = 0;   // past the end: an empty round
+    }
+  };
+  // the point range of this warp's tile (none when the tile is heavy)
+  auto pair_range = [&](const int32_t* sl, int32_t& s, int32_t& e) {
+    s = sl[warp];
+    e = sl[warp + 1];
+    if (e - s >= heavy_thr) e = s;
+  };
+  auto issue_ranks = [&](uint32_t m) {
+    int32_t* sl = slot_of(m);
+    int32_t* pt = sl + kAHdr + 4 * lane;
+    int32_t s, e;
+    pair_range(sl, s, e);
+    const int32_t i = s + lane;
+    if (i < e) {
+      cpa4(pt + 0, p.ranks_bev + i);
+      cpa4(pt + 1, p.ranks_feat + i);
+      cpa4(pt + 2, p.ranks_depth + i);
+    } else {
+      pt[0] = -1;
+    }
+  };
+  auto issue_depth = [&](uint32_t m) {   // depth gather + fix-up of the landed ranks
+    int32_t* sl = slot_of(m);
+    int32_t* pt = sl + kAHdr + 4 * lane;
+    const int32_t rb = pt[0];
+    if (rb >= 0) {
+      cpa4(pt + 3, p.depth + pt[2]);
+      const int32_t up = lane ? pt[-4] : -1;
+      // byte offset of the feature row (a multiple of 256) | first point of its voxel
+      pt[2] = (int32_t)(((uint32_t)pt[1] * row_bytes) | (rb != up ? 1u : 0u));
+    }
+  };
+
+#pragma unroll
+  for (int i = 0; i < 3 * kADist; ++i) issue_bounds(i);
+  cpa_commit(); cpa_wait<0>(); __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 2 * kADist; ++i) issue_ranks(i);
+  cpa_commit(); cpa_wait<0>(); __syncwarp();
+#pragma unroll
+  for (int i = 0; i < kADist; ++i) issue_depth(i);
+  cpa_commit(); cpa_wait<0>(); __syncwarp();
+
+  const uint32_t lane_off = (uint32_t)lane * (VEC * 4);
+
+  for (uint32_t m = 0; m < my_rounds; ++m) {
+    cpa_wait<kADist - 1>();
+    __syncwarp();
+    int32_t* sl = slot_of(m);
+    int32_t s0, e0;
+    pair_range(sl, s0, e0);
+    bool live_w;
+    const int base_row = rows_before(lane <= kRoundTiles ? sl[lane] : 0,
+                                     lane < kRoundTiles ? (uint32_t)sl[17 + lane] : 0u, lane, warp,
+                                     heavy_thr, live_w);
+    issue_bounds(m + 3 * kADist);
+    issue_ranks(m + 2 * kADist);
+    issue_depth(m + kADist);
+    cpa_commit();
+
+    for (int pass = 0; pass < p.n_pass; ++pass) {
+      const uint32_t unit = m * (uint32_t)p.n_pass + pass;
+      const int slot = (int)(unit % (uint32_t)p.ns);
+      const uint32_t gen = unit / (uint32_t)p.ns;
+      // the slot's previous use has been read out by all E warps
+      if (gen > 0) mbar_wait(&sh->empty[slot], (gen - 1) & 1u);
+      if (e0 > s0) {
+        char* const slotb = reinterpret_cast<char*>(cta_ring + (size_t)slot * (kSlotRows * CU));
+        const char* const featb = reinterpret_cast<const char*>(p.feat) + pass * (CU * 4);
+        // byte offset, inside the slot, of this lane's piece of the row being accumulated; the
+        // first point always opens a voxel, so the -1 row is stepped over before any store
+        uint32_t rowoff = (uint32_t)(base_row - 1) * (CU * 4) + lane_off;
+        float acc[VEC];
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+        for (int32_t base = s0; base < e0; base += 32) {
+          const int cnt = min(32, e0 - base);
+          if (base != s0 || (pass > 0 && e0 - s0 > 32)) {
+            // more than 32 points: the records of every 32-point piece but the prefetched
+            // first one (of the first pass) are fetched synchronously
+            const int32_t i = base + lane;
+            __syncwarp();
+            int32_t rb = -1, rf = 0;
+            float d = 0.f;
+            if (i < e0) {
+              rb = __ldg(p.ranks_bev + i);
+              rf = __ldg(p.ranks_feat + i);
+              d = __ldg(p.depth + __ldg(p.ranks_depth + i));
+            }
+            int32_t up = __shfl_up_sync(0xffffffffu, rb, 1);
+            int32_t* pt = sl + kAHdr + 4 * lane;
+            if (lane == 0) up = base == s0 ? -1 : sl[kAHdr + 4 * 31 + 0];   // last point before
+            __syncwarp();
+            pt[0] = rb;
+            pt[2] = (int32_t)(((uint32_t)rf * row_bytes) | (rb != up ? 1u : 0u));
+            pt[3] = __float_as_int(d);
+            __syncwarp();
+          }
+          const int32_t* pts = sl + kAHdr + 2;   // record j: {row offset | first, depth} at pts[4 j]
+          // Branch-free body: loads in groups of four (a group past the last point is skipped
+          // as a whole, warp-uniformly), then one predicated fma chain per point; the running
+          // sum is stored after EVERY point (the last store of a voxel leaves its total), which
+          // costs L2 some repeated row writes and saves the flush branches.
+          for (int j0 = 0; j0 < cnt; j0 += U) {
+            int2 q[U];
+            V f[U];
+#pragma unroll
+            for (int g = 0; g < U; g += 4) {
+              if (j0 + g < cnt) {
+#pragma unroll
+                for (int uu = 0; uu < 4; ++uu) {
+                  const int u = g + uu;
+                  q[u] = *reinterpret_cast<const int2*>(pts + 4 * min(j0 + u, cnt - 1));
+                  f[u] = __ldg(reinterpret_cast<const V*>(featb + (((uint32_t)q[u].x & ~1u) + lane_off)));
+                }
+              }
+            }
+#pragma unroll
+            for (int g = 0; g < U; g += 4) {
+              if (j0 + g < cnt) {
+#pragma unroll
+                for (int uu = 0; uu < 4; ++uu) {
+                  const int u = g + uu;
+                  const bool ok = j0 + u < cnt;
+                  const bool first = q[u].x & 1;
+                  const float dj = __int_as_float(q[u].y);
+                  rowoff += (ok && first) ? (uint32_t)(CU * 4) : 0u;
+                  const float* fv = reinterpret_cast<const float*>(&f[u]);
+#pragma unroll
+                  for (int i = 0; i < VEC; ++i)
+                    acc[i] = ok ? fmaf(fv[i], dj, first ? 0.f : acc[i]) : acc[i];
+                  if (ok) *reinterpret_cast<V*>(slotb + rowoff) = *reinterpret_cast<const V*>(acc);
+                }
+              }
+            }
+          }
+        }
+      }
+      // this warp's rows of the unit are in the slot
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sh->full[slot]);
+    }
+  }
+  cpa_wait<0>();
+}
+
+// ------------------------------------------------------------------------------------------
+// role E: ring -> dense volume.  Warp ew: tile ew of every round; group = ew / 8.
+// ------------------------------------------------------------------------------------------
+// staged row j of a tile: 16 chunks of 16 bytes, chunk k at position k ^ swz(j) so that the
+// eight lanes of a store quad-row (eight different rows, same channel) hit different banks
+__device__ __forceinline__ uint32_t e_swz(uint32_t j) { return (j ^ (j >> 2)) & 7u; }
+
+template <int VEC>
+__device__ __forceinline__ void role_expand(const FwdStreamParams& p, float* stage,
+                                            StreamShared* sh, int lane, int ew) {
+  constexpr int CU = 32 * VEC;
+  constexpr int kSub = CU / kEChunk;
+  __builtin_assume(__isShared(stage));
+  if (blockIdx.x >= p.n_rounds) return;
+  const uint32_t my_rounds = (p.n_rounds - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  const int32_t heavy_thr = p.heavy ? __ldg(p.heavy + 1) : 0x7fffffff;
+  const float* const cta_ring = p.ring + (size_t)blockIdx.x * p.ns * (kSlotRows * CU);
+  const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
+  const int q4 = (lane & 7) * 4, r = lane >> 3;
+  const int group = ew / kEGroup;
+
+  // zero row (row 32; nothing is ever copied there)
+  for (int i = lane; i < kEChunk; i += 32) stage[32 * kEChunk + i] = 0.f;
+  __syncwarp();
+
+  // round header of the NEXT round travels in registers (lane l: tile_start / mask of tile l)
+  auto load_header = [&](uint32_t m, int32_t& ts, uint32_t& occ) {
+    ts = 0;
+    occ = 0u;
+    if (m < my_rounds) {
+      const uint32_t t0 = (blockIdx.x + m * gridDim.x) * kRoundTiles;
+      ts = __ldg(p.tile_start + min(t0 + min(lane, kRoundTiles), p.n_tiles));
+      if (lane < kRoundTiles && t0 + lane < p.n_tiles) occ = __ldg(p.tile_occ + t0 + lane);
+    }
+  };
+  int32_t ts_n;
+  uint32_t occ_n;
+  load_header(0, ts_n, occ_n);
+  for (uint32_t m = 0; m < my_rounds; ++m) {
+    const int32_t ts = ts_n;
+    const uint32_t occ_l = occ_n;
+    load_header(m + 1, ts_n, occ_n);
+    bool live_w;
+    const int base = rows_before(ts, occ_l, lane, ew, heavy_thr, live_w);
+    const uint32_t occ = __shfl_sync(0xffffffffu, occ_l, ew);
+    const uint32_t t = (blockIdx.x + m * gridDim.x) * kRoundTiles + ew;
+    const bool mine = live_w && t < p.n_tiles;
+    const int n = __popc(occ);
+    const uint32_t b = t / p.tiles_per_sample;
+    const uint32_t v0 = (t - b * p.tiles_per_sample) * kTileVoxels;
+    // shared-memory address of channel r of the staged row of each of this lane's four voxels,
+    // the row's swizzle folded in; the zero row for empty voxels
+    uint32_t a[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int v = q4 + i;
+      const bool set = (occ >> v) & 1u;
+      const uint32_t j = set ? (uint32_t)__popc(occ & ((1u << v) - 1u)) : 32u;
+      a[i] = stage_s + j * (kEChunk * 4) + (uint32_t)r * 4u;
+      if (set) a[i] ^= e_swz(j) << 4;
+    }
+    for (int pass = 0; pass < p.n_pass; ++pass) {
+      const uint32_t unit = m * (uint32_t)p.n_pass + pass;
+      const int slot = (int)(unit % (uint32_t)p.ns);
+      const uint32_t gen = unit / (uint32_t)p.ns;
+      // Role A has put the unit's rows into the slot.  EVERY E warp waits here, also one whose
+      // tile is empty: a warp must not run a slot generation ahead of the others (its arrival
+      // on `empty` would complete a phase a slower warp still belongs to).
+      mbar_wait(&sh->full[slot], gen & 1u);
+      const float* src = cta_ring + (size_t)slot * (kSlotRows * CU) + (size_t)base * CU +
+                         (lane & 15) * 4;
+      float* o = p.out + ((int64_t)b * p.C + pass * CU + r) * p.V + v0 + q4;
+      const int64_t ostep = 4 * p.V;
+#pragma unroll 1
+      for (int sub = 0; sub < kSub; ++sub, src += kEChunk) {
+        if (mine && n > 0) {
+          for (int j = lane >> 4; j < n; j += 2)
+            cpa16_cg(stage_s + (uint32_t)j * (kEChunk * 4) + ((((uint32_t)lane & 15u) ^ e_swz(j)) << 4),
+                     src + (size_t)j * CU);
+        }
+        cpa_commit();
+        cpa_wait<0>();
+        __syncwarp();
+        if (sub == kSub - 1 && lane == 0) mbar_arrive(&sh->empty[slot]);   // slot needed no more
+        // the group's 8 tiles are written together: aligned 1 KB runs per channel plane
+        if (group == 0) asm volatile("bar.sync 1, %0;" ::"n"(kEGroup * 32) : "memory");
+        else asm volatile("bar.sync 2, %0;" ::"n"(kEGroup * 32) : "memory");
+        if (mine) {
+          if (n == 0) {
+#pragma unroll 4
+            for (int k = 0; k < kEChunk / 4; ++k, o += ostep)
+              st_stream4(o, make_float4(0.f, 0.f, 0.f, 0.f));
+          } else {
+#pragma unroll
+            for (int k0 = 0; k0 < kEChunk / 4; k0 += 4) {   // 16 loads in flight, then 4 stores
+              float4 v4[4];
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) {
+                const uint32_t x = (uint32_t)((k0 + kk) << 4);
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v4[kk].x) : "r"(a[0] ^ x));
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v4[kk].y) : "r"(a[1] ^ x));
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v4[kk].z) : "r"(a[2] ^ x));
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v4[kk].w) : "r"(a[3] ^ x));
+              }
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk, o += ostep) st_stream4(o, v4[kk]);
+            }
+          }
+        } else {
+          o += (kEChunk / 4) * ostep;
+        }
+        __syncwarp();   // the staging buffer is refilled next
+      }
+    }
+  }
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(kStreamWarps * 32, 1)
+k_fwd_stream(const FwdStreamParams p) {
+  extern __shared__ __align__(16) float fs_smem_raw[];
+  __shared__ StreamShared sh;
+  // the E staging addresses are formed with XORs on bits 4..7: 256-byte aligned base
+  float* fs_smem = reinterpret_cast<float*>(
+      (reinterpret_cast<uintptr_t>(fs_smem_raw) + 255) & ~(uintptr_t)255);
+  pdl_launch_dependents();   // the heavy-tile grid may be queued behind this one
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x < kMaxSlots) {
+    mbar_init(&sh.full[threadIdx.x], kAWarps);
+    mbar_init(&sh.empty[threadIdx.x], kEWarps);
+  }
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  __syncthreads();
+  constexpr int kEStageFloats = kEWarps * kERows * kEChunk;
+  if (warp < kAWarps) {
+    reg_inc<kARegs>();
+    role_rows<VEC>(p, reinterpret_cast<int32_t*>(fs_smem + kEStageFloats) +
+                          warp * (kASlots * kASlotInts), &sh, lane, warp);
+  } else {
+    reg_dec<kERegs>();
+    const int ew = warp - kAWarps;
+    role_expand<VEC>(p, fs_smem + ew * kERows * kEChunk, &sh, lane, ew);
+  }
+}
+
+bool fwd_stream_supported(int B, int C, int64_t V, const void* feat, const void* out,
+                          int64_t n_feat_rows) {
+  if (V % kTileVoxels != 0) return false;
+  // The kernel handles C = 64 and every multiple of 128 (bit-identical; tools/fwd_check.py runs
+  // them all through stream_force), but it only WINS for 64-channel rows (318 vs 337 us at C2);
+  // wider rows at VEON's point density are faster through the general kernel (B200, round 2:
+  // 1.15-1.5 ms vs 1.10 ms for a 2.6 GB volume), so they stay there.
+  if (C != 64 && !(stream_force && C % 128 == 0)) return false;
+  if (((uintptr_t)feat | (uintptr_t)out) & 15) return false;
+  if ((int64_t)B * V > 0x7fffffffLL || n_feat_rows * (int64_t)C > 0x3fffffffLL) return false;
+  return true;
+}
+
+template <int VEC>
+static int launch_stream_kernel(FwdStreamParams& p, size_t ring_bytes, cudaStream_t stream) {
+  constexpr int CU = 32 * VEC;
+  const size_t smem = sizeof(float) * kEWarps * kERows * kEChunk +
+                      sizeof(int32_t) * kAWarps * kASlots * kASlotInts + 256;
+  static int per_sm[kMaxDevices] = {};
+  const int dev = current_device();
+  if (per_sm[dev] == 0) {
+    VEON_CUDA_TRY(cudaFuncSetAttribute(k_fwd_stream<VEC>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int n = 0;
+    VEON_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_fwd_stream<VEC>,
+                                                                kStreamWarps * 32, smem));
+    per_sm[dev] = n > 0 ? n : -1;
+  }
+  if (per_sm[dev] < 1) return VEON_E_UNSUPPORTED;
+  int64_t grid = sm_count();
+  if (grid > p.n_rounds) grid = p.n_rounds;
+  // ring slots per CTA from what the caller gave us
+  const size_t slot_bytes = sizeof(float) * kSlotRows * CU;
+  const int64_t ns = (int64_t)(ring_bytes / ((size_t)grid * slot_bytes));
+  if (ns < 2) return VEON_E_WORKSPACE;
+  p.ns = ns > kMaxSlots ? kMaxSlots : (int)ns;
+  p.n_pass = p.C / CU;
+  k_fwd_stream<VEC><<<(unsigned)grid, kStreamWarps * 32, smem, stream>>>(p);
+  VEON_LAUNCH_CHECK();
+  return 0;
+}
+
+size_t fwd_stream_workspace_bytes(int C) {
+  // (SM count of the current device) x 8 slots (C = 64) / 4 slots (wider rows) = 148 x 1 MB
+  const int CU = C == 64 ? 64 : 128;
+  return (size_t)sm_count() * (C == 64 ? 8 : 4) * sizeof(float) * kSlotRows * CU;
+}
+
+int launch_fwd_stream(const float* depth, const float* feat, const int32_t* rd, const int32_t* rf,
+                      const int32_t* rb, const int32_t* tile_start, const uint32_t* tile_occ,
+                      const int32_t* heavy, int64_t heavy_ints, int B, int C, int64_t V,
+                      float* out, void* workspace, size_t ws_bytes, cudaStream_t stream) {
+  const int64_t tps = V / kTileVoxels, n_tiles = (int64_t)B * tps;
+  if (!workspace || ((uintptr_t)workspace & 255)) return VEON_E_WORKSPACE;
+  FwdStreamParams p;
+  p.depth = depth; p.feat = feat; p.ranks_depth = rd; p.ranks_feat = rf; p.ranks_bev = rb;
+  p.tile_start = tile_start; p.tile_occ = tile_occ; p.heavy = heavy;
+  p.ring = reinterpret_cast<float*>(workspace);
+  p.out = out; p.V = V; p.n_tiles = (uint32_t)n_tiles;
+  p.n_rounds = (uint32_t)ceil_div64(n_tiles, kRoundTiles);
+  p.tiles_per_sample = (uint32_t)tps;
+  p.C = C; p.n_pass = 1; p.ns = 2;
+  int rc = C == 64 ? launch_stream_kernel<2>(p, ws_bytes, stream)
+                   : launch_stream_kernel<4>(p, ws_bytes, stream);
+  if (rc) return rc;
+  if (heavy) return launch_heavy_behind(depth, feat, rd, rf, rb, tile_start, heavy, heavy_ints, B, C,
+                                        V, out, stream);
+  return 0;
+}
+
+}  // namespace veon
