@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """bench.py -- 6-camera samples/s of the lift (voxel_pooling_prepare_v2 +
 bev_pool_v2 forward + backward) on N B200s, with the roofline of the dominant
-kernel and the CPU baseline beside it.
+kernel, the other BASELINE workloads, the reference's own CUDA kernels on the
+same GPU and the CPU baseline beside it.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
@@ -9,14 +10,27 @@ kernel and the CPU baseline beside it.
 One "step" = one pass of the hot path over one batch of synthetic
 nuScenes-shaped input: BASELINE.json configs[1] (6 cams 16x44 feats, D=88,
 C=64, batch 8 per GPU; weak scaling: every rank lifts its own 8 samples, no
-data-path collective).  Prints ONE JSON line on rank 0.
+data-path collective).  The K-step region is repeated until at least one
+second of GPU time has been measured; `value` is the median repeat.  Prints
+ONE JSON line on rank 0.
+
+Secondary objects of the line (all device-timed with CUDA events):
+  workloads        C3 (C=512), C4 (C=768, D=118, B=16) lift fwd+bwd and the real VEON neck
+                   (C=256, 32x88, two-hot depth, 2x2x2 max) -- N=1 only
+  reference_cuda   the reference's own kernels (oracle/_ref, compiled unmodified) in the
+                   reference's own flow (memset, permute, argsort) on the same inputs -- N=1 only
+  pipeline         lift + classify (C3 geometry, Q=18 / Q=67) INCLUDING the NCCL all-gather of
+                   the uint8 occupancy volumes on a side stream, per-GPU batch 8..64 -- every N
+  tail, tail_lowres, downsample   as in round 1
 """
 import argparse
+import ctypes
 import json
 import os
 import sys
 import threading
 import time
+import types
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
@@ -24,6 +38,8 @@ if ROOT not in sys.path:
 
 METRIC = "6-cam samples/sec for lift (bev_pool_v2 fwd+bwd)"
 UNIT = "samples/s"
+KEYS = ("sensor2ego", "ego2global", "intrins", "post_rots", "post_trans", "bda")
+VOX = 640000
 
 
 def parse():
@@ -36,10 +52,14 @@ def parse():
     ap.add_argument("--batch", type=int, default=0, help="override samples per GPU per step")
     ap.add_argument("--cpu-seconds", type=float, default=15.0,
                     help="budget of the cpu_baseline leg (rank 0, N=1 only)")
+    ap.add_argument("--min-seconds", type=float, default=1.0,
+                    help="the K-step region is repeated until this much GPU time is measured")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-tail", action="store_true", help="skip the secondary tail measurement")
-    ap.add_argument("--sync-free", type=int, default=0,
-                    help="1: skip the host read-back of the counts (see LSSViewTransformer)")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="headline + e2e only (no workloads / comparator / pipeline / tail legs)")
+    ap.add_argument("--host-sync", type=int, default=0,
+                    help="1: read the point / interval counts back every step (the reference's "
+                         "empty-input check); default 0 = LSSViewTransformer(sync_free=True)")
     return ap.parse_args()
 
 
@@ -174,25 +194,30 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------- ours
-def algorithmic_bytes(cfg, B, n_kept, n_int):
+def algorithmic_bytes(cfg, B, n_kept, n_int, C=None):
     """compulsory traffic per step (every input element read once, every
     output element written once)."""
-    V, C = 640000, cfg.channels
+    C = cfg.channels if C is None else C
     H, W = cfg.feat_hw
     NHW = cfg.n_cams * H * W
     P = NHW * cfg.D * B
-    fwd = 4 * V * C * B + 4 * NHW * C * B + 4 * n_kept + 8 * n_kept + 12 * n_int
+    fwd = 4 * VOX * C * B + 4 * NHW * C * B + 4 * n_kept + 8 * n_kept + 12 * n_int
     n_bp = NHW * B
     bwd = 4 * n_int * C + 4 * NHW * C * B + 4 * n_kept + 4 * P + 4 * NHW * C * B + 12 * n_kept + 8 * n_bp
     prep = 12 * P + 12 * n_kept + 8 * n_int
     return {"prepare": prep, "pool_fwd": fwd, "pool_bwd": bwd}
 
 
-def bind_to_gpu_numa_node(local):
-    """Pin this rank's threads (and so, by first touch, its pinned host buffers) to the
-    CPUs of the NUMA node its GPU hangs off.  With 8 ranks each streaming 20 MB per
-    direction per step, host buffers on the far socket cost more than anything on the GPU.
-    Best effort: returns the node or None."""
+def numa_info(local):
+    """NUMA placement of this rank's GPU.  Binding the rank's threads (and so, by first touch, its
+    pinned buffers) to the GPU's node is attempted; on a single-node guest there is nothing to
+    bind to and the reason is reported instead of a silent null."""
+    info = {"node": None}
+    try:
+        nodes = [d for d in os.listdir("/sys/devices/system/node") if d.startswith("node")]
+        info["host_nodes"] = len(nodes)
+    except Exception:
+        info["host_nodes"] = None
     try:
         import pynvml
         pynvml.nvmlInit()
@@ -205,16 +230,307 @@ def bind_to_gpu_numa_node(local):
         with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
             node = int(f.read().strip())
         if node < 0:
-            return None
+            info["why"] = "sysfs reports numa_node=-1 for the GPU (single-node guest): nothing to bind"
+            return info
         with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
             cpus = set()
             for part in f.read().strip().split(","):
                 a, _, b = part.partition("-")
                 cpus.update(range(int(a), int(b or a) + 1))
         os.sched_setaffinity(0, cpus)
-        return node
-    except Exception:
-        return None
+        info["node"] = node
+        info["cpus_bound"] = len(cpus)
+    except Exception as e:   # noqa: BLE001
+        info["why"] = f"{type(e).__name__}: {e}"
+    return info
+
+
+def reference_cuda_leg(cfg, B, dev, peak_gbs):
+    """The GPU comparator SURVEY 8(d) asks for: the reference's OWN kernels (bev_pool_cuda.cu,
+    compiled unmodified into oracle/_ref) driven by the reference's OWN operator file (memset
+    :27, permute :91, argsort :47-57, contiguous :69) and the reference's own
+    voxel_pooling_prepare_v2 (view_transformer.py:202-260), on the same C2 inputs, same GPU,
+    CUDA events.  Comparator only: nothing of it is on the product path."""
+    import torch
+    so = os.path.join(ROOT, "oracle", "_ref", "libbev_pool_v2_ref.so")
+    if not os.path.isfile(so):
+        return {"unavailable": "oracle/_ref not built (make -C oracle ref)"}
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    try:
+        from _ref_loader import (load_reference_bev_pool, load_reference_view_transformer,
+                                 reference_available)
+        if not reference_available():
+            return {"unavailable": "reference python files not staged"}
+        lib = ctypes.CDLL(so)
+        fwd = getattr(lib, "_Z11bev_pool_v2iiPKfS0_PKiS2_S2_S2_S2_Pf")
+        bwd = getattr(lib, "_Z16bev_pool_v2_gradiiPKfS0_S0_PKiS2_S2_S2_S2_PfS3_")
+    except Exception as e:   # noqa: BLE001
+        return {"unavailable": f"{type(e).__name__}: {e}"}
+    vp = lambda t: ctypes.c_void_p(t.data_ptr())   # noqa: E731
+
+    # torch's default stream IS the legacy default stream the reference launches on
+    def f_fwd(depth, feat, out, rd, rf, rb, ln, st):
+        fwd(ctypes.c_int(feat.size(4)), ctypes.c_int(ln.size(0)), vp(depth), vp(feat), vp(rd),
+            vp(rf), vp(rb), vp(st), vp(ln), vp(out))
+
+    def f_bwd(og, dg, fg, depth, feat, rd, rf, rb, ln, st):
+        bwd(ctypes.c_int(og.size(4)), ctypes.c_int(ln.size(0)), vp(og), vp(depth), vp(feat),
+            vp(rd), vp(rf), vp(rb), vp(st), vp(ln), vp(dg), vp(fg))
+
+    ext = types.SimpleNamespace(bev_pool_v2_forward=f_fwd, bev_pool_v2_backward=f_bwd)
+    ref_op = load_reference_bev_pool(ext)
+    ref_vt = load_reference_view_transformer(ref_op.bev_pool_v2)
+    from veon_b200 import synthetic as S
+    C = cfg.channels
+    assert B * VOX * C < 2 ** 31, "the reference kernels index with 32-bit ints"
+    neck = ref_vt.LSSViewTransformer(grid_config=cfg.grid_config, input_size=cfg.input_size,
+                                     downsample=cfg.downsample, in_channels=8, out_channels=C,
+                                     collapse_z=False)
+    coor = torch.from_numpy(S.lidar_coor_np(cfg, batch=B)).to(dev)
+    _, N, D, H, W, _ = coor.shape
+    g = torch.Generator(device=dev).manual_seed(99)
+    depth = torch.softmax(torch.randn(B, N, D, H, W, device=dev, generator=g) * 4, dim=2)
+    feat = torch.randn(B, N, H, W, C, device=dev, generator=g)
+    og = torch.randn(B, C, 16, 200, 200, device=dev, generator=g)
+    shape = (B, 16, 200, 200, C)
+
+    def ev():
+        return torch.cuda.Event(enable_timing=True)
+    n, warm = 10, 3
+    tp, tf, tb = [], [], []
+    for i in range(n + warm):
+        e = [ev() for _ in range(4)]
+        e[0].record()
+        rb, rd, rf, st, ln = neck.voxel_pooling_prepare_v2(coor)
+        e[1].record()
+        d = depth.detach().requires_grad_()
+        f = feat.detach().requires_grad_()
+        out = ref_op.bev_pool_v2(d, f, rd, rf, rb, shape, st, ln)
+        e[2].record()
+        out.backward(og)
+        e[3].record()
+        torch.cuda.synchronize()
+        if i >= warm:
+            tp.append(e[0].elapsed_time(e[1]))
+            tf.append(e[1].elapsed_time(e[2]))
+            tb.append(e[2].elapsed_time(e[3]))
+        del out, d, f
+    med = lambda v: sorted(v)[len(v) // 2]   # noqa: E731
+    alg = algorithmic_bytes(cfg, B, int(rb.numel()), int(st.numel()))
+    res = {"what": "reference voxel_pooling_prepare_v2 (ATen ops) + reference QuickCumsumCuda / "
+                   "bev_pool_v2 (its memset, permute, argsort, contiguous) on the reference's own "
+                   "kernels compiled unmodified for sm_100a; same inputs, same GPU, CUDA events, "
+                   f"median of {n}",
+           "samples_per_call": B,
+           "prepare_ms": med(tp), "pool_fwd_ms": med(tf), "pool_bwd_ms": med(tb),
+           "step_ms": med(tp) + med(tf) + med(tb),
+           "samples_per_s": B / ((med(tp) + med(tf) + med(tb)) * 1e-3),
+           "fwd_gbs_algorithmic": alg["pool_fwd"] / (med(tf) * 1e-3) / 1e9,
+           "bwd_gbs_algorithmic": alg["pool_bwd"] / (med(tb) * 1e-3) / 1e9,
+           "fwd_bwd_frac_of_hbm_peak": (alg["pool_fwd"] + alg["pool_bwd"]) /
+                                       ((med(tf) + med(tb)) * 1e-3) / 1e9 / peak_gbs}
+    del coor, depth, feat, og
+    torch.cuda.empty_cache()
+    return res
+
+
+def lift_workload(name, cfg_name, B, C, dev, peak_gbs, raw_neck=False, n_min=6, seconds=0.4):
+    """One of the other BASELINE workloads through the public neck API on device-resident
+    inputs: whole-step samples/s + the per-call device times of prepare / forward / backward
+    with their algorithmic GB/s and fraction of the measured HBM peak."""
+    import torch
+    from veon_b200 import bev_pool as BP, synthetic as S
+    from veon_b200.view_transformer import LSSViewTransformer, LSSViewTransformerRaw
+    cfg = S.CONFIGS[cfg_name]
+    H, W = cfg.feat_hw
+    N, D = cfg.n_cams, cfg.D
+    g = torch.Generator(device=dev).manual_seed(5)
+    cal = S.calibration(cfg, batch=B)
+    metas = [torch.from_numpy(cal[k]).to(dev) for k in KEYS]
+    feat = torch.randn(B, N, C, H, W, device=dev, generator=g)
+    if raw_neck:
+        neck = LSSViewTransformerRaw(cfg.grid_config, cfg.input_size, cfg.downsample, 8, C,
+                                     sync_free=True)
+        metric = torch.from_numpy(S.metric_depth_np(cfg, batch=B)).to(dev)
+        og = torch.randn(B, C, 8, 100, 100, device=dev, generator=g)
+    else:
+        neck = LSSViewTransformer(cfg.grid_config, cfg.input_size, cfg.downsample, 8, C,
+                                  collapse_z=False, sync_free=True)
+        depth0 = torch.softmax(torch.randn(B, N, D, H, W, device=dev, generator=g) * 4, dim=2)
+        og = torch.randn(B, C, 16, 200, 200, device=dev, generator=g)
+    img = torch.zeros(B, N, 1, H, W, device=dev)
+
+    def step():
+        f = feat.detach().requires_grad_()
+        if raw_neck:
+            with torch.no_grad():   # the depth estimator is frozen in VEON: two-hot forward only
+                d = neck.get_two_hot_depth(metric)
+            d = d.requires_grad_()
+            out = neck([f] + metas, d)
+        else:
+            d = depth0.detach().requires_grad_()
+            out, _ = neck.view_transform([img] + metas, d.view(B * N, D, H, W),
+                                         f.view(B * N, C, H, W))
+        out.backward(og)
+
+    for _ in range(3):
+        step()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    step()
+    e1.record()
+    torch.cuda.synchronize()
+    n = max(n_min, int(seconds * 1e3 / max(e0.elapsed_time(e1), 1e-3)))
+    e0.record()
+    for _ in range(n):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms_step = e0.elapsed_time(e1) / n
+    BP.enable_kernel_timing(True)
+    for _ in range(min(n, 10)):
+        step()
+    t = BP.kernel_timings_ms()
+    BP.enable_kernel_timing(False)
+    avg = {k: sum(v) / len(v) for k, v in t.items()}
+    coor = neck.get_lidar_coor(*metas)
+    prep = BP.prepare_ranks(coor, neck.grid_lower_bound, neck.grid_interval, neck.grid_size)
+    n_kept, n_int = prep.plan.n_points, prep.plan.n_intervals
+    del coor, prep
+    alg = algorithmic_bytes(cfg, B, n_kept, n_int, C)
+    fwd_ms = avg.get("pool_fwd")
+    bwd_ms = avg.get("pool_bwd", avg.get("pool_bwd_ds"))
+    out = {"workload": name, "samples_per_call": B, "channels": C, "D": D, "feat_hw": [H, W],
+           "ms_per_step": ms_step, "samples_per_s": B / (ms_step * 1e-3), "timed_steps": n,
+           "n_kept": n_kept, "n_intervals": n_int,
+           "phases_ms": {k: round(v, 4) for k, v in avg.items()}}
+    if fwd_ms:
+        out["fwd_gbs_algorithmic"] = alg["pool_fwd"] / (fwd_ms * 1e-3) / 1e9
+        out["fwd_frac_of_hbm_peak"] = out["fwd_gbs_algorithmic"] / peak_gbs
+    if bwd_ms and not raw_neck:
+        out["bwd_gbs_algorithmic"] = alg["pool_bwd"] / (bwd_ms * 1e-3) / 1e9
+        out["bwd_frac_of_hbm_peak"] = out["bwd_gbs_algorithmic"] / peak_gbs
+    if fwd_ms and bwd_ms and not raw_neck:
+        out["fwd_bwd_frac_of_hbm_peak"] = (alg["pool_fwd"] + alg["pool_bwd"]) / \
+            ((fwd_ms + bwd_ms) * 1e-3) / 1e9 / peak_gbs
+    if raw_neck:
+        out["note"] = ("LSSViewTransformerRaw training step: two-hot depth producer (no grad) + "
+                       "geometry + prepare + pool + 2x2x2 max as one autograd node + backward from "
+                       "the [B,C,8,100,100] gradient; the forward fraction counts the full-"
+                       "resolution volume the pooling kernel writes")
+    del feat, og, neck
+    torch.cuda.empty_cache()
+    return out
+
+
+def pipeline_leg(dev, world, rank, peak_gbs, batches=(8, 16, 32, 64), Qs=(18, 67)):
+    """BASELINE configs[2] + [4]: lift + classify on C3 geometry (C=512 image features, Q prompt
+    rows) with the NCCL all-gather of the finished uint8 occupancy volumes on a side stream
+    (it overlaps the next step's compute), per-GPU batch swept.  Gathered volumes are verified
+    once against the local ones outside the timed region."""
+    import torch
+    import torch.distributed as dist
+    from veon_b200 import synthetic as S
+    from veon_b200.dist import all_gather_occupancy
+    from veon_b200.pipeline import lift_classify
+    from veon_b200.tail import class_of_prompt
+    from veon_b200.view_transformer import LSSViewTransformer
+    SIZES = [16, 1, 1, 1, 8, 1, 1, 3, 1, 1, 1, 1, 5, 3, 5, 13, 4]   # nuscenes_brief prompts per class
+    c3 = S.CONFIGS["C3"]
+    Ct, N, D = 512, c3.n_cams, c3.D
+    H, W = c3.feat_hw
+    neck = LSSViewTransformer(c3.grid_config, c3.input_size, c3.downsample, 8, Ct, collapse_z=False,
+                              sync_free=True)
+    side = torch.cuda.Stream(dev)
+    rows = []
+    g = torch.Generator(device=dev).manual_seed(11 + rank)
+    for Q in Qs:
+        refl = list(range(Q - 1)) if Q == 18 else [k for k, n in enumerate(SIZES) for _ in range(n)]
+        cls_t = class_of_prompt(refl).to(dev)
+        wt = torch.randn(Q, Ct, device=dev, generator=g)
+        wt = 100.0 * wt / wt.norm(dim=1, keepdim=True)
+        gate_w = torch.randn(2, Ct, device=dev, generator=g)
+        for Bp in (batches if Q == 18 else batches[:1]):
+            cal = S.calibration(c3, batch=min(Bp, 8), sample_offset=rank * 1000)
+            metas = [torch.from_numpy(cal[k]).to(dev) for k in KEYS]
+            if Bp > 8:   # repeat the 8 calibrated rigs (the index preparation still runs per sample)
+                metas = [m.repeat((Bp // 8,) + (1,) * (m.dim() - 1)) for m in metas]
+            depth = torch.softmax(torch.randn(Bp * N, D, H, W, device=dev, generator=g) * 4, 1)
+            feat = torch.randn(Bp * N, Ct, H, W, device=dev, generator=g) * 0.05
+            img = torch.zeros(Bp, N, 1, H, W, device=dev)
+            n_total = Bp * world
+            # one call lifts at most 16 samples: the reference's float32 voxel rank is exact only
+            # while B * 640 000 < 2^24 (B <= 26, SURVEY 7), so larger batches go in chunks
+            CH = 16
+
+            def one():
+                if Bp <= CH:
+                    return lift_classify(neck, [img] + metas, depth, feat, wt, cls_t, gate_w)
+                labs = []
+                for b0 in range(0, Bp, CH):
+                    sl = slice(b0, b0 + CH)
+                    labs.append(lift_classify(neck, [img[sl]] + [m[sl] for m in metas],
+                                              depth[b0 * N:(b0 + CH) * N], feat[b0 * N:(b0 + CH) * N],
+                                              wt, cls_t, gate_w))
+                return torch.cat(labs, 0)
+
+            def gather(lab):
+                # sample i -> rank i mod world (veon_b200.dist.shard_samples)
+                return all_gather_occupancy(lab, n_total) if world > 1 else lab
+            # correctness of the collective, outside the timed region
+            lab = one()
+            allv = gather(lab)
+            torch.cuda.synchronize()
+            ok = bool(torch.equal(allv[rank::world], lab)) if world > 1 else True
+            # the all-gather alone
+            ag_us = None
+            if world > 1:
+                dist.barrier()
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                for _ in range(10):
+                    gather(lab)
+                b.record()
+                torch.cuda.synchronize()
+                ag_us = a.elapsed_time(b) * 100.0
+            for _ in range(2):
+                one()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            main = torch.cuda.current_stream(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            steps = 10
+            e0.record()
+            for _ in range(steps):
+                lab = one()
+                done = torch.cuda.Event()
+                done.record(main)
+                with torch.cuda.stream(side):
+                    side.wait_event(done)
+                    lab.record_stream(side)
+                    allv = gather(lab)
+            main.wait_stream(side)
+            e1.record()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+            ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            ms = float(ms.item())
+            rows.append({"Q": Q, "samples_per_gpu_per_step": Bp, "ms_per_step": ms,
+                         "samples_per_s": n_total / (ms * 1e-3),
+                         "all_gather_us": ag_us, "gathered_bytes": n_total * VOX,
+                         "gather_verified": ok})
+            del depth, feat, img, metas
+            torch.cuda.empty_cache()
+    return {"what": "lift_classify (C3 geometry: 6 cams 32x88, D=88, C=512 image features -> per-pixel "
+                    "logits on tcgen05 -> get_lidar_coor + prepare_v2 + bev_pool_v2 of Q+2 channels -> "
+                    "merge/argmax/gate -> uint8 [B,200,200,16]) + all_gather_occupancy over NCCL on a "
+                    "side stream; weak scaling, samples dealt round-robin; max over ranks",
+            "n_gpus": world, "rows": rows}
 
 
 def run_ours(args):
@@ -228,7 +544,7 @@ def run_ours(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
-    numa_node = bind_to_gpu_numa_node(local) if world > 1 else None
+    numa = numa_info(local)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -238,9 +554,19 @@ def run_ours(args):
     cfg = S.CONFIGS[args.workload]
     B = args.batch or cfg.batch
     C = cfg.channels
+    sync_free = not bool(args.host_sync)
     neck = LSSViewTransformer(cfg.grid_config, cfg.input_size, cfg.downsample, in_channels=8,
-                              out_channels=C, collapse_z=False, sync_free=bool(args.sync_free))
+                              out_channels=C, collapse_z=False, sync_free=sync_free)
     lower, interval, size = S.grid_vectors(cfg.grid_config)
+
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except Exception:
+        pass
+    peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "6650 GB/s (of fallback)"
 
     # rotating input sets so that a step's inputs are not L2-hot from the previous step
     n_sets = 4
@@ -251,7 +577,7 @@ def run_ours(args):
         Bc, N, D, H, W, _ = coor.shape
         depth = torch.softmax(torch.randn(B, N, D, H, W, device=dev, generator=g) * 4, dim=2)
         feat = torch.randn(B, N, C, H, W, device=dev, generator=g)
-        host_sets.append((coor.pin_memory(), depth.cpu().pin_memory(), feat.cpu().pin_memory()))
+        host_sets.append((depth.cpu(), feat.cpu()))
         dev_sets.append((coor.to(dev), depth, feat))
     out_grad = torch.randn(B, C, 16, 200, 200, device=dev, generator=g)
 
@@ -264,23 +590,25 @@ def run_ours(args):
         return depth.grad, feat.grad
 
     # ---- end to end: the user's call, view_transform(input, depth, tran_feat), on HOST data.
-    # Per step: calibration + depth + feat from pinned host memory -> device (copy stream,
-    # overlapped with the previous step's compute), get_lidar_coor + prepare + pool forward +
-    # backward on device, depth_grad + feat_grad back to pinned host memory (D2H stream).
-    KEYS = ("sensor2ego", "ego2global", "intrins", "post_rots", "post_trans", "bda")
-    e2e_host = []
-    meta_shapes = None
+    # Per step ONE pinned buffer travels each way: [calibration | depth | feat] host -> device on a
+    # copy stream (overlapped with the previous step's compute), get_lidar_coor + prepare + pool
+    # forward + backward on device, [depth_grad | feat_grad] device -> host on a D2H stream.
+    n_d, n_f = B * N * D * H * W, B * N * C * H * W
+    e2e_host, meta_shapes, n_meta = [], None, 0
     for i in range(n_sets):
         cal = S.calibration(cfg, batch=B, sample_offset=rank * 1000 + i * B)
-        # the six calibration tensors travel as ONE pinned buffer (one H2D copy), and are
-        # handed to view_transform as views of it
         parts = [torch.from_numpy(cal[k]).reshape(-1) for k in KEYS]
         meta_shapes = [tuple(cal[k].shape) for k in KEYS]
-        packed = torch.cat(parts).pin_memory()
-        _, hd, hf = host_sets[i]
-        e2e_host.append((packed, hd.view(B * N, D, H, W), hf.view(B * N, C, H, W)))
+        hd, hf = host_sets[i]
+        n_meta = (sum(p.numel() for p in parts) + 63) // 64 * 64      # keeps the pieces 256-B aligned
+        packed = torch.zeros(n_meta + n_d + n_f, dtype=torch.float32)
+        packed[:sum(p.numel() for p in parts)] = torch.cat(parts)
+        packed[n_meta:n_meta + n_d] = hd.reshape(-1)
+        packed[n_meta + n_d:] = hf.reshape(-1)
+        e2e_host.append(packed.pin_memory())
+    del host_sets
 
-    def unpack_metas(packed_dev):
+    def unpack(packed_dev):
         out, o = [], 0
         for shp in meta_shapes:
             n = 1
@@ -288,19 +616,17 @@ def run_ours(args):
                 n *= v
             out.append(packed_dev[o:o + n].view(shp))
             o += n
-        return out
+        depth = packed_dev[n_meta:n_meta + n_d].view(B * N, D, H, W)
+        feat = packed_dev[n_meta + n_d:].view(B * N, C, H, W)
+        return out, depth, feat
 
     img_shape = torch.zeros(B, N, 1, H, W, device=dev)      # only its shape is read
     copy_stream, d2h_stream = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
     ready = [torch.cuda.Event(), torch.cuda.Event()]
     consumed = [torch.cuda.Event(), torch.cuda.Event()]
-    dg_host = [torch.empty((B * N, D, H, W), dtype=torch.float32).pin_memory() for _ in range(2)]
-    fg_host = [torch.empty((B * N, C, H, W), dtype=torch.float32).pin_memory() for _ in range(2)]
-
-    # static device staging buffers (two slots): no allocator traffic on the side streams
-    dev_in = [(torch.empty_like(e2e_host[0][0], device=dev),
-               torch.empty((B * N, D, H, W), dtype=torch.float32, device=dev),
-               torch.empty((B * N, C, H, W), dtype=torch.float32, device=dev)) for _ in range(2)]
+    grad_host = [torch.empty(n_d + n_f, dtype=torch.float32).pin_memory() for _ in range(2)]
+    grad_dev = [torch.empty(n_d + n_f, dtype=torch.float32, device=dev) for _ in range(2)]
+    dev_in = [torch.empty_like(e2e_host[0], device=dev) for _ in range(2)]   # static staging
 
     def e2e_h2d(i, gate=None):
         slot = i % 2
@@ -308,27 +634,26 @@ def run_ours(args):
             copy_stream.wait_event(consumed[slot])          # the slot's previous user is done
             if gate is not None:
                 copy_stream.wait_event(gate)
-            for dst, src in zip(dev_in[slot], e2e_host[i % n_sets]):
-                dst.copy_(src, non_blocking=True)
+            dev_in[slot].copy_(e2e_host[i % n_sets], non_blocking=True)
             ready[slot].record(copy_stream)
 
-    def e2e_d2h(slot, dgrad, fgrad, gate):
+    def e2e_d2h(slot, gate):
         with torch.cuda.stream(d2h_stream):
-            d2h_stream.wait_event(consumed[slot])
             d2h_stream.wait_event(gate)
-            dgrad.record_stream(d2h_stream)
-            fgrad.record_stream(d2h_stream)
-            dg_host[slot].copy_(dgrad, non_blocking=True)
-            fg_host[slot].copy_(fgrad, non_blocking=True)
+            grad_host[slot].copy_(grad_dev[slot], non_blocking=True)
+            d2h_done[slot].record(d2h_stream)
 
-    def run_e2e(steps):
+    d2h_done = [torch.cuda.Event(), torch.cuda.Event()]
+
+    def run_e2e(steps, compute=True):
         """Every step copies its inputs in and its gradients out.  The copies are queued from
         the neck's `prepared_hook`: H2D of step i+1 and D2H of step i-1 are released when the
         index preparation of step i is done, so they overlap the two long pooling kernels
         instead of the dozen short launches before them (those are measurably slower while
-        PCIe is saturated; tools/e2e_timeline.py)."""
+        PCIe is saturated; tools/e2e_timeline.py).  compute=False: the same copies with no
+        kernels in between -- the ceiling the host side sets."""
         main = torch.cuda.current_stream(dev)
-        for ev in consumed:
+        for ev in consumed + d2h_done:
             ev.record(main)
         gate = torch.cuda.Event()
         state = {"i": 0, "pending": None}
@@ -339,10 +664,10 @@ def run_ours(args):
             if state["i"] + 1 < steps:
                 e2e_h2d(state["i"] + 1, gate)
             if state["pending"] is not None:
-                e2e_d2h(*state["pending"], gate)
+                e2e_d2h(state["pending"], gate)
                 state["pending"] = None
 
-        neck.prepared_hook = hook
+        neck.prepared_hook = hook if compute else None
         try:
             e2e_h2d(0)
             for i in range(steps):
@@ -351,19 +676,25 @@ def run_ours(args):
                 if i >= 2:
                     done[(i - 2) % 4].synchronize()
                 main.wait_event(ready[slot])
-                packed_dev, depth, feat = dev_in[slot]
-                metas = unpack_metas(packed_dev)
-                depth = depth.detach().requires_grad_()
-                feat = feat.detach().requires_grad_()
-                bev, _ = neck.view_transform([img_shape] + metas, depth, feat)
-                bev.backward(out_grad)
+                main.wait_event(d2h_done[slot])        # grad_dev[slot] has left for the host
+                if compute:
+                    metas, depth, feat = unpack(dev_in[slot])
+                    depth = depth.detach().requires_grad_()
+                    feat = feat.detach().requires_grad_()
+                    bev, _ = neck.view_transform([img_shape] + metas, depth, feat)
+                    bev.backward(out_grad)
+                    # one packed result buffer per step (two small device copies, one D2H)
+                    grad_dev[slot][:n_d].copy_(depth.grad.reshape(-1))
+                    grad_dev[slot][n_d:].copy_(feat.grad.reshape(-1))
+                else:
+                    hook()
                 consumed[slot].record(main)
                 done[i % 4].record(main)
-                state["pending"] = (slot, depth.grad, feat.grad)
+                state["pending"] = slot
         finally:
             neck.prepared_hook = None
         gate.record(main)
-        e2e_d2h(*state["pending"], gate)
+        e2e_d2h(state["pending"], gate)
         main.wait_stream(d2h_stream)
 
     def barrier():
@@ -371,72 +702,51 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, warmup, whole_loop=False):
+    def timed(fn, steps, warmup, whole_loop=False, min_seconds=0.0, max_repeats=400):
+        """W warm-up steps, then the K-step region (barrier + synchronize on both sides, CUDA
+        events, max over ranks) repeated until `min_seconds` of GPU time: returns the MEDIAN
+        region in ms, the launches of one region, the number of repeats and the total time."""
         if whole_loop:
             fn(warmup)
         else:
             for i in range(warmup):
                 fn(i)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        l0 = lib.veon_kernel_launch_count()
-        e0.record()
-        if whole_loop:
-            fn(steps)
-        else:
-            for i in range(steps):
-                fn(i)
-        e1.record()
-        barrier()
-        launches = lib.veon_kernel_launch_count() - l0
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        return float(ms.item()), launches
+
+        def region():
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            l0 = lib.veon_kernel_launch_count()
+            e0.record()
+            if whole_loop:
+                fn(steps)
+            else:
+                for i in range(steps):
+                    fn(i)
+            e1.record()
+            barrier()
+            launches = lib.veon_kernel_launch_count() - l0
+            ms = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            return float(ms.item()), launches
+        ms0, launches = region()
+        repeats = max(3, min(max_repeats, int(min_seconds * 1e3 / max(ms0, 1e-3)) + 1))
+        if world > 1:      # every rank must run the same number of regions (collectives inside)
+            r = torch.tensor([repeats], device=dev)
+            dist.broadcast(r, 0)
+            repeats = int(r.item())
+        all_ms = [ms0] + [region()[0] for _ in range(repeats - 1)]
+        s = sorted(all_ms)
+        return s[len(s) // 2], launches, len(all_ms), sum(all_ms) * 1e-3, s[0], s[-1]
 
     K, Wm = max(args.steps, 1), max(args.warmup, 3)
     with ClockSampler(local) as clocks:
-        ms_total, launches = timed(step_device, K, Wm)
-    ms_e2e, _ = timed(run_e2e, K, max(3, Wm // 2), whole_loop=True)
-
-    # ---- secondary: the same device-resident job with the index preparation of step i+1
-    # issued on a second stream, under the pooling kernels of step i.  The preparation only
-    # depends on the calibration (not on features or weights), so a training / serving loop can
-    # run it one step ahead through the public prepare_ranks() + pool_prepared() pair.  Reported
-    # next to `value` (which keeps the strictly sequential step), never instead of it.
-    prep_stream = torch.cuda.Stream(dev)
-    grid_vecs = (neck.grid_lower_bound, neck.grid_interval, neck.grid_size)
-
-    def run_pipelined(steps):
-        main = torch.cuda.current_stream(dev)
-        preps, evs = [None, None], [torch.cuda.Event(), torch.cuda.Event()]
-        used = [torch.cuda.Event(), torch.cuda.Event()]   # main is done with a slot's plan
-        for ev in used:
-            ev.record(main)
-
-        def prepare(i):
-            with torch.cuda.stream(prep_stream):
-                prep_stream.wait_event(used[i % 2])   # its buffers go back to this stream's pool
-                preps[i % 2] = None
-                preps[i % 2] = BP.prepare_ranks(dev_sets[i % n_sets][0], *grid_vecs)
-                evs[i % 2].record(prep_stream)
-        prepare(0)
-        for i in range(steps):
-            if i + 1 < steps:
-                prepare(i + 1)
-            _, depth, feat = dev_sets[i % n_sets]
-            depth = depth.detach().requires_grad_()
-            feat = feat.detach().requires_grad_()
-            main.wait_event(evs[i % 2])
-            prep = preps[i % 2]
-            bev = BP.pool_prepared(depth, feat.permute(0, 1, 3, 4, 2), prep,
-                                   neck._bev_shape(depth, feat.shape[2]))
-            if prep.plan.n_intervals == 0:          # the faithful path's read-back
-                raise RuntimeError("no point inside the grid")
-            bev.backward(out_grad)
-            used[i % 2].record(main)
-        prep_stream.wait_stream(main)
-    ms_pipe, _ = timed(run_pipelined, K, max(3, Wm // 2), whole_loop=True)
+        ms_total, launches, reps, total_s, ms_min, ms_max = timed(step_device, K, Wm,
+                                                                  min_seconds=args.min_seconds)
+    ms_e2e, _, reps_e2e, total_e2e, _, _ = timed(run_e2e, K, max(3, Wm // 2), whole_loop=True,
+                                                 min_seconds=args.min_seconds / 2)
+    ms_copy, _, _, _, _, _ = timed(lambda n: run_e2e(n, compute=False), K, 3, whole_loop=True,
+                                   min_seconds=0.2)
 
     # live per-call device times (CUDA events on the launching stream) over K more steps
     BP.enable_kernel_timing(True)
@@ -449,29 +759,26 @@ def run_ours(args):
     # counts for the algorithmic-byte denominators
     prep = BP.prepare_ranks(dev_sets[0][0], lower, interval, size)
     n_kept, n_int = prep.plan.n_points, prep.plan.n_intervals
+    del prep
     alg = algorithmic_bytes(cfg, B, n_kept, n_int)
 
-    peaks = {}
-    try:
-        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            peaks = json.load(f)
-    except Exception:
-        pass
-    peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "6650 GB/s (of fallback)"
-    traffic = None
+    traffic, traffic_src = None, None
     try:
         with open(os.path.join(ROOT, "profiles", "roofline_traffic.json")) as f:
-            traffic = json.load(f).get(args.workload, {}).get("pool_fwd_dram_bytes_per_launch")
+            tj = json.load(f).get(args.workload, {})
+            traffic = tj.get("pool_fwd_dram_bytes_per_launch")
+            traffic_src = "static, from profiles/roofline_traffic.json (" + tj.get("source", "ncu --set full") + ")"
     except Exception:
         pass
-    fwd_ms = avg.get("pool_fwd")
+    fwd_ms, bwd_ms = avg.get("pool_fwd"), avg.get("pool_bwd")
     achieved = alg["pool_fwd"] / (fwd_ms * 1e-3) / 1e9 if fwd_ms else None
+    fb = (alg["pool_fwd"] + alg["pool_bwd"]) / ((fwd_ms + bwd_ms) * 1e-3) / 1e9 \
+        if fwd_ms and bwd_ms else None
 
     value = world * B * K / (ms_total * 1e-3)
     e2e_value = world * B * K / (ms_e2e * 1e-3)
-    h2d = sum(x.numel() * x.element_size() for x in e2e_host[0])
-    d2h = dg_host[0].numel() * 4 + fg_host[0].numel() * 4
+    h2d = e2e_host[0].numel() * 4
+    d2h = grad_host[0].numel() * 4
 
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
@@ -479,145 +786,143 @@ def run_ours(args):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_dict(cfg, B, {
             "l2": f"inputs rotate over {n_sets} sets; each step streams a "
-                  f"{4 * 640000 * C * B / 1e9:.2f} GB volume (>> 126 MB L2)",
-            "host_sync_per_step": 0 if args.sync_free else 1,
-            "numa_node": numa_node,
+                  f"{4 * VOX * C * B / 1e9:.2f} GB volume (>> 126 MB L2)",
+            "host_sync_per_step": 0 if sync_free else 1,
+            "numa": numa,
             "n_kept": n_kept, "n_intervals": n_int}),
+        "timing": {"what": f"median of {reps} repeats of the {K}-step region "
+                           "(barrier + synchronize on both sides, CUDA events, max over ranks)",
+                   "repeats": reps, "timed_region_s_total": round(total_s, 3),
+                   "ms_per_step_min": ms_min / K, "ms_per_step_max": ms_max / K},
         "gpu_launches": int(launches),
         "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": ms_e2e / K,
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "what": "pinned host calibration+depth+feat -> LSSViewTransformer.view_transform "
-                        "(get_lidar_coor fused into prepare_v2, bev_pool_v2) -> backward -> depth_grad "
-                        "+ feat_grad to pinned host; copies on side streams, double-buffered, "
-                        "released from the neck's prepared_hook"},
-        "roofline": {"bound": "hbm", "kernel": "k_pool_fwd + k_pool_fwd_heavy (one veon_bev_pool_v2_fwd_planar call; the heavy-tile grid runs in the tail of the main grid)",
+                "repeats": reps_e2e, "timed_region_s_total": round(total_e2e, 3),
+                "copies_only_samples_per_s": world * B * K / (ms_copy * 1e-3),
+                "what": "ONE pinned buffer [calibration|depth|feat] host -> device, "
+                        "LSSViewTransformer.view_transform (get_lidar_coor fused into prepare_v2, "
+                        "bev_pool_v2) -> backward -> ONE pinned buffer [depth_grad|feat_grad] device -> "
+                        "host; copies on side streams, double-buffered, released from the neck's "
+                        "prepared_hook.  copies_only = the same transfers with no kernels between "
+                        "them: the ceiling the host side (PCIe + pinned-memory bandwidth shared by "
+                        "all ranks) sets"},
+        "roofline": {"bound": "hbm",
+                     "kernel": "veon_bev_pool_v2_fwd_planar: k_fwd_stream (role A rows -> L2 ring -> "
+                               "role E dense volume) + k_pool_fwd_heavy queued behind it",
                      "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                      "frac": (achieved / peak_gbs) if achieved else None, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": alg["pool_fwd"],
-                     "ms_per_launch": fwd_ms, "traffic": traffic},
-        "value_prepare_overlapped": {
-            "value": world * B * K / (ms_pipe * 1e-3), "unit": UNIT, "ms_per_step": ms_pipe / K,
-            "what": "same work per step; prepare_ranks() of step i+1 runs on a second stream under "
-                    "the pooling kernels of step i (it depends on the calibration only)"},
+                     "ms_per_launch": fwd_ms, "traffic": traffic, "traffic_source": traffic_src},
+        "roofline_fwd_bwd": {
+            "what": "north_star target quantity: bev_pool_v2 forward + backward, algorithmic bytes of "
+                    "both over the sum of their device times, against the measured HBM copy peak",
+            "achieved": fb, "peak": peak_gbs, "unit": "GB/s", "frac": (fb / peak_gbs) if fb else None,
+            "algorithmic_bytes": alg["pool_fwd"] + alg["pool_bwd"],
+            "ms": (fwd_ms + bwd_ms) if fwd_ms and bwd_ms else None},
         "phases_ms": {k: round(v, 4) for k, v in avg.items()},
         "phases_gbs_algorithmic": {
             k: round(alg[a] / (avg[k] * 1e-3) / 1e9, 1)
             for k, a in (("prepare_v2", "prepare"), ("pool_fwd", "pool_fwd"), ("pool_bwd", "pool_bwd"))
             if k in avg},
+        "phases_frac_of_hbm_peak": {
+            k: round(alg[a] / (avg[k] * 1e-3) / 1e9 / peak_gbs, 4)
+            for k, a in (("prepare_v2", "prepare"), ("pool_fwd", "pool_fwd"), ("pool_bwd", "pool_bwd"))
+            if k in avg},
         "clocks": clocks.summary(),
     }
-    # ---- secondary: the open-vocabulary tail (tcgen05 3xTF32 logits + fused argmax), reported
-    # as samples/s, algorithmic GB/s and fraction of the HBM roofline (it is HBM-bound: 9 flop/B)
-    if not args.no_tail:
-        from veon_b200.tail import class_of_prompt, voxel_text_argmax
-        Bt, Ct, Qt = 2, 512, 18
+    # free the headline buffers before the big secondary workloads
+    del dev_sets, e2e_host, grad_host, grad_dev, dev_in
+    torch.cuda.empty_cache()
+
+    if not args.no_extras:
+        # ---- the north-star pipeline with its one collective, at EVERY N
+        line["pipeline"] = pipeline_leg(dev, world, rank, peak_gbs)
+    if not args.no_extras and world == 1:
+        # ---- the other BASELINE workloads (device-resident inputs, public neck API)
+        line["workloads"] = [
+            lift_workload("C3: VEON ViT-B CLIP-dim lift, C=512, batch 8", "C3", 8, 512, dev, peak_gbs),
+            lift_workload("C4: VEON* ViT-L, 32x88 feats, D=118, C=768, batch 16", "C4", 16, 768,
+                          dev, peak_gbs, n_min=3, seconds=0.3),
+            lift_workload("VEON-real: LSSViewTransformerRaw, C=256, 32x88 feats, D=88, two-hot depth, "
+                          "2x2x2 max, batch 4", "C3", 4, 256, dev, peak_gbs, raw_neck=True),
+        ]
+        # ---- the reference's own CUDA kernels and flow on this GPU
+        rc = reference_cuda_leg(cfg, B, dev, peak_gbs)
+        if "unavailable" not in rc:
+            ours = {"prepare": avg.get("prepare_v2"), "pool_fwd": fwd_ms, "pool_bwd": bwd_ms}
+            rc["speedup_vs_reference_cuda"] = {
+                "prepare": rc["prepare_ms"] / ours["prepare"] if ours["prepare"] else None,
+                "pool_fwd": rc["pool_fwd_ms"] / ours["pool_fwd"] if ours["pool_fwd"] else None,
+                "pool_bwd": rc["pool_bwd_ms"] / ours["pool_bwd"] if ours["pool_bwd"] else None,
+                "step": rc["step_ms"] / (ms_total / K)}
+        line["reference_cuda"] = rc
+
+        # ---- the open-vocabulary tail (tcgen05 3xTF32 logits + fused argmax): HBM-bound, 9 flop/B
+        from veon_b200.tail import class_of_prompt, voxel_text_argmax, voxel_text_argmax_lowres
+        Bt, Ct = 2, 512
         gt = torch.Generator(device=dev).manual_seed(7)
         feat_occ = torch.sigmoid(torch.randn(Bt, Ct, 16, 200, 200, device=dev, generator=gt)) - 0.5
-        wt = torch.randn(Qt, Ct, device=dev, generator=gt)
-        wt = 100.0 * wt / wt.norm(dim=1, keepdim=True)
         bin_occ = torch.randn(Bt, 2, 16, 200, 200, device=dev, generator=gt)
-        cls_t = class_of_prompt(list(range(Qt - 1))).to(dev)
-        for _ in range(3):
-            voxel_text_argmax(feat_occ, wt, cls_t, bin_occ)
-        torch.cuda.synchronize()
-        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        nt = 10
-        t0.record()
-        for _ in range(nt):
-            voxel_text_argmax(feat_occ, wt, cls_t, bin_occ)
-        t1.record()
-        torch.cuda.synchronize()
-        ms_t = t0.elapsed_time(t1) / nt
-        bytes_t = Bt * (4 * 640000 * Ct + 8 * 640000 + 640000) + 4 * Qt * Ct
-        line["tail"] = {"what": f"veon_voxel_text_argmax, C={Ct}, Q={Qt} prompt rows, {Bt} samples/call, "
-                                "3xTF32 tcgen05 + fused class-max/argmax/gate -> uint8 [B,200,200,16]",
-                        "samples_per_s_per_gpu": Bt / (ms_t * 1e-3), "ms_per_call": ms_t,
-                        "achieved_gbs_algorithmic": bytes_t / (ms_t * 1e-3) / 1e9,
-                        "frac_of_hbm_peak": bytes_t / (ms_t * 1e-3) / 1e9 / peak_gbs,
-                        "tf32_tflops_issued": 3 * 2.0 * Bt * 640000 * Ct * 32 / (ms_t * 1e-3) / 1e12}
-        if world == 1:   # the two 8f-4 legs are single-GPU figures (every rank would repeat them)
-            # ---- secondary: the same tail from the decoder's resolution: the reference
-            # up-samples feat_occ [B,C,8,100,100] to 16x200x200 and classifies there; ours classifies
-            # the low-resolution volume (tcgen05) and interpolates the Q logit channels
-            from veon_b200.tail import voxel_text_argmax_lowres
-            Bl = 8
-            feat_lr = torch.sigmoid(torch.randn(Bl, Ct, 8, 100, 100, device=dev, generator=gt)) - 0.5
-            bin_lr = torch.randn(Bl, 2, 8, 100, 100, device=dev, generator=gt)
-            ws_lr = torch.empty(Bl * Qt * 80000, dtype=torch.float32, device=dev)
-            for _ in range(3):
-                voxel_text_argmax_lowres(feat_lr, wt, cls_t, bin_lr, workspace=ws_lr)
-            torch.cuda.synchronize()
-            t0.record()
-            for _ in range(nt):
-                voxel_text_argmax_lowres(feat_lr, wt, cls_t, bin_lr, workspace=ws_lr)
-            t1.record()
-            torch.cuda.synchronize()
-            ms_l = t0.elapsed_time(t1) / nt
-            bytes_l = Bl * (4 * 80000 * Ct + 8 * 80000 + 640000) + 4 * Qt * Ct
-            line["tail_lowres"] = {
-                "what": f"veon_voxel_text_argmax_lowres, C={Ct}, Q={Qt}, {Bl} samples/call, feat_occ "
-                        "[B,C,8,100,100] -> logits (tcgen05 3xTF32) -> trilinear up-sampling of the Q "
-                        "logits + class-max/argmax/gate -> uint8 [B,200,200,16]; equals the full-"
-                        "resolution route on >= 99.99 % of voxels (tests/test_tail_gpu.py)",
-                "samples_per_s_per_gpu": Bl / (ms_l * 1e-3), "ms_per_call": ms_l,
-                "achieved_gbs_algorithmic": bytes_l / (ms_l * 1e-3) / 1e9,
-                "frac_of_hbm_peak": bytes_l / (ms_l * 1e-3) / 1e9 / peak_gbs,
-                "speedup_vs_full_resolution_tail": (Bl / ms_l) / (Bt / ms_t)}
-            del feat_lr, bin_lr, ws_lr
-            # ---- secondary: BASELINE configs[2] as one pipeline, lift + classify (C=512, Q=18) with
-            # the classifier in front of the pooling (veon_b200.pipeline.lift_classify)
-            from veon_b200.pipeline import lift_classify
-            c3 = S.CONFIGS["C3"]
-            Bp, Np, Dp = 8, c3.n_cams, c3.D
-            Hp, Wp = c3.feat_hw
-            neck3 = LSSViewTransformer(c3.grid_config, c3.input_size, c3.downsample, 8, Ct,
-                                       collapse_z=False)
-            cal3 = S.calibration(c3, batch=Bp)
-            metas3 = [torch.from_numpy(cal3[k]).to(dev) for k in
-                      ("sensor2ego", "ego2global", "intrins", "post_rots", "post_trans", "bda")]
-            depth3 = torch.softmax(torch.randn(Bp * Np, Dp, Hp, Wp, device=dev, generator=gt) * 4, 1)
-            feat3 = torch.randn(Bp * Np, Ct, Hp, Wp, device=dev, generator=gt) * 0.05
-            gate_w = torch.randn(2, Ct, device=dev, generator=gt)
-            img3 = torch.zeros(Bp, Np, 1, Hp, Wp, device=dev)
-            for _ in range(3):
-                lift_classify(neck3, [img3] + metas3, depth3, feat3, wt, cls_t, gate_w)
-            torch.cuda.synchronize()
-            t0.record()
-            for _ in range(nt):
-                lift_classify(neck3, [img3] + metas3, depth3, feat3, wt, cls_t, gate_w)
-            t1.record()
-            torch.cuda.synchronize()
-            ms_p = t0.elapsed_time(t1) / nt
-            line["lift_classify"] = {
-                "what": f"C3 geometry (6 cams 32x88, D={Dp}), C={Ct} image features -> per-pixel logits "
-                        f"(tcgen05) -> get_lidar_coor + prepare_v2 + bev_pool_v2 forward of Q+2={Qt + 2} "
-                        "channels -> merge/argmax/gate -> uint8 [B,200,200,16]; equals pooling the C-channel "
-                        "features and classifying the volume on >= 99.99 % of voxels (tests/test_tail_gpu.py)",
-                "samples_per_call": Bp, "ms_per_call": ms_p,
-                "samples_per_s_per_gpu": Bp / (ms_p * 1e-3)}
-            del depth3, feat3, neck3
-        del feat_occ, bin_occ
-        # ---- secondary: the neck's 2x2x2 max-downsample of the pooled volume
-        vol = out_grad.detach().clone().requires_grad_()
-        go_ds = torch.randn(B, C, 8, 100, 100, device=dev, generator=gt)
 
-        def ev_ms(fn, n=10):
-            for _ in range(2):
+        def ev_ms(fn, seconds=0.3, n_min=10):
+            for _ in range(3):
                 fn()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            n = max(n_min, int(seconds * 1e3 / max(a.elapsed_time(b), 1e-3)))
             a.record()
             for _ in range(n):
                 fn()
             b.record()
             torch.cuda.synchronize()
             return a.elapsed_time(b) / n
+        SIZES = [16, 1, 1, 1, 8, 1, 1, 3, 1, 1, 1, 1, 5, 3, 5, 13, 4]
+        line["tail"] = []
+        for Qt in (18, 67):
+            refl = list(range(Qt - 1)) if Qt == 18 else [k for k, n in enumerate(SIZES) for _ in range(n)]
+            cls_t = class_of_prompt(refl).to(dev)
+            wt = torch.randn(Qt, Ct, device=dev, generator=gt)
+            wt = 100.0 * wt / wt.norm(dim=1, keepdim=True)
+            ms_t = ev_ms(lambda: voxel_text_argmax(feat_occ, wt, cls_t, bin_occ))
+            bytes_t = Bt * (4 * VOX * Ct + 8 * VOX + VOX) + 4 * Qt * Ct
+            line["tail"].append({
+                "what": f"veon_voxel_text_argmax, C={Ct}, Q={Qt} prompt rows, {Bt} samples/call, "
+                        "3xTF32 tcgen05 + fused class-max/argmax/gate -> uint8 [B,200,200,16]",
+                "samples_per_s_per_gpu": Bt / (ms_t * 1e-3), "ms_per_call": ms_t,
+                "achieved_gbs_algorithmic": bytes_t / (ms_t * 1e-3) / 1e9,
+                "frac_of_hbm_peak": bytes_t / (ms_t * 1e-3) / 1e9 / peak_gbs})
+        del feat_occ, bin_occ
+        # the same tail from the decoder's resolution
+        Bl, Qt = 8, 18
+        cls_t = class_of_prompt(list(range(Qt - 1))).to(dev)
+        wt = torch.randn(Qt, Ct, device=dev, generator=gt)
+        wt = 100.0 * wt / wt.norm(dim=1, keepdim=True)
+        feat_lr = torch.sigmoid(torch.randn(Bl, Ct, 8, 100, 100, device=dev, generator=gt)) - 0.5
+        bin_lr = torch.randn(Bl, 2, 8, 100, 100, device=dev, generator=gt)
+        ws_lr = torch.empty(Bl * Qt * 80000, dtype=torch.float32, device=dev)
+        ms_l = ev_ms(lambda: voxel_text_argmax_lowres(feat_lr, wt, cls_t, bin_lr, workspace=ws_lr))
+        bytes_l = Bl * (4 * 80000 * Ct + 8 * 80000 + VOX) + 4 * Qt * Ct
+        line["tail_lowres"] = {
+            "what": f"veon_voxel_text_argmax_lowres, C={Ct}, Q={Qt}, {Bl} samples/call, feat_occ "
+                    "[B,C,8,100,100] -> logits (tcgen05 3xTF32) -> trilinear up-sampling of the Q "
+                    "logits + class-max/argmax/gate -> uint8 [B,200,200,16]",
+            "samples_per_s_per_gpu": Bl / (ms_l * 1e-3), "ms_per_call": ms_l,
+            "achieved_gbs_algorithmic": bytes_l / (ms_l * 1e-3) / 1e9,
+            "frac_of_hbm_peak": bytes_l / (ms_l * 1e-3) / 1e9 / peak_gbs}
+        del feat_lr, bin_lr, ws_lr
+        # the neck's 2x2x2 max-downsample of the pooled volume
+        vol = out_grad.detach().clone().requires_grad_()
+        go_ds = torch.randn(B, C, 8, 100, 100, device=dev, generator=gt)
         with torch.no_grad():
             ms_df = ev_ms(lambda: BP.MaxDown2x2x2.apply(vol))
         ms_dfb = ev_ms(lambda: torch.autograd.grad(BP.MaxDown2x2x2.apply(vol), vol, go_ds))
         vb = 4.0 * vol.numel()
         line["downsample"] = {
             "what": "2x2x2 max-downsample of the [B,C,16,200,200] volume "
-                    "(view_transformer_raw.py:549-553) and ATen-exact gradient, own kernels",
+                    "(view_transformer_raw.py:549-553) and its gradient (to the first arg-max), own kernels",
             "fwd_ms": ms_df, "fwd_gbs": 1.125 * vb / (ms_df * 1e-3) / 1e9,
             "bwd_ms": ms_dfb - ms_df, "bwd_gbs": 2.25 * vb / ((ms_dfb - ms_df) * 1e-3) / 1e9,
             "frac_of_hbm_peak_fwd": 1.125 * vb / (ms_df * 1e-3) / 1e9 / peak_gbs}

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define VEON_ABI_VERSION 5
+#define VEON_ABI_VERSION 6
 
 #define VEON_E_BADARG    (-1)  /* NULL pointer / non-positive dimension          */
 #define VEON_E_WORKSPACE (-2)  /* workspace smaller than *_workspace_bytes()     */
@@ -276,12 +276,14 @@ int veon_maxdown2_bwd(const float* in, const float* out, const float* grad_out,
                       int64_t BC, int Z, int Y, int X, float* grad_in, void* stream);
 
 /* QuickCumsumCuda.backward (bev_pool.py:43-83) for a [B,C,Z,Y,X] out_grad.
- *   rows_ws      float[n_intervals * C] scratch (compacted gradient rows)
- *   ctrl_ws      int32[B + 1] scratch (work-queue ticket + per-sample completion
- *                counters of the fused single-launch kernel; NULL selects the
- *                two-launch path)
+ *   rows_ws      float scratch of at least veon_bev_pool_v2_bwd_workspace_floats() elements
+ *                (one compact gradient row per interval; rows_ws_floats says how many floats it
+ *                holds, VEON_E_WORKSPACE if too few)
  *   depth_grad   [B,N,D,H,W], feat_grad [B,N,H,W,C]: fully written (no need to
- *                zero).  Deterministic: no atomics, fixed summation order. */
+ *                zero).  Deterministic: no atomics, fixed summation order.
+ *   Two launches: a row pass over the occupied 32-voxel tiles of out_grad and a pixel pass. */
+size_t veon_bev_pool_v2_bwd_workspace_floats(int64_t n_intervals, int B, int N, int D, int H,
+                                             int W, int C, int64_t voxels_per_sample);
 int veon_bev_pool_v2_bwd_planar(const float* out_grad,
                                 const float* depth, const float* feat,
                                 const int32_t* tile_istart,
@@ -290,7 +292,7 @@ int veon_bev_pool_v2_bwd_planar(const float* out_grad,
                                 int64_t n_intervals,
                                 int B, int N, int D, int H, int W, int C,
                                 int64_t voxels_per_sample,
-                                float* rows_ws, int32_t* ctrl_ws,
+                                float* rows_ws, int64_t rows_ws_floats,
                                 float* depth_grad, float* feat_grad,
                                 void* stream);
 

@@ -60,9 +60,11 @@ _SIGNATURES = {
     "veon_bev_pool_v2_fwd_workspace_bytes": (c_size_t, [c_int, c_int, c_int64]),
     "veon_bev_pool_v2_fwd_planar": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64,
                                             c_int, c_int, c_int64, c_int64, _P, _P, c_size_t, _P]),
+    "veon_bev_pool_v2_bwd_workspace_floats": (c_size_t, [c_int64, c_int, c_int, c_int, c_int, c_int,
+                                                         c_int, c_int64]),
     "veon_bev_pool_v2_bwd_planar": (c_int, [_P, _P, _P, _P, _P, _P, c_int64,
                                             c_int, c_int, c_int, c_int, c_int, c_int, c_int64,
-                                            _P, _P, _P, _P, _P]),
+                                            _P, c_int64, _P, _P, _P]),
     "veon_voxel_text_argmax": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int,
                                        c_int, _P, _P]),
     "veon_semantic_inference_3d": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P]),

@@ -589,13 +589,13 @@ def _bwd_planar(grad_planar, depth, feat, rb, ist, plan, C):
     with torch.cuda.device(dev):
         depth_grad = torch.empty_like(depth)
         feat_grad = torch.empty_like(feat)
-        rows = torch.empty(max(n_int, 1) * C, dtype=torch.float32, device=dev)
-        ctrl = torch.empty(B + 1, dtype=torch.int32, device=dev)
+        n_rows = lib.veon_bev_pool_v2_bwd_workspace_floats(n_int, B, N, D, H, W, C, plan.V)
+        rows = torch.empty(max(n_rows, 1), dtype=torch.float32, device=dev)
         with _timed("pool_bwd", dev):
             rc = lib.veon_bev_pool_v2_bwd_planar(
                 _ptr(grad_planar), _ptr(depth), _ptr(feat), _ptr(plan.tile_istart),
                 _ptr(plan.tile_occ), _ptr(plan.point_interval), n_int, B, N, D, H, W, C, plan.V,
-                _ptr(rows), _ptr(ctrl), _ptr(depth_grad), _ptr(feat_grad), _stream_ptr(dev))
+                _ptr(rows), rows.numel(), _ptr(depth_grad), _ptr(feat_grad), _stream_ptr(dev))
     _lib.check(rc, "veon_bev_pool_v2_bwd_planar")
     return depth_grad, feat_grad
 

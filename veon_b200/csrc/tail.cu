@@ -122,21 +122,16 @@ static int tail_dispatch(const float* feat_occ, const float* text_w,
                          const int32_t* class_of_prompt, const float* bin_occ, int B, int C,
                          int Q, int Z, int Y, int X, int free_label, uint8_t* labels,
                          float* logits, cudaStream_t stream) {
-  {  // tcgen05 path unless VEON_TAIL_IMPL=ffma or the shape does not fit (C % 32, V % 4, Q > 128)
-    static int use_tc = -1;
-    if (use_tc < 0) {
-      const char* e = getenv("VEON_TAIL_IMPL");
-      use_tc = (e && e[0] == 'f') ? 0 : 1;
-    }
-    if (use_tc) {
-      const int rc = veon_tail_tc_launch(feat_occ, text_w, class_of_prompt, bin_occ, B, C, Q, Z, Y, X,
-                                         free_label, labels, logits, stream);
-      if (rc != VEON_E_UNSUPPORTED) return rc;
-    }
+  {  // tcgen05 path unless the shape does not fit it (C % 32, V % 4, Q > 128)
+    const int rc = veon_tail_tc_launch(feat_occ, text_w, class_of_prompt, bin_occ, B, C, Q, Z, Y, X,
+                                       free_label, labels, logits, stream);
+    if (rc != VEON_E_UNSUPPORTED) return rc;
   }
   const size_t smem = sizeof(float) * (size_t)kTailQT * C;
   if (smem > 200 * 1024) return VEON_E_UNSUPPORTED;
-  static size_t attr_smem = 48 * 1024;
+  static size_t attr_smem_dev[kMaxDevices] = {};
+  size_t& attr_smem = attr_smem_dev[current_device()];
+  if (attr_smem == 0) attr_smem = 48 * 1024;
   if (smem > attr_smem) {
     VEON_CUDA_TRY(cudaFuncSetAttribute(k_voxel_text_argmax<false>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

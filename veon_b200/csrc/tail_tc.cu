@@ -426,7 +426,8 @@ using namespace veon;
 // logits != nullptr: write sem_occ [B,Q,V] (cls / bin_occ / labels unused).
 template <int WP, bool LOGITS>
 static int launch_variant(const tc::Params& p, unsigned grid, size_t smem, cudaStream_t stream) {
-  static size_t attr_smem = 0;
+  static size_t attr_smem_dev[kMaxDevices] = {};   // per device: one process may drive several GPUs
+  size_t& attr_smem = attr_smem_dev[current_device()];
   if (smem > attr_smem) {
     VEON_CUDA_TRY(cudaFuncSetAttribute(tc::k_tail_tc<WP, LOGITS>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
