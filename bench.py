@@ -526,7 +526,55 @@ def pipeline_leg(dev, world, rank, peak_gbs, batches=(8, 16, 32, 64), Qs=(18, 67
                          "gather_verified": ok})
             del depth, feat, img, metas
             torch.cuda.empty_cache()
-    return {"what": "lift_classify (C3 geometry: 6 cams 32x88, D=88, C=512 image features -> per-pixel "
+    sharded = None
+    if world > 1:
+        # ---- fewer samples than GPUs: the CAMERAS of every sample are dealt over the
+        # ranks, one NCCL all-reduce sums the [B,Q+2,Z,Y,X] logit volumes, everyone classifies
+        from veon_b200.dist import lift_classify_camera_sharded
+        Bc, Q = 2, 18
+        gs = torch.Generator(device=dev).manual_seed(77)            # the SAME inputs on every rank
+        cls_t = class_of_prompt(list(range(Q - 1))).to(dev)
+        wt = torch.randn(Q, Ct, device=dev, generator=gs)
+        wt = 100.0 * wt / wt.norm(dim=1, keepdim=True)
+        gate_w = torch.randn(2, Ct, device=dev, generator=gs)
+        cal = S.calibration(c3, batch=Bc, sample_offset=5000)
+        metas = [torch.from_numpy(cal[k]).to(dev) for k in KEYS]
+        depth = torch.softmax(torch.randn(Bc * N, D, H, W, device=dev, generator=gs) * 4, 1)
+        feat = torch.randn(Bc * N, Ct, H, W, device=dev, generator=gs) * 0.05
+        img = torch.zeros(Bc, N, 1, H, W, device=dev)
+
+        def one_sharded():
+            return lift_classify_camera_sharded(neck, [img] + metas, depth, feat, wt, cls_t, gate_w)
+        lab = one_sharded()
+        ref = lift_classify(neck, [img] + metas, depth, feat, wt, cls_t, gate_w)
+        agree = float((lab == ref).float().mean())
+        for _ in range(2):
+            one_sharded()
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            one_sharded()
+        e1.record()
+        dist.barrier()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1) / 10], device=dev, dtype=torch.float64)
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        e0.record()
+        for _ in range(10):
+            lift_classify(neck, [img] + metas, depth, feat, wt, cls_t, gate_w)
+        e1.record()
+        torch.cuda.synchronize()
+        sharded = {"what": f"camera-group sharding: {Bc} samples on {world} GPUs, each rank lifts the "
+                           f"logits of its cameras (6 cameras dealt round-robin), one all-reduce of the "
+                           f"[{Bc},20,16,200,200] volume ({Bc * 20 * VOX * 4 / 1e6:.0f} MB), classify",
+                   "samples": Bc, "ms_per_step": float(ms.item()),
+                   "samples_per_s": Bc / (float(ms.item()) * 1e-3),
+                   "one_gpu_unsharded_ms": e0.elapsed_time(e1) / 10,
+                   "labels_agree_with_unsharded": agree}
+    return {"camera_sharded": sharded,
+            "what": "lift_classify (C3 geometry: 6 cams 32x88, D=88, C=512 image features -> per-pixel "
                     "logits on tcgen05 -> get_lidar_coor + prepare_v2 + bev_pool_v2 of Q+2 channels -> "
                     "merge/argmax/gate -> uint8 [B,200,200,16]) + all_gather_occupancy over NCCL on a "
                     "side stream; weak scaling, samples dealt round-robin; max over ranks",

@@ -187,6 +187,35 @@ int veon_prepare_v2_calib(const float* frustum, const float* sensor2ego, const f
                           void* xform_workspace, size_t xform_workspace_bytes,
                           void* workspace, size_t workspace_bytes, void* stream);
 
+/* veon_prepare_v2_calib with an inference-time point filter: a point whose depth
+ * weight depth[b,n,d,h,w] is <= depth_eps is dropped like an out-of-grid point.  VEON's two-hot
+ * depth (view_transformer_raw.py:406-429) leaves most bins at the e^-16 clamp, i.e. ~1e-7 of
+ * the weight: with depth_eps = 1e-6 about 90 % of the points carry no signal and leave the
+ * pooled volume unchanged to ~1e-6 relative.  The gradient of a dropped point is zero, so this
+ * is for inference; depth_eps >= 0. */
+int veon_prepare_v2_calib_sparse(const float* frustum, const float* sensor2ego,
+                                 const float* cam2imgs, const float* post_rots,
+                                 const float* post_trans, const float* bda,
+                                 const float* depth, float depth_eps,
+                                 int B, int N, int D, int H, int W,
+                                 const float* lower, const float* interval, const float* grid_size,
+                                 int32_t* ranks_bev, int32_t* ranks_depth, int32_t* ranks_feat,
+                                 int32_t* interval_starts, int32_t* interval_lengths,
+                                 int64_t* counts, int64_t* counts_host,
+                                 int32_t* tile_start, int32_t* tile_istart, uint32_t* tile_occ,
+                                 int32_t* tile_heavy, int32_t* point_interval,
+                                 void* xform_workspace, size_t xform_workspace_bytes,
+                                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* 64-bit hash of the BITS of the five calibration tensors get_lidar_coor consumes (layouts as in
+ * veon_lidar_coor), written to `out` -- device memory or pinned host memory the device can
+ * write (then readable after an event on `stream`, no copy).  Key of a rank cache that
+ * generalises the reference's `accelerate` mode (view_transformer.py:154-173) to any number of
+ * recurring rigs. */
+int veon_calib_hash(const float* sensor2ego, const float* cam2imgs, const float* post_rots,
+                    const float* post_trans, const float* bda, int B, int N, uint64_t* out,
+                    void* stream);
+
 /* Build the same plan from rank arrays the caller already holds (the
  * `accelerate=True` cache, view_transformer.py:154-173, or any user input) and
  * validate them.  *flags (device int32) receives an OR of VEON_PLAN_* bits; the
@@ -330,6 +359,16 @@ int veon_voxel_text_argmax(const float* feat_occ, const float* text_w,
 int veon_semantic_inference_3d(const float* text_w, const float* feat_occ,
                                int B, int C, int Q, int Z, int Y, int X,
                                float* sem_occ, void* stream);
+
+/* Training-time voxel x text arg-max over a point list (Proj2Dto3DLoss,
+ * loss/occ_loss_utils/occ3d_nuscenes.py:472-482): logits [Q, ldn] = the Q prompt rows (no
+ * background row) over N <= ldn points, as veon_semantic_inference_3d writes them for a [C, N]
+ * operand; class_of_prompt [Q] non-decreasing merged class of each row
+ * (_merge_classes_prob, :249-265).  prompt_idx[n] = arg-max prompt, class_idx[n] = arg-max of
+ * the per-class maxima; first index on ties, like torch.max(dim).indices.  int64 outputs. */
+int veon_point_text_argmax(const float* logits, const int32_t* class_of_prompt, int Q,
+                           int64_t N, int64_t ldn, int64_t* prompt_idx, int64_t* class_idx,
+                           void* stream);
 
 /* ------------------------------------------------------------------------
  * (5) Tail at the decoder's resolution.  The reference

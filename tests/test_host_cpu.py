@@ -207,6 +207,61 @@ def test_all_gather_occupancy_world_size_2_gloo(tmp_path):
         assert "ok" in o
 
 
+def test_shard_cameras():
+    from veon_b200.dist import shard_cameras
+    for n, g in ((6, 1), (6, 2), (6, 4), (6, 8), (5, 3)):
+        seen = sorted(c for r in range(g) for c in shard_cameras(n, g, r))
+        assert seen == list(range(n))
+    with pytest.raises(ValueError):
+        shard_cameras(6, 2, 2)
+
+
+_CAM_WORKER = r"""
+import os, sys, types, torch, torch.distributed as dist
+sys.path.insert(0, {root!r})
+import veon_b200.dist as VD, veon_b200.pipeline as VP, veon_b200.tail as VT
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+r = dist.get_rank()
+# stand-ins for the two CUDA stages (this test is about the sharding logic, on the CPU): the
+# "lift" of a camera group is the sum of its cameras' per-camera volumes, the classifier an argmax
+B, N, Q, Z, Y, X = 2, 6, 5, 2, 3, 4
+g = torch.Generator().manual_seed(0)
+per_cam = torch.randn(N, B, 8, Z, Y, X, generator=g)            # same on both ranks
+seen = []
+def fake_lift_logits(neck, input, depth, feat, w, gate, channel_pad=4, cameras=None):
+    seen.append(list(cameras))
+    return per_cam[list(cameras)].sum(0).clone()
+def fake_classify(sem, gate, cls, free_label=17):
+    return sem.argmax(1).to(torch.uint8)
+VP.lift_logits = fake_lift_logits
+VT.classify_logits = fake_classify
+neck = types.SimpleNamespace()
+inp = [torch.zeros(B, N, 1, 2, 2)] + [None] * 6
+w = torch.zeros(Q, 4)
+lab = VD.lift_classify_camera_sharded(neck, inp, None, torch.zeros(B * N, 4, 2, 2), w, None, None)
+assert seen == [VD.shard_cameras(N, 2, r)], seen
+want = per_cam.sum(0)[:, :Q].argmax(1).to(torch.uint8)
+assert torch.equal(lab, want), (lab.shape, want.shape)
+dist.destroy_process_group()
+print("rank", r, "ok")
+"""
+
+
+def test_camera_group_sharding_world_size_2_gloo(tmp_path):
+    """every rank lifts ITS cameras, one all-reduce sums the logit volumes, all ranks classify the
+    same sum (the CUDA stages are replaced by stand-ins: the host logic is what runs here)"""
+    import socket
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    script = tmp_path / "c.py"
+    script.write_text(_CAM_WORKER.format(root=ROOT, port=port))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+        assert "ok" in o
+
+
 @pytest.mark.needs_reference
 def test_operator_surface_matches_reference_call_sites():
     """CPU-side drop-in check (the GPU-side one needs both a GPU and
@@ -311,3 +366,24 @@ def test_ext_stand_in_has_the_pybind_surface_and_refuses_cpu_tensors():
     i = torch.zeros(1, dtype=torch.int32)
     with pytest.raises(RuntimeError):
         ext.bev_pool_v2_forward(t, t, t, i, i, i, i, i)
+
+
+def test_prepare_vocabulary_matches_the_reference_expression():
+    """san_in_veon_temporal.py:261-266 over clip_utils/classifier.py:107-112: exp(logit_scale) x
+    L2-normalised [text rows ; background row], detached; and the semkitti re-ordering is refused"""
+    import torch
+    import torch.nn.functional as F
+    from veon_b200.tail import class_of_prompt, prepare_vocabulary
+    g = torch.Generator().manual_seed(0)
+    emb = torch.randn(66, 512, generator=g)
+    bg = torch.randn(1, 512, generator=g) * 512 ** -0.5
+    logit_scale = torch.tensor(4.6052, requires_grad=True)
+    want = logit_scale.exp() * F.normalize(torch.cat([emb, bg], dim=0), p=2, dim=-1)
+    got = prepare_vocabulary(emb, bg, logit_scale)
+    assert got.shape == (67, 512) and not got.requires_grad
+    assert torch.allclose(got, want.detach(), rtol=0, atol=1e-5)
+    with pytest.raises(NotImplementedError):
+        class_of_prompt([0, 0, 1], mode="semkitti")
+    # loss-side grouping (no background row): occ3d_nuscenes.py:249-265
+    assert class_of_prompt([0, 0, 1, 2, 2], background=False).tolist() == [0, 0, 1, 2, 2]
+    assert class_of_prompt([0, 0, 1, 2, 2]).tolist() == [0, 0, 1, 2, 2, 3]

@@ -274,3 +274,103 @@ def test_fused_geometry_gives_the_same_ranks_and_volume():
     neck.fuse_geometry = False
     plain, _ = neck.view_transform([img] + metas, depth, feat)
     assert torch.equal(fused, plain)
+
+
+# ---- round 2: calibration-keyed rank cache (8f-3), negligible-depth skip (8f-2), range check ------
+def test_rank_cache_keyed_on_the_calibration():
+    """`rank_cache=N` keeps the prepared ranks of the last N calibrations (64-bit hash of the
+    calibration tensors' bits): same volume bit for bit, the preparation runs once per rig, a
+    changed calibration is a miss, and the least recently used rig is the one that is dropped."""
+    from veon_b200 import bev_pool as BP
+    from veon_b200.view_transformer import LSSViewTransformer
+    cfg = S.CONFIGS["small"]
+    B, C = 2, 32
+    plain = LSSViewTransformer(cfg.grid_config, cfg.input_size, cfg.downsample, 8, C, collapse_z=False)
+    cached = LSSViewTransformer(cfg.grid_config, cfg.input_size, cfg.downsample, 8, C,
+                                collapse_z=False, rank_cache=2)
+    img, metas, depth, feat = inputs(cfg, B, C, seed=21)
+    rigs = [metas]
+    for k in (1, 2):                       # two more rigs: a shifted and a rotated one
+        m = [t.clone() for t in metas]
+        m[0][..., :3, 3] += 0.05 * k
+        m[4][..., 0] += 2.0 * k
+        rigs.append(m)
+    want = [plain.view_transform([img] + m, depth, feat)[0] for m in rigs]
+    order = [0, 0, 1, 0, 1, 2, 0, 1]
+    BP.enable_kernel_timing(True)
+    for i in order:
+        # fresh tensor objects every call: the key is the VALUES, not the objects
+        got, _ = cached.view_transform([img] + [t.clone() for t in rigs[i]], depth, feat)
+        assert torch.equal(got, want[i])
+    n_prepare = len(BP.kernel_timings_ms().get("prepare_v2", []))
+    BP.enable_kernel_timing(False)
+    # two slots, least recently used out: misses at calls 1 (rig 0), 3 (rig 1), 6 (rig 2, drops
+    # rig 0), 7 (rig 0, drops rig 1), 8 (rig 1, drops rig 2) => 5 preparations for 8 calls
+    assert cached.rank_cache_misses == n_prepare == 5 and cached.rank_cache_hits == 3
+    # a single changed bit is a different rig
+    assert BP.calib_hash(*[rigs[0][k] for k in (0, 2, 3, 4, 5)]) != \
+        BP.calib_hash(*[rigs[1][k] for k in (0, 2, 3, 4, 5)])
+    assert BP.calib_hash(*[rigs[0][k] for k in (0, 2, 3, 4, 5)]) == \
+        BP.calib_hash(*[rigs[0][k].clone() for k in (0, 2, 3, 4, 5)])
+
+
+def test_negligible_depth_bins_can_be_skipped_at_inference():
+    """with VEON's two-hot depth (view_transformer_raw.py:406-429, clamp at -16) most
+    bins weigh ~e^-16 of their pixel.  depth_eps drops them before they are ranked: far fewer
+    points, the pooled volume within the north_star tolerance (max-abs <= 1e-3 relative; in fact
+    ~1e-6), and the exact path whenever a gradient is wanted."""
+    from veon_b200 import bev_pool as BP
+    from veon_b200.view_transformer import LSSViewTransformerRaw
+    cfg = S.CONFIGS["C1"]
+    B, C = 2, 64
+    H, W = cfg.feat_hw
+    img, metas, _, feat = inputs(cfg, B, C, seed=22)
+    exact = LSSViewTransformerRaw(cfg.grid_config, cfg.input_size, cfg.downsample, 8, C, use_ds=False)
+    sparse = LSSViewTransformerRaw(cfg.grid_config, cfg.input_size, cfg.downsample, 8, C, use_ds=False,
+                                   depth_eps=1e-6)
+    metric = torch.from_numpy(S.metric_depth_np(cfg, batch=B)).cuda()
+    depth5 = exact.get_two_hot_depth(metric)                       # [B,N,D,H,W], peaky
+    assert float((depth5 > 1e-6).float().mean()) < 0.15
+    feat5 = feat.view(B, cfg.n_cams, C, H, W)
+    with torch.no_grad():
+        a = exact([feat5] + metas, depth5)
+        b = sparse([feat5] + metas, depth5)
+    assert a.shape == b.shape == (B, C, 16, 200, 200)
+    err = float((a - b).abs().max() / a.abs().max())
+    assert err <= 1e-3, err
+    assert err <= 1e-5, err
+    # the point list really shrank
+    fr = exact._frustum_on(metas[0].device)
+    grid = (exact.grid_lower_bound, exact.grid_interval, exact.grid_size)
+    full = BP.prepare_ranks_calib(fr, metas[0], metas[2], metas[3], metas[4], metas[5], *grid)
+    thin = BP.prepare_ranks_calib(fr, metas[0], metas[2], metas[3], metas[4], metas[5], *grid,
+                                  depth=depth5, depth_eps=1e-6)
+    assert thin.plan.n_points < 0.2 * full.plan.n_points
+    kept = thin.ranks_depth[:thin.plan.n_points].long()
+    assert bool((depth5.reshape(-1)[kept] > 1e-6).all())
+    # training: depth_eps is ignored, gradients are the exact ones
+    f1 = feat5.detach().clone().requires_grad_()
+    f2 = feat5.detach().clone().requires_grad_()
+    go = torch.randn(a.shape, generator=torch.Generator().manual_seed(1)).cuda()
+    exact([f1] + metas, depth5).backward(go)
+    sparse([f2] + metas, depth5).backward(go)
+    assert torch.equal(f1.grad, f2.grad)
+
+
+def test_out_of_range_ranks_are_refused():
+    """The reference checks nothing (bev_pool.cpp has no CHECK_* macros: a bad rank is a silent
+    out-of-bounds access); here a plan flagged VEON_PLAN_OUT_OF_RANGE raises."""
+    from veon_b200.bev_pool import bev_pool_v2
+    B, N, D, H, W, C = 1, 1, 2, 2, 2, 4
+    depth = torch.rand(B, N, D, H, W, device="cuda")
+    feat = torch.rand(B, N, H, W, C, device="cuda")
+    rd = torch.tensor([0, 4, 1, 6], dtype=torch.int32, device="cuda")
+    rf = torch.tensor([0, 0, 1, 2], dtype=torch.int32, device="cuda")
+    st = torch.tensor([0, 2], dtype=torch.int32, device="cuda")
+    ln = torch.tensor([2, 2], dtype=torch.int32, device="cuda")
+    for bad in (dict(rb=[0, 0, 1, 99]), dict(rd=[0, 4, 1, 8]), dict(rf=[0, 0, 1, 4])):
+        r = dict(rb=[0, 0, 1, 1], rd=rd.tolist(), rf=rf.tolist())
+        r.update(bad)
+        t = {k: torch.tensor(v, dtype=torch.int32, device="cuda") for k, v in r.items()}
+        with pytest.raises(ValueError):
+            bev_pool_v2(depth, feat, t["rd"], t["rf"], t["rb"], (1, 1, 2, 2, C), st, ln)

@@ -328,3 +328,92 @@ def test_full_volume_c512_q18_and_q67():
         assert float((got == want).mean()) >= 0.9999
         want64 = O.voxel_text_labels(feat.numpy(), w.numpy(), cls, bin_occ.numpy(), dtype=np.float64)
         assert float((got == want64).mean()) >= 0.9999
+
+
+# ---- training-time arg-max over point lists, camera-group sharding ----------
+def _loss_merge(tensor, class_reflection):
+    """loss/occ_loss_utils/occ3d_nuscenes.py:249-265 (_merge_classes_prob, dim=1), literally"""
+    dim_length = tensor.shape[1]
+    assert dim_length == len(class_reflection)
+    merged, left = [], 0
+    while left < dim_length:
+        right = left
+        while right < dim_length - 1 and class_reflection[left] == class_reflection[right + 1]:
+            right += 1
+        merged.append(tensor[:, left:right + 1].max(dim=1, keepdim=True).values)
+        left = right + 1
+    return torch.cat(merged, dim=1)
+
+
+@pytest.mark.parametrize("N,C,refl", [
+    (50000, 512, [k for k, n in enumerate(SIZES) for _ in range(n)]),   # real 66 prompts, ViT-B dim
+    (12345, 768, list(range(17))),                                        # N % 4 != 0, ViT-L dim
+    (777, 30, [0, 0, 1, 2, 2, 2]),                                        # FFMA logits path
+    (0, 64, [0, 1]),
+])
+def test_point_text_argmax_matches_the_loss_expressions(N, C, refl):
+    """occ3d_nuscenes.py:472-482: einsum('nc,dc->nd', feat, W[:-1]) -> max(dim=1).indices and the
+    merged-class arg-max.  Checked against the same torch expressions in float64: equal wherever
+    the decision margin exceeds the logit tolerance, >= 99.99 % overall."""
+    from veon_b200.tail import point_text_argmax
+    g = torch.Generator().manual_seed(N + C)
+    feat = torch.sigmoid(torch.randn(N, C, generator=g)) - 0.5
+    w = torch.randn(len(refl) + 1, C, generator=g)
+    w = 100.0 * w / w.norm(dim=1, keepdim=True)
+    p_idx, c_idx = point_text_argmax(feat.cuda(), w.cuda(), refl)
+    torch.cuda.synchronize()
+    assert p_idx.shape == c_idx.shape == (N,) and p_idx.dtype == c_idx.dtype == torch.int64
+    if N == 0:
+        return
+    probs = torch.einsum("nc,dc->nd", feat.double(), w[:-1].double())
+    want_p = probs.max(dim=1).indices
+    merged = _loss_merge(probs, refl)
+    want_c = merged.max(dim=1).indices
+    p_idx, c_idx = p_idx.cpu(), c_idx.cpu()
+    assert float((p_idx == want_p).float().mean()) >= 0.9999
+    assert float((c_idx == want_c).float().mean()) >= 0.9999
+    scale = probs.abs().max()
+    chosen_p = probs.gather(1, p_idx[:, None]).squeeze(1)
+    chosen_c = merged.gather(1, c_idx[:, None]).squeeze(1)
+    assert float(((probs.max(1).values - chosen_p) / scale).max()) <= 2e-5
+    assert float(((merged.max(1).values - chosen_c) / scale).max()) <= 2e-5
+
+
+def test_camera_group_sharding_sums_to_the_unsharded_labels():
+    """SURVEY 8e, B < G: the logit volumes of disjoint camera groups add up to the full one
+    (pooling is linear), so all-reducing them and classifying gives the unsharded labels up to
+    float re-association: >= 99.99 % of voxels.  (Two 'ranks' emulated in one process; the
+    all-reduce itself runs in tests/test_host_cpu.py over gloo and in bench.py over NCCL.)"""
+    from veon_b200 import synthetic as S
+    from veon_b200.dist import shard_cameras
+    from veon_b200.pipeline import lift_classify, lift_logits
+    from veon_b200.tail import class_of_prompt, classify_logits
+    from veon_b200.view_transformer import LSSViewTransformer
+    cfg = S.CONFIGS["small"]
+    B, C = 1, 64
+    refl = list(range(17))
+    Q = len(refl) + 1
+    H, W = cfg.feat_hw
+    g = torch.Generator().manual_seed(14)
+    cal = S.calibration(cfg, batch=B)
+    metas = [torch.from_numpy(cal[k]).cuda() for k in
+             ("sensor2ego", "ego2global", "intrins", "post_rots", "post_trans", "bda")]
+    depth = torch.softmax(torch.randn(B * cfg.n_cams, cfg.D, H, W, generator=g) * 4, dim=1).cuda()
+    feat = (torch.randn(B * cfg.n_cams, C, H, W, generator=g) * 0.05).cuda()
+    w = torch.randn(Q, C, generator=g)
+    w = (100.0 * w / w.norm(dim=1, keepdim=True)).cuda()
+    gate_w = torch.randn(2, C, generator=g).cuda()
+    cls = class_of_prompt(refl).cuda()
+    img = torch.zeros(B, cfg.n_cams, 8, H, W, device="cuda")
+    neck = LSSViewTransformer(cfg.grid_config, cfg.input_size, cfg.downsample, 8, C, collapse_z=False)
+    want = lift_classify(neck, [img] + metas, depth, feat, w, cls, gate_w)
+    for world in (2, 3):
+        vol = None
+        for r in range(world):
+            part = lift_logits(neck, [img] + metas, depth, feat, w, gate_w,
+                               cameras=shard_cameras(cfg.n_cams, world, r))
+            vol = part if vol is None else vol + part
+        got = classify_logits(vol[:, :Q], vol[:, Q:Q + 2], cls, 17)
+        torch.cuda.synchronize()
+        assert got.shape == want.shape
+        assert float((got == want).float().mean()) >= 0.9999

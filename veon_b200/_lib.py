@@ -54,6 +54,11 @@ _SIGNATURES = {
     "veon_prepare_v2_calib": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int,
                                       _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
                                       _P, c_size_t, _P, c_size_t, _P]),
+    "veon_prepare_v2_calib_sparse": (c_int, [_P, _P, _P, _P, _P, _P, _P, ctypes.c_float,
+                                             c_int, c_int, c_int, c_int, c_int,
+                                             _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P,
+                                             _P, c_size_t, _P, c_size_t, _P]),
+    "veon_calib_hash": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, _P, _P]),
     "veon_pool_plan_build": (c_int, [_P, _P, _P, _P, _P, c_int64, c_int64,
                                      c_int, c_int, c_int, c_int, c_int, c_int64,
                                      _P, _P, _P, _P, _P, _P, _P]),
@@ -68,6 +73,7 @@ _SIGNATURES = {
     "veon_voxel_text_argmax": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int,
                                        c_int, _P, _P]),
     "veon_semantic_inference_3d": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P]),
+    "veon_point_text_argmax": (c_int, [_P, _P, c_int, c_int64, c_int64, _P, _P, _P]),
     "veon_upsample_classify": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                        c_int, c_int, _P, _P]),
     "veon_classify_logits": (c_int, [_P, c_int64, _P, c_int64, _P, c_int, c_int, c_int, c_int, c_int,

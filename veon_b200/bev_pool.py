@@ -30,6 +30,7 @@ __all__ = ["bev_pool_v2", "QuickCumsumCuda", "TRTBEVPoolv2",
            "pool_prepared", "lidar_coor"]
 
 LAYOUT_BZYXC, LAYOUT_BCZYX = 0, 1
+PLAN_OUT_OF_RANGE = 8       # VEON_PLAN_OUT_OF_RANGE
 TILE_VOXELS = 32
 
 
@@ -184,17 +185,53 @@ def _counts_slot(dev):
 
 
 def prepare_ranks_calib(frustum, sensor2ego, cam2imgs, post_rots, post_trans, bda,
-                        grid_lower_bound, grid_interval, grid_size):
+                        grid_lower_bound, grid_interval, grid_size, depth=None, depth_eps=None):
     """`prepare_ranks(lidar_coor(...))` in one call with the geometry fused into the
     classification kernel: the [B,N,D,H,W,3] coordinate tensor is never written.
-    Same ranks, bit for bit."""
+    Same ranks, bit for bit.
+
+    depth [B,N,D,H,W] + depth_eps (inference only): points whose depth weight is
+    <= depth_eps are dropped as well (`veon_prepare_v2_calib_sparse`)."""
     _require_cuda(frustum, sensor2ego, cam2imgs, post_rots, post_trans, bda)
     calib = [t.detach().contiguous().float() for t in
              (frustum, sensor2ego, cam2imgs, post_rots, post_trans, bda)]
     B, N = sensor2ego.shape[:2]
     D, H, W, _ = frustum.shape
+    sparse = None
+    if depth_eps is not None:
+        if depth is None or tuple(depth.shape) != (B, N, D, H, W):
+            raise ValueError("depth_eps needs depth [B,N,D,H,W]")
+        _require_cuda(depth)
+        sparse = (depth.detach().contiguous().float(), float(depth_eps))
     return _prepare(None, calib, (B, N, D, H, W), sensor2ego.device, grid_lower_bound,
-                    grid_interval, grid_size)
+                    grid_interval, grid_size, sparse)
+
+
+# Pinned host slots for calibration hashes (same life-cycle rules as the counts ring)
+_HASH_RING = {}
+
+
+def calib_hash(sensor2ego, cam2imgs, post_rots, post_trans, bda):
+    """64-bit hash of the calibration tensors' bits (`veon_calib_hash`): one tiny kernel that
+    writes into pinned host memory + an event wait (no copy queued on the stream).  Returns a
+    python int."""
+    _require_cuda(sensor2ego, cam2imgs, post_rots, post_trans, bda)
+    lib = _lib.load()
+    dev = sensor2ego.device
+    B, N = sensor2ego.shape[:2]
+    args = [t.detach().contiguous().float() for t in (sensor2ego, cam2imgs, post_rots, post_trans, bda)]
+    ring = _HASH_RING.get(dev.index)
+    if ring is None:
+        ring = _HASH_RING[dev.index] = [torch.zeros(16, dtype=torch.int64).pin_memory(), 0]
+    slot = ring[1] = (ring[1] + 1) % 16
+    out = ring[0][slot:slot + 1]
+    with torch.cuda.device(dev):
+        rc = lib.veon_calib_hash(*[_ptr(a) for a in args], B, N, _ptr(out), _stream_ptr(dev))
+        _lib.check(rc, "veon_calib_hash")
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev))
+    ev.synchronize()
+    return int(out[0])
 
 
 def prepare_ranks(coor, grid_lower_bound, grid_interval, grid_size):
@@ -211,18 +248,35 @@ def prepare_ranks(coor, grid_lower_bound, grid_interval, grid_size):
                     grid_interval, grid_size)
 
 
-def _prepare(coor, calib, dims, dev, grid_lower_bound, grid_interval, grid_size):
+_TENSOR_VALUES = {}
+
+
+def _values(x):
+    """The floats of a 3-vector as a tuple.  Reading a tensor element by element costs a few
+    microseconds per call, so tensors are remembered by (object, in-place version); plain
+    sequences / ndarrays (which have no version counter) are simply re-read every time."""
+    if isinstance(x, torch.Tensor):
+        hit = _TENSOR_VALUES.get(id(x))
+        if hit is not None and hit[0]() is x and hit[1] == x._version:
+            return hit[2]
+        vals = tuple(float(v) for v in x.tolist())
+        if len(_TENSOR_VALUES) > 256:
+            _TENSOR_VALUES.clear()
+        _TENSOR_VALUES[id(x)] = (weakref.ref(x), x._version, vals)
+        return vals
+    return tuple(float(v) for v in x)
+
+
+def _prepare(coor, calib, dims, dev, grid_lower_bound, grid_interval, grid_size, sparse=None):
     lib = _lib.load()
     B, N, D, H, W = (int(v) for v in dims)
     P = B * N * D * H * W
-    key = (B, N, D, H, W, id(grid_lower_bound), id(grid_interval), id(grid_size),
-           getattr(grid_lower_bound, "_version", 0), getattr(grid_interval, "_version", 0),
-           getattr(grid_size, "_version", 0))
+    # keyed on the VALUES (three small tuples): a list / ndarray mutated in place, or a
+    # recycled id(), can never hand back stale geometry
+    lower, interval, size = _values(grid_lower_bound), _values(grid_interval), _values(grid_size)
+    key = (B, N, D, H, W, lower, interval, size)
     geo = _GEOMETRY_CACHE.get(key)
-    if geo is None or geo[0] is not grid_size:
-        lower = [float(v) for v in grid_lower_bound]
-        interval = [float(v) for v in grid_interval]
-        size = [float(v) for v in grid_size]
+    if geo is None:
         V = int(size[0]) * int(size[1]) * int(size[2])
         c_size = _lib.float3(size)
         ws_bytes = lib.veon_prepare_v2_workspace_bytes(B, N, D, H, W, c_size)
@@ -231,10 +285,8 @@ def _prepare(coor, calib, dims, dev, grid_lower_bound, grid_interval, grid_size)
         n_tiles = lib.veon_pool_num_tiles(B, V)
         if len(_GEOMETRY_CACHE) > 64:
             _GEOMETRY_CACHE.clear()
-        # (the grid objects are kept alive by the entry, so their ids stay unique)
-        geo = (grid_size, grid_lower_bound, grid_interval, _lib.float3(lower),
-               _lib.float3(interval), c_size, V, ws_bytes, n_tiles,
-               lib.veon_pool_heavy_list_ints(P, n_tiles),
+        geo = (None, None, None, _lib.float3(lower), _lib.float3(interval), c_size, V, ws_bytes,
+               n_tiles, lib.veon_pool_heavy_list_ints(P, n_tiles),
                lib.veon_prepare_v2_voxel_start_offset(B, N, D, H, W, c_size))
         _GEOMETRY_CACHE[key] = geo
     _, _, _, c_lower, c_interval, c_size, V, ws_bytes, n_tiles, nh, vs_off = geo
@@ -270,9 +322,15 @@ def _prepare(coor, calib, dims, dev, grid_lower_bound, grid_interval, grid_size)
             else:
                 xbytes = lib.veon_lidar_coor_workspace_bytes(B, N)
                 xws = torch.empty(xbytes, dtype=torch.uint8, device=dev)
-                rc = lib.veon_prepare_v2_calib(*[_ptr(a) for a in calib], B, N, D, H, W, c_lower,
-                                               c_interval, c_size, *outs, _ptr(xws), xbytes,
-                                               _ptr(ws), ws_bytes, _stream_ptr(dev))
+                if sparse is None:
+                    rc = lib.veon_prepare_v2_calib(*[_ptr(a) for a in calib], B, N, D, H, W,
+                                                   c_lower, c_interval, c_size, *outs, _ptr(xws),
+                                                   xbytes, _ptr(ws), ws_bytes, _stream_ptr(dev))
+                else:
+                    rc = lib.veon_prepare_v2_calib_sparse(
+                        *[_ptr(a) for a in calib], _ptr(sparse[0]), sparse[1], B, N, D, H, W,
+                        c_lower, c_interval, c_size, *outs, _ptr(xws), xbytes, _ptr(ws), ws_bytes,
+                        _stream_ptr(dev))
         _lib.check(rc, "veon_prepare_v2")
         ev = torch.cuda.Event()
         ev.record(torch.cuda.current_stream(dev))
@@ -641,6 +699,11 @@ class QuickCumsumCuda(torch.autograd.Function):
         if plan is None:
             plan = _plan_for(ranks_depth, ranks_feat, ranks_bev, interval_starts,
                              interval_lengths, dims, V)
+        if plan.flags & PLAN_OUT_OF_RANGE:
+            # the reference would read / write out of bounds here (it checks nothing,
+            # bev_pool.cpp has no CHECK_* macros); so would the unchecked generic kernels
+            raise ValueError("bev_pool_v2: a rank lies outside its tensor (ranks_depth >= "
+                             "depth.numel(), ranks_feat >= feat rows or ranks_bev >= B*Z*Y*X)")
         if plan.ok:
             out = _fwd_planar(depth, feat, ranks_depth, ranks_feat, ranks_bev, plan,
                               B, C, V, (B, C, Z, Y, X))

@@ -140,3 +140,59 @@ extern "C" int veon_transpose_batched(const float* src, int64_t batch, int R, in
   VEON_LAUNCH_CHECK();
   return 0;
 }
+
+// ---- calibration hash (rank cache keyed on the calibration) ------------------------
+// The reference's `accelerate` cache (view_transformer.py:154-173) assumes the calibration never
+// changes.  A 64-bit hash of the five calibration tensors' BITS lets a caller keep the prepared
+// ranks of every rig it has seen and re-use them whenever the same calibration comes back -- one
+// tiny kernel and an 8-byte read instead of the whole index preparation.
+namespace veon {
+__device__ __forceinline__ unsigned long long mix64(unsigned long long x) {   // splitmix64 finaliser
+  x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull;
+  x ^= x >> 27; x *= 0x94d049bb133111ebull;
+  x ^= x >> 31;
+  return x;
+}
+struct HashSpan { const float* p; int n; };
+struct HashJobs { HashSpan s[5]; };
+
+__global__ void __launch_bounds__(256)
+k_calib_hash(HashJobs jobs, unsigned long long seed, unsigned long long* __restrict__ out) {
+  __shared__ unsigned long long part[8];
+  unsigned long long h = 0;
+  unsigned long long base = 0;
+  for (int j = 0; j < 5; ++j) {
+    for (int i = threadIdx.x; i < jobs.s[j].n; i += blockDim.x)
+      h += mix64((unsigned long long)__float_as_uint(jobs.s[j].p[i]) ^ ((base + i + 1) * 0x9e3779b97f4a7c15ull));
+    base += (unsigned long long)jobs.s[j].n + 0x10000ull;   // position AND tensor matter
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) h += __shfl_xor_sync(0xffffffffu, h, o);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = h;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    unsigned long long t = seed;
+    for (int w = 0; w < 8; ++w) t += part[w];
+    *out = mix64(t);
+    __threadfence_system();
+  }
+}
+}  // namespace veon
+
+extern "C" int veon_calib_hash(const float* sensor2ego, const float* cam2imgs,
+                               const float* post_rots, const float* post_trans, const float* bda,
+                               int B, int N, uint64_t* out, void* stream) {
+  if (!sensor2ego || !cam2imgs || !post_rots || !post_trans || !bda || !out || B <= 0 || N <= 0)
+    return VEON_E_BADARG;
+  veon::HashJobs jobs;
+  jobs.s[0] = {sensor2ego, B * N * 16};
+  jobs.s[1] = {cam2imgs, B * N * 9};
+  jobs.s[2] = {post_rots, B * N * 9};
+  jobs.s[3] = {post_trans, B * N * 3};
+  jobs.s[4] = {bda, B * 9};
+  veon::k_calib_hash<<<1, 256, 0, (cudaStream_t)stream>>>(
+      jobs, ((unsigned long long)(unsigned)B << 32) | (unsigned)N,
+      reinterpret_cast<unsigned long long*>(out));
+  VEON_LAUNCH_CHECK();
+  return 0;
+}

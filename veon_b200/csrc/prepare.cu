@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(256)
 k_classify(const float* __restrict__ coor, const float* __restrict__ frustum,
            const CamXform* __restrict__ xf, int64_t DHW, int64_t P, int64_t pts_per_sample,
            GridF g, int64_t nbins, int32_t* __restrict__ key, int32_t* __restrict__ slot,
-           int32_t* __restrict__ count) {
+           int32_t* __restrict__ count, const float* __restrict__ depth_w, float depth_eps) {
   pdl_prologue();
   int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= P) return;
@@ -161,6 +161,9 @@ k_classify(const float* __restrict__ coor, const float* __restrict__ frustum,
   // cvttss2si yields INT64_MIN).  (-1,0) truncates to -0.0 which IS kept.
   bool kept = (tx >= 0.0f) && (tx < g.gs[0]) && (ty >= 0.0f) && (ty < g.gs[1]) &&
               (tz >= 0.0f) && (tz < g.gs[2]);
+  // opt-in (inference): a point whose depth weight is negligible is dropped like an out-of-grid
+  // one -- VEON's two-hot depth leaves ~90 % of the bins at the e^-16 clamp
+  if (depth_w != nullptr && kept) kept = __ldg(depth_w + p) > depth_eps;
   int32_t k = -1, s = 0;
   if (kept) {
     float b = (float)(p / pts_per_sample);
@@ -654,7 +657,8 @@ static int prepare_impl(const float* coor, const float* frustum, const CamXform*
                                int64_t* counts, int64_t* counts_host, int32_t* tile_start,
                                int32_t* tile_istart, uint32_t* tile_occ, int32_t* tile_heavy,
                                int32_t* point_interval, void* workspace,
-                               size_t workspace_bytes, void* stream_) {
+                               size_t workspace_bytes, void* stream_,
+                               const float* depth_w = nullptr, float depth_eps = 0.f) {
   cudaStream_t stream = (cudaStream_t)stream_;
   int64_t P;
   int rc = check_dims(B, N, D, H, W, &P);
@@ -688,11 +692,11 @@ static int prepare_impl(const float* coor, const float* frustum, const CamXform*
   if (coor) {
     VEON_CUDA_TRY(launch_pdl(k_classify<false>, dim3(pblocks), dim3(256), 0, stream, coor,
                              (const float*)nullptr, (const CamXform*)nullptr, DHW, P,
-                             pts_per_sample, g, nbins, w.key, w.slot, w.count));
+                             pts_per_sample, g, nbins, w.key, w.slot, w.count, depth_w, depth_eps));
   } else {
     VEON_CUDA_TRY(launch_pdl(k_classify<true>, dim3(pblocks), dim3(256), 0, stream,
                              (const float*)nullptr, frustum, xf, DHW, P, pts_per_sample, g, nbins,
-                             w.key, w.slot, w.count));
+                             w.key, w.slot, w.count, depth_w, depth_eps));
   }
   VEON_LAUNCH_CHECK();
   const bool want_tiles = tile_start && tile_istart && tile_occ;
@@ -746,6 +750,53 @@ extern "C" int veon_prepare_v2(const float* coor, int B, int N, int D, int H, in
 
 // get_lidar_coor fused into the preparation: same ranks as
 // veon_lidar_coor + veon_prepare_v2, without the [B,N,D,H,W,3] coordinate tensor.
+// depth / depth_eps (veon_prepare_v2_calib_sparse): points with depth weight <= depth_eps are
+// dropped as well.
+static int prepare_calib(const float* frustum, const float* sensor2ego,
+                                     const float* cam2imgs, const float* post_rots,
+                                     const float* post_trans, const float* bda, int B, int N,
+                                     int D, int H, int W, const float* lower,
+                                     const float* interval, const float* grid_size,
+                                     int32_t* ranks_bev, int32_t* ranks_depth,
+                                     int32_t* ranks_feat, int32_t* interval_starts,
+                                     int32_t* interval_lengths, int64_t* counts,
+                                     int64_t* counts_host, int32_t* tile_start,
+                                     int32_t* tile_istart, uint32_t* tile_occ,
+                                     int32_t* tile_heavy, int32_t* point_interval,
+                                     void* xform_workspace, size_t xform_workspace_bytes,
+                                     void* workspace, size_t workspace_bytes, void* stream_,
+                                     const float* depth_w, float depth_eps) {
+  if (!frustum || !sensor2ego || !cam2imgs || !post_rots || !post_trans || !bda ||
+      !xform_workspace || B <= 0 || N <= 0)
+    return VEON_E_BADARG;
+  if (xform_workspace_bytes < sizeof(CamXform) * (size_t)B * N) return VEON_E_WORKSPACE;
+  CamXform* xf = (CamXform*)xform_workspace;
+  int rc = launch_cam_xforms(sensor2ego, cam2imgs, post_rots, post_trans, bda, B, N, xf,
+                             (cudaStream_t)stream_);
+  if (rc) return rc;
+  return prepare_impl(nullptr, frustum, xf, B, N, D, H, W, lower, interval, grid_size, ranks_bev,
+                      ranks_depth, ranks_feat, interval_starts, interval_lengths, counts,
+                      counts_host, tile_start, tile_istart, tile_occ, tile_heavy, point_interval,
+                      workspace, workspace_bytes, stream_, depth_w, depth_eps);
+}
+
+extern "C" int veon_prepare_v2_calib_sparse(
+    const float* frustum, const float* sensor2ego, const float* cam2imgs, const float* post_rots,
+    const float* post_trans, const float* bda, const float* depth, float depth_eps, int B, int N,
+    int D, int H, int W, const float* lower, const float* interval, const float* grid_size,
+    int32_t* ranks_bev, int32_t* ranks_depth, int32_t* ranks_feat, int32_t* interval_starts,
+    int32_t* interval_lengths, int64_t* counts, int64_t* counts_host, int32_t* tile_start,
+    int32_t* tile_istart, uint32_t* tile_occ, int32_t* tile_heavy, int32_t* point_interval,
+    void* xform_workspace, size_t xform_workspace_bytes, void* workspace, size_t workspace_bytes,
+    void* stream_) {
+  if (!depth || !(depth_eps >= 0.f)) return VEON_E_BADARG;
+  return prepare_calib(frustum, sensor2ego, cam2imgs, post_rots, post_trans, bda, B, N, D, H, W,
+                       lower, interval, grid_size, ranks_bev, ranks_depth, ranks_feat,
+                       interval_starts, interval_lengths, counts, counts_host, tile_start,
+                       tile_istart, tile_occ, tile_heavy, point_interval, xform_workspace,
+                       xform_workspace_bytes, workspace, workspace_bytes, stream_, depth, depth_eps);
+}
+
 extern "C" int veon_prepare_v2_calib(const float* frustum, const float* sensor2ego,
                                      const float* cam2imgs, const float* post_rots,
                                      const float* post_trans, const float* bda, int B, int N,
@@ -759,18 +810,11 @@ extern "C" int veon_prepare_v2_calib(const float* frustum, const float* sensor2e
                                      int32_t* tile_heavy, int32_t* point_interval,
                                      void* xform_workspace, size_t xform_workspace_bytes,
                                      void* workspace, size_t workspace_bytes, void* stream_) {
-  if (!frustum || !sensor2ego || !cam2imgs || !post_rots || !post_trans || !bda ||
-      !xform_workspace || B <= 0 || N <= 0)
-    return VEON_E_BADARG;
-  if (xform_workspace_bytes < sizeof(CamXform) * (size_t)B * N) return VEON_E_WORKSPACE;
-  CamXform* xf = (CamXform*)xform_workspace;
-  int rc = launch_cam_xforms(sensor2ego, cam2imgs, post_rots, post_trans, bda, B, N, xf,
-                             (cudaStream_t)stream_);
-  if (rc) return rc;
-  return prepare_impl(nullptr, frustum, xf, B, N, D, H, W, lower, interval, grid_size, ranks_bev,
-                      ranks_depth, ranks_feat, interval_starts, interval_lengths, counts,
-                      counts_host, tile_start, tile_istart, tile_occ, tile_heavy, point_interval,
-                      workspace, workspace_bytes, stream_);
+  return prepare_calib(frustum, sensor2ego, cam2imgs, post_rots, post_trans, bda, B, N, D, H, W,
+                       lower, interval, grid_size, ranks_bev, ranks_depth, ranks_feat,
+                       interval_starts, interval_lengths, counts, counts_host, tile_start,
+                       tile_istart, tile_occ, tile_heavy, point_interval, xform_workspace,
+                       xform_workspace_bytes, workspace, workspace_bytes, stream_, nullptr, 0.f);
 }
 
 extern "C" int veon_pool_plan_build(const int32_t* ranks_depth, const int32_t* ranks_feat,

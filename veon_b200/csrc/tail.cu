@@ -171,3 +171,49 @@ extern "C" int veon_semantic_inference_3d(const float* text_w, const float* feat
   return tail_dispatch(feat_occ, text_w, nullptr, nullptr, B, C, Q, Z, Y, X, 0, nullptr, sem_occ,
                        (cudaStream_t)stream);
 }
+
+// ---- training-time voxel x text arg-max over a POINT LIST ----------------------
+// Proj2Dto3DLoss, loss/occ_loss_utils/occ3d_nuscenes.py:472-482: for the N selected voxels
+//   pred_probs    = einsum('nc,dc->nd', feat[N,C], W[:-1])          (no background row)
+//   pred_indices  = max(pred_probs, dim=1).indices                  best PROMPT
+//   pred_class    = max over the prompts of each class (_merge_classes_prob, :249-265), then
+//   pred_class_idx = max(., dim=1).indices                          best merged CLASS
+// Here: logits [Q, ldn] (row q = prompt q over the points, as veon_semantic_inference_3d writes
+// them for a [C, N] operand), one thread per point walks the Q rows once: coalesced reads, both
+// arg-maxes with first-index ties (torch.max(dim) returns the first maximum).
+__global__ void __launch_bounds__(256)
+k_point_argmax(const float* __restrict__ logits, const int32_t* __restrict__ class_of_prompt, int Q,
+               int64_t N, int64_t ldn, int64_t* __restrict__ prompt_idx,
+               int64_t* __restrict__ class_idx) {
+  const int64_t n = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  float best_p = 0.f, best_c = 0.f, run = 0.f;
+  int arg_p = -1, arg_c = -1, run_cls = -1;
+  for (int q = 0; q < Q; ++q) {
+    const float x = __ldg(logits + (int64_t)q * ldn + n);
+    const int cq = __ldg(class_of_prompt + q);
+    if (arg_p < 0 || x > best_p) { best_p = x; arg_p = q; }
+    if (cq != run_cls) {           // a new class starts: close the previous one
+      if (run_cls >= 0 && (arg_c < 0 || run > best_c)) { best_c = run; arg_c = run_cls; }
+      run_cls = cq;
+      run = x;
+    } else if (x > run) {
+      run = x;
+    }
+  }
+  if (run_cls >= 0 && (arg_c < 0 || run > best_c)) arg_c = run_cls;
+  prompt_idx[n] = arg_p;
+  class_idx[n] = arg_c;
+}
+
+extern "C" int veon_point_text_argmax(const float* logits, const int32_t* class_of_prompt, int Q,
+                                      int64_t N, int64_t ldn, int64_t* prompt_idx,
+                                      int64_t* class_idx, void* stream) {
+  if (!logits || !class_of_prompt || !prompt_idx || !class_idx || Q <= 0 || N < 0 || ldn < N)
+    return VEON_E_BADARG;
+  if (N == 0) return 0;
+  k_point_argmax<<<(unsigned)ceil_div64(N, 256), 256, 0, (cudaStream_t)stream>>>(
+      logits, class_of_prompt, Q, N, ldn, prompt_idx, class_idx);
+  VEON_LAUNCH_CHECK();
+  return 0;
+}

@@ -23,7 +23,7 @@ import torch
 
 from . import tail as _tail
 
-__all__ = ["lift_classify", "lift_then_classify"]
+__all__ = ["lift_classify", "lift_logits", "lift_then_classify"]
 
 
 def _heads(ov_classifier_weight, gate_weight, channel_pad=4):
@@ -38,26 +38,49 @@ def _heads(ov_classifier_weight, gate_weight, channel_pad=4):
     return rows.contiguous()
 
 
+def lift_logits(neck, input, depth, tran_feat, ov_classifier_weight, gate_weight, channel_pad=4,
+                cameras=None):
+    """The pooled LOGIT volume [B, Q', Z, Y, X] (Q' = Q + 2 gate channels, padded to a multiple of
+    `channel_pad`): classifier on the image features, then the lift of those Q' channels.
+
+    `cameras`: optional list of camera indices -- only their pixels are lifted.  Pooling is a sum
+    over points, so the volumes of disjoint camera groups ADD UP to the full volume (up to float
+    re-association): that is what camera-group sharding all-reduces (veon_b200.dist)."""
+    B, N = input[0].shape[:2]
+    BN, C, H, W = tran_feat.shape
+    rows = _heads(ov_classifier_weight, gate_weight, channel_pad)
+    with torch.no_grad():
+        metas = list(input[1:7])
+        d5 = depth.reshape(B, N, neck.D, H, W)
+        f5 = tran_feat.reshape(B, N, C, H, W)
+        if cameras is not None:
+            idx = torch.as_tensor(list(cameras), device=tran_feat.device, dtype=torch.long)
+            # every calibration tensor but bda [B,3,3] carries the camera axis
+            metas = [m.index_select(1, idx.to(m.device)).contiguous() if i < 5 else m
+                     for i, m in enumerate(metas)]
+            d5 = d5.index_select(1, idx).contiguous()
+            f5 = f5.index_select(1, idx).contiguous()
+            N = len(cameras)
+        # per-pixel logits: the classifier over each camera's feature map, [B*N, Q', 1, H, W]
+        px = _tail.semantic_inference_3d(rows, f5.reshape(B * N, C, 1, H, W))
+        px5 = px.view(B, N, rows.shape[0], H, W)
+        if metas[0].is_cuda and neck.fuse_geometry:
+            vol = neck._voxel_pooling_calib(metas, d5, px5)
+        else:
+            vol = neck.voxel_pooling_v2(neck.get_lidar_coor(*metas), d5, px5)
+        if vol.dim() != 5:
+            raise RuntimeError("lift_logits needs collapse_z=False and points inside the grid")
+        return vol
+
+
 def lift_classify(neck, input, depth, tran_feat, ov_classifier_weight, prompt_class, gate_weight,
                   free_label=17, channel_pad=4):
     """neck: LSSViewTransformer; input = (img [B,N,*,H,W], sensor2ego, ego2global, cam2imgs,
     post_rots, post_trans, bda); depth [B*N,D,H,W]; tran_feat [B*N,C,H,W];
     ov_classifier_weight [Q,C]; prompt_class [Q]; gate_weight [2,C] -> uint8 [B,X,Y,Z]."""
-    B, N = input[0].shape[:2]
-    BN, C, H, W = tran_feat.shape
     Q = ov_classifier_weight.shape[0]
-    rows = _heads(ov_classifier_weight, gate_weight, channel_pad)
+    vol = lift_logits(neck, input, depth, tran_feat, ov_classifier_weight, gate_weight, channel_pad)
     with torch.no_grad():
-        # per-pixel logits: the classifier over each camera's feature map, [B*N, Q', 1, H, W]
-        px = _tail.semantic_inference_3d(rows, tran_feat.reshape(BN, C, 1, H, W))
-        d5 = depth.reshape(B, N, neck.D, H, W)
-        px5 = px.view(B, N, rows.shape[0], H, W)
-        if input[1].is_cuda and neck.fuse_geometry:
-            vol = neck._voxel_pooling_calib(input[1:7], d5, px5)
-        else:
-            vol = neck.voxel_pooling_v2(neck.get_lidar_coor(*input[1:7]), d5, px5)
-        if vol.dim() != 5:
-            raise RuntimeError("lift_classify needs collapse_z=False and points inside the grid")
         return _tail.classify_logits(vol[:, :Q], vol[:, Q:Q + 2], prompt_class, free_label)
 
 

@@ -18,26 +18,58 @@ import torch
 from . import _lib
 
 __all__ = ["class_of_prompt", "voxel_text_argmax", "semantic_inference_3d", "classify_logits",
-           "upsample_classify", "voxel_text_argmax_lowres"]
+           "upsample_classify", "voxel_text_argmax_lowres", "prepare_vocabulary",
+           "point_text_argmax"]
 
 
-def class_of_prompt(class_reflection):
+def class_of_prompt(class_reflection, mode="nuscenes", background=True):
     """Merged class id of each classifier row: contiguous runs of equal
     `class_reflection` form one class and the extra trailing background row is
-    its own class (san_in_veon_entry_temporal.py:273-286)."""
+    its own class (san_in_veon_entry_temporal.py:273-286).
+
+    background=False: the grouping of the LOSS-side `_merge_classes_prob`
+    (loss/occ_loss_utils/occ3d_nuscenes.py:249-265): no trailing row.
+
+    mode: the reference moves the background/free class to index 0 for "semkitti"
+    (san_in_veon_entry_temporal.py:288-293: `merged[0] = merged.pop(-1)`).  That re-ordering
+    is not expressible as the non-decreasing row -> class map the fused kernels take, so only
+    "nuscenes" is supported here and "semkitti" is refused instead of being silently wrong."""
+    if mode != "nuscenes":
+        raise NotImplementedError(
+            "class_of_prompt: only mode='nuscenes' (free class last) is supported; the "
+            "reference's semkitti branch moves the free class to index 0")
     refl = [int(v) for v in class_reflection]
-    n = len(refl) + 1
+    n = len(refl) + (1 if background else 0)
+    last_mergeable = n - 2 if background else n - 1
     out = []
     k = 0
     i = 0
     while i < n:
         j = i
-        while j < n - 2 and refl[i] == refl[j + 1]:
+        while j < last_mergeable and refl[i] == refl[j + 1]:
             j += 1
         out.extend([k] * (j - i + 1))
         k += 1
         i = j + 1
     return torch.tensor(out, dtype=torch.int32)
+
+
+def prepare_vocabulary(text_embeddings, bg_embed, logit_scale):
+    """The classifier weight the tail multiplies with -- `SANInVeonTemporal.prepare_vocabulary`
+    (san_in_veon_temporal.py:261-266) on top of `LearnableBgOvClassifier.
+    get_classifier_by_vocabulary` (clip_utils/classifier.py:107-112):
+
+        W = exp(logit_scale) * L2-normalise(cat([text_embeddings, bg_embed]), dim=-1), detached.
+
+    text_embeddings [Q-1, C]: one row per prompt, what the CLIP text encoder + template
+    averaging produced (open_clip, un-vendored: outside this path); bg_embed [1, C] the
+    learnable background embedding; logit_scale the CLIP log-temperature (scalar tensor or
+    float; exp(.) ~ 100).  Init-time only: plain torch ops, device-agnostic."""
+    emb = torch.cat([torch.as_tensor(text_embeddings).float(),
+                     torch.as_tensor(bg_embed).float().reshape(1, -1)], dim=0)
+    emb = torch.nn.functional.normalize(emb, p=2, dim=-1)
+    scale = torch.as_tensor(logit_scale, dtype=torch.float32, device=emb.device).exp()
+    return (scale * emb).clone().detach()
 
 
 def voxel_text_argmax(feat_occ, ov_classifier_weight, prompt_class, bin_occ, free_label=17):
@@ -194,3 +226,52 @@ def voxel_text_argmax_lowres(feat_occ_lr, ov_classifier_weight, prompt_class, bi
             ctypes.c_void_p(workspace.data_ptr()), ws_bytes, _stream(dev))
     _lib.check(rc, "veon_voxel_text_argmax_lowres")
     return labels
+
+
+def point_text_argmax(pred_feat, ov_classifier_weight, class_reflection):
+    """The training-time voxel x text arg-max of `Proj2Dto3DLoss`
+    (loss/occ_loss_utils/occ3d_nuscenes.py:472-482) for a POINT LIST:
+
+        pred_probs_3d      = einsum('nc,dc->nd', pred_feat, ov_classifier_weight[:-1])
+        pred_indices_3d    = max(pred_probs_3d, dim=1).indices
+        pred_indices_3d_ds = max(_merge_classes_prob(pred_probs_3d, 1, class_reflection), 1).indices
+
+    pred_feat [N, C] (rows = the selected voxels), ov_classifier_weight [Q, C] INCLUDING the
+    trailing background row (dropped here, as the reference does), class_reflection: the Q-1
+    class ids.  Returns (pred_indices_3d, pred_indices_3d_ds), int64 [N].  The [N, Q-1] logits
+    are not returned (the reference uses them for nothing else).
+
+    How: the point rows are turned into a [C, N] operand (own transpose kernel), the logits come
+    from the tcgen05 3xTF32 kernel of the inference tail, one pass over them takes both
+    arg-maxes."""
+    _cuda_only(pred_feat, ov_classifier_weight)
+    lib = _lib.load()
+    f = pred_feat.detach().contiguous().float()
+    w = ov_classifier_weight.detach()[:-1].contiguous().float()
+    N, C = f.shape
+    Q = w.shape[0]
+    if w.shape[1] != C or len(class_reflection) != Q:
+        raise ValueError("inconsistent point_text_argmax shapes")
+    dev = f.device
+    cls = class_of_prompt(class_reflection, background=False).to(dev)
+    with torch.cuda.device(dev):
+        p_idx = torch.empty(N, dtype=torch.int64, device=dev)
+        c_idx = torch.empty(N, dtype=torch.int64, device=dev)
+        if N == 0:
+            return p_idx, c_idx
+        ldn = (N + 3) // 4 * 4                      # the tensor path wants V % 4 == 0
+        ft = torch.zeros((C, ldn), dtype=torch.float32, device=dev) if ldn != N else \
+            torch.empty((C, ldn), dtype=torch.float32, device=dev)
+        if ldn == N:
+            rc = lib.veon_transpose_batched(ctypes.c_void_p(f.data_ptr()), 1, N, C,
+                                            ctypes.c_void_p(ft.data_ptr()), _stream(dev))
+            _lib.check(rc, "veon_transpose_batched")
+        else:
+            ft[:, :N] = f.t()
+        logits = semantic_inference_3d(w, ft.view(1, C, 1, 1, ldn))      # [1, Q, 1, 1, ldn]
+        rc = lib.veon_point_text_argmax(ctypes.c_void_p(logits.data_ptr()),
+                                        ctypes.c_void_p(cls.data_ptr()), Q, N, ldn,
+                                        ctypes.c_void_p(p_idx.data_ptr()),
+                                        ctypes.c_void_p(c_idx.data_ptr()), _stream(dev))
+    _lib.check(rc, "veon_point_text_argmax")
+    return p_idx, c_idx

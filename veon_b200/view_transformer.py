@@ -36,7 +36,7 @@ class LSSViewTransformer(nn.Module):
 
     def __init__(self, grid_config, input_size, downsample=16, in_channels=512,
                  out_channels=64, accelerate=False, sid=False, collapse_z=True,
-                 sync_free=False):
+                 sync_free=False, rank_cache=0, depth_eps=None):
         super().__init__()
         self.grid_config = grid_config
         self.downsample = downsample
@@ -63,6 +63,17 @@ class LSSViewTransformer(nn.Module):
         # view_transform.  Same float operations in the same order, so the pooled
         # volume is the same bits; set False to run the two steps separately.
         self.fuse_geometry = True
+        # Extra (not in the reference), SURVEY 8f-3: keep the prepared ranks of the last
+        # `rank_cache` distinct calibrations, keyed by a 64-bit hash of the calibration tensors'
+        # bits (one tiny kernel + an 8-byte read instead of the whole index preparation).  It
+        # generalises `accelerate` (:154-173), which caches ONE rig for ever.  0 = off.
+        self.rank_cache = int(rank_cache)
+        self._rank_cache = {}
+        self.rank_cache_hits = self.rank_cache_misses = 0
+        # Extra (not in the reference), SURVEY 8f-2, INFERENCE only: drop the points whose depth
+        # weight is <= depth_eps before they are ranked (VEON's two-hot depth leaves ~90 % of
+        # the bins at the e^-16 clamp).  Ignored whenever a gradient is wanted; None = exact.
+        self.depth_eps = depth_eps
 
     # -- a1 ------------------------------------------------------------------
     def create_grid_infos(self, x, y, z, **kwargs):
@@ -161,9 +172,29 @@ class LSSViewTransformer(nn.Module):
         """voxel_pooling_v2 with get_lidar_coor folded into the index preparation:
         `calib` = the six tensors get_lidar_coor takes; no coordinate tensor is written."""
         sensor2ego, _ego2global, cam2imgs, post_rots, post_trans, bda = calib
-        prep = _bp.prepare_ranks_calib(self._frustum_on(sensor2ego.device), sensor2ego, cam2imgs,
-                                       post_rots, post_trans, bda, self.grid_lower_bound,
-                                       self.grid_interval, self.grid_size)
+        frustum = self._frustum_on(sensor2ego.device)
+        grid = (self.grid_lower_bound, self.grid_interval, self.grid_size)
+        wants_grad = torch.is_grad_enabled() and (depth.requires_grad or feat.requires_grad)
+        if self.depth_eps is not None and not wants_grad:
+            # depth-dependent ranks: nothing to cache
+            prep = _bp.prepare_ranks_calib(frustum, sensor2ego, cam2imgs, post_rots, post_trans,
+                                           bda, *grid, depth=depth, depth_eps=self.depth_eps)
+        elif self.rank_cache > 0:
+            key = (_bp.calib_hash(sensor2ego, cam2imgs, post_rots, post_trans, bda),
+                   tuple(depth.shape), sensor2ego.device.index)
+            prep = self._rank_cache.pop(key, None)
+            if prep is None:
+                self.rank_cache_misses += 1
+                prep = _bp.prepare_ranks_calib(frustum, sensor2ego, cam2imgs, post_rots,
+                                               post_trans, bda, *grid)
+            else:
+                self.rank_cache_hits += 1
+            self._rank_cache[key] = prep                      # most recently used last
+            while len(self._rank_cache) > self.rank_cache:
+                self._rank_cache.pop(next(iter(self._rank_cache)))
+        else:
+            prep = _bp.prepare_ranks_calib(frustum, sensor2ego, cam2imgs, post_rots, post_trans,
+                                           bda, *grid)
         return self._pool_prepared(prep, depth, feat)
 
     def _pool_prepared(self, prep, depth, feat):
