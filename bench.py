@@ -494,12 +494,19 @@ def pipeline_leg(dev, world, rank, peak_gbs, batches=(8, 16, 32, 64), Qs=(18, 67
                 b.record()
                 torch.cuda.synchronize()
                 ag_us = a.elapsed_time(b) * 100.0
-            for _ in range(2):
-                one()
+            main = torch.cuda.current_stream(dev)
+            for _ in range(3):                 # warm-up of the whole loop, side stream included
+                lab = one()
+                done = torch.cuda.Event()
+                done.record(main)
+                with torch.cuda.stream(side):
+                    side.wait_event(done)
+                    lab.record_stream(side)
+                    allv = gather(lab)
+            main.wait_stream(side)
             if world > 1:
                 dist.barrier()
             torch.cuda.synchronize()
-            main = torch.cuda.current_stream(dev)
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             steps = 10
             e0.record()
@@ -596,7 +603,19 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # NCCL prints its version banner to STDOUT when the first communicator comes up; the
+        # contract is ONE JSON line there, so stdout points at stderr until that has happened
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     lib = _lib.load()
 
     cfg = S.CONFIGS[args.workload]

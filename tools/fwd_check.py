@@ -6,8 +6,11 @@ import time
 
 import torch
 
+import os
 sys.path.insert(0, ".")
 from veon_b200 import _lib, bev_pool as BP, synthetic as S  # noqa: E402
+if os.environ.get("VEON_LIB"):          # an experimental build of tools/build_variant.sh
+    _lib.LIB_PATH = os.environ["VEON_LIB"]
 
 
 def setup(cfg_name, B, C, seed=0):
@@ -85,7 +88,7 @@ def main():
             del scratch
             line = f"time {cfg} B={B} C={C}: general {tg * 1e3:.1f} us"
             slot = 512 * min(C, 128) * 4
-            for ns in (2, 4, 8, 16):
+            for ns in (4, 8, 16) if C <= 512 else (8, 16):
                 BP.FWD_RING_BYTES = 148 * ns * slot
                 ts = ev_ms(lambda: BP._fwd_planar(depth, feat, prep.ranks_depth, prep.ranks_feat,
                                                   prep.ranks_bev, prep.plan, B, C, 640000, shape), n=10)

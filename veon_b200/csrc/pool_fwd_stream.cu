@@ -81,6 +81,21 @@ __device__ __forceinline__ void cpa16_cg(uint32_t smem_dst, const void* gsrc) { 
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
 }
 
+#ifdef VEON_FWD_TRACE   // tools/fwd_trace.sh only: cycles per phase, CTA 0, every warp
+__device__ unsigned long long veon_fwd_trace[32 * 8];
+#define VEON_T0 long long _tt = clock64();
+#define VEON_TACC(slotid)                                                             \
+  {                                                                                   \
+    const long long _n = clock64();                                                   \
+    if (blockIdx.x == 0 && (threadIdx.x & 31) == 0)                                   \
+      veon_fwd_trace[(threadIdx.x >> 5) * 8 + (slotid)] += (unsigned long long)(_n - _tt); \
+    _tt = _n;                                                                         \
+  }
+#else
+#define VEON_T0
+#define VEON_TACC(slotid)
+#endif
+
 template <int VEC> struct VecT;
 template <> struct VecT<2> { using T = float2; };
 template <> struct VecT<4> { using T = float4; };
@@ -105,17 +120,26 @@ struct FwdStreamParams {
   float* out;
   int64_t V;
   uint32_t n_tiles, n_rounds, tiles_per_sample;
-  int C, n_pass, ns;         // n_pass = C / CU passes per round; ns ring slots per CTA
+  int C, n_pass, ns_log2;    // n_pass = C / CU passes per round; 2^ns_log2 ring slots per CTA
 };
 
-// One full / empty mbarrier pair per ring slot (the classic producer-consumer pipeline): every
-// A warp arrives on full[s] when its rows of the unit are in the slot, every E warp on empty[s]
-// when it has copied its rows out; a generation of the slot = one phase of each.  Waiting
-// threads are suspended by the hardware (try_wait), they do not spin through the issue slots.
+// Per ring slot: `full`, an mbarrier on which every tile of a round arrives when its rows of the
+// unit are in the slot (a generation of the slot = one phase; the E warps, which visit every
+// unit in order, wait on it suspended by the hardware, not spinning through the issue slots);
+// and `drained`, a plain counter every E warp bumps when it has copied its rows out.  The
+// way back is a COUNTER, not an mbarrier phase, on purpose: role A claims its tiles
+// dynamically, so a warp may meet a slot it has not touched for several generations, and a
+// parity wait can only tell the current phase from the one before it.
 struct StreamShared {
   uint64_t full[kMaxSlots];
-  uint64_t empty[kMaxSlots];
+  volatile uint32_t drained[kMaxSlots];   // + 1 per E warp per use of the slot
+  uint32_t next_item;   // role A: next (round, tile) of this CTA's sequence to be claimed
+  // what role E needs to know about tile w of the unit in slot s, published by the A warp that
+  // produced it (before its arrival on `full`): .x = occupancy mask, .y = first slot row of the
+  // tile | kMetaMine when the tile is this kernel's (inside the volume, not heavy)
+  uint2 meta[kMaxSlots][kRoundTiles];
 };
+constexpr uint32_t kMetaMine = 0x80000000u;
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)),
                "r"(count) : "memory");
@@ -129,8 +153,8 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {   //
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "W_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
-      "@!p bra W_%=;\n\t}" ::"r"(a), "r"(parity) : "memory");
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@!p bra W_%=;\n\t}" ::"r"(a), "r"(parity), "r"(20000u) : "memory");   // suspend <= 20 us per try
 }
 
 // Rows the round's tiles in front of tile w contribute to the slot (their occupied voxels; a
@@ -146,48 +170,64 @@ __device__ __forceinline__ int rows_before(int32_t ts, uint32_t occ, int lane, i
 
 // ------------------------------------------------------------------------------------------
 // role A: rows of the occupied voxels -> the CTA's ring.  CU = 32 * VEC channels per pass; a
-// lane owns VEC consecutive channels.  Warp w: tile w of every round.
+// lane owns VEC consecutive channels.
+// The tiles of the CTA's rounds are CLAIMED one by one from a shared counter (three stages
+// ahead, when their index records start to travel), not dealt statically: a warp that draws a
+// 90-point tile simply claims fewer, so a round is not held up by its slowest tile any longer
+// than the ring's slack allows.  A tile's arrival on its unit's `full` barrier is per tile.
 // ------------------------------------------------------------------------------------------
+constexpr int kHdrItem = 33;   // header word: the claimed item (round-in-CTA * 16 + tile-in-round)
+
 template <int VEC>
 __device__ __forceinline__ void role_rows(const FwdStreamParams& p, int32_t* ring_idx,
-                                          StreamShared* sh, int lane, int warp) {
+                                          StreamShared* sh, int lane) {
   using V = typename VecT<VEC>::T;
   constexpr int CU = 32 * VEC;
   __builtin_assume(__isShared(ring_idx));   // LDS/STS instead of generic accesses
   constexpr int U = VEC == 2 ? 12 : 8;   // feature-row pieces in flight per lane (3 / 4 KB per warp)
   if (blockIdx.x >= p.n_rounds) return;
   const uint32_t my_rounds = (p.n_rounds - blockIdx.x + gridDim.x - 1) / gridDim.x;
+  const uint32_t my_items = my_rounds * kRoundTiles;
   const int32_t heavy_thr = p.heavy ? __ldg(p.heavy + 1) : 0x7fffffff;
-  float* const cta_ring = p.ring + (size_t)blockIdx.x * p.ns * (kSlotRows * CU);
+  const uint32_t ns_mask = (1u << p.ns_log2) - 1u;
+  float* const cta_ring = p.ring + ((size_t)blockIdx.x << p.ns_log2) * (kSlotRows * CU);
   const uint32_t row_bytes = (uint32_t)p.C * 4u;
 
-  auto slot_of = [&](uint32_t m) { return ring_idx + (m & (kASlots - 1)) * kASlotInts; };
-  auto round_of = [&](uint32_t m) { return blockIdx.x + m * gridDim.x; };
-  auto issue_bounds = [&](uint32_t m) {   // header of my m-th round
-    int32_t* sl = slot_of(m);
-    if (m < my_rounds) {
-      const uint32_t t0 = round_of(m) * kRoundTiles;
+  auto slot_of = [&](uint32_t k) { return ring_idx + (k & (kASlots - 1)) * kASlotInts; };
+  // stage 1 of this warp's k-th item: claim it, start its round header
+  auto issue_bounds = [&](uint32_t k) {
+    int32_t* sl = slot_of(k);
+    uint32_t g = 0;
+    if (lane == 0) g = atomicAdd(&sh->next_item, 1u);
+    g = __shfl_sync(0xffffffffu, g, 0);
+    if (g < my_items) {
+      const uint32_t t0 = (blockIdx.x + (g / kRoundTiles) * gridDim.x) * kRoundTiles;
+      // 17 tile_start words (lanes 0..16) + 16 masks (lanes 17..31 and, for the last one, lane 16)
       if (lane <= kRoundTiles) cpa4(sl + lane, p.tile_start + min(t0 + lane, p.n_tiles));
-      else if (lane < 2 * kRoundTiles + 1) {
-        const uint32_t t = t0 + (lane - kRoundTiles - 1);
-        if (t < p.n_tiles) cpa4(sl + lane, p.tile_occ + t);
-        else sl[lane] = 0;
+      if (lane >= kRoundTiles) {
+        const int wq = lane == kRoundTiles ? kRoundTiles - 1 : lane - kRoundTiles - 1;
+        const uint32_t t = t0 + wq;
+        if (t < p.n_tiles) cpa4(sl + 17 + wq, p.tile_occ + t);
+        else sl[17 + wq] = 0;
       }
-    } else if (lane < 2 * kRoundTiles + 1) {
-      sl[lane] = 0;   // past the end: an empty round
+    } else {
+      sl[lane] = 0;   // past the end: an empty item
+      if (lane == 0) sl[32] = 0;
     }
+    if (lane == 0) sl[kHdrItem] = (int32_t)g;
   };
-  // the point range of this warp's tile (none when the tile is heavy)
-  auto pair_range = [&](const int32_t* sl, int32_t& s, int32_t& e) {
-    s = sl[warp];
-    e = sl[warp + 1];
+  // the point range of the item's tile (none when the tile is heavy)
+  auto tile_range = [&](const int32_t* sl, int32_t& s, int32_t& e) {
+    const int w = sl[kHdrItem] & (kRoundTiles - 1);
+    s = sl[w];
+    e = sl[w + 1];
     if (e - s >= heavy_thr) e = s;
   };
-  auto issue_ranks = [&](uint32_t m) {
-    int32_t* sl = slot_of(m);
+  auto issue_ranks = [&](uint32_t k) {
+    int32_t* sl = slot_of(k);
     int32_t* pt = sl + kAHdr + 4 * lane;
     int32_t s, e;
-    pair_range(sl, s, e);
+    tile_range(sl, s, e);
     const int32_t i = s + lane;
     if (i < e) {
       cpa4(pt + 0, p.ranks_bev + i);
@@ -197,8 +237,8 @@ __device__ __forceinline__ void role_rows(const FwdStreamParams& p, int32_t* rin
       pt[0] = -1;
     }
   };
-  auto issue_depth = [&](uint32_t m) {   // depth gather + fix-up of the landed ranks
-    int32_t* sl = slot_of(m);
+  auto issue_depth = [&](uint32_t k) {   // depth gather + fix-up of the landed ranks
+    int32_t* sl = slot_of(k);
     int32_t* pt = sl + kAHdr + 4 * lane;
     const int32_t rb = pt[0];
     if (rb >= 0) {
@@ -221,27 +261,36 @@ __device__ __forceinline__ void role_rows(const FwdStreamParams& p, int32_t* rin
 
   const uint32_t lane_off = (uint32_t)lane * (VEC * 4);
 
-  for (uint32_t m = 0; m < my_rounds; ++m) {
+  VEON_T0
+  for (uint32_t k = 0;; ++k) {
     cpa_wait<kADist - 1>();
     __syncwarp();
-    int32_t* sl = slot_of(m);
+    VEON_TACC(0)
+    int32_t* sl = slot_of(k);
+    const uint32_t g = (uint32_t)sl[kHdrItem];
+    if (g >= my_items) break;   // claims only grow: everything this warp still holds is past the end
+    const uint32_t m = g / kRoundTiles;
+    const int w = (int)(g & (kRoundTiles - 1));
     int32_t s0, e0;
-    pair_range(sl, s0, e0);
+    tile_range(sl, s0, e0);
     bool live_w;
     const int base_row = rows_before(lane <= kRoundTiles ? sl[lane] : 0,
-                                     lane < kRoundTiles ? (uint32_t)sl[17 + lane] : 0u, lane, warp,
+                                     lane < kRoundTiles ? (uint32_t)sl[17 + lane] : 0u, lane, w,
                                      heavy_thr, live_w);
-    issue_bounds(m + 3 * kADist);
-    issue_ranks(m + 2 * kADist);
-    issue_depth(m + kADist);
+    __syncwarp();               // the header has been read: its slot may be claimed again below
+    issue_bounds(k + 3 * kADist);
+    issue_ranks(k + 2 * kADist);
+    issue_depth(k + kADist);
     cpa_commit();
 
     for (int pass = 0; pass < p.n_pass; ++pass) {
       const uint32_t unit = m * (uint32_t)p.n_pass + pass;
-      const int slot = (int)(unit % (uint32_t)p.ns);
-      const uint32_t gen = unit / (uint32_t)p.ns;
-      // the slot's previous use has been read out by all E warps
-      if (gen > 0) mbar_wait(&sh->empty[slot], (gen - 1) & 1u);
+      const uint32_t slot = unit & ns_mask;
+      const uint32_t gen = unit >> p.ns_log2;
+      // every earlier use of the slot has been read out by all E warps
+      VEON_TACC(1)
+      while (sh->drained[slot] < kEWarps * gen) __nanosleep(256);
+      VEON_TACC(2)
       if (e0 > s0) {
         char* const slotb = reinterpret_cast<char*>(cta_ring + (size_t)slot * (kSlotRows * CU));
         const char* const featb = reinterpret_cast<const char*>(p.feat) + pass * (CU * 4);
@@ -283,22 +332,22 @@ __device__ __forceinline__ void role_rows(const FwdStreamParams& p, int32_t* rin
             int2 q[U];
             V f[U];
 #pragma unroll
-            for (int g = 0; g < U; g += 4) {
-              if (j0 + g < cnt) {
+            for (int gq = 0; gq < U; gq += 4) {
+              if (j0 + gq < cnt) {
 #pragma unroll
                 for (int uu = 0; uu < 4; ++uu) {
-                  const int u = g + uu;
+                  const int u = gq + uu;
                   q[u] = *reinterpret_cast<const int2*>(pts + 4 * min(j0 + u, cnt - 1));
                   f[u] = __ldg(reinterpret_cast<const V*>(featb + (((uint32_t)q[u].x & ~1u) + lane_off)));
                 }
               }
             }
 #pragma unroll
-            for (int g = 0; g < U; g += 4) {
-              if (j0 + g < cnt) {
+            for (int gq = 0; gq < U; gq += 4) {
+              if (j0 + gq < cnt) {
 #pragma unroll
                 for (int uu = 0; uu < 4; ++uu) {
-                  const int u = g + uu;
+                  const int u = gq + uu;
                   const bool ok = j0 + u < cnt;
                   const bool first = q[u].x & 1;
                   const float dj = __int_as_float(q[u].y);
@@ -314,9 +363,15 @@ __device__ __forceinline__ void role_rows(const FwdStreamParams& p, int32_t* rin
           }
         }
       }
-      // this warp's rows of the unit are in the slot
+      // this tile's rows of the unit are in the slot
       __syncwarp();
-      if (lane == 0) mbar_arrive(&sh->full[slot]);
+      VEON_TACC(3)
+      if (lane == 0) {
+        const uint32_t t = (blockIdx.x + m * gridDim.x) * kRoundTiles + w;
+        sh->meta[slot][w] = make_uint2((uint32_t)sl[17 + w],
+                                       (uint32_t)base_row | ((live_w && t < p.n_tiles) ? kMetaMine : 0u));
+        mbar_arrive(&sh->full[slot]);   // release: the rows and the meta word are visible with it
+      }
     }
   }
   cpa_wait<0>();
@@ -337,8 +392,8 @@ __device__ __forceinline__ void role_expand(const FwdStreamParams& p, float* sta
   __builtin_assume(__isShared(stage));
   if (blockIdx.x >= p.n_rounds) return;
   const uint32_t my_rounds = (p.n_rounds - blockIdx.x + gridDim.x - 1) / gridDim.x;
-  const int32_t heavy_thr = p.heavy ? __ldg(p.heavy + 1) : 0x7fffffff;
-  const float* const cta_ring = p.ring + (size_t)blockIdx.x * p.ns * (kSlotRows * CU);
+  const uint32_t ns_mask = (1u << p.ns_log2) - 1u;
+  const float* const cta_ring = p.ring + ((size_t)blockIdx.x << p.ns_log2) * (kSlotRows * CU);
   const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
   const int q4 = (lane & 7) * 4, r = lane >> 3;
   const int group = ew / kEGroup;
@@ -347,50 +402,47 @@ __device__ __forceinline__ void role_expand(const FwdStreamParams& p, float* sta
   for (int i = lane; i < kEChunk; i += 32) stage[32 * kEChunk + i] = 0.f;
   __syncwarp();
 
-  // round header of the NEXT round travels in registers (lane l: tile_start / mask of tile l)
-  auto load_header = [&](uint32_t m, int32_t& ts, uint32_t& occ) {
-    ts = 0;
-    occ = 0u;
-    if (m < my_rounds) {
-      const uint32_t t0 = (blockIdx.x + m * gridDim.x) * kRoundTiles;
-      ts = __ldg(p.tile_start + min(t0 + min(lane, kRoundTiles), p.n_tiles));
-      if (lane < kRoundTiles && t0 + lane < p.n_tiles) occ = __ldg(p.tile_occ + t0 + lane);
+  // (sample, tile inside the sample) of this warp's tile, advanced by the round stride
+  uint32_t t = blockIdx.x * kRoundTiles + ew;
+  uint32_t b = t / p.tiles_per_sample, vt = t - b * p.tiles_per_sample;
+  const uint32_t t_step = gridDim.x * kRoundTiles;
+  VEON_T0
+  for (uint32_t m = 0; m < my_rounds; ++m, t += t_step, vt += t_step) {
+    while (vt >= p.tiles_per_sample) {
+      vt -= p.tiles_per_sample;
+      ++b;
     }
-  };
-  int32_t ts_n;
-  uint32_t occ_n;
-  load_header(0, ts_n, occ_n);
-  for (uint32_t m = 0; m < my_rounds; ++m) {
-    const int32_t ts = ts_n;
-    const uint32_t occ_l = occ_n;
-    load_header(m + 1, ts_n, occ_n);
-    bool live_w;
-    const int base = rows_before(ts, occ_l, lane, ew, heavy_thr, live_w);
-    const uint32_t occ = __shfl_sync(0xffffffffu, occ_l, ew);
-    const uint32_t t = (blockIdx.x + m * gridDim.x) * kRoundTiles + ew;
-    const bool mine = live_w && t < p.n_tiles;
-    const int n = __popc(occ);
-    const uint32_t b = t / p.tiles_per_sample;
-    const uint32_t v0 = (t - b * p.tiles_per_sample) * kTileVoxels;
-    // shared-memory address of channel r of the staged row of each of this lane's four voxels,
-    // the row's swizzle folded in; the zero row for empty voxels
-    uint32_t a[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int v = q4 + i;
-      const bool set = (occ >> v) & 1u;
-      const uint32_t j = set ? (uint32_t)__popc(occ & ((1u << v) - 1u)) : 32u;
-      a[i] = stage_s + j * (kEChunk * 4) + (uint32_t)r * 4u;
-      if (set) a[i] ^= e_swz(j) << 4;
-    }
+    const uint32_t v0 = vt * kTileVoxels;
+    uint32_t occ = 0u, a[4] = {0u, 0u, 0u, 0u};
+    int base = 0, n = 0;
+    bool mine = false;
     for (int pass = 0; pass < p.n_pass; ++pass) {
       const uint32_t unit = m * (uint32_t)p.n_pass + pass;
-      const int slot = (int)(unit % (uint32_t)p.ns);
-      const uint32_t gen = unit / (uint32_t)p.ns;
+      const uint32_t slot = unit & ns_mask;
+      const uint32_t gen = unit >> p.ns_log2;
       // Role A has put the unit's rows into the slot.  EVERY E warp waits here, also one whose
-      // tile is empty: a warp must not run a slot generation ahead of the others (its arrival
-      // on `empty` would complete a phase a slower warp still belongs to).
+      // tile is empty: no E warp may run a slot generation ahead of the others (its tick on
+      // `drained` would be taken for a slower warp's).
+      VEON_TACC(0)
       mbar_wait(&sh->full[slot], gen & 1u);
+      VEON_TACC(1)
+      if (pass == 0) {   // what role A published about this warp's tile (the same for every pass)
+        const uint2 mt = sh->meta[slot][ew];
+        occ = mt.x;
+        base = (int)(mt.y & ~kMetaMine);
+        mine = (mt.y & kMetaMine) != 0u;
+        n = __popc(occ);
+        // shared-memory address of channel r of the staged row of each of this lane's four
+        // voxels, the row's swizzle folded in; the zero row for empty voxels
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int v = q4 + i;
+          const bool set = (occ >> v) & 1u;
+          const uint32_t j = set ? (uint32_t)__popc(occ & ((1u << v) - 1u)) : 32u;
+          a[i] = stage_s + j * (kEChunk * 4) + (uint32_t)r * 4u;
+          if (set) a[i] ^= e_swz(j) << 4;
+        }
+      }
       const float* src = cta_ring + (size_t)slot * (kSlotRows * CU) + (size_t)base * CU +
                          (lane & 15) * 4;
       float* o = p.out + ((int64_t)b * p.C + pass * CU + r) * p.V + v0 + q4;
@@ -405,10 +457,15 @@ __device__ __forceinline__ void role_expand(const FwdStreamParams& p, float* sta
         cpa_commit();
         cpa_wait<0>();
         __syncwarp();
-        if (sub == kSub - 1 && lane == 0) mbar_arrive(&sh->empty[slot]);   // slot needed no more
+        if (sub == kSub - 1 && lane == 0)   // slot needed no more (this warp's copies have landed)
+          atomicAdd(const_cast<uint32_t*>(&sh->drained[slot]), 1u);
+        VEON_TACC(2)
+#ifndef VEON_FWD_NO_LOCKSTEP
         // the group's 8 tiles are written together: aligned 1 KB runs per channel plane
         if (group == 0) asm volatile("bar.sync 1, %0;" ::"n"(kEGroup * 32) : "memory");
         else asm volatile("bar.sync 2, %0;" ::"n"(kEGroup * 32) : "memory");
+#endif
+        VEON_TACC(3)
         if (mine) {
           if (n == 0) {
 #pragma unroll 4
@@ -434,6 +491,7 @@ __device__ __forceinline__ void role_expand(const FwdStreamParams& p, float* sta
           o += (kEChunk / 4) * ostep;
         }
         __syncwarp();   // the staging buffer is refilled next
+        VEON_TACC(4)
       }
     }
   }
@@ -450,16 +508,17 @@ k_fwd_stream(const FwdStreamParams p) {
   pdl_launch_dependents();   // the heavy-tile grid may be queued behind this one
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (threadIdx.x < kMaxSlots) {
-    mbar_init(&sh.full[threadIdx.x], kAWarps);
-    mbar_init(&sh.empty[threadIdx.x], kEWarps);
+    mbar_init(&sh.full[threadIdx.x], kRoundTiles);   // one arrival per tile of the round
+    sh.drained[threadIdx.x] = 0;
   }
+  if (threadIdx.x == 0) sh.next_item = 0;
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
   constexpr int kEStageFloats = kEWarps * kERows * kEChunk;
   if (warp < kAWarps) {
     reg_inc<kARegs>();
     role_rows<VEC>(p, reinterpret_cast<int32_t*>(fs_smem + kEStageFloats) +
-                          warp * (kASlots * kASlotInts), &sh, lane, warp);
+                          warp * (kASlots * kASlotInts), &sh, lane);
   } else {
     reg_dec<kERegs>();
     const int ew = warp - kAWarps;
@@ -502,17 +561,24 @@ static int launch_stream_kernel(FwdStreamParams& p, size_t ring_bytes, cudaStrea
   const size_t slot_bytes = sizeof(float) * kSlotRows * CU;
   const int64_t ns = (int64_t)(ring_bytes / ((size_t)grid * slot_bytes));
   if (ns < 2) return VEON_E_WORKSPACE;
-  p.ns = ns > kMaxSlots ? kMaxSlots : (int)ns;
+  p.ns_log2 = 1;   // the largest power of two that fits, at most kMaxSlots
+  while ((2 << p.ns_log2) <= ns && (2 << p.ns_log2) <= kMaxSlots) ++p.ns_log2;
   p.n_pass = p.C / CU;
+  // a tile's passes must not need one slot twice: the second use would wait for the round to
+  // be consumed, i.e. for tiles the very same warp may still hold a claim on
+  if (p.n_pass > (1 << p.ns_log2)) return VEON_E_WORKSPACE;
   k_fwd_stream<VEC><<<(unsigned)grid, kStreamWarps * 32, smem, stream>>>(p);
   VEON_LAUNCH_CHECK();
   return 0;
 }
 
 size_t fwd_stream_workspace_bytes(int C) {
-  // (SM count of the current device) x 8 slots (C = 64) / 4 slots (wider rows) = 148 x 1 MB
+  // (SM count of the current device) x 8 slots (C = 64) / 4 slots (wider rows, at least one per
+  // 128-channel pass) = 148 x 1 MB at least
   const int CU = C == 64 ? 64 : 128;
-  return (size_t)sm_count() * (C == 64 ? 8 : 4) * sizeof(float) * kSlotRows * CU;
+  int ns = C == 64 ? 8 : 4;
+  while (ns < C / CU) ns *= 2;
+  return (size_t)sm_count() * ns * sizeof(float) * kSlotRows * CU;
 }
 
 int launch_fwd_stream(const float* depth, const float* feat, const int32_t* rd, const int32_t* rf,
@@ -528,7 +594,7 @@ int launch_fwd_stream(const float* depth, const float* feat, const int32_t* rd, 
   p.out = out; p.V = V; p.n_tiles = (uint32_t)n_tiles;
   p.n_rounds = (uint32_t)ceil_div64(n_tiles, kRoundTiles);
   p.tiles_per_sample = (uint32_t)tps;
-  p.C = C; p.n_pass = 1; p.ns = 2;
+  p.C = C; p.n_pass = 1; p.ns_log2 = 1;
   int rc = C == 64 ? launch_stream_kernel<2>(p, ws_bytes, stream)
                    : launch_stream_kernel<4>(p, ws_bytes, stream);
   if (rc) return rc;
@@ -538,3 +604,13 @@ int launch_fwd_stream(const float* depth, const float* feat, const int32_t* rd, 
 }
 
 }  // namespace veon
+
+#ifdef VEON_FWD_TRACE
+extern "C" int veon_internal_fwd_trace(unsigned long long* host_out, int clear) {
+  if (clear) {
+    static unsigned long long zeros[32 * 8] = {};
+    return (int)cudaMemcpyToSymbol(veon::veon_fwd_trace, zeros, sizeof(zeros));
+  }
+  return (int)cudaMemcpyFromSymbol(host_out, veon::veon_fwd_trace, sizeof(unsigned long long) * 32 * 8);
+}
+#endif
