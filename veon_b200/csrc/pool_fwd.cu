@@ -872,13 +872,13 @@ static int launch_heavy(const float* depth, const float* feat, const int32_t* rd
 int launch_heavy_behind(const float* depth, const float* feat, const int32_t* rd,
                         const int32_t* rf, const int32_t* rb, const int32_t* tile_start,
                         const int32_t* heavy, int64_t heavy_ints, int B, int C, int64_t V,
-                        float* out, cudaStream_t stream) {
+                        float* out, int min_points, cudaStream_t stream) {
   if (!heavy || heavy_ints < 2 || (C & 3) != 0 || ((uintptr_t)feat & 15) != 0)
     return VEON_E_BADARG;
   return C <= 32 ? launch_heavy<1>(depth, feat, rd, rf, rb, tile_start, heavy, heavy_ints, B, C, V,
-                                   out, true, 0, stream)
+                                   out, true, min_points, stream)
                  : launch_heavy<2>(depth, feat, rd, rf, rb, tile_start, heavy, heavy_ints, B, C, V,
-                                   out, true, 0, stream);
+                                   out, true, min_points, stream);
 }
 
 // general route: k_pool_fwd over every (tile, channel chunk), the heavy tiles queued behind it

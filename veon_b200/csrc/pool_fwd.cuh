@@ -19,6 +19,6 @@ int launch_fwd_stream(const float* depth, const float* feat, const int32_t* rd, 
 int launch_heavy_behind(const float* depth, const float* feat, const int32_t* rd,
                         const int32_t* rf, const int32_t* rb, const int32_t* tile_start,
                         const int32_t* heavy, int64_t heavy_ints, int B, int C, int64_t V,
-                        float* out, cudaStream_t stream);
+                        float* out, int min_points, cudaStream_t stream);
 
 }  // namespace veon

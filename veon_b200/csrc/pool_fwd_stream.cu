@@ -67,6 +67,10 @@ constexpr int kAHdr = 36;
 constexpr int kASlotInts = kAHdr + 4 * 32;
 constexpr int kADist = 1;               // prefetch distance in rounds per stage
 constexpr int kASlots = 4 * kADist;
+// Tiles at or above the plan's heavy threshold (96 points) are left to the CTA-per-tile kernel.
+// Raising the bar for this kernel (role A claims dynamically and the ring has rounds of slack)
+// was measured and loses: 128 / 256 / 384 / 768 points -> 321 / 357 / 386 / 487 us at C2.
+constexpr int kStreamHeavyMin = 0;
 constexpr int kEChunk = 64;             // channels per E item
 constexpr int kERows = 33;              // staged rows per tile: <= 32 occupied voxels + 1 of zeros
 
@@ -188,7 +192,7 @@ __device__ __forceinline__ void role_rows(const FwdStreamParams& p, int32_t* rin
   if (blockIdx.x >= p.n_rounds) return;
   const uint32_t my_rounds = (p.n_rounds - blockIdx.x + gridDim.x - 1) / gridDim.x;
   const uint32_t my_items = my_rounds * kRoundTiles;
-  const int32_t heavy_thr = p.heavy ? __ldg(p.heavy + 1) : 0x7fffffff;
+  const int32_t heavy_thr = p.heavy ? max(__ldg(p.heavy + 1), kStreamHeavyMin) : 0x7fffffff;
   const uint32_t ns_mask = (1u << p.ns_log2) - 1u;
   float* const cta_ring = p.ring + ((size_t)blockIdx.x << p.ns_log2) * (kSlotRows * CU);
   const uint32_t row_bytes = (uint32_t)p.C * 4u;
@@ -599,7 +603,7 @@ int launch_fwd_stream(const float* depth, const float* feat, const int32_t* rd, 
                    : launch_stream_kernel<4>(p, ws_bytes, stream);
   if (rc) return rc;
   if (heavy) return launch_heavy_behind(depth, feat, rd, rf, rb, tile_start, heavy, heavy_ints, B, C,
-                                        V, out, stream);
+                                        V, out, kStreamHeavyMin, stream);
   return 0;
 }
 
