@@ -647,3 +647,33 @@ extern "C" int veon_bev_pool_v2_bwd_planar_ds(
   return pixel_pass(pk, rows_ws, depth, feat, point_interval, (int64_t)B * N * H * W, D, H * W, C,
                     depth_grad, feat_grad, stream);
 }
+
+// ---- experiment hooks (not part of include/veon_lift.h; used by tools/bwd_pipeline.py) -------------
+// the two passes on their own, and an L2 access-policy window for a stream
+extern "C" int veon_internal_bwd_rows(const float* out_grad, const int32_t* tile_istart,
+                                      const uint32_t* tile_occ, int64_t n_tiles, int64_t tps,
+                                      int64_t V, int C, float* rows, void* stream) {
+  return C <= 32 ? launch_rows<1>(out_grad, tile_istart, tile_occ, 0, n_tiles, tps, V, C, rows, (cudaStream_t)stream)
+                 : launch_rows<2>(out_grad, tile_istart, tile_occ, 0, n_tiles, tps, V, C, rows, (cudaStream_t)stream);
+}
+extern "C" int veon_internal_bwd_pixels(const float* rows, const float* depth, const float* feat,
+                                        const int32_t* point_interval, int64_t pixels, int D, int HW,
+                                        int C, float* depth_grad, float* feat_grad, void* stream) {
+  const int pk = C <= 32 ? 1 : (C <= 64 ? 2 : (C <= 256 ? 4 : 8));
+  return pixel_pass(pk, rows, depth, feat, point_interval, pixels, D, HW, C, depth_grad, feat_grad,
+                    (cudaStream_t)stream);
+}
+extern "C" int veon_internal_l2_window(void* stream, void* base, size_t bytes, float hit_ratio,
+                                       size_t set_aside_bytes) {
+  if (set_aside_bytes) {
+    cudaError_t e = cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, set_aside_bytes);
+    if (e != cudaSuccess) return (int)e;
+  }
+  cudaStreamAttrValue a = {};
+  a.accessPolicyWindow.base_ptr = base;
+  a.accessPolicyWindow.num_bytes = bytes;
+  a.accessPolicyWindow.hitRatio = hit_ratio;
+  a.accessPolicyWindow.hitProp = bytes ? cudaAccessPropertyPersisting : cudaAccessPropertyNormal;
+  a.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+  return (int)cudaStreamSetAttribute((cudaStream_t)stream, cudaStreamAttributeAccessPolicyWindow, &a);
+}
