@@ -2,6 +2,9 @@
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import torch
+from veon_b200 import _lib
+if os.environ.get("VEON_LIB"):          # an experimental build of tools/build_variant.sh
+    _lib.LIB_PATH = os.environ["VEON_LIB"]
 from veon_b200.tail import class_of_prompt, voxel_text_argmax
 SIZES = [16, 1, 1, 1, 8, 1, 1, 3, 1, 1, 1, 1, 5, 3, 5, 13, 4]
 dev = torch.device("cuda", 0)
@@ -16,7 +19,7 @@ for C, refl, B in ((512, list(range(17)), 2), (512, [k for k, n in enumerate(SIZ
     for _ in range(3): voxel_text_argmax(feat, w, cls, bin_occ)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    n = 10; e0.record()
+    n = 50; e0.record()
     for _ in range(n): lab = voxel_text_argmax(feat, w, cls, bin_occ)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / n

@@ -23,7 +23,11 @@
 //     STS.128): 16 B of shared-memory traffic per element instead of 20-24 B if
 //     a TMA-landed tile had to be re-read to be split; at ~22 B/clk/SM of HBM the
 //     shared-memory port is the scarce resource of this kernel.
-// Warp roles (21 warps): 0-15 producers (the loads of the next stage are in flight while the
+//   * W never passes through registers: k_w_image splits it once per call into a global image
+//     laid out chunk by chunk exactly like a stage's [W_hi ; W_lo] block (K-major SW128), and one
+//     lane copies a chunk per stage with a 1-D bulk copy that completes on the stage's `full`
+//     barrier.  The producers' registers hold nothing but rows in flight (kSets stages).
+// Warp roles (21 warps): 0-15 A producers (kSets - 1 later stages' loads in flight while the
 // current one is split and stored), 16 MMA issuer (+TMEM alloc), 17-20 epilogue.
 #include <math.h>
 
@@ -34,11 +38,21 @@ namespace tc {
 
 constexpr int KC = 32;        // channels per pipeline stage = 4 UMMA K-steps of 8 (tf32)
 constexpr int TM = 128;       // voxels per tile = UMMA M
-constexpr int kProdWarps = 16;  // 2 channel rows of the 32-row stage each
+constexpr int kProdWarps = 16;  // warp % 4 = TMEM lane quarter (32 voxels), warp / 4 = channel group
+constexpr int kRows = KC / 4;   // channels of a stage per producer thread
+constexpr uint32_t kTmemCols = 512;
 constexpr int kMmaWarp = 16;
 constexpr int kEpiWarp0 = 17;   // 17..20: warp % 4 = 1,2,3,0 -> the four TMEM lane quarters
-constexpr int kWarps = 21;
+constexpr int kLoadWarp0 = 21;  // 21, 22: loaders
+constexpr int kLoadWarps = 2;
+constexpr int kWarps = 23;
+constexpr int kRaw = 7;                        // raw tiles in flight per SM
+constexpr uint32_t kRawBytes = KC * TM * 4;    // 16 KB
 constexpr int kMaxStages = 6;
+#ifndef VEON_TAIL_SETS
+#define VEON_TAIL_SETS 3
+#endif
+constexpr int kSets = VEON_TAIL_SETS;   // stages of A in flight per producer lane
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -63,6 +77,17 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "r"(addr), "r"(parity)
         : "memory");
   } while (!done);
+}
+__device__ __forceinline__ bool elect_one() {   // one lane of the (converged) warp
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void fence_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -115,10 +140,10 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) |
          ((uint64_t)((sbo_bytes >> 4) & 0x3fffu) << 32) | (1ull << 46) | (layout_type << 61);
 }
-// instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32, A MN-major,
-// B K-major, M=128, N=n
+// instruction descriptor (cute::UMMA::InstrDescriptor): D=f32, A=B=tf32, A (tensor memory)
+// and B K-major, M=128, N=n
 __host__ __device__ constexpr uint32_t make_idesc(int n) {
-  return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) |
+  return (1u << 4) | (2u << 7) | (2u << 10) | (0u << 15) | (0u << 16) | ((uint32_t)(n >> 3) << 17) |
          ((uint32_t)(TM >> 4) << 24);
 }
 
@@ -128,44 +153,109 @@ __device__ __forceinline__ float tf32_hi(float x) {  // exactly TF32-representab
 
 struct Params {
   const float* feat;     // [B,C,V]
-  const float* w;        // [Q,C]
+  const float* w_image;  // k_w_image's output
   const int32_t* cls;    // [Q]
   const float* bin_occ;  // [B,2,V]
   uint8_t* labels;       // [B,X,Y,Z]
   float* logits;         // LOGITS variant: sem_occ [B,Q,V] instead of labels
   int B, C, Q, Z, Y, X, npad, stages, free_label;
   int64_t V;
-  uint32_t tmem_cols;
 };
 
-// WP = float4 pieces of the W chunk a producer thread owns (1 for npad <= 64, else 2).
-// With WP == 1 three named register sets fit (three stages of A in flight per lane).
+// [W_hi ; W_lo] of every 32-channel chunk in the shared-memory layout of a stage's W block:
+// row n (prompt) of the chunk = 128 B at (n/8)*1024 + (n%8)*128, its 16-byte pieces XOR-swizzled
+// by n%8; the lo rows follow the npad hi rows.  Rows >= Q are zero.
+__global__ void k_w_image(const float* __restrict__ w, int Q, int C, int npad, float* __restrict__ image) {
+  const int n_chunks = C / KC;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)n_chunks * npad * 8) return;
+  const int j4 = (int)(idx & 7), n = (int)((idx >> 3) % npad), ch = (int)((idx >> 3) / npad);
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (n < Q) v = __ldg(reinterpret_cast<const float4*>(w + (int64_t)n * C + ch * KC) + j4);
+  float4 hi, lo;
+  hi.x = tf32_hi(v.x); hi.y = tf32_hi(v.y); hi.z = tf32_hi(v.z); hi.w = tf32_hi(v.w);
+  lo.x = v.x - hi.x; lo.y = v.y - hi.y; lo.z = v.z - hi.z; lo.w = v.w - hi.w;
+  uint8_t* blk = reinterpret_cast<uint8_t*>(image) + (size_t)ch * (2 * npad * KC * 4);
+  const uint32_t off = (uint32_t)(n >> 3) * 1024u + (uint32_t)(n & 7) * 128u + (uint32_t)((j4 ^ (n & 7)) << 4);
+  *reinterpret_cast<float4*>(blk + off) = hi;
+  *reinterpret_cast<float4*>(blk + off + (uint32_t)npad * 128u) = lo;
+}
+
+#ifdef VEON_TAIL_TRACE   // tools/tail_trace.py only: cycles per phase, CTA 0, every warp
+__device__ unsigned long long veon_tail_trace[32 * 8];
+#define VEON_T0 long long _tt = clock64(), _ta[4] = {0, 0, 0, 0};
+#define VEON_TACC(slotid)          \
+  {                                \
+    const long long _n = clock64(); \
+    _ta[slotid] += _n - _tt;       \
+    _tt = _n;                      \
+  }
+#define VEON_TEND                                                                   \
+  if (blockIdx.x == 0 && (threadIdx.x & 31) == 0)                                   \
+    for (int _i = 0; _i < 4; ++_i) veon_tail_trace[(threadIdx.x >> 5) * 8 + _i] = _ta[_i];
+#else
+#define VEON_T0
+#define VEON_TACC(slotid)
+#define VEON_TEND
+#endif
+
+// 32 lanes x 8 consecutive columns <- 8 registers per thread (thread i <-> lane base+i)
+__device__ __forceinline__ void tc_st8(uint32_t taddr, const float* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr),
+      "r"(__float_as_uint(v[0])), "r"(__float_as_uint(v[1])), "r"(__float_as_uint(v[2])),
+      "r"(__float_as_uint(v[3])), "r"(__float_as_uint(v[4])), "r"(__float_as_uint(v[5])),
+      "r"(__float_as_uint(v[6])), "r"(__float_as_uint(v[7]))
+      : "memory");
+}
+// A from tensor memory (lanes = rows, one 32-bit column per K element), B from shared memory
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc,
+                                               uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+
+// Tensor-memory map (all 512 columns): [0, 2*npad) two accumulator buffers of npad columns
+// (every (voxel, prompt) sum lives in ONE column: a_hi*w_hi + a_hi*w_lo + a_lo*w_hi), then
+// `stages` operand slots of 2*KC columns: a_hi (KC columns, one per channel) and a_lo.
+// Shared memory holds only the W ring: one [W_hi ; W_lo] block per stage.
 // LOGITS: the epilogue stores the raw logits (semantic_inference_3d alone) instead of labels.
-template <int WP, bool LOGITS>
+template <bool LOGITS>
 __global__ void __launch_bounds__(kWarps * 32, 1) k_tail_tc(const Params p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int npad = p.npad, stages = p.stages;
-  const uint32_t a_bytes = KC * TM * 4;          // 16 KB per A buffer (hi or lo)
   const uint32_t w_bytes = 2 * npad * KC * 4;    // [W_hi ; W_lo] chunk
-  const uint32_t stage_bytes = 2 * a_bytes + w_bytes;
-  uint8_t* stage_base = smem_raw;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)stages * stage_bytes);
-  uint64_t* full = bars;                  // [stages]   producers -> MMA
-  uint64_t* empty = bars + kMaxStages;    // [stages]   MMA -> producers
+  uint8_t* raw_base = smem_raw;                                  // [kRaw] raw tiles [KC][TM] f32
+  uint8_t* stage_base = smem_raw + (size_t)kRaw * kRawBytes;     // [stages] W blocks
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage_base + (size_t)stages * w_bytes);
+  uint64_t* full = bars;                  // [stages]   converters + W copy -> MMA
+  uint64_t* empty = bars + kMaxStages;    // [stages]   MMA -> converters
   uint64_t* acc_full = bars + 2 * kMaxStages;   // [2]  MMA -> epilogue
   uint64_t* acc_empty = acc_full + 2;           // [2]  epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* raw_full = acc_empty + 2;           // [kRaw] loader (bulk copies) -> converters
+  uint64_t* raw_empty = raw_full + kRaw;        // [kRaw] converters -> loader
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(raw_empty + kRaw);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < stages; ++s) { mbar_init(full + s, kProdWarps); mbar_init(empty + s, 1); }
+    for (int s = 0; s < stages; ++s) {
+      mbar_init(full + s, kProdWarps + 1);   // + the expect_tx arrival of the W copy
+      mbar_init(empty + s, 1);
+    }
     for (int a = 0; a < 2; ++a) { mbar_init(acc_full + a, 1); mbar_init(acc_empty + a, 4); }
+    for (int r = 0; r < kRaw; ++r) { mbar_init(raw_full + r, 32 * kLoadWarps); mbar_init(raw_empty + r, kProdWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == kMmaWarp) {  // TMEM allocation is warp-wide
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32(tmem_slot)),
-                 "r"(p.tmem_cols)
+                 "r"(kTmemCols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -173,191 +263,180 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_tail_tc(const Params p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  const uint32_t a_base = tmem_base + 2u * (uint32_t)npad;   // first operand slot
 
   const int64_t vtiles = (p.V + TM - 1) / TM;
   const int64_t n_tiles = (int64_t)p.B * vtiles;
   const int n_chunks = p.C / KC;
+  const int64_t my_tiles = (n_tiles > (int64_t)blockIdx.x)
+                               ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const int64_t n_stages_total = my_tiles * n_chunks;
 
-  if (warp < kProdWarps) {
-    // ============================ PRODUCERS ============================
-    // Everything that does not change from stage to stage is set up once: the lane's
-    // two shared-memory offsets, and the (up to two) W pieces this thread owns.
-    const int ma = lane >> 3, j = lane & 7;
-    const int row0 = 2 * warp;  // this warp's two channel rows inside a 32-row stage
-    uint32_t a_off[2];
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      // channel row kl of the chunk = row kl%4 of 4-row group kl/4; the lane's 16 bytes are
-      // half of 32-byte chunk j/2, which is XOR-swizzled by the row
-      const int kl = row0 + i, kg4 = kl >> 2, kin = kl & 3;
-      a_off[i] = (uint32_t)(kg4 * 4 + ma) * 512u + (uint32_t)kin * 128u +
-                 (uint32_t)(((j >> 1) ^ kin) << 5) + (uint32_t)((j & 1) << 4);
-    }
-    constexpr int kWPieces = WP;  // npad * 8 float4 pieces over 512 threads (npad <= 64 * WP)
-    const float4* w_src[kWPieces];
-    uint32_t w_hi_off[kWPieces], w_lo_off[kWPieces];
-    bool w_has[kWPieces], w_real[kWPieces];
-#pragma unroll
-    for (int q = 0; q < kWPieces; ++q) {
-      const int idx = threadIdx.x + q * kProdWarps * 32;
-      const int n = idx >> 3, j4 = idx & 7, n2 = n + npad;
-      w_has[q] = idx < npad * 8;
-      w_real[q] = w_has[q] && n < p.Q;
-      w_src[q] = reinterpret_cast<const float4*>(p.w + (int64_t)(w_real[q] ? n : 0) * p.C) + j4;
-      w_hi_off[q] = 2 * a_bytes + (uint32_t)(n >> 3) * 1024u + (uint32_t)(n & 7) * 128u +
-                    (uint32_t)((j4 ^ (n & 7)) << 4);
-      w_lo_off[q] = 2 * a_bytes + (uint32_t)(n2 >> 3) * 1024u + (uint32_t)(n2 & 7) * 128u +
-                    (uint32_t)((j4 ^ (n2 & 7)) << 4);
-    }
-    const int64_t chunk_stride = (int64_t)KC * p.V;  // floats between consecutive chunks
-    auto tile_src = [&](int64_t tile, bool& vin) -> const float* {
+  if (warp >= kLoadWarp0) {
+    // ============================ LOADERS ============================
+    // 16-byte cp.async copies, a warp-instruction per 512-byte row segment (128 voxels of one
+    // channel plane), completion reported to the raw slot's barrier.  Nothing passes through
+    // registers, so the bytes in flight are bounded only by the raw ring (kRaw x 16 KB per SM).
+    // (One 512-byte bulk copy per row instead: 77 cycles per copy, 1.9 TB/s in all.)
+    const int lw = warp - kLoadWarp0;                       // rows lw, lw + kLoadWarps, ...
+    uint32_t rs = 0, rphase = 0;
+    bool first_round = true;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int64_t b = tile / vtiles;
       const int64_t v = (tile - b * vtiles) * TM + 4 * lane;
-      vin = (tile < n_tiles) && (v < p.V);  // V % 4 == 0: the float4 is fully in or out
-      return p.feat + ((int64_t)b * p.C + row0) * p.V + v;
-    };
-    auto load_rows = [&](const float* src, bool vin, float4* a) {
+      const uint32_t nbytes = v < p.V ? 16u : 0u;           // V % 4 == 0; past the end: zero-fill
+      const float* src = p.feat + ((int64_t)b * p.C + lw) * p.V + (v < p.V ? v : 0);
+      for (int ch = 0; ch < n_chunks; ++ch, src += (int64_t)KC * p.V) {
+        if (!first_round) mbar_wait(raw_empty + rs, rphase);
+        const uint32_t dst = smem_u32(raw_base + (size_t)rs * kRawBytes) + (uint32_t)(lw * TM * 4 + lane * 16);
+#ifndef VEON_TAIL_X_NOLOAD
 #pragma unroll
-      for (int i = 0; i < 2; ++i)
-        a[i] = vin ? ld_stream4(src + (int64_t)i * p.V) : make_float4(0.f, 0.f, 0.f, 0.f);
-    };
-    uint32_t s = 0, phase = 0;  // stage slot and the parity its `empty` barrier completes next
-    bool first_round = true;
-    // position of the stage whose data is being LOADED (runs one stage ahead of the stores)
-    int64_t ltile = blockIdx.x;
-    int lch = 0;
-    bool vin;
-    const float* src = tile_src(ltile, vin);
-    auto load_stage = [&](float4* a, float4* wv) {
-      load_rows(src, vin, a);
-#pragma unroll
-      for (int q = 0; q < kWPieces; ++q)
-        wv[q] = w_real[q] ? __ldg(w_src[q] + lch * (KC / 4)) : make_float4(0.f, 0.f, 0.f, 0.f);
-      // advance the load position
-      if (++lch == n_chunks) {
-        lch = 0;
-        ltile += gridDim.x;
-        src = tile_src(ltile, vin);
-      } else {
-        src += chunk_stride;
-      }
-    };
-    auto store_stage = [&](const float4* a, const float4* wv) {
-      if (!first_round) mbar_wait(empty + s, phase);
-      uint8_t* st = stage_base + (size_t)s * stage_bytes;
-#pragma unroll
-      for (int q = 0; q < kWPieces; ++q) {
-        if (w_has[q]) {
-          float4 hi, lo;
-          hi.x = tf32_hi(wv[q].x); hi.y = tf32_hi(wv[q].y);
-          hi.z = tf32_hi(wv[q].z); hi.w = tf32_hi(wv[q].w);
-          lo.x = wv[q].x - hi.x; lo.y = wv[q].y - hi.y;
-          lo.z = wv[q].z - hi.z; lo.w = wv[q].w - hi.w;
-          *reinterpret_cast<float4*>(st + w_hi_off[q]) = hi;
-          *reinterpret_cast<float4*>(st + w_lo_off[q]) = lo;
+        for (int r = 0; r < KC / kLoadWarps; ++r)
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(
+                           dst + (uint32_t)(r * kLoadWarps * TM * 4)),
+                       "l"(src + (int64_t)r * kLoadWarps * p.V), "r"(nbytes)
+                       : "memory");
+#endif
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(raw_full + rs))
+                     : "memory");
+        if (++rs == kRaw) {
+          rs = 0;
+          if (first_round) first_round = false; else rphase ^= 1;
         }
       }
+    }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+  } else if (warp < kProdWarps) {
+    // ============================ CONVERTERS ============================
+    // thread <-> voxel (TMEM lane 32*quarter + lane; a warp reaches only the lanes of warp % 4),
+    // warp / 4 = which 8 of the stage's 32 channels.  Column reads of the raw tile are
+    // conflict-free (lanes = consecutive voxels); the values go hi/lo-split from registers
+    // straight into tensor memory, so the tensor core never reads A from shared memory.
+    const int quarter = warp & 3, grp = warp >> 2;
+    const uint32_t lane_field = (uint32_t)(32 * quarter) << 16;
+    const float* raw_col = reinterpret_cast<const float*>(raw_base) + (kRows * grp) * TM + 32 * quarter + lane;
+    uint32_t s = 0, phase = 0;     // operand slot and the parity its `empty` barrier completes next
+    uint32_t rs = 0, rphase = 0;   // raw slot and the parity its `raw_full` barrier completes next
+    bool first_round = true;
+    int sch = 0;
+    VEON_T0
+    for (int64_t k = 0; k < n_stages_total; ++k) {
+      mbar_wait(raw_full + rs, rphase);
+      VEON_TACC(0)
+      float hi[kRows], lo[kRows];
+      const float* col = raw_col + (size_t)rs * (kRawBytes / 4);
 #pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        float4 hi, lo;
-        hi.x = tf32_hi(a[i].x); hi.y = tf32_hi(a[i].y);
-        hi.z = tf32_hi(a[i].z); hi.w = tf32_hi(a[i].w);
-        lo.x = a[i].x - hi.x; lo.y = a[i].y - hi.y;
-        lo.z = a[i].z - hi.z; lo.w = a[i].w - hi.w;
-        *reinterpret_cast<float4*>(st + a_off[i]) = hi;
-        *reinterpret_cast<float4*>(st + a_bytes + a_off[i]) = lo;
+      for (int i = 0; i < kRows; ++i) {
+        const float a = col[i * TM];
+        hi[i] = tf32_hi(a);
+        lo[i] = a - hi[i];
       }
-      fence_async_smem();  // generic-proxy writes -> visible to the tensor core (async proxy)
+      __syncwarp();
+      if (lane == 0) mbar_arrive(raw_empty + rs);   // the values are in registers
+      if (++rs == kRaw) { rs = 0; rphase ^= 1; }
+      VEON_TACC(2)
+      if (!first_round) {
+        mbar_wait(empty + s, phase);
+        tc_fence_after();
+      }
+      VEON_TACC(1)
+      if (threadIdx.x == 0) {   // this stage's [W_hi ; W_lo] block: one bulk copy, L2-resident source
+        const uint32_t bar = smem_u32(full + s);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(w_bytes)
+                     : "memory");
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                smem_u32(stage_base + (size_t)s * w_bytes)),
+            "l"(reinterpret_cast<const uint8_t*>(p.w_image) + (size_t)sch * w_bytes), "r"(w_bytes), "r"(bar)
+            : "memory");
+      }
+      if (++sch == n_chunks) sch = 0;
+      const uint32_t slot = a_base + s * (2 * KC) + lane_field + (uint32_t)(kRows * grp);
+      tc_st8(slot, hi);
+      tc_st8(slot + KC, lo);
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(full + s);
+      VEON_TACC(3)
       if (++s == (uint32_t)stages) {
         s = 0;
         if (first_round) first_round = false; else phase ^= 1;
       }
-    };
-    // Two named register sets, loop unrolled by two: the loads of stage k+1 are issued
-    // before stage k is written, and no register is ever copied while its load is in flight
-    // (a rotating copy would wait for the load it copies).  When the thread owns a single W
-    // piece (npad <= 64) a third set fits: three stages of A in flight per lane.
-    const int64_t my_tiles = (n_tiles > (int64_t)blockIdx.x)
-                                 ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-    const int64_t n_stages_total = my_tiles * n_chunks;
-    if constexpr (WP == 1) {   // (a fourth set spills: 2 319 instead of 3 087 samples/s)
-      float4 a0[2], a1[2], a2[2], w0[1], w1[1], w2[1];
-      if (n_stages_total > 0) load_stage(a0, w0);
-      if (n_stages_total > 1) load_stage(a1, w1);
-      for (int64_t k = 0; k < n_stages_total; k += 3) {
-        if (k + 2 < n_stages_total) load_stage(a2, w2);
-        store_stage(a0, w0);
-        if (k + 1 >= n_stages_total) break;
-        if (k + 3 < n_stages_total) load_stage(a0, w0);
-        store_stage(a1, w1);
-        if (k + 2 >= n_stages_total) break;
-        if (k + 4 < n_stages_total) load_stage(a1, w1);
-        store_stage(a2, w2);
-      }
-    } else {
-      float4 a0[2], a1[2], w0[kWPieces], w1[kWPieces];
-      if (n_stages_total > 0) load_stage(a0, w0);
-      for (int64_t k = 0; k < n_stages_total; k += 2) {
-        if (k + 1 < n_stages_total) load_stage(a1, w1);
-        store_stage(a0, w0);
-        if (k + 1 >= n_stages_total) break;
-        if (k + 2 < n_stages_total) load_stage(a0, w0);
-        store_stage(a1, w1);
-      }
     }
+    VEON_TEND
   } else if (warp == kMmaWarp) {
     // ============================ MMA ISSUER ============================
-    if (lane == 0) {
-      const uint32_t idesc_main = make_idesc(2 * npad), idesc_lo = make_idesc(npad);
-      uint32_t it = 0, tcount = 0;
+    // The whole warp runs this loop and one elected lane issues: with warp-uniform control flow
+    // the descriptors and tensor-memory addresses live in uniform registers.  (Inside an
+    // `if (lane == 0)` branch every tcgen05.mma was wrapped in an ELECT / 4 x R2UR / branch
+    // loop, ~75 cycles per instruction: the issuing thread, not the tensor pipe, set the pace.)
+    {
+      const uint32_t idesc = make_idesc(npad);
+      const uint32_t w_lo_off = (uint32_t)npad * 128u;   // the lo rows follow the npad hi rows
+      const uint32_t tmem0 = __shfl_sync(0xffffffffu, tmem_base, 0);
+      const uint32_t a0 = tmem0 + 2u * (uint32_t)npad;
+      const uint32_t sw0 = smem_u32(stage_base);
+      const bool leader = elect_one();
+      uint32_t s = 0, fphase = 0, tcount = 0;
+      VEON_T0
       for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
-        const int acc = tcount & 1;
+        const uint32_t acc = tcount & 1;
         const uint32_t around = tcount >> 1;
         if (around > 0) mbar_wait(acc_empty + acc, (around - 1) & 1);
         tc_fence_after();
-        const uint32_t d = tmem_base + (uint32_t)(acc * 2 * npad);
-        for (int ch = 0; ch < n_chunks; ++ch, ++it) {
-          const int s = it % stages;
-          mbar_wait(full + s, (it / stages) & 1);
+        VEON_TACC(0)
+        const uint32_t d = tmem0 + acc * (uint32_t)npad;
+        for (int ch = 0; ch < n_chunks; ++ch) {
+          mbar_wait(full + s, fphase);
           tc_fence_after();
-          const uint32_t sa = smem_u32(stage_base + (size_t)s * stage_bytes);
-          const uint32_t sw = sa + 2 * a_bytes;
+          VEON_TACC(1)
+          const uint32_t sw = sw0 + s * w_bytes;
+          const uint32_t a_hi = a0 + s * (2 * KC), a_lo = a_hi + KC;
+#ifndef VEON_TAIL_X_NOMMA
 #pragma unroll
-          for (int k = 0; k < KC / 8; ++k)  // a_hi * [w_hi ; w_lo]
-            tc_mma_tf32(d, make_desc(sa + k * 4096, 512, 2048, kSw128Base32),
-                        make_desc(sw + k * 32, 16, 1024, kSw128), idesc_main,
-                        (ch > 0 || k > 0) ? 1u : 0u);
-#pragma unroll
-          for (int k = 0; k < KC / 8; ++k)  // a_lo * w_hi, into the w_hi columns
-            tc_mma_tf32(d, make_desc(sa + a_bytes + k * 4096, 512, 2048, kSw128Base32),
-                        make_desc(sw + k * 32, 16, 1024, kSw128), idesc_lo, 1u);
-          tc_commit(empty + s);  // smem stage reusable once these MMAs have read it
+          for (int k = 0; k < KC / 8; ++k) {
+            const uint64_t w_hi = make_desc(sw + k * 32, 16, 1024, kSw128);
+            const uint64_t w_lo = make_desc(sw + w_lo_off + k * 32, 16, 1024, kSw128);
+            if (leader) {
+              tc_mma_tf32_ts(d, a_hi + 8 * k, w_hi, idesc, (ch > 0 || k > 0) ? 1u : 0u);
+              tc_mma_tf32_ts(d, a_hi + 8 * k, w_lo, idesc, 1u);
+              tc_mma_tf32_ts(d, a_lo + 8 * k, w_hi, idesc, 1u);
+            }
+          }
+#endif
+          if (leader) tc_commit(empty + s);  // operand slot + W block reusable once these MMAs have read them
+          __syncwarp();
+          VEON_TACC(2)
+          if (++s == (uint32_t)stages) { s = 0; fphase ^= 1; }
         }
-        tc_commit(acc_full + acc);
+        if (leader) tc_commit(acc_full + acc);
+        __syncwarp();
       }
+      VEON_TEND
     }
   } else {
     // ============================ EPILOGUE ============================
     const int quarter = warp & 3;  // TMEM lanes a warp may touch: 32*(warp%4) ..
     uint32_t tcount = 0;
+    VEON_T0
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+      VEON_TACC(1)
       const int acc = tcount & 1;
       mbar_wait(acc_full + acc, (tcount >> 1) & 1);
       tc_fence_after();
+      VEON_TACC(0)
       const int64_t b = tile / vtiles;
       const int64_t v = (tile - b * vtiles) * TM + 32 * quarter + lane;
-      const uint32_t taddr = tmem_base + (uint32_t)(acc * 2 * npad) + ((uint32_t)(32 * quarter) << 16);
+      const uint32_t taddr = tmem_base + (uint32_t)(acc * npad) + ((uint32_t)(32 * quarter) << 16);
       if constexpr (LOGITS) {
         float* dst = p.logits + (int64_t)b * p.Q * p.V + v;  // lanes = consecutive voxels
         for (int q0 = 0; q0 < npad; q0 += 16) {
-          float m[16], x[16];
+          float m[16];
           tc_ld16(taddr + q0, m);
-          tc_ld16(taddr + npad + q0, x);
 #pragma unroll
           for (int i = 0; i < 16; ++i)
-            if (q0 + i < p.Q && v < p.V) dst[(int64_t)(q0 + i) * p.V] = m[i] + x[i];
+            if (q0 + i < p.Q && v < p.V) dst[(int64_t)(q0 + i) * p.V] = m[i];
         }
         tc_fence_before();
         __syncwarp();
@@ -368,14 +447,13 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_tail_tc(const Params p) {
       int best_cls = -1, cur_cls = -1;
       bool bad = false;
       for (int q0 = 0; q0 < npad; q0 += 16) {
-        float m[16], x[16];
-        tc_ld16(taddr + q0, m);          // a_hi*w_hi + a_lo*w_hi
-        tc_ld16(taddr + npad + q0, x);   // a_hi*w_lo
+        float m[16];
+        tc_ld16(taddr + q0, m);
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const int q = q0 + i;
           if (q < p.Q) {
-            const float logit = m[i] + x[i];
+            const float logit = m[i];
             const int cls = __ldg(p.cls + q);
             bad |= !(logit < INFINITY);
             if (cls != cur_cls) {
@@ -406,13 +484,14 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_tail_tc(const Params p) {
         p.labels[(((int64_t)b * p.X + xx) * p.Y + yy) * p.Z + zz] = (uint8_t)label;
       }
     }
+    VEON_TEND
   }
   tc_fence_before();
   __syncthreads();
   if (warp == kMmaWarp) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
-                 "r"(p.tmem_cols)
+                 "r"(kTmemCols)
                  : "memory");
   }
 }
@@ -422,18 +501,28 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_tail_tc(const Params p) {
 
 using namespace veon;
 
+#ifdef VEON_TAIL_TRACE
+extern "C" int veon_internal_tail_trace(unsigned long long* host_out, int clear) {
+  if (clear) {
+    static unsigned long long zeros[32 * 8] = {};
+    return (int)cudaMemcpyToSymbol(tc::veon_tail_trace, zeros, sizeof(zeros));
+  }
+  return (int)cudaMemcpyFromSymbol(host_out, tc::veon_tail_trace, sizeof(unsigned long long) * 32 * 8);
+}
+#endif
+
 // returns 0 when launched, VEON_E_UNSUPPORTED when the shape does not fit this path.
 // logits != nullptr: write sem_occ [B,Q,V] (cls / bin_occ / labels unused).
-template <int WP, bool LOGITS>
+template <bool LOGITS>
 static int launch_variant(const tc::Params& p, unsigned grid, size_t smem, cudaStream_t stream) {
   static size_t attr_smem_dev[kMaxDevices] = {};   // per device: one process may drive several GPUs
   size_t& attr_smem = attr_smem_dev[current_device()];
   if (smem > attr_smem) {
-    VEON_CUDA_TRY(cudaFuncSetAttribute(tc::k_tail_tc<WP, LOGITS>,
+    VEON_CUDA_TRY(cudaFuncSetAttribute(tc::k_tail_tc<LOGITS>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_smem = smem;
   }
-  tc::k_tail_tc<WP, LOGITS><<<grid, tc::kWarps * 32, smem, stream>>>(p);
+  tc::k_tail_tc<LOGITS><<<grid, tc::kWarps * 32, smem, stream>>>(p);
   VEON_LAUNCH_CHECK();
   return 0;
 }
@@ -445,29 +534,33 @@ int veon_tail_tc_launch(const float* feat_occ, const float* text_w, const int32_
   const int npad = ((Q + 15) / 16) * 16;
   if (C % tc::KC != 0 || (V & 3) != 0 || npad > 128 || (((uintptr_t)feat_occ | (uintptr_t)text_w) & 15))
     return VEON_E_UNSUPPORTED;
-  const size_t stage_bytes = 2 * (size_t)tc::KC * tc::TM * 4 + 2 * (size_t)npad * tc::KC * 4;
+  const size_t w_bytes = 2 * (size_t)npad * tc::KC * 4;
   const size_t tail = 1024;  // barriers + tmem slot
-  int stages = (int)((227 * 1024 - tail) / stage_bytes);
+  int stages = (int)((tc::kTmemCols - 2 * npad) / (2 * tc::KC));   // operand slots in tensor memory
   if (stages > tc::kMaxStages) stages = tc::kMaxStages;
+  const size_t raw = (size_t)tc::kRaw * tc::kRawBytes;
+  if (raw + (size_t)stages * w_bytes + tail > 227 * 1024) stages = (int)((227 * 1024 - tail - raw) / w_bytes);
   if (stages < 2) return VEON_E_UNSUPPORTED;
-  const size_t smem = stages * stage_bytes + tail;
-  const bool one_piece = npad <= 64;
-  uint32_t cols = 32;
-  while (cols < (uint32_t)(4 * npad)) cols <<= 1;  // 2 accumulators x 2*npad columns
-  if (cols > 512) return VEON_E_UNSUPPORTED;
+  const size_t smem = raw + stages * w_bytes + tail;
   tc::Params p;
-  p.feat = feat_occ; p.w = text_w; p.cls = cls; p.bin_occ = bin_occ; p.labels = labels;
+  p.feat = feat_occ; p.cls = cls; p.bin_occ = bin_occ; p.labels = labels;
   p.logits = logits;
   p.B = B; p.C = C; p.Q = Q; p.Z = Z; p.Y = Y; p.X = X; p.npad = npad; p.stages = stages;
-  p.free_label = free_label; p.V = V; p.tmem_cols = cols;
+  p.free_label = free_label; p.V = V;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t n_tiles = (int64_t)B * ((V + tc::TM - 1) / tc::TM);
   const unsigned grid = (unsigned)(n_tiles < sms ? n_tiles : sms);
-  if (logits)
-    return one_piece ? launch_variant<1, true>(p, grid, smem, stream)
-                     : launch_variant<2, true>(p, grid, smem, stream);
-  return one_piece ? launch_variant<1, false>(p, grid, smem, stream)
-                   : launch_variant<2, false>(p, grid, smem, stream);
+  // the split weight image lives in a stream-ordered allocation for the duration of the call
+  float* image = nullptr;
+  const size_t image_bytes = (size_t)(C / tc::KC) * 2 * npad * tc::KC * 4;
+  VEON_CUDA_TRY(cudaMallocAsync((void**)&image, image_bytes, stream));
+  const int64_t pieces = (int64_t)(C / tc::KC) * npad * 8;
+  tc::k_w_image<<<(unsigned)((pieces + 255) / 256), 256, 0, stream>>>(text_w, Q, C, npad, image);
+  p.w_image = image;
+  const int rc = logits ? launch_variant<true>(p, grid, smem, stream)
+                        : launch_variant<false>(p, grid, smem, stream);
+  cudaFreeAsync(image, stream);
+  return rc;
 }
