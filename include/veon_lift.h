@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define VEON_ABI_VERSION 6
+#define VEON_ABI_VERSION 7
 
 #define VEON_E_BADARG    (-1)  /* NULL pointer / non-positive dimension          */
 #define VEON_E_WORKSPACE (-2)  /* workspace smaller than *_workspace_bytes()     */
@@ -350,7 +350,21 @@ int veon_bev_pool_v2_bwd_planar_ds(const float* grad_ds, const uint8_t* mask,
 int veon_voxel_text_argmax(const float* feat_occ, const float* text_w,
                            const int32_t* class_of_prompt, const float* bin_occ,
                            int B, int C, int Q, int Z, int Y, int X,
-                           int free_label, uint8_t* labels, void* stream);
+                           int free_label, uint8_t* labels, const void* w_image, void* stream);
+
+/* The text classifier is fixed per vocabulary (the reference builds it once,
+ * san_in_veon_temporal.py:261-266), so its tensor-core operand form is prepared once too:
+ * [W_hi ; W_lo] (the 3xTF32 split) of every 32-channel chunk in the shared-memory layout of
+ * the tail kernel's B operand.  veon_text_classifier_image_bytes(Q, C) = its size (0 when the
+ * tensor-core path does not take the shape: C % 32 != 0 or Q > 128);
+ * veon_text_classifier_image fills `image` (>= that many bytes, 16-byte aligned,
+ * VEON_E_WORKSPACE if short).  The three tail entry points take it as `w_image`; it must come
+ * from the same text_w, Q and C.  w_image == NULL is allowed: the library then builds the image
+ * for the duration of the call in a stream-ordered allocation (cudaMallocAsync on `stream`), the
+ * one place where it allocates. */
+size_t veon_text_classifier_image_bytes(int Q, int C);
+int veon_text_classifier_image(const float* text_w, int Q, int C, void* image, size_t image_bytes,
+                               void* stream);
 
 /* semantic_inference_3d alone (san_in_veon_temporal.py:257-259, argument order of the
  * reference method): sem_occ[b,q,z,y,x] = sum_c text_w[q,c] * feat_occ[b,c,z,y,x], fp32
@@ -358,7 +372,7 @@ int veon_voxel_text_argmax(const float* feat_occ, const float* text_w,
  *   text_w [Q,C]; feat_occ [B,C,Z,Y,X]; sem_occ [B,Q,Z,Y,X] (written, not accumulated). */
 int veon_semantic_inference_3d(const float* text_w, const float* feat_occ,
                                int B, int C, int Q, int Z, int Y, int X,
-                               float* sem_occ, void* stream);
+                               float* sem_occ, const void* w_image, void* stream);
 
 /* Training-time voxel x text arg-max over a point list (Proj2Dto3DLoss,
  * loss/occ_loss_utils/occ3d_nuscenes.py:472-482): logits [Q, ldn] = the Q prompt rows (no
@@ -402,7 +416,8 @@ int veon_voxel_text_argmax_lowres(const float* feat_occ_lr, const float* text_w,
                                   const int32_t* class_of_prompt, const float* bin_occ_lr,
                                   int B, int C, int Q, int Zi, int Yi, int Xi,
                                   int Z, int Y, int X, int free_label, uint8_t* labels,
-                                  void* workspace, size_t ws_bytes, void* stream);
+                                  void* workspace, size_t ws_bytes, const void* w_image,
+                                  void* stream);
 
 #ifdef __cplusplus
 }

@@ -60,7 +60,13 @@ def test_argument_errors_do_not_need_a_gpu():
     assert lib.veon_pool_heavy_list_ints(1000, 10) == 12 and lib.veon_pool_heavy_list_ints(64, 10) == 4
     assert lib.veon_prepare_v2_voxel_start_offset(8, 6, 88, 16, 44, gs) % 256 == 0
     # the tail's entry points
-    assert lib.veon_semantic_inference_3d(null, null, 1, 64, 18, 8, 100, 100, null, null) == -1
+    assert lib.veon_semantic_inference_3d(null, null, 1, 64, 18, 8, 100, 100, null, null, null) == -1
+    # the classifier's tensor-core operand image: [W_hi ; W_lo] of every 32-channel chunk
+    assert lib.veon_text_classifier_image_bytes(18, 512) == 16 * 2 * 32 * 32 * 4
+    assert lib.veon_text_classifier_image_bytes(67, 512) == 16 * 2 * 80 * 32 * 4
+    assert lib.veon_text_classifier_image_bytes(18, 100) == 0       # C % 32: the FFMA kernel's shapes
+    assert lib.veon_text_classifier_image_bytes(200, 512) == 0
+    assert lib.veon_text_classifier_image(null, 18, 512, null, 0, null) == -1
     assert lib.veon_upsample_classify(null, null, null, 1, 18, 8, 100, 100, 16, 200, 200, 17,
                                       null, null) == -1
     assert lib.veon_classify_logits(null, 0, null, 0, null, 1, 18, 16, 200, 200, 17, null, null) == -1
@@ -68,9 +74,9 @@ def test_argument_errors_do_not_need_a_gpu():
     assert lib.veon_voxel_text_argmax_lowres_workspace_bytes(0, 18, 8, 100, 100) == 0
     some = ctypes.cast((ctypes.c_float * 4)(), ctypes.c_void_p)
     assert lib.veon_voxel_text_argmax_lowres(some, some, some, some, 1, 64, 18, 8, 100, 100, 16, 200,
-                                             200, 17, some, null, 0, null) == -1      # no workspace
+                                             200, 17, some, null, 0, null, null) == -1  # no workspace
     assert lib.veon_voxel_text_argmax_lowres(some, some, some, some, 1, 64, 18, 8, 100, 100, 16, 200,
-                                             200, 17, some, some, 16, null) == -2     # too small
+                                             200, 17, some, some, 16, null, null) == -2  # too small
     # a pooled volume that the fused / down-sample kernels do not take is refused, not mangled
     buf = (ctypes.c_float * 16)()
     p = ctypes.cast(buf, ctypes.c_void_p)

@@ -417,3 +417,45 @@ def test_camera_group_sharding_sums_to_the_unsharded_labels():
         torch.cuda.synchronize()
         assert got.shape == want.shape
         assert float((got == want).float().mean()) >= 0.9999
+
+
+def test_prepared_classifier_image_and_call_time_image_agree():
+    """`w_image` of the C ABI: a classifier image prepared once with veon_text_classifier_image and
+    NULL (the library builds it for the call in a stream-ordered allocation) give the same labels
+    and the same logits, also after the stream has been synchronised in between (the allocation
+    pool may have been trimmed)."""
+    import ctypes
+    from veon_b200 import _lib
+    from veon_b200.tail import class_of_prompt
+    lib = _lib.load()
+    refl = [k for k, n in enumerate(SIZES) for _ in range(n)]
+    B, C, Z, Y, X = 2, 256, 4, 30, 52
+    feat, w, bin_occ = synth(B, C, refl, Z, Y, X, seed=11)
+    feat, w, bin_occ = feat.cuda(), w.cuda(), bin_occ.cuda()
+    cls = class_of_prompt(refl).cuda()
+    Q = w.shape[0]
+    P = ctypes.c_void_p
+    st = P(torch.cuda.current_stream().cuda_stream)
+    need = lib.veon_text_classifier_image_bytes(Q, C)
+    assert need == (C // 32) * 2 * 80 * 32 * 4
+    image = torch.empty(need, dtype=torch.uint8, device="cuda")
+    assert lib.veon_text_classifier_image(P(w.data_ptr()), Q, C, P(image.data_ptr()), need - 16, st) == -2
+    assert lib.veon_text_classifier_image(P(w.data_ptr()), Q, C, P(image.data_ptr()), need, st) == 0
+    labels = [torch.empty((B, X, Y, Z), dtype=torch.uint8, device="cuda") for _ in range(3)]
+    logits = [torch.empty((B, Q, Z, Y, X), device="cuda") for _ in range(2)]
+    for out, img in ((labels[0], P(image.data_ptr())), (labels[1], None)):
+        assert lib.veon_voxel_text_argmax(P(feat.data_ptr()), P(w.data_ptr()), P(cls.data_ptr()),
+                                          P(bin_occ.data_ptr()), B, C, Q, Z, Y, X, 17,
+                                          P(out.data_ptr()), img, st) == 0
+    torch.cuda.synchronize()
+    assert lib.veon_voxel_text_argmax(P(feat.data_ptr()), P(w.data_ptr()), P(cls.data_ptr()),
+                                      P(bin_occ.data_ptr()), B, C, Q, Z, Y, X, 17,
+                                      P(labels[2].data_ptr()), None, st) == 0
+    for out, img in ((logits[0], P(image.data_ptr())), (logits[1], None)):
+        assert lib.veon_semantic_inference_3d(P(w.data_ptr()), P(feat.data_ptr()), B, C, Q, Z, Y, X,
+                                              P(out.data_ptr()), img, st) == 0
+    torch.cuda.synchronize()
+    assert torch.equal(labels[0], labels[1]) and torch.equal(labels[0], labels[2])
+    assert torch.equal(logits[0], logits[1])
+    want = torch.einsum("qc,bczyx->bqzyx", w.double(), feat.double())
+    assert float((logits[0].double() - want).abs().max() / want.abs().max()) < 1e-5

@@ -71,8 +71,11 @@ _SIGNATURES = {
                                             c_int, c_int, c_int, c_int, c_int, c_int, c_int64,
                                             _P, c_int64, _P, _P, _P]),
     "veon_voxel_text_argmax": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int,
-                                       c_int, _P, _P]),
-    "veon_semantic_inference_3d": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P]),
+                                       c_int, _P, _P, _P]),
+    "veon_text_classifier_image_bytes": (c_size_t, [c_int, c_int]),
+    "veon_text_classifier_image": (c_int, [_P, c_int, c_int, _P, c_size_t, _P]),
+    "veon_semantic_inference_3d": (c_int, [_P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P, _P,
+                                           _P]),
     "veon_point_text_argmax": (c_int, [_P, _P, c_int, c_int64, c_int64, _P, _P, _P]),
     "veon_upsample_classify": (c_int, [_P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                        c_int, c_int, _P, _P]),
@@ -81,7 +84,7 @@ _SIGNATURES = {
     "veon_voxel_text_argmax_lowres_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "veon_voxel_text_argmax_lowres": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int,
                                               c_int, c_int, c_int, c_int, c_int, _P, _P, c_size_t,
-                                              _P]),
+                                              _P, _P]),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)

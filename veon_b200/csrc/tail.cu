@@ -115,16 +115,17 @@ using namespace veon;
 // tensor-core path (tail_tc.cu); VEON_E_UNSUPPORTED when the shape does not fit it
 int veon_tail_tc_launch(const float* feat_occ, const float* text_w, const int32_t* cls,
                         const float* bin_occ, int B, int C, int Q, int Z, int Y, int X,
-                        int free_label, uint8_t* labels, float* logits, cudaStream_t stream);
+                        int free_label, uint8_t* labels, float* logits, const void* w_image,
+                        cudaStream_t stream);
 
 // labels (logits == nullptr) or raw logits (labels == nullptr) of B volumes
 static int tail_dispatch(const float* feat_occ, const float* text_w,
                          const int32_t* class_of_prompt, const float* bin_occ, int B, int C,
                          int Q, int Z, int Y, int X, int free_label, uint8_t* labels,
-                         float* logits, cudaStream_t stream) {
+                         float* logits, const void* w_image, cudaStream_t stream) {
   {  // tcgen05 path unless the shape does not fit it (C % 32, V % 4, Q > 128)
     const int rc = veon_tail_tc_launch(feat_occ, text_w, class_of_prompt, bin_occ, B, C, Q, Z, Y, X,
-                                       free_label, labels, logits, stream);
+                                       free_label, labels, logits, w_image, stream);
     if (rc != VEON_E_UNSUPPORTED) return rc;
   }
   const size_t smem = sizeof(float) * (size_t)kTailQT * C;
@@ -154,22 +155,22 @@ static int tail_dispatch(const float* feat_occ, const float* text_w,
 extern "C" int veon_voxel_text_argmax(const float* feat_occ, const float* text_w,
                                       const int32_t* class_of_prompt, const float* bin_occ,
                                       int B, int C, int Q, int Z, int Y, int X, int free_label,
-                                      uint8_t* labels, void* stream) {
+                                      uint8_t* labels, const void* w_image, void* stream) {
   if (!feat_occ || !text_w || !class_of_prompt || !bin_occ || !labels || B <= 0 || C <= 0 ||
       Q <= 0 || Z <= 0 || Y <= 0 || X <= 0 || B > 65535)
     return VEON_E_BADARG;
   return tail_dispatch(feat_occ, text_w, class_of_prompt, bin_occ, B, C, Q, Z, Y, X, free_label,
-                       labels, nullptr, (cudaStream_t)stream);
+                       labels, nullptr, w_image, (cudaStream_t)stream);
 }
 
 extern "C" int veon_semantic_inference_3d(const float* text_w, const float* feat_occ, int B, int C,
                                           int Q, int Z, int Y, int X, float* sem_occ,
-                                          void* stream) {
+                                          const void* w_image, void* stream) {
   if (!feat_occ || !text_w || !sem_occ || B <= 0 || C <= 0 || Q <= 0 || Z <= 0 || Y <= 0 ||
       X <= 0 || B > 65535)
     return VEON_E_BADARG;
   return tail_dispatch(feat_occ, text_w, nullptr, nullptr, B, C, Q, Z, Y, X, 0, nullptr, sem_occ,
-                       (cudaStream_t)stream);
+                       w_image, (cudaStream_t)stream);
 }
 
 // ---- training-time voxel x text arg-max over a POINT LIST ----------------------

@@ -324,12 +324,12 @@ extern "C" int veon_voxel_text_argmax_lowres(const float* feat_occ_lr, const flo
                                              const float* bin_occ_lr, int B, int C, int Q, int Zi,
                                              int Yi, int Xi, int Z, int Y, int X, int free_label,
                                              uint8_t* labels, void* workspace, size_t ws_bytes,
-                                             void* stream) {
+                                             const void* w_image, void* stream) {
   if (!workspace) return VEON_E_BADARG;
   if (ws_bytes < veon_voxel_text_argmax_lowres_workspace_bytes(B, Q, Zi, Yi, Xi))
     return VEON_E_WORKSPACE;
   float* sem_lr = static_cast<float*>(workspace);
-  const int rc = veon_semantic_inference_3d(text_w, feat_occ_lr, B, C, Q, Zi, Yi, Xi, sem_lr, stream);
+  const int rc = veon_semantic_inference_3d(text_w, feat_occ_lr, B, C, Q, Zi, Yi, Xi, sem_lr, w_image, stream);
   if (rc != 0) return rc;
   return veon_upsample_classify(sem_lr, bin_occ_lr, class_of_prompt, B, Q, Zi, Yi, Xi, Z, Y, X,
                                 free_label, labels, stream);

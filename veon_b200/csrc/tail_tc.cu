@@ -5,30 +5,28 @@
 //   occupancy gate, free label, [B,X,Y,Z] uint8            veon_temporal.py:223-229,240
 //
 // GEMM view per CTA tile: M = 128 voxels, N = padded prompt count, K = C.
-//   * A = feat tile.  In memory the voxel index is contiguous, i.e. A is
-//     "MN-major"; kind::tf32 accepts that (with the SWIZZLE_128B_BASE32B layout,
-//     the only one allowed for MN-major 32-bit operands), so the tile sits in
-//     shared memory in the same orientation as in HBM: atoms of 4 channel rows x
-//     32 voxels (512 B), 32-byte chunks XOR-swizzled by the row index; descriptor
-//     LBO = 512 B between 32-voxel groups, SBO = 2 KB between 4-row groups.
-//   * B = W, K-major SW128.
-//   * D in TMEM (fp32), two accumulator buffers so the epilogue of tile i
-//     overlaps the main loop of tile i+1.
+//   * A = feat tile, from TENSOR MEMORY (tcgen05.mma with a TMEM A operand: lanes = voxels, one
+//     32-bit column per channel).  In HBM the voxel index is contiguous, so a thread that owns
+//     a voxel reads a COLUMN of the tile: loader warps bring the raw [32 channels][128 voxels]
+//     block into a shared-memory ring with 16-byte cp.async copies (completion on the slot's
+//     mbarrier; nothing in registers, ~112 KB in flight per SM), converter threads read their
+//     column (conflict-free), split it and write hi and lo with tcgen05.st.  The tensor core
+//     therefore never reads A through the shared-memory pipe, which carries 128 + 128
+//     wavefronts per stage instead of the 128 (LDG) + 256 (STS hi/lo) + 256 (MMA reads) of the
+//     round-1 kernel that kept A in shared memory (MN-major SWIZZLE_128B_BASE32B).
+//   * B = W, K-major SW128, from shared memory: k_w_image splits W once per call into a global
+//     image laid out chunk by chunk exactly like a stage's [W_hi ; W_lo] block, and one lane
+//     copies a chunk per stage with a 1-D bulk copy that completes on the stage's `full` barrier.
+//   * D in TMEM (fp32), two accumulator buffers so the epilogue of tile i overlaps the main
+//     loop of tile i+1.
 //   * fp32 fidelity: 3xTF32.  a = a_hi + a_lo, w = w_hi + w_lo with *_hi exactly
-//     TF32-representable; D = a_hi*[w_hi ; w_lo] (one MMA, N = 2*Npad, the
-//     w_lo product lands in its own TMEM columns) + a_lo*w_hi.  Error ~2^-21
-//     relative, which is what keeps the labels at >= 99.99 % agreement (plain
-//     TF32 would flip ~0.3 % of near-tie voxels).
-//   * The split is done IN REGISTERS on the way in (LDG.128 -> hi/lo -> two
-//     STS.128): 16 B of shared-memory traffic per element instead of 20-24 B if
-//     a TMA-landed tile had to be re-read to be split; at ~22 B/clk/SM of HBM the
-//     shared-memory port is the scarce resource of this kernel.
-//   * W never passes through registers: k_w_image splits it once per call into a global image
-//     laid out chunk by chunk exactly like a stage's [W_hi ; W_lo] block (K-major SW128), and one
-//     lane copies a chunk per stage with a 1-D bulk copy that completes on the stage's `full`
-//     barrier.  The producers' registers hold nothing but rows in flight (kSets stages).
-// Warp roles (21 warps): 0-15 A producers (kSets - 1 later stages' loads in flight while the
-// current one is split and stored), 16 MMA issuer (+TMEM alloc), 17-20 epilogue.
+//     TF32-representable; every (voxel, prompt) column accumulates a_hi*w_hi + a_hi*w_lo +
+//     a_lo*w_hi.  Error ~2^-21 relative, which is what keeps the labels at >= 99.99 %
+//     agreement (plain TF32 would flip ~0.3 % of near-tie voxels).
+//   * The MMA warp runs its loop warp-uniformly and an elected lane issues, so descriptors and
+//     tensor-memory addresses stay in uniform registers (see the note in that role).
+// Warp roles (23 warps): 0-15 converters, 16 MMA issuer (+TMEM alloc), 17-20 epilogue,
+// 21-22 loaders.
 #include <math.h>
 
 #include "common.cuh"
@@ -42,17 +40,13 @@ constexpr int kProdWarps = 16;  // warp % 4 = TMEM lane quarter (32 voxels), war
 constexpr int kRows = KC / 4;   // channels of a stage per producer thread
 constexpr uint32_t kTmemCols = 512;
 constexpr int kMmaWarp = 16;
-constexpr int kEpiWarp0 = 17;   // 17..20: warp % 4 = 1,2,3,0 -> the four TMEM lane quarters
+// warps 17..20: epilogue (warp % 4 = 1,2,3,0 -> the four TMEM lane quarters)
 constexpr int kLoadWarp0 = 21;  // 21, 22: loaders
 constexpr int kLoadWarps = 2;
 constexpr int kWarps = 23;
 constexpr int kRaw = 7;                        // raw tiles in flight per SM
 constexpr uint32_t kRawBytes = KC * TM * 4;    // 16 KB
 constexpr int kMaxStages = 6;
-#ifndef VEON_TAIL_SETS
-#define VEON_TAIL_SETS 3
-#endif
-constexpr int kSets = VEON_TAIL_SETS;   // stages of A in flight per producer lane
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -134,7 +128,6 @@ __device__ __forceinline__ void tc_ld16(uint32_t taddr, float* v) {
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout, version 1):
 // start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version 1<<46 | layout type [61,64)
 constexpr uint64_t kSw128 = 2;         // SWIZZLE_128B         (B operand, K-major)
-constexpr uint64_t kSw128Base32 = 1;   // SWIZZLE_128B_BASE32B (the only MN-major layout for tf32)
 __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes,
                                               uint32_t sbo_bytes, uint64_t layout_type) {
   return (uint64_t)((saddr >> 4) & 0x3fffu) | ((uint64_t)((lbo_bytes >> 4) & 0x3fffu) << 16) |
@@ -418,6 +411,15 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_tail_tc(const Params p) {
   } else {
     // ============================ EPILOGUE ============================
     const int quarter = warp & 3;  // TMEM lanes a warp may touch: 32*(warp%4) ..
+    uint32_t heads0 = 0, heads1 = 0, heads2 = 0, heads3 = 0;   // bit q: prompt q starts a class
+    if constexpr (!LOGITS) {
+      auto head_word = [&](int base) -> uint32_t {
+        const int q = base + lane;
+        const bool h = q < p.Q && (q == 0 || __ldg(p.cls + q) != __ldg(p.cls + q - 1));
+        return __ballot_sync(0xffffffffu, h);
+      };
+      heads0 = head_word(0); heads1 = head_word(32); heads2 = head_word(64); heads3 = head_word(96);
+    }
     uint32_t tcount = 0;
     VEON_T0
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
@@ -443,33 +445,36 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_tail_tc(const Params p) {
         if (lane == 0) mbar_arrive(acc_empty + acc);
         continue;
       }
-      float best = 0.f, cur = 0.f;
-      int best_cls = -1, cur_cls = -1;
+      // class-wise max over the prompts and first-index arg-max over the classes, branch-free:
+      // `heads` marks the first prompt of every class; a group is closed when the next one
+      // starts.  Padded columns (q >= Q) enter as -inf and change nothing.
+      float best = -INFINITY, cur = -INFINITY;
+      int best_q = 0, cur_q = 0;
       bool bad = false;
+#pragma unroll 1
       for (int q0 = 0; q0 < npad; q0 += 16) {
         float m[16];
         tc_ld16(taddr + q0, m);
+        const uint32_t word = (q0 & 64) ? ((q0 & 32) ? heads3 : heads2) : ((q0 & 32) ? heads1 : heads0);
+        const uint32_t h16 = word >> (q0 & 16);
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const int q = q0 + i;
-          if (q < p.Q) {
-            const float logit = m[i];
-            const int cls = __ldg(p.cls + q);
-            bad |= !(logit < INFINITY);
-            if (cls != cur_cls) {
-              if (cur_cls >= 0 && (best_cls < 0 || cur > best)) { best = cur; best_cls = cur_cls; }
-              cur_cls = cls;
-              cur = logit;
-            } else {
-              cur = fmaxf(cur, logit);
-            }
-          }
+          const float logit = q < p.Q ? m[i] : -INFINITY;
+          bad |= !(logit < INFINITY);
+          const bool head = (h16 >> i) & 1u;
+          const bool take = head && (cur > best);
+          best = take ? cur : best;
+          best_q = take ? cur_q : best_q;
+          cur = head ? logit : fmaxf(cur, logit);
+          cur_q = head ? q : cur_q;
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty + acc);  // accumulator drained
-      if (cur_cls >= 0 && (best_cls < 0 || cur > best)) { best = cur; best_cls = cur_cls; }
+      if (cur > best) { best = cur; best_q = cur_q; }
+      const int best_cls = __ldg(p.cls + best_q);
       if (v < p.V) {
         bad |= (best == -INFINITY);
         const float b0 = __ldg(p.bin_occ + ((int64_t)b * 2 + 0) * p.V + v);
@@ -478,9 +483,10 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_tail_tc(const Params p) {
         const float e0 = expf(b0 - mx), e1 = expf(b1 - mx);
         const bool occupied = (e0 / (e0 + e1)) > 0.5f;
         const int label = (occupied && !bad) ? best_cls : p.free_label;
-        const int xx = (int)(v % p.X);
-        const int yy = (int)((v / p.X) % p.Y);
-        const int zz = (int)(v / ((int64_t)p.X * p.Y));
+        const uint32_t vv = (uint32_t)v, row = vv / (uint32_t)p.X;   // V < 2^31 (checked by the launcher)
+        const int xx = (int)(vv - row * (uint32_t)p.X);
+        const int zz = (int)(row / (uint32_t)p.Y);
+        const int yy = (int)(row - (uint32_t)zz * (uint32_t)p.Y);
         p.labels[(((int64_t)b * p.X + xx) * p.Y + yy) * p.Z + zz] = (uint8_t)label;
       }
     }
@@ -527,12 +533,33 @@ static int launch_variant(const tc::Params& p, unsigned grid, size_t smem, cudaS
   return 0;
 }
 
+extern "C" size_t veon_text_classifier_image_bytes(int Q, int C) {
+  const int npad = ((Q + 15) / 16) * 16;
+  if (Q <= 0 || C <= 0 || C % tc::KC != 0 || npad > 128) return 0;
+  return (size_t)(C / tc::KC) * 2 * npad * tc::KC * 4;
+}
+
+extern "C" int veon_text_classifier_image(const float* text_w, int Q, int C, void* image,
+                                          size_t image_bytes, void* stream) {
+  const size_t need = veon_text_classifier_image_bytes(Q, C);
+  if (!text_w || !image || ((uintptr_t)text_w & 15) || ((uintptr_t)image & 15)) return VEON_E_BADARG;
+  if (need == 0) return VEON_E_UNSUPPORTED;
+  if (image_bytes < need) return VEON_E_WORKSPACE;
+  const int npad = ((Q + 15) / 16) * 16;
+  const int64_t pieces = (int64_t)(C / tc::KC) * npad * 8;
+  tc::k_w_image<<<(unsigned)((pieces + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      text_w, Q, C, npad, static_cast<float*>(image));
+  VEON_LAUNCH_CHECK();
+  return 0;
+}
+
 int veon_tail_tc_launch(const float* feat_occ, const float* text_w, const int32_t* cls,
                         const float* bin_occ, int B, int C, int Q, int Z, int Y, int X,
-                        int free_label, uint8_t* labels, float* logits, cudaStream_t stream) {
+                        int free_label, uint8_t* labels, float* logits, const void* w_image,
+                        cudaStream_t stream) {
   const int64_t V = (int64_t)Z * Y * X;
   const int npad = ((Q + 15) / 16) * 16;
-  if (C % tc::KC != 0 || (V & 3) != 0 || npad > 128 || (((uintptr_t)feat_occ | (uintptr_t)text_w) & 15))
+  if (C % tc::KC != 0 || (V & 3) != 0 || V >= (int64_t(1) << 31) || npad > 128 || (((uintptr_t)feat_occ | (uintptr_t)text_w) & 15))
     return VEON_E_UNSUPPORTED;
   const size_t w_bytes = 2 * (size_t)npad * tc::KC * 4;
   const size_t tail = 1024;  // barriers + tmem slot
@@ -552,15 +579,21 @@ int veon_tail_tc_launch(const float* feat_occ, const float* text_w, const int32_
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int64_t n_tiles = (int64_t)B * ((V + tc::TM - 1) / tc::TM);
   const unsigned grid = (unsigned)(n_tiles < sms ? n_tiles : sms);
-  // the split weight image lives in a stream-ordered allocation for the duration of the call
+  if (w_image) {
+    if ((uintptr_t)w_image & 15) return VEON_E_BADARG;
+    p.w_image = static_cast<const float*>(w_image);
+    return logits ? launch_variant<true>(p, grid, smem, stream)
+                  : launch_variant<false>(p, grid, smem, stream);
+  }
+  // no prepared image: build one for the duration of the call in a stream-ordered allocation
   float* image = nullptr;
-  const size_t image_bytes = (size_t)(C / tc::KC) * 2 * npad * tc::KC * 4;
+  const size_t image_bytes = veon_text_classifier_image_bytes(Q, C);
   VEON_CUDA_TRY(cudaMallocAsync((void**)&image, image_bytes, stream));
-  const int64_t pieces = (int64_t)(C / tc::KC) * npad * 8;
-  tc::k_w_image<<<(unsigned)((pieces + 255) / 256), 256, 0, stream>>>(text_w, Q, C, npad, image);
+  int rc = veon_text_classifier_image(text_w, Q, C, image, image_bytes, stream);
   p.w_image = image;
-  const int rc = logits ? launch_variant<true>(p, grid, smem, stream)
-                        : launch_variant<false>(p, grid, smem, stream);
+  if (rc == 0)
+    rc = logits ? launch_variant<true>(p, grid, smem, stream)
+                : launch_variant<false>(p, grid, smem, stream);
   cudaFreeAsync(image, stream);
   return rc;
 }

@@ -95,6 +95,7 @@ def voxel_text_argmax(feat_occ, ov_classifier_weight, prompt_class, bin_occ, fre
             ctypes.c_void_p(feat_occ.data_ptr()), ctypes.c_void_p(w.data_ptr()),
             ctypes.c_void_p(cls.data_ptr()), ctypes.c_void_p(bin_occ.data_ptr()),
             B, C, Q, Z, Y, X, int(free_label), ctypes.c_void_p(labels.data_ptr()),
+            _classifier_image(lib, w, dev),
             ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
     _lib.check(rc, "veon_voxel_text_argmax")
     return labels
@@ -108,6 +109,30 @@ def _cuda_only(*tensors):
 
 def _stream(dev):
     return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+_IMAGE_BUFFERS = {}
+
+
+def _classifier_image(lib, w, dev):
+    """The classifier in the tail kernel's tensor-core operand form
+    (`veon_text_classifier_image`), rebuilt on the current stream into a buffer kept per
+    (device, stream); None when the tensor-core path does not take the shape."""
+    Q, C = w.shape
+    need = lib.veon_text_classifier_image_bytes(int(Q), int(C))
+    if need == 0:
+        return None
+    stream = torch.cuda.current_stream(dev)
+    key = (dev.index, stream.cuda_stream)
+    buf = _IMAGE_BUFFERS.get(key)
+    if buf is None or buf.numel() < need:
+        buf = torch.empty(need, dtype=torch.uint8, device=dev)
+        _IMAGE_BUFFERS[key] = buf
+    rc = lib.veon_text_classifier_image(ctypes.c_void_p(w.data_ptr()), int(Q), int(C),
+                                        ctypes.c_void_p(buf.data_ptr()), ctypes.c_size_t(buf.numel()),
+                                        ctypes.c_void_p(stream.cuda_stream))
+    _lib.check(rc, "veon_text_classifier_image")
+    return ctypes.c_void_p(buf.data_ptr())
 
 
 def semantic_inference_3d(ov_classifier_weight, mask_pred):
@@ -128,7 +153,7 @@ def semantic_inference_3d(ov_classifier_weight, mask_pred):
         sem = torch.empty((B, Q, Z, Y, X), dtype=torch.float32, device=dev)
         rc = lib.veon_semantic_inference_3d(
             ctypes.c_void_p(w.data_ptr()), ctypes.c_void_p(feat.data_ptr()), B, C, Q, Z, Y, X,
-            ctypes.c_void_p(sem.data_ptr()), _stream(dev))
+            ctypes.c_void_p(sem.data_ptr()), _classifier_image(lib, w, dev), _stream(dev))
     _lib.check(rc, "veon_semantic_inference_3d")
     return sem
 
@@ -223,7 +248,8 @@ def voxel_text_argmax_lowres(feat_occ_lr, ov_classifier_weight, prompt_class, bi
             ctypes.c_void_p(feat.data_ptr()), ctypes.c_void_p(w.data_ptr()),
             ctypes.c_void_p(cls.data_ptr()), ctypes.c_void_p(gate.data_ptr()),
             B, C, Q, Zi, Yi, Xi, Z, Y, X, int(free_label), ctypes.c_void_p(labels.data_ptr()),
-            ctypes.c_void_p(workspace.data_ptr()), ws_bytes, _stream(dev))
+            ctypes.c_void_p(workspace.data_ptr()), ws_bytes, _classifier_image(lib, w, dev),
+            _stream(dev))
     _lib.check(rc, "veon_voxel_text_argmax_lowres")
     return labels
 
