@@ -5,7 +5,7 @@
 # veon_b200/csrc/Makefile alone and carries none of these flags.
 set -e
 cd "$(dirname "$0")/.."
-out=/tmp/veon_variants/$1
+out=${VEON_VARIANT_DIR:-/tmp/veon_variants}/$1
 mkdir -p $out
 for f in veon_b200/csrc/*.cu; do
   b=$(basename $f .cu)
