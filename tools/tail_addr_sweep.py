@@ -3,6 +3,8 @@ at different offsets inside one big allocation."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import torch
+from veon_b200 import _lib
+if os.environ.get("VEON_LIB"): _lib.LIB_PATH = os.environ["VEON_LIB"]
 from veon_b200.tail import class_of_prompt, voxel_text_argmax
 dev = torch.device("cuda", 0)
 C, B, V = 512, 2, 640000

@@ -57,10 +57,24 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+#ifndef VEON_TAIL_SUSPEND_NS
+#define VEON_TAIL_SUSPEND_NS 0
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   const uint32_t addr = smem_u32(bar);
   uint32_t done = 0;
   do {  // try_wait suspends the thread in hardware for a bounded time, so this is not a hot spin
+#if VEON_TAIL_SUSPEND_NS > 0
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity), "r"((uint32_t)VEON_TAIL_SUSPEND_NS)
+        : "memory");
+#else
     asm volatile(
         "{\n\t"
         ".reg .pred p;\n\t"
@@ -70,6 +84,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "=r"(done)
         : "r"(addr), "r"(parity)
         : "memory");
+#endif
   } while (!done);
 }
 __device__ __forceinline__ bool elect_one() {   // one lane of the (converged) warp
@@ -261,8 +276,16 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_tail_tc(const Params p) {
   const int64_t vtiles = (p.V + TM - 1) / TM;
   const int64_t n_tiles = (int64_t)p.B * vtiles;
   const int n_chunks = p.C / KC;
+#ifdef VEON_TAIL_BLOCKED   // experiment: a contiguous run of tiles per CTA instead of a grid stride
+  const int64_t per_cta = (n_tiles + gridDim.x - 1) / gridDim.x;
+  const int64_t tile_begin = (int64_t)blockIdx.x * per_cta, tile_step = 1;
+  const int64_t tile_end = tile_begin + per_cta < n_tiles ? tile_begin + per_cta : n_tiles;
+  const int64_t my_tiles = tile_end > tile_begin ? tile_end - tile_begin : 0;
+#else
+  const int64_t tile_begin = blockIdx.x, tile_step = gridDim.x, tile_end = n_tiles;
   const int64_t my_tiles = (n_tiles > (int64_t)blockIdx.x)
                                ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+#endif
   const int64_t n_stages_total = my_tiles * n_chunks;
 
   if (warp >= kLoadWarp0) {
@@ -274,7 +297,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_tail_tc(const Params p) {
     const int lw = warp - kLoadWarp0;                       // rows lw, lw + kLoadWarps, ...
     uint32_t rs = 0, rphase = 0;
     bool first_round = true;
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (int64_t tile = tile_begin; tile < tile_end; tile += tile_step) {
       const int64_t b = tile / vtiles;
       const int64_t v = (tile - b * vtiles) * TM + 4 * lane;
       const uint32_t nbytes = v < p.V ? 16u : 0u;           // V % 4 == 0; past the end: zero-fill
@@ -373,7 +396,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_tail_tc(const Params p) {
       const bool leader = elect_one();
       uint32_t s = 0, fphase = 0, tcount = 0;
       VEON_T0
-      for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+      for (int64_t tile = tile_begin; tile < tile_end; tile += tile_step, ++tcount) {
         const uint32_t acc = tcount & 1;
         const uint32_t around = tcount >> 1;
         if (around > 0) mbar_wait(acc_empty + acc, (around - 1) & 1);
@@ -422,7 +445,7 @@ __global__ void __launch_bounds__(kWarps * 32, 1) k_tail_tc(const Params p) {
     }
     uint32_t tcount = 0;
     VEON_T0
-    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++tcount) {
+    for (int64_t tile = tile_begin; tile < tile_end; tile += tile_step, ++tcount) {
       VEON_TACC(1)
       const int acc = tcount & 1;
       mbar_wait(acc_full + acc, (tcount >> 1) & 1);
