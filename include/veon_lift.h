@@ -411,6 +411,26 @@ int veon_classify_logits(const float* sem_occ, int64_t sem_batch_stride,
                          const float* bin_occ, int64_t bin_batch_stride,
                          const int32_t* class_of_prompt, int B, int Q, int Z, int Y, int X,
                          int free_label, uint8_t* labels, void* stream);
+/* Lift + classify in one pass (BASELINE configs[2]): pooling is linear, so the
+ * classifier and the gate head run on the image features first (veon_semantic_inference_3d over
+ * [B*N, C, H*W]) and the per-pixel rows
+ *     pix [n_pix_rows, Cp] = [gate 0, gate 1, logit 0 .. Q-1, zero padding]   (Cp = 4k <= 32, 8k in 40..64 or 12k in 72..96)
+ * are pooled with the unchanged index preparation.  A lane owns a voxel and holds the sums in
+ * registers (the same fma chain in rank order as veon_bev_pool_v2_fwd_planar: the same bits; rows
+ * wider than 32 channels are walked in two or three passes, the class-merge state carried between
+ * them), so the tile ends as 32 labels -- class merge, first-index arg-max, gate (the rule of
+ * veon_classify_logits) -- and the pooled logit volume [B,Cp,Z,Y,X] is never written.
+ * Tiles from 512 points up go to a CTA each, which classifies from its shared-memory tile.
+ * Needs the plan's tile_start / tile_heavy tables, V % 32 == 0 and B*V <= 2^24, else
+ * VEON_E_UNSUPPORTED / VEON_E_RANGE (the caller then pools the volume and calls
+ * veon_classify_logits).  labels uint8 [B,X,Y,Z]. */
+int veon_lift_classify_fwd(const float* depth, const float* pix,
+                           const int32_t* ranks_depth, const int32_t* ranks_feat,
+                           const int32_t* ranks_bev, const int32_t* tile_start,
+                           const int32_t* tile_heavy, int64_t tile_heavy_ints,
+                           int B, int Cp, int Q, int Z, int Y, int X, int64_t n_pix_rows,
+                           const int32_t* class_of_prompt, int free_label,
+                           uint8_t* labels, void* stream);
 size_t veon_voxel_text_argmax_lowres_workspace_bytes(int B, int Q, int Zi, int Yi, int Xi);
 int veon_voxel_text_argmax_lowres(const float* feat_occ_lr, const float* text_w,
                                   const int32_t* class_of_prompt, const float* bin_occ_lr,

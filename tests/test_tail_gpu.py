@@ -253,6 +253,45 @@ def test_lift_classify_in_logit_space_matches_feature_space_and_oracle():
     assert 0.001 < float((got != 17).float().mean()) < 0.9
 
 
+@pytest.mark.parametrize("cfg_name,Q", [("small", 18), ("small", 67), ("small", 5), ("C3", 18), ("C3", 67)])
+def test_fused_lift_classify_equals_pool_then_classify(cfg_name, Q):
+    """veon_lift_classify_fwd (labels straight from the pooling kernel's registers, the logit
+    volume never written) against pooling the volume and running classify_logits on it: the same
+    labels voxel for voxel -- the sums are the same bits and the rule is the same.  C3 density
+    exercises the CTA-per-tile kernel (tiles of 512+ points), Q = 67 the one-point-per-trip form."""
+    from veon_b200 import synthetic as S
+    from veon_b200.pipeline import lift_classify
+    from veon_b200.tail import class_of_prompt
+    from veon_b200.view_transformer import LSSViewTransformer
+    cfg = S.CONFIGS[cfg_name]
+    B, C = 2, 64
+    refl = ([k for k, n in enumerate(SIZES) for _ in range(n)] if Q == 67 else list(range(Q - 1)))
+    H, W = cfg.feat_hw
+    g = torch.Generator().manual_seed(Q)
+    cal = S.calibration(cfg, batch=B)
+    metas = [torch.from_numpy(cal[k]).cuda() for k in
+             ("sensor2ego", "ego2global", "intrins", "post_rots", "post_trans", "bda")]
+    depth = torch.softmax(torch.randn(B * cfg.n_cams, cfg.D, H, W, generator=g) * 4, dim=1).cuda()
+    feat = (torch.randn(B * cfg.n_cams, C, H, W, generator=g) * 0.05).cuda()
+    w = torch.randn(Q, C, generator=g)
+    w = (100.0 * w / w.norm(dim=1, keepdim=True)).cuda()
+    gate_w = torch.randn(2, C, generator=g).cuda()
+    cls = class_of_prompt(refl).cuda()
+    img = torch.zeros(B, cfg.n_cams, 8, H, W, device="cuda")
+    neck = LSSViewTransformer(cfg.grid_config, cfg.input_size, cfg.downsample, 8, C, collapse_z=False)
+    from veon_b200 import bev_pool as BP
+    BP.enable_kernel_timing(True)
+    fused = lift_classify(neck, [img] + metas, depth, feat, w, cls, gate_w)
+    torch.cuda.synchronize()
+    assert "lift_classify_fwd" in BP.kernel_timings_ms()       # the fused kernel did run
+    BP.enable_kernel_timing(False)
+    plain = lift_classify(neck, [img] + metas, depth, feat, w, cls, gate_w, fused=False)
+    torch.cuda.synchronize()
+    assert fused.shape == plain.shape == (B, 200, 200, 16) and fused.dtype == torch.uint8
+    assert torch.equal(fused, plain), int((fused != plain).sum())
+    assert 0.001 < float((fused != 17).float().mean()) < 0.9
+
+
 @pytest.mark.parametrize("voc", ["nuscenes_brief", "nuscenes_default"])
 def test_tail_kernels_match_reference_golden(golden_dir, voc):
     """the reference's own `semantic_inference_3d` / `_merge_classes_prob` outputs and the label

@@ -16,8 +16,9 @@ from veon_b200.view_transformer import LSSViewTransformer
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 10
 pad = int(sys.argv[3]) if len(sys.argv) > 3 else 4
+Q_ARG = int(sys.argv[4]) if len(sys.argv) > 4 else 18
 dev = torch.device("cuda", 0)
-cfg = S.CONFIGS["C3"]; C = cfg.channels; Q = 18
+cfg = S.CONFIGS["C3"]; C = cfg.channels; Q = Q_ARG
 N, D = cfg.n_cams, cfg.D; H, W = cfg.feat_hw
 neck = LSSViewTransformer(cfg.grid_config, cfg.input_size, cfg.downsample, 8, C, collapse_z=False)
 KEYS = ("sensor2ego", "ego2global", "intrins", "post_rots", "post_trans", "bda")
@@ -28,7 +29,8 @@ depth = torch.softmax(torch.randn(B * N, D, H, W, device=dev, generator=g) * 4, 
 feat = torch.randn(B * N, C, H, W, device=dev, generator=g) * 0.05
 w = torch.randn(Q, C, device=dev, generator=g); w = 100 * w / w.norm(dim=1, keepdim=True)
 gate_w = torch.randn(2, C, device=dev, generator=g)
-cls = T.class_of_prompt(list(range(Q - 1))).to(dev)
+SIZES = [16, 1, 1, 1, 8, 1, 1, 3, 1, 1, 1, 1, 5, 3, 5, 13, 4]
+cls = T.class_of_prompt(list(range(Q - 1)) if Q != 67 else [k for k, n in enumerate(SIZES) for _ in range(n)]).to(dev)
 img = torch.zeros(B, N, 1, H, W, device=dev)
 
 

@@ -81,6 +81,8 @@ _SIGNATURES = {
                                        c_int, c_int, _P, _P]),
     "veon_classify_logits": (c_int, [_P, c_int64, _P, c_int64, _P, c_int, c_int, c_int, c_int, c_int,
                                      c_int, _P, _P]),
+    "veon_lift_classify_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int,
+                                       c_int, c_int, c_int64, _P, c_int, _P, _P]),
     "veon_voxel_text_argmax_lowres_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int, c_int]),
     "veon_voxel_text_argmax_lowres": (c_int, [_P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int,
                                               c_int, c_int, c_int, c_int, c_int, _P, _P, c_size_t,

@@ -773,6 +773,35 @@ def pool_prepared(depth, feat, prep, bev_feat_shape):
     return x.permute(0, 4, 1, 2, 3).contiguous()
 
 
+def lift_classify_prepared(depth, pix, prep, Q, prompt_class, grid_zyx, free_label=17):
+    """Fused lift + classify (`veon_lift_classify_fwd`): depth [B,N,D,H,W]; pix [B,N,Cp,H,W]
+    channels-first per-pixel rows ordered [gate 0, gate 1, logit 0..Q-1, zero padding]; prep from
+    `prepare_ranks*`; -> uint8 labels [B,X,Y,Z], or None when the kernel does not take the shape
+    (the caller then pools the volume and classifies it).  No gradient."""
+    _require_cuda(depth, pix, prompt_class)
+    lib = _lib.load()
+    Z, Y, X = (int(v) for v in grid_zyx)
+    B, N, Cp, H, W = (int(v) for v in pix.shape)
+    if not prep.plan.ok or prep.plan.tile_heavy is None:
+        return None
+    dev = pix.device
+    depth = depth.detach().contiguous().float()
+    rows = _transpose_batched(pix.detach().contiguous().float(), B * N, Cp, H * W, (B, N, H, W, Cp))
+    cls = prompt_class.contiguous().int()
+    with torch.cuda.device(dev):
+        labels = torch.empty((B, X, Y, Z), dtype=torch.uint8, device=dev)
+        with _timed("lift_classify_fwd", dev):
+            rc = lib.veon_lift_classify_fwd(
+                _ptr(depth), _ptr(rows), _ptr(prep.ranks_depth), _ptr(prep.ranks_feat),
+                _ptr(prep.ranks_bev), _ptr(prep.plan.tile_start), _ptr(prep.plan.tile_heavy),
+                prep.plan.tile_heavy.numel(), B, Cp, int(Q), Z, Y, X, rows.numel() // Cp, _ptr(cls),
+                int(free_label), _ptr(labels), _stream_ptr(dev))
+    if rc in (-4, -5):      # VEON_E_UNSUPPORTED / VEON_E_RANGE: shape outside the fused kernel
+        return None
+    _lib.check(rc, "veon_lift_classify_fwd")
+    return labels
+
+
 class TRTBEVPoolv2(torch.autograd.Function):
     """ONNX/TensorRT export shim with the reference's symbolic
     (bev_pool.py:95-142): emits `mmdeploy::bev_pool_v2`; eager `forward`

@@ -119,4 +119,30 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// _merge_classes_prob + the label rule for one voxel (san_in_veon_entry_temporal.py:273-297,
+// veon_temporal.py:223-229,240); shared by the classify kernels and the fused lift + classify.
+struct ClassMerge {  // running per-class max over prompt rows + first-index arg-max over classes
+  float best = 0.f, cur = 0.f;
+  int best_cls = -1, cur_cls = -1;
+  bool bad = false;
+  __device__ __forceinline__ void push(int cls, float logit) {
+    bad |= !(logit < INFINITY);  // NaN / +inf => the softmax score is NaN => free
+    if (cls != cur_cls) {
+      if (cur_cls >= 0 && (best_cls < 0 || cur > best)) { best = cur; best_cls = cur_cls; }
+      cur_cls = cls;
+      cur = logit;
+    } else {
+      cur = fmaxf(cur, logit);
+    }
+  }
+  __device__ __forceinline__ int label(float b0, float b1, int free_label) {
+    if (cur_cls >= 0 && (best_cls < 0 || cur > best)) { best = cur; best_cls = cur_cls; }
+    bad |= (best == -INFINITY);
+    const float m = fmaxf(b0, b1);  // softmax(bin_occ)[0] > 0.5, evaluated like torch.softmax
+    const float e0 = expf(b0 - m), e1 = expf(b1 - m);
+    const bool occupied = (e0 / (e0 + e1)) > 0.5f;
+    return (occupied && !bad) ? best_cls : free_label;
+  }
+};
+
 }  // namespace veon

@@ -336,14 +336,27 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
 }
 
-template <int KCH>
+// Fused lift + classify (veon_lift_classify_fwd): the pooled channels are
+// [gate 0, gate 1, logit 0 .. Q-1, padding] and a tile ends as 32 labels instead of C planes.
+struct ClsArgs {
+  const int32_t* cls;   // [Q] merged class of every prompt row
+  uint8_t* labels;      // [B,X,Y,Z]
+  int Q, X, Y, Z, free_label;
+};
+__device__ __forceinline__ void store_label(const ClsArgs& ca, uint32_t b, uint32_t v, int label) {
+  const uint32_t row = v / (uint32_t)ca.X, x = v - row * (uint32_t)ca.X;
+  const uint32_t z = row / (uint32_t)ca.Y, y = row - z * (uint32_t)ca.Y;
+  ca.labels[(((int64_t)b * ca.X + x) * ca.Y + y) * ca.Z + z] = (uint8_t)label;
+}
+
+template <int KCH, bool CLS = false>
 __global__ void __launch_bounds__(kHeavyThreads)
 k_pool_fwd_heavy(const float* __restrict__ depth, const float* __restrict__ feat,
                  const int32_t* __restrict__ ranks_depth, const int32_t* __restrict__ ranks_feat,
                  const int32_t* __restrict__ ranks_bev, const int32_t* __restrict__ tile_start,
                  const int32_t* __restrict__ heavy, int heavy_cap, uint32_t tiles_per_sample,
                  int64_t V, int C, uint32_t n_chunks, int vec_ok, float* __restrict__ out,
-                 int join, int min_points) {
+                 int join, int min_points, ClsArgs ca = ClsArgs()) {
   constexpr int CC = 32 * KCH;
   constexpr int kSegs = CC / 4;  // 16-byte segments per staged row
   extern __shared__ __align__(16) float hsm[];
@@ -454,7 +467,14 @@ k_pool_fwd_heavy(const float* __restrict__ depth, const float* __restrict__ feat
       __syncthreads();
     }
 
-    {  // write-out: thread (row = tid/8, q = tid%8) moves voxels 4q..4q+3 of channel row (+32j)
+    if constexpr (CLS) {  // one chunk holds every channel: lanes = voxels, classify from the tile
+      if (warp == 0 && v0 + lane < V) {
+        ClassMerge m;
+        for (int q = 0; q < ca.Q; ++q) m.push(__ldg(ca.cls + q), tile[(2 + q) * kRowPitch + lane]);
+        store_label(ca, b, (uint32_t)(v0 + lane),
+                    m.label(tile[lane], tile[kRowPitch + lane], ca.free_label));
+      }
+    } else {  // write-out: thread (row = tid/8, q = tid%8) moves voxels 4q..4q+3 of channel row (+32j)
       const int q4 = (tid & 7) * 4;
       const bool fast = vec_ok && (v0 + kTileVoxels <= V);
       for (int c = tid >> 3; c < cmax; c += kHeavyThreads / 8) {
@@ -678,18 +698,33 @@ k_pool_ds_fwd(const float* __restrict__ depth, const float* __restrict__ feat,
 // points to the CTA-per-tile kernel: 252 us of a 437 us call); k_pool_fwd_heavy skips those.
 constexpr int kNarrowWarps = 8;
 constexpr int kNarrowHeavyMin = 512;
-template <int NV>  // 16-byte pieces per feature row: C = 4 * NV
+// Fused lift + classify (CLS): NP passes of 4*NV channels each over the tile's points; the
+// class-merge state lives in registers between the passes (the merge is a scan over the prompt
+// rows in order), so Q + 2 <= 96 channels need no more registers than 32 do.
+template <int NV, bool CLS = false, int NP = 1>  // 16-byte pieces per pass: C = 4 * NV * NP
 __global__ void __launch_bounds__(kNarrowWarps * 32, (NV <= 5) ? 3 : 2)
 k_pool_fwd_narrow(const float* __restrict__ depth, const float* __restrict__ feat,
                   const int32_t* __restrict__ ranks_depth, const int32_t* __restrict__ ranks_feat,
                   const int32_t* __restrict__ ranks_bev, const int32_t* __restrict__ tile_start,
                   const int32_t* __restrict__ heavy, uint32_t n_tiles, uint32_t tiles_per_sample,
-                  int64_t V, float* __restrict__ out, uint32_t zero, int heavy_min, int join) {
-  constexpr int C = 4 * NV;
+                  int64_t V, float* __restrict__ out, uint32_t zero, int heavy_min, int join,
+                  ClsArgs ca) {
+  static_assert(CLS || NP == 1, "several passes only make sense when the sums are consumed here");
+  constexpr int CP = 4 * NV;        // channels per pass
+  constexpr int C = CP * NP;        // row length
   __shared__ int32_t seg_s[kNarrowWarps][32];
   pdl_launch_dependents();  // the heavy-tile grid may be queued behind this one
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   int32_t* seg = seg_s[warp];
+  uint32_t heads[3] = {0u, 0u, 0u};   // CLS: bit q = prompt row q starts a class (Q <= 94)
+  if constexpr (CLS) {
+#pragma unroll
+    for (int w = 0; w < 3; ++w) {
+      const int q = 32 * w + lane;
+      const bool h = q < ca.Q && (q == 0 || __ldg(ca.cls + q) != __ldg(ca.cls + q - 1));
+      heads[w] = __ballot_sync(0xffffffffu, h);
+    }
+  }
   const int32_t heavy_thr = heavy ? max(__ldg(heavy + 1), heavy_min) : 0x7fffffff;
   const uint32_t TW = gridDim.x * kNarrowWarps;
   // The per-tile chain (bounds -> ranks_bev -> segment table -> ranks -> rows -> stores) is a
@@ -720,9 +755,7 @@ k_pool_fwd_narrow(const float* __restrict__ depth, const float* __restrict__ fea
     const uint32_t b = t / tiles_per_sample;
     const uint32_t v0 = (t - b * tiles_per_sample) * kTileVoxels;
     const int32_t g0 = (int32_t)((int64_t)b * V) + (int32_t)v0;  // rank of the tile's first voxel
-    float acc[C];
-#pragma unroll
-    for (int c = 0; c < C; ++c) acc[c] = 0.f;
+    int32_t st = -1, en = 0;   // this lane's voxel: its points are [st, en)
     if (e0 > s0) {
       // first point of every occupied voxel
       seg[lane] = -1;
@@ -751,14 +784,26 @@ k_pool_fwd_narrow(const float* __restrict__ depth, const float* __restrict__ fea
         }
       }
       __syncwarp();
-      const int32_t st = seg[lane];
+      st = seg[lane];
       const uint32_t occ = __ballot_sync(0xffffffffu, st >= 0);
       const uint32_t higher = (lane == 31) ? 0u : (occ >> (lane + 1));
       const int nxt = higher ? lane + __ffs(higher) : 0;
       const int32_t nst = __shfl_sync(0xffffffffu, st, nxt);
-      const int32_t en = higher ? nst : e0;
+      en = higher ? nst : e0;
       __syncwarp();  // seg is rewritten for the next tile
+    }
+    // CLS: class-wise max over the prompt rows, first-index arg-max over the classes -- the
+    // branch-free form of ClassMerge -- carried from pass to pass
+    float best = -INFINITY, cur = -INFINITY, gate0 = 0.f, gate1 = 0.f;
+    int best_q = 0, cur_q = 0;
+    bool bad = false;
+#pragma unroll 1
+    for (int pass = 0; pass < NP; ++pass) {
+      float acc[CP];
+#pragma unroll
+      for (int c = 0; c < CP; ++c) acc[c] = 0.f;
       if (st >= 0) {
+        const float* fbase = feat + pass * CP;
         int32_t i = st;
         bool two = i + 1 < en;
         int32_t r0 = __ldg(ranks_depth + i), f0 = __ldg(ranks_feat + i);
@@ -769,8 +814,8 @@ k_pool_fwd_narrow(const float* __restrict__ depth, const float* __restrict__ fea
           // point's loads into); a missing second point is (+0) * (-0): acc + (-0) == acc bit for
           // bit, whatever acc is.
           const float d0 = __ldg(depth + r0), d1 = two ? __ldg(depth + r1) : -0.f;
-          const float4* row0 = reinterpret_cast<const float4*>(feat + (int64_t)f0 * C);
-          const float4* row1 = reinterpret_cast<const float4*>(feat + (int64_t)f1 * C);
+          const float4* row0 = reinterpret_cast<const float4*>(fbase + (int64_t)f0 * C);
+          const float4* row1 = reinterpret_cast<const float4*>(fbase + (int64_t)f1 * C);
           float4 a[NV], q[NV];
 #pragma unroll
           for (int k = 0; k < NV; ++k) a[k] = __ldg(row0 + k);
@@ -810,27 +855,55 @@ k_pool_fwd_narrow(const float* __restrict__ depth, const float* __restrict__ fea
           if (!more) break;
         }
       }
-    }
-    float* o = out + (int64_t)b * C * V + v0 + lane;
+      if constexpr (CLS) {
+        // rows are [gate 0, gate 1, logit 0 .. Q-1, padding]: channel c of pass p is prompt
+        // p * CP + c - 2; padding enters as -inf and changes nothing
+        if (pass == 0) { gate0 = acc[0]; gate1 = acc[1]; }
 #pragma unroll
-    for (int c = 0; c < C; ++c) st_stream(o + (int64_t)c * V, acc[c]);
+        for (int c = 0; c < CP; ++c) {
+          const int q = pass * CP + c - 2;
+          const bool real = q >= 0 && q < ca.Q;
+          const float logit = real ? acc[c] : -INFINITY;
+          bad |= !(logit < INFINITY);
+          const uint32_t word = q < 32 ? heads[0] : (q < 64 ? heads[1] : heads[2]);
+          const bool head = real && ((word >> (q & 31)) & 1u);
+          const bool take = head && (cur > best);
+          best = take ? cur : best;
+          best_q = take ? cur_q : best_q;
+          cur = head ? logit : fmaxf(cur, logit);
+          cur_q = head ? q : cur_q;
+        }
+      } else {
+        float* o = out + (int64_t)b * C * V + v0 + lane;
+#pragma unroll
+        for (int c = 0; c < CP; ++c) st_stream(o + (int64_t)c * V, acc[c]);
+      }
+    }
+    if constexpr (CLS) {
+      if (cur > best) { best = cur; best_q = cur_q; }
+      bad |= (best == -INFINITY);
+      const float mx = fmaxf(gate0, gate1);
+      const float e0g = expf(gate0 - mx), e1g = expf(gate1 - mx);
+      const bool occupied = (e0g / (e0g + e1g)) > 0.5f;
+      store_label(ca, b, v0 + lane, (occupied && !bad) ? __ldg(ca.cls + best_q) : ca.free_label);
+    }
   }
   if (join) pdl_wait();   // launched behind the heavy grid: complete after it (see k_pool_fwd_heavy)
 }
 
 
 // ---- launchers ---------------------------------------------------------------------------------
-template <int KCH>
+template <int KCH, bool CLS = false>
 static int heavy_config(size_t& smem, int& ctas_per_sm) {
   constexpr int CC = 32 * KCH;
   smem = sizeof(float) * (kHeavyChunk * CC + CC * kRowPitch + 2 * kHeavyChunk + 128);
   static int cached[kMaxDevices] = {};
   const int dev = current_device();
   if (cached[dev] == 0) {
-    VEON_CUDA_TRY(cudaFuncSetAttribute(k_pool_fwd_heavy<KCH>,
+    VEON_CUDA_TRY(cudaFuncSetAttribute(k_pool_fwd_heavy<KCH, CLS>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int n = 0;
-    VEON_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_pool_fwd_heavy<KCH>,
+    VEON_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_pool_fwd_heavy<KCH, CLS>,
                                                                 kHeavyThreads, smem));
     cached[dev] = n < 1 ? 1 : (n > 8 ? 8 : n);
   }
@@ -839,15 +912,15 @@ static int heavy_config(size_t& smem, int& ctas_per_sm) {
 }
 
 // the heavy-tile grid; pdl: queued as a programmatic dependent of the previous launch (joins it)
-template <int KCH>
+template <int KCH, bool CLS = false>
 static int launch_heavy(const float* depth, const float* feat, const int32_t* rd, const int32_t* rf,
                         const int32_t* rb, const int32_t* tile_start, const int32_t* heavy,
                         int64_t heavy_ints, int B, int C, int64_t V, float* out, bool pdl,
-                        int min_points, cudaStream_t stream) {
+                        int min_points, cudaStream_t stream, ClsArgs ca = ClsArgs()) {
   constexpr int CC = 32 * KCH;
   size_t smem;
   int per_sm;
-  int rc = heavy_config<KCH>(smem, per_sm);
+  int rc = heavy_config<KCH, CLS>(smem, per_sm);
   if (rc) return rc;
   const int64_t tps = ceil_div64(V, kTileVoxels);
   const int n_chunks = (C + CC - 1) / CC;
@@ -857,13 +930,13 @@ static int launch_heavy(const float* depth, const float* feat, const int32_t* rd
   if (blocks > (int64_t)per_sm * sm_count()) blocks = (int64_t)per_sm * sm_count();
   if (blocks <= 0) return 0;
   if (pdl) {
-    VEON_CUDA_TRY(launch_pdl(k_pool_fwd_heavy<KCH>, dim3((unsigned)blocks), dim3(kHeavyThreads),
+    VEON_CUDA_TRY(launch_pdl(k_pool_fwd_heavy<KCH, CLS>, dim3((unsigned)blocks), dim3(kHeavyThreads),
                              smem, stream, depth, feat, rd, rf, rb, tile_start, heavy, heavy_cap,
-                             (uint32_t)tps, V, C, (uint32_t)n_chunks, vec_ok, out, 1, min_points));
+                             (uint32_t)tps, V, C, (uint32_t)n_chunks, vec_ok, out, 1, min_points, ca));
   } else {
-    k_pool_fwd_heavy<KCH><<<(unsigned)blocks, kHeavyThreads, smem, stream>>>(
+    k_pool_fwd_heavy<KCH, CLS><<<(unsigned)blocks, kHeavyThreads, smem, stream>>>(
         depth, feat, rd, rf, rb, tile_start, heavy, heavy_cap, (uint32_t)tps, V, C,
-        (uint32_t)n_chunks, vec_ok, out, 0, min_points);
+        (uint32_t)n_chunks, vec_ok, out, 0, min_points, ca);
   }
   VEON_LAUNCH_CHECK();
   return 0;
@@ -938,29 +1011,31 @@ static int launch_fwd(const float* depth, const float* feat, const int32_t* rd,
 // CTA works ~100 us on one 1 000-point tile at C3 density: behind the persistent main grid the
 // two nearly serialise, 344 vs 295 us); k_pool_fwd_narrow moves in beside it as its programmatic
 // dependent and joins it at the end
-template <int NV>
+template <int NV, bool CLS = false, int NP = 1>
 static int launch_fwd_narrow(const float* depth, const float* feat, const int32_t* rd,
                              const int32_t* rf, const int32_t* rb, const int32_t* tile_start,
                              const int32_t* heavy, int64_t heavy_ints, int B, int64_t V,
-                             float* out, cudaStream_t stream) {
-  constexpr int C = 4 * NV;
+                             float* out, cudaStream_t stream, ClsArgs ca = ClsArgs()) {
+  constexpr int C = 4 * NV * NP;
+  constexpr int KCH = (C + 31) / 32;   // the heavy CTA holds every channel of its tile
   const int64_t tps = V / kTileVoxels, n_tiles = (int64_t)B * tps;
   static int ctas_per_sm[kMaxDevices] = {};
   const int dev = current_device();
   if (ctas_per_sm[dev] == 0) {
     int n = 0;
-    VEON_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_pool_fwd_narrow<NV>,
+    VEON_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_pool_fwd_narrow<NV, CLS, NP>,
                                                                 kNarrowWarps * 32, 0));
     ctas_per_sm[dev] = n < 1 ? 1 : n;
   }
   int64_t blocks = ceil_div64(n_tiles, kNarrowWarps);
   if (blocks > (int64_t)ctas_per_sm[dev] * sm_count()) blocks = (int64_t)ctas_per_sm[dev] * sm_count();
-  int rc = launch_heavy<1>(depth, feat, rd, rf, rb, tile_start, heavy, heavy_ints, B, C, V, out,
-                           false, kNarrowHeavyMin, stream);
+  int rc = launch_heavy<KCH, CLS>(depth, feat, rd, rf, rb, tile_start, heavy, heavy_ints, B, C, V,
+                                  out, false, kNarrowHeavyMin, stream, ca);
   if (rc) return rc;
-  VEON_CUDA_TRY(launch_pdl(k_pool_fwd_narrow<NV>, dim3((unsigned)blocks), dim3(kNarrowWarps * 32),
-                           0, stream, depth, feat, rd, rf, rb, tile_start, heavy,
-                           (uint32_t)n_tiles, (uint32_t)tps, V, out, 0u, kNarrowHeavyMin, 1));
+  VEON_CUDA_TRY(launch_pdl(k_pool_fwd_narrow<NV, CLS, NP>, dim3((unsigned)blocks),
+                           dim3(kNarrowWarps * 32), 0, stream, depth, feat, rd, rf, rb, tile_start,
+                           heavy, (uint32_t)n_tiles, (uint32_t)tps, V, out, 0u, kNarrowHeavyMin, 1,
+                           ca));
   VEON_LAUNCH_CHECK();
   return 0;
 }
@@ -1026,6 +1101,48 @@ extern "C" int veon_bev_pool_v2_fwd_planar(const float* depth, const float* feat
                          tile_heavy_ints, B, C, V, fit32, out, stream);
   return launch_fwd<2>(depth, feat, ranks_depth, ranks_feat, ranks_bev, tile_start, tile_heavy,
                        tile_heavy_ints, B, C, V, fit32, out, stream);
+}
+
+// Fused lift + classify: pools the [gate 0, gate 1, logit 0..Q-1, pad] rows and ends every tile
+// as 32 labels -- the pooled logit volume is never written.
+extern "C" int veon_lift_classify_fwd(const float* depth, const float* pix,
+                                      const int32_t* ranks_depth, const int32_t* ranks_feat,
+                                      const int32_t* ranks_bev, const int32_t* tile_start,
+                                      const int32_t* tile_heavy, int64_t tile_heavy_ints, int B,
+                                      int C, int Q, int Z, int Y, int X, int64_t n_pix_rows,
+                                      const int32_t* class_of_prompt, int free_label,
+                                      uint8_t* labels, void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  if (!depth || !pix || !ranks_depth || !ranks_feat || !ranks_bev || !tile_start || !tile_heavy ||
+      tile_heavy_ints < 2 || !class_of_prompt || !labels || B <= 0 || C <= 0 || Q <= 0 ||
+      Z <= 0 || Y <= 0 || X <= 0 || n_pix_rows <= 0)
+    return VEON_E_BADARG;
+  const int64_t V = (int64_t)Z * Y * X;
+  if ((C & 3) != 0 || Q + 2 > C || C > 96 || Q > 94 || V % kTileVoxels != 0 ||
+      ((uintptr_t)pix & 15) != 0)
+    return VEON_E_UNSUPPORTED;
+  // 32-bit row offsets; rank arithmetic is exact only while B*V <= 2^24
+  if (n_pix_rows * (int64_t)C > 0x3fffffffLL || B >= 65536 || (int64_t)B * V > (1 << 24))
+    return VEON_E_RANGE;
+  ClsArgs ca;
+  ca.cls = class_of_prompt; ca.labels = labels; ca.Q = Q; ca.X = X; ca.Y = Y; ca.Z = Z;
+  ca.free_label = free_label;
+  // Cp = 4 * NV * NP: one pass up to 32 channels, two up to 64, three up to 96
+#define VEON_CLS_CASE(NV_, NP_)                                                                   \
+  if (C == 4 * NV_ * NP_)                                                                         \
+    return launch_fwd_narrow<NV_, true, NP_>(depth, pix, ranks_depth, ranks_feat, ranks_bev,      \
+                                             tile_start, tile_heavy, tile_heavy_ints, B, V,       \
+                                             nullptr, stream, ca);
+  if (C <= 32) {
+    VEON_CLS_CASE(1, 1) VEON_CLS_CASE(2, 1) VEON_CLS_CASE(3, 1) VEON_CLS_CASE(4, 1)
+    VEON_CLS_CASE(5, 1) VEON_CLS_CASE(6, 1) VEON_CLS_CASE(7, 1) VEON_CLS_CASE(8, 1)
+  } else if (C <= 64) {
+    VEON_CLS_CASE(5, 2) VEON_CLS_CASE(6, 2) VEON_CLS_CASE(7, 2) VEON_CLS_CASE(8, 2)
+  } else {
+    VEON_CLS_CASE(6, 3) VEON_CLS_CASE(7, 3) VEON_CLS_CASE(8, 3)
+  }
+#undef VEON_CLS_CASE
+  return VEON_E_UNSUPPORTED;
 }
 
 extern "C" int veon_bev_pool_v2_ds_fwd(const float* depth, const float* feat,

@@ -73,12 +73,46 @@ def lift_logits(neck, input, depth, tran_feat, ov_classifier_weight, gate_weight
         return vol
 
 
+def _heads_gate_first(ov_classifier_weight, gate_weight):
+    """[gate 0, gate 1, prompt rows, zero padding to a multiple of 4]: the row order of the fused
+    lift + classify kernel (the gate channels sit at fixed register positions)."""
+    w = ov_classifier_weight.detach().float()
+    g = gate_weight.detach().float()
+    if g.shape != (2, w.shape[1]):
+        raise ValueError("gate_weight must be [2, C]")
+    rows = torch.cat((g, w), 0)
+    # the kernel walks the row in 1, 2 or 3 passes of equal width (<= 32 channels each)
+    n = rows.shape[0]
+    step = 4 if n <= 32 else (8 if n <= 64 else 12)
+    pad = max(-n % step, (40 if step == 8 else 72 if step == 12 else 0) - n)
+    if pad:
+        rows = torch.cat((rows, rows.new_zeros(pad, rows.shape[1])), 0)
+    return rows.contiguous()
+
+
 def lift_classify(neck, input, depth, tran_feat, ov_classifier_weight, prompt_class, gate_weight,
-                  free_label=17, channel_pad=4):
+                  free_label=17, channel_pad=4, fused=True):
     """neck: LSSViewTransformer; input = (img [B,N,*,H,W], sensor2ego, ego2global, cam2imgs,
     post_rots, post_trans, bda); depth [B*N,D,H,W]; tran_feat [B*N,C,H,W];
-    ov_classifier_weight [Q,C]; prompt_class [Q]; gate_weight [2,C] -> uint8 [B,X,Y,Z]."""
+    ov_classifier_weight [Q,C]; prompt_class [Q]; gate_weight [2,C] -> uint8 [B,X,Y,Z].
+
+    fused=True (default): the pooling kernel classifies each tile itself and the pooled logit
+    volume is never written (`veon_lift_classify_fwd`, Q <= 94 prompt rows); otherwise, or when
+    that kernel does not take the shape, the volume is pooled and `classify_logits` reads it.
+    Both give the same labels (the same sums, bit for bit, through the same rule)."""
     Q = ov_classifier_weight.shape[0]
+    if (fused and Q <= 94 and tran_feat.is_cuda and neck.fuse_geometry
+            and not neck.collapse_z):
+        B, N = input[0].shape[:2]
+        BN, C, H, W = tran_feat.shape
+        with torch.no_grad():
+            rows = _heads_gate_first(ov_classifier_weight, gate_weight)
+            px = _tail.semantic_inference_3d(rows, tran_feat.reshape(B * N, C, 1, H, W))
+            labels = neck.lift_labels_calib(list(input[1:7]), depth.reshape(B, N, neck.D, H, W),
+                                            px.view(B, N, rows.shape[0], H, W), Q, prompt_class,
+                                            free_label)
+        if labels is not None:
+            return labels
     vol = lift_logits(neck, input, depth, tran_feat, ov_classifier_weight, gate_weight, channel_pad)
     with torch.no_grad():
         return _tail.classify_logits(vol[:, :Q], vol[:, Q:Q + 2], prompt_class, free_label)

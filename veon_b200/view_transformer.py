@@ -171,10 +171,15 @@ class LSSViewTransformer(nn.Module):
     def _voxel_pooling_calib(self, calib, depth, feat):
         """voxel_pooling_v2 with get_lidar_coor folded into the index preparation:
         `calib` = the six tensors get_lidar_coor takes; no coordinate tensor is written."""
+        wants_grad = torch.is_grad_enabled() and (depth.requires_grad or feat.requires_grad)
+        return self._pool_prepared(self._prepare_calib(calib, depth, wants_grad), depth, feat)
+
+    def _prepare_calib(self, calib, depth, wants_grad=False):
+        """The prepared ranks + plan for a calibration (fused geometry; rank cache / negligible
+        depth bins when configured)."""
         sensor2ego, _ego2global, cam2imgs, post_rots, post_trans, bda = calib
         frustum = self._frustum_on(sensor2ego.device)
         grid = (self.grid_lower_bound, self.grid_interval, self.grid_size)
-        wants_grad = torch.is_grad_enabled() and (depth.requires_grad or feat.requires_grad)
         if self.depth_eps is not None and not wants_grad:
             # depth-dependent ranks: nothing to cache
             prep = _bp.prepare_ranks_calib(frustum, sensor2ego, cam2imgs, post_rots, post_trans,
@@ -195,7 +200,20 @@ class LSSViewTransformer(nn.Module):
         else:
             prep = _bp.prepare_ranks_calib(frustum, sensor2ego, cam2imgs, post_rots, post_trans,
                                            bda, *grid)
-        return self._pool_prepared(prep, depth, feat)
+        return prep
+
+    def lift_labels_calib(self, calib, depth, pix, Q, prompt_class, free_label=17):
+        """Fused lift + classify of per-pixel rows `pix` [B,N,Cp,H,W] = [gate 0, gate 1,
+        logit 0..Q-1, padding] (veon_b200.pipeline.lift_classify): uint8 labels [B,X,Y,Z], or None
+        when the fused kernel does not take the shape.  Inference only."""
+        with torch.no_grad():
+            prep = self._prepare_calib(calib, depth)
+            prep.plan.sync_free = self.sync_free
+            if self.prepared_hook is not None:
+                self.prepared_hook()
+            gs = self.grid_size
+            return _bp.lift_classify_prepared(depth, pix, prep, Q, prompt_class,
+                                              (int(gs[2]), int(gs[1]), int(gs[0])), free_label)
 
     def _pool_prepared(self, prep, depth, feat):
         feat_last = feat.permute(0, 1, 3, 4, 2)
