@@ -71,7 +71,7 @@ constexpr int kASlots = 4 * kADist;
 // Raising the bar for this kernel (role A claims dynamically and the ring has rounds of slack)
 // was measured and loses: 128 / 256 / 384 / 768 points -> 321 / 357 / 386 / 487 us at C2.
 constexpr int kStreamHeavyMin = 0;
-constexpr int kEChunk = 64;             // channels per E item
+constexpr int kEChunk = 32;             // channels per E step (two staging buffers per warp)
 constexpr int kERows = 33;              // staged rows per tile: <= 32 occupied voxels + 1 of zeros
 
 __device__ __forceinline__ void cpa4(void* smem_dst, const void* gsrc) {
@@ -384,15 +384,27 @@ __device__ __forceinline__ void role_rows(const FwdStreamParams& p, int32_t* rin
 // ------------------------------------------------------------------------------------------
 // role E: ring -> dense volume.  Warp ew: tile ew of every round; group = ew / 8.
 // ------------------------------------------------------------------------------------------
-// staged row j of a tile: 16 chunks of 16 bytes, chunk k at position k ^ swz(j) so that the
+// staged row j of a tile: 8 chunks of 16 bytes, chunk k at position k ^ swz(j) so that the
 // eight lanes of a store quad-row (eight different rows, same channel) hit different banks
 __device__ __forceinline__ uint32_t e_swz(uint32_t j) { return (j ^ (j >> 2)) & 7u; }
+
+// One E step = (unit, 32-channel sub-chunk).  The steps are software-pipelined over two staging
+// buffers: the copies of step i+1 (ring -> shared memory, L2 latency) are in flight while step i is
+// written out, and the wait for role A's next unit happens a step early.
+struct ECursor {
+  uint32_t m, pass, sub;      // round of this CTA, channel pass, sub-chunk
+  uint32_t b, vt;             // sample and tile inside the sample of this warp's tile
+  uint32_t occ;
+  int base, n;
+  bool mine;
+};
 
 template <int VEC>
 __device__ __forceinline__ void role_expand(const FwdStreamParams& p, float* stage,
                                             StreamShared* sh, int lane, int ew) {
   constexpr int CU = 32 * VEC;
   constexpr int kSub = CU / kEChunk;
+  constexpr uint32_t kBufBytes = kERows * kEChunk * 4;
   __builtin_assume(__isShared(stage));
   if (blockIdx.x >= p.n_rounds) return;
   const uint32_t my_rounds = (p.n_rounds - blockIdx.x + gridDim.x - 1) / gridDim.x;
@@ -401,103 +413,137 @@ __device__ __forceinline__ void role_expand(const FwdStreamParams& p, float* sta
   const uint32_t stage_s = (uint32_t)__cvta_generic_to_shared(stage);
   const int q4 = (lane & 7) * 4, r = lane >> 3;
   const int group = ew / kEGroup;
+  const uint32_t t_step = gridDim.x * kRoundTiles;
 
-  // zero row (row 32; nothing is ever copied there)
-  for (int i = lane; i < kEChunk; i += 32) stage[32 * kEChunk + i] = 0.f;
+  // zero rows (row 32 of both buffers; nothing is ever copied there)
+  for (int i = lane; i < kEChunk; i += 32) {
+    stage[32 * kEChunk + i] = 0.f;
+    stage[kERows * kEChunk + 32 * kEChunk + i] = 0.f;
+  }
   __syncwarp();
 
-  // (sample, tile inside the sample) of this warp's tile, advanced by the round stride
-  uint32_t t = blockIdx.x * kRoundTiles + ew;
-  uint32_t b = t / p.tiles_per_sample, vt = t - b * p.tiles_per_sample;
-  const uint32_t t_step = gridDim.x * kRoundTiles;
-  VEON_T0
-  for (uint32_t m = 0; m < my_rounds; ++m, t += t_step, vt += t_step) {
-    while (vt >= p.tiles_per_sample) {
-      vt -= p.tiles_per_sample;
-      ++b;
+  auto start = [&](ECursor& c) {
+    c.m = 0; c.pass = 0; c.sub = 0;
+    const uint32_t t = blockIdx.x * kRoundTiles + ew;
+    c.b = t / p.tiles_per_sample;
+    c.vt = t - c.b * p.tiles_per_sample;
+    c.occ = 0u; c.base = 0; c.n = 0; c.mine = false;
+  };
+  auto advance = [&](ECursor& c) {
+    if (++c.sub < (uint32_t)kSub) return;
+    c.sub = 0;
+    if (++c.pass < (uint32_t)p.n_pass) return;
+    c.pass = 0;
+    ++c.m;
+    c.vt += t_step;
+    while (c.vt >= p.tiles_per_sample) {
+      c.vt -= p.tiles_per_sample;
+      ++c.b;
     }
-    const uint32_t v0 = vt * kTileVoxels;
-    uint32_t occ = 0u, a[4] = {0u, 0u, 0u, 0u};
-    int base = 0, n = 0;
-    bool mine = false;
-    for (int pass = 0; pass < p.n_pass; ++pass) {
-      const uint32_t unit = m * (uint32_t)p.n_pass + pass;
-      const uint32_t slot = unit & ns_mask;
-      const uint32_t gen = unit >> p.ns_log2;
+  };
+  // start the copies of the cursor's step into buffer `buf`
+  auto issue = [&](ECursor& c, uint32_t buf) {
+    const uint32_t unit = c.m * (uint32_t)p.n_pass + c.pass;
+    const uint32_t slot = unit & ns_mask;
+    if (c.sub == 0) {
       // Role A has put the unit's rows into the slot.  EVERY E warp waits here, also one whose
       // tile is empty: no E warp may run a slot generation ahead of the others (its tick on
       // `drained` would be taken for a slower warp's).
-      VEON_TACC(0)
-      mbar_wait(&sh->full[slot], gen & 1u);
-      VEON_TACC(1)
-      if (pass == 0) {   // what role A published about this warp's tile (the same for every pass)
+      mbar_wait(&sh->full[slot], (unit >> p.ns_log2) & 1u);
+      if (c.pass == 0) {   // what role A published about this warp's tile (the same for every pass)
         const uint2 mt = sh->meta[slot][ew];
-        occ = mt.x;
-        base = (int)(mt.y & ~kMetaMine);
-        mine = (mt.y & kMetaMine) != 0u;
-        n = __popc(occ);
-        // shared-memory address of channel r of the staged row of each of this lane's four
-        // voxels, the row's swizzle folded in; the zero row for empty voxels
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int v = q4 + i;
-          const bool set = (occ >> v) & 1u;
-          const uint32_t j = set ? (uint32_t)__popc(occ & ((1u << v) - 1u)) : 32u;
-          a[i] = stage_s + j * (kEChunk * 4) + (uint32_t)r * 4u;
-          if (set) a[i] ^= e_swz(j) << 4;
-        }
-      }
-      const float* src = cta_ring + (size_t)slot * (kSlotRows * CU) + (size_t)base * CU +
-                         (lane & 15) * 4;
-      float* o = p.out + ((int64_t)b * p.C + pass * CU + r) * p.V + v0 + q4;
-      const int64_t ostep = 4 * p.V;
-#pragma unroll 1
-      for (int sub = 0; sub < kSub; ++sub, src += kEChunk) {
-        if (mine && n > 0) {
-          for (int j = lane >> 4; j < n; j += 2)
-            cpa16_cg(stage_s + (uint32_t)j * (kEChunk * 4) + ((((uint32_t)lane & 15u) ^ e_swz(j)) << 4),
-                     src + (size_t)j * CU);
-        }
-        cpa_commit();
-        cpa_wait<0>();
-        __syncwarp();
-        if (sub == kSub - 1 && lane == 0)   // slot needed no more (this warp's copies have landed)
-          atomicAdd(const_cast<uint32_t*>(&sh->drained[slot]), 1u);
-        VEON_TACC(2)
-#ifndef VEON_FWD_NO_LOCKSTEP
-        // the group's 8 tiles are written together: aligned 1 KB runs per channel plane
-        if (group == 0) asm volatile("bar.sync 1, %0;" ::"n"(kEGroup * 32) : "memory");
-        else asm volatile("bar.sync 2, %0;" ::"n"(kEGroup * 32) : "memory");
-#endif
-        VEON_TACC(3)
-        if (mine) {
-          if (n == 0) {
-#pragma unroll 4
-            for (int k = 0; k < kEChunk / 4; ++k, o += ostep)
-              st_stream4(o, make_float4(0.f, 0.f, 0.f, 0.f));
-          } else {
-#pragma unroll
-            for (int k0 = 0; k0 < kEChunk / 4; k0 += 4) {   // 16 loads in flight, then 4 stores
-              float4 v4[4];
-#pragma unroll
-              for (int kk = 0; kk < 4; ++kk) {
-                const uint32_t x = (uint32_t)((k0 + kk) << 4);
-                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v4[kk].x) : "r"(a[0] ^ x));
-                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v4[kk].y) : "r"(a[1] ^ x));
-                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v4[kk].z) : "r"(a[2] ^ x));
-                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v4[kk].w) : "r"(a[3] ^ x));
-              }
-#pragma unroll
-              for (int kk = 0; kk < 4; ++kk, o += ostep) st_stream4(o, v4[kk]);
-            }
-          }
-        } else {
-          o += (kEChunk / 4) * ostep;
-        }
-        __syncwarp();   // the staging buffer is refilled next
-        VEON_TACC(4)
+        c.occ = mt.x;
+        c.base = (int)(mt.y & ~kMetaMine);
+        c.mine = (mt.y & kMetaMine) != 0u;
+        c.n = __popc(c.occ);
       }
     }
+    if (c.mine && c.n > 0) {
+      const float* src = cta_ring + (size_t)slot * (kSlotRows * CU) + (size_t)c.base * CU +
+                         c.sub * kEChunk + (lane & 7) * 4;
+      const uint32_t dst = stage_s + buf * kBufBytes;
+      for (int j = lane >> 3; j < c.n; j += 4)
+        cpa16_cg(dst + (uint32_t)j * (kEChunk * 4) + ((((uint32_t)lane & 7u) ^ e_swz(j)) << 4),
+                 src + (size_t)j * CU);
+    }
+    cpa_commit();
+  };
+
+  const uint32_t n_steps = my_rounds * (uint32_t)p.n_pass * kSub;
+  ECursor wc, ic;     // step being written, step whose copies are issued next
+  start(wc);
+  start(ic);
+  static_assert(kSub >= 2, "the issue cursor must still be on the write cursor's tile one step on");
+  VEON_T0
+  issue(ic, 0);
+  wc.occ = ic.occ; wc.base = ic.base; wc.n = ic.n; wc.mine = ic.mine;
+  uint32_t rel[4] = {0u, 0u, 0u, 0u};
+  for (uint32_t st = 0; st < n_steps; ++st) {
+    const uint32_t buf = st & 1u;
+    VEON_TACC(0)
+    // this step's copies (issued a step ago) have landed; the slot is released BEFORE the wait
+    // for role A's next unit: an A warp may be blocked on exactly this slot while other tiles
+    // of the next unit are still unclaimed (tiles are claimed dynamically)
+    cpa_wait<0>();
+    __syncwarp();
+    const uint32_t unit = wc.m * (uint32_t)p.n_pass + wc.pass;
+    if (wc.sub == (uint32_t)kSub - 1 && lane == 0)   // slot needed no more
+      atomicAdd(const_cast<uint32_t*>(&sh->drained[unit & ns_mask]), 1u);
+    VEON_TACC(2)
+    if (st + 1 < n_steps) {   // the next step's copies fly during the barrier and the write-out
+      advance(ic);
+      issue(ic, buf ^ 1u);    // (a new tile's meta stays in `ic` until the write cursor gets there)
+    }
+    VEON_TACC(1)
+#ifndef VEON_FWD_NO_LOCKSTEP
+    // the group's 8 tiles are written together: aligned 1 KB runs per channel plane
+    if (group == 0) asm volatile("bar.sync 1, %0;" ::"n"(kEGroup * 32) : "memory");
+    else asm volatile("bar.sync 2, %0;" ::"n"(kEGroup * 32) : "memory");
+#endif
+    VEON_TACC(3)
+    if (wc.sub == 0 && wc.pass == 0) {
+      // offset of channel r of the staged row of each of this lane's four voxels inside a
+      // buffer, the row's swizzle folded in; the zero row for empty voxels
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int v = q4 + i;
+        const bool set = (wc.occ >> v) & 1u;
+        const uint32_t j = set ? (uint32_t)__popc(wc.occ & ((1u << v) - 1u)) : 32u;
+        rel[i] = j * (kEChunk * 4) + (uint32_t)r * 4u;
+        if (set) rel[i] ^= e_swz(j) << 4;
+      }
+    }
+    if (wc.mine) {
+      float* o = p.out + ((int64_t)wc.b * p.C + wc.pass * CU + wc.sub * kEChunk + r) * p.V +
+                 wc.vt * kTileVoxels + q4;
+      const int64_t ostep = 4 * p.V;
+      if (wc.n == 0) {
+#pragma unroll 4
+        for (int k = 0; k < kEChunk / 4; ++k, o += ostep)
+          st_stream4(o, make_float4(0.f, 0.f, 0.f, 0.f));
+      } else {
+        const uint32_t bs = stage_s + buf * kBufBytes;
+#pragma unroll
+        for (int k0 = 0; k0 < kEChunk / 4; k0 += 4) {   // 16 loads in flight, then 4 stores
+          float4 v4[4];
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint32_t x = (uint32_t)((k0 + kk) << 4);
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v4[kk].x) : "r"(bs + (rel[0] ^ x)));
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v4[kk].y) : "r"(bs + (rel[1] ^ x)));
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v4[kk].z) : "r"(bs + (rel[2] ^ x)));
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v4[kk].w) : "r"(bs + (rel[3] ^ x)));
+          }
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk, o += ostep) st_stream4(o, v4[kk]);
+        }
+      }
+    }
+    __syncwarp();   // this buffer is refilled by the step after next
+    VEON_TACC(4)
+    // move the write cursor; a new tile takes over the meta the issue cursor has read
+    advance(wc);
+    if (wc.sub == 0 && wc.pass == 0) { wc.occ = ic.occ; wc.base = ic.base; wc.n = ic.n; wc.mine = ic.mine; }
   }
 }
 
@@ -518,7 +564,7 @@ k_fwd_stream(const FwdStreamParams p) {
   if (threadIdx.x == 0) sh.next_item = 0;
   asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   __syncthreads();
-  constexpr int kEStageFloats = kEWarps * kERows * kEChunk;
+  constexpr int kEStageFloats = kEWarps * 2 * kERows * kEChunk;
   if (warp < kAWarps) {
     reg_inc<kARegs>();
     role_rows<VEC>(p, reinterpret_cast<int32_t*>(fs_smem + kEStageFloats) +
@@ -526,7 +572,7 @@ k_fwd_stream(const FwdStreamParams p) {
   } else {
     reg_dec<kERegs>();
     const int ew = warp - kAWarps;
-    role_expand<VEC>(p, fs_smem + ew * kERows * kEChunk, &sh, lane, ew);
+    role_expand<VEC>(p, fs_smem + ew * 2 * kERows * kEChunk, &sh, lane, ew);
   }
 }
 
@@ -546,7 +592,7 @@ bool fwd_stream_supported(int B, int C, int64_t V, const void* feat, const void*
 template <int VEC>
 static int launch_stream_kernel(FwdStreamParams& p, size_t ring_bytes, cudaStream_t stream) {
   constexpr int CU = 32 * VEC;
-  const size_t smem = sizeof(float) * kEWarps * kERows * kEChunk +
+  const size_t smem = sizeof(float) * kEWarps * 2 * kERows * kEChunk +
                       sizeof(int32_t) * kAWarps * kASlots * kASlotInts + 256;
   static int per_sm[kMaxDevices] = {};
   const int dev = current_device();
