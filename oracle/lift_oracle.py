@@ -338,3 +338,21 @@ def two_hot_depth(depths, depth_cfg, gamma=4, downsample=0):
     e = np.exp(gap - m, dtype=_f32)
     dist = (e / e.sum(axis=-1, keepdims=True, dtype=_f32)).astype(_f32)
     return np.ascontiguousarray(np.moveaxis(dist[..., :D], -1, 2))
+
+
+def lidar_coor_torch(frustum, sensor2ego, ego2global, cam2imgs, post_rots, post_trans, bda):
+    """`LSSViewTransformer.get_lidar_coor` (view_transformer.py:114-152) written with torch ops in
+    the reference's operation order: the float reference the CUDA geometry kernels are validated
+    against (tests only; `frustum` [D,H,W,3] from the neck)."""
+    import torch
+    fr = frustum.to(sensor2ego)                           # [D,H,W,3]
+    undo_aug = torch.inverse(post_rots)                   # [B,N,3,3]
+    cam2ego = sensor2ego[..., :3, :3] @ torch.inverse(cam2imgs)
+    ego_t = sensor2ego[..., :3, 3]
+    img = fr[None, None] - post_trans[:, :, None, None, None, :]
+    img = torch.einsum("bnij,bndhwj->bndhwi", undo_aug, img)
+    depth = img[..., 2:3]
+    cam = torch.cat((img[..., :2] * depth, depth), dim=-1)   # pixel * depth, depth
+    ego = torch.einsum("bnij,bndhwj->bndhwi", cam2ego, cam)
+    ego = ego + ego_t[:, :, None, None, None, :]
+    return torch.einsum("bij,bndhwj->bndhwi", bda, ego)

