@@ -374,3 +374,35 @@ def test_out_of_range_ranks_are_refused():
         t = {k: torch.tensor(v, dtype=torch.int32, device="cuda") for k, v in r.items()}
         with pytest.raises(ValueError):
             bev_pool_v2(depth, feat, t["rd"], t["rf"], t["rb"], (1, 1, 2, 2, C), st, ln)
+
+
+def test_inference_ranks_without_backward_tables():
+    """prepare_ranks_calib(backward_tables=False): same ranks, plan and pooled volume, no
+    point -> interval table; a backward through them is refused, not wrong."""
+    from veon_b200 import bev_pool as BP
+    from veon_b200.view_transformer import LSSViewTransformer
+    cfg = S.CONFIGS["small"]
+    B, C = 2, 16
+    H, W = cfg.feat_hw
+    neck = LSSViewTransformer(cfg.grid_config, cfg.input_size, cfg.downsample, 8, C, collapse_z=False)
+    cal = S.calibration(cfg, batch=B)
+    metas = [torch.from_numpy(cal[k]).cuda() for k in KEYS]
+    g = torch.Generator().manual_seed(5)
+    depth = torch.softmax(torch.randn(B, cfg.n_cams, cfg.D, H, W, generator=g) * 4, dim=2).cuda()
+    feat = torch.randn(B, cfg.n_cams, C, H, W, generator=g).cuda()
+    full = neck._prepare_calib(metas, depth)
+    lean = neck._prepare_calib(metas, depth, backward_tables=False)
+    torch.cuda.synchronize()
+    assert lean.plan.point_interval is None and full.plan.point_interval is not None
+    for a, b in ((full.ranks_bev, lean.ranks_bev), (full.ranks_depth, lean.ranks_depth),
+                 (full.ranks_feat, lean.ranks_feat), (full.plan.tile_start, lean.plan.tile_start),
+                 (full.plan.tile_occ, lean.plan.tile_occ)):
+        n = full.plan.n_points if a.numel() >= full.plan.n_points and a is not full.plan.tile_start \
+            and a is not full.plan.tile_occ else a.numel()
+        assert torch.equal(a[:n], b[:n])
+    with torch.no_grad():
+        assert torch.equal(neck._pool_prepared(full, depth, feat), neck._pool_prepared(lean, depth, feat))
+    d = depth.clone().requires_grad_()
+    out = neck._pool_prepared(lean, d, feat)
+    with pytest.raises(RuntimeError, match="backward_tables=False"):
+        out.sum().backward()

@@ -185,13 +185,16 @@ def _counts_slot(dev):
 
 
 def prepare_ranks_calib(frustum, sensor2ego, cam2imgs, post_rots, post_trans, bda,
-                        grid_lower_bound, grid_interval, grid_size, depth=None, depth_eps=None):
+                        grid_lower_bound, grid_interval, grid_size, depth=None, depth_eps=None,
+                        backward_tables=True):
     """`prepare_ranks(lidar_coor(...))` in one call with the geometry fused into the
     classification kernel: the [B,N,D,H,W,3] coordinate tensor is never written.
     Same ranks, bit for bit.
 
     depth [B,N,D,H,W] + depth_eps (inference only): points whose depth weight is
-    <= depth_eps are dropped as well (`veon_prepare_v2_calib_sparse`)."""
+    <= depth_eps are dropped as well (`veon_prepare_v2_calib_sparse`).
+    backward_tables=False (inference): the point -> interval table of the backward is not built;
+    a backward through such ranks raises."""
     _require_cuda(frustum, sensor2ego, cam2imgs, post_rots, post_trans, bda)
     calib = [t.detach().contiguous().float() for t in
              (frustum, sensor2ego, cam2imgs, post_rots, post_trans, bda)]
@@ -204,7 +207,7 @@ def prepare_ranks_calib(frustum, sensor2ego, cam2imgs, post_rots, post_trans, bd
         _require_cuda(depth)
         sparse = (depth.detach().contiguous().float(), float(depth_eps))
     return _prepare(None, calib, (B, N, D, H, W), sensor2ego.device, grid_lower_bound,
-                    grid_interval, grid_size, sparse)
+                    grid_interval, grid_size, sparse, backward_tables)
 
 
 # Pinned host slots for calibration hashes (same life-cycle rules as the counts ring)
@@ -267,7 +270,8 @@ def _values(x):
     return tuple(float(v) for v in x)
 
 
-def _prepare(coor, calib, dims, dev, grid_lower_bound, grid_interval, grid_size, sparse=None):
+def _prepare(coor, calib, dims, dev, grid_lower_bound, grid_interval, grid_size, sparse=None,
+             backward_tables=True):
     lib = _lib.load()
     B, N, D, H, W = (int(v) for v in dims)
     P = B * N * D * H * W
@@ -312,9 +316,11 @@ def _prepare(coor, calib, dims, dev, grid_lower_bound, grid_interval, grid_size,
         # directly (no D2H copy that could queue behind the caller's bulk transfers on
         # the copy engine); they are valid once `ev` has completed.
         counts_host, slot = _counts_slot(dev)
+        # the pixel-major point -> interval table only serves the backward: an inference caller
+        # saves its 4-byte-per-point fill and the scattered writes of the ranking kernel
         outs = (_ptr(ranks[0]), _ptr(ranks[1]), _ptr(ranks[2]), _ptr(ranks[3]), _ptr(ranks[4]),
                 _ptr(counts), _ptr(counts_host), _ptr(tiles[0]), _ptr(tiles[1]), _ptr(tiles[2]),
-                _ptr(heavy), _ptr(point_interval))
+                _ptr(heavy), _ptr(point_interval) if backward_tables else None)
         with _timed("prepare_v2", dev):
             if calib is None:
                 rc = lib.veon_prepare_v2(_ptr(coor), B, N, D, H, W, c_lower, c_interval, c_size,
@@ -340,7 +346,7 @@ def _prepare(coor, calib, dims, dev, grid_lower_bound, grid_interval, grid_size,
     # first point of every voxel: lives in the preparation workspace (kept alive by this view)
     if B * V < (1 << 24) and vs_off % 4 == 0:
         plan.voxel_start = ws[vs_off // 4: vs_off // 4 + B * V + 1]
-    plan.point_interval = point_interval
+    plan.point_interval = point_interval if backward_tables else None
     plan.dims = (B, N, D, H, W)
     plan.V = V
     plan.counts_dev, plan.counts_host, plan.counts_event = counts, counts_host, ev
@@ -547,6 +553,7 @@ class PoolMaxDown(torch.autograd.Function):
         dev = feat.device
         g = grad_ds.contiguous().float()
         n_int = plan.interval_capacity()
+        _need_backward_tables(plan)
         with torch.cuda.device(dev):
             depth_grad = torch.empty_like(depth)
             feat_grad = torch.empty_like(feat)
@@ -639,7 +646,14 @@ def _fwd_planar(depth, feat, rd, rf, rb, plan, B, C, V, shape5):
     return out
 
 
+def _need_backward_tables(plan):
+    if plan.point_interval is None:
+        raise RuntimeError("these ranks were prepared with backward_tables=False (inference): "
+                           "no gradient can flow through the pooling")
+
+
 def _bwd_planar(grad_planar, depth, feat, rb, ist, plan, C):
+    _need_backward_tables(plan)
     lib = _lib.load()
     dev = feat.device
     B, N, D, H, W = plan.dims

@@ -158,9 +158,11 @@ class LSSViewTransformer(nn.Module):
         wants_grad = torch.is_grad_enabled() and (depth.requires_grad or feat.requires_grad)
         return self._pool_prepared(self._prepare_calib(calib, depth, wants_grad), depth, feat)
 
-    def _prepare_calib(self, calib, depth, wants_grad=False):
+    def _prepare_calib(self, calib, depth, wants_grad=False, backward_tables=True):
         """The prepared ranks + plan for a calibration (fused geometry; rank cache / negligible
-        depth bins when configured)."""
+        depth bins when configured).  backward_tables=False: inference, the backward's point ->
+        interval table is not built (never combined with the rank cache, whose entries may
+        serve a training step later)."""
         sensor2ego, _ego2global, cam2imgs, post_rots, post_trans, bda = calib
         frustum = self._frustum_on(sensor2ego.device)
         grid = (self.grid_lower_bound, self.grid_interval, self.grid_size)
@@ -183,7 +185,7 @@ class LSSViewTransformer(nn.Module):
                 self._rank_cache.pop(next(iter(self._rank_cache)))
         else:
             prep = _bp.prepare_ranks_calib(frustum, sensor2ego, cam2imgs, post_rots, post_trans,
-                                           bda, *grid)
+                                           bda, *grid, backward_tables=backward_tables)
         return prep
 
     def lift_labels_calib(self, calib, depth, pix, Q, prompt_class, free_label=17):
@@ -191,7 +193,7 @@ class LSSViewTransformer(nn.Module):
         logit 0..Q-1, padding] (veon_b200.pipeline.lift_classify): uint8 labels [B,X,Y,Z], or None
         when the fused kernel does not take the shape.  Inference only."""
         with torch.no_grad():
-            prep = self._prepare_calib(calib, depth)
+            prep = self._prepare_calib(calib, depth, backward_tables=False)
             prep.plan.sync_free = self.sync_free
             if self.prepared_hook is not None:
                 self.prepared_hook()
