@@ -1,6 +1,8 @@
 """Experiment: the backward as per-sample row / pixel launches on two streams (rows of sample s+1
 overlap the pixels of sample s), optionally with the row scratch pinned in L2 by an access-policy
-window.  Compared with the library's two launches over all samples."""
+window.  Compared with the library's two launches over all samples.  Needs a tools build of the
+library (the per-pass entry points are not in the shipped one):
+    VEON_LIB=$(tools/build_variant.sh tools "-DVEON_TOOLS" | tail -1) python tools/bwd_pipeline.py"""
 import ctypes
 import sys
 

@@ -648,6 +648,7 @@ extern "C" int veon_bev_pool_v2_bwd_planar_ds(
                     depth_grad, feat_grad, stream);
 }
 
+#ifdef VEON_TOOLS   // tools/build_variant.sh NAME "-DVEON_TOOLS": never in the shipped library
 // ---- experiment hooks (not part of include/veon_lift.h; used by tools/bwd_pipeline.py) -------------
 // the two passes on their own, and an L2 access-policy window for a stream
 extern "C" int veon_internal_bwd_rows(const float* out_grad, const int32_t* tile_istart,
@@ -677,3 +678,4 @@ extern "C" int veon_internal_l2_window(void* stream, void* base, size_t bytes, f
   a.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
   return (int)cudaStreamSetAttribute((cudaStream_t)stream, cudaStreamAttributeAccessPolicyWindow, &a);
 }
+#endif  // VEON_TOOLS
