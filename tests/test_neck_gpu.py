@@ -406,3 +406,37 @@ def test_inference_ranks_without_backward_tables():
     out = neck._pool_prepared(lean, d, feat)
     with pytest.raises(RuntimeError, match="backward_tables=False"):
         out.sum().backward()
+
+
+def test_prefetched_ranks_are_picked_up_and_give_the_same_volume():
+    """prefetch_ranks(coor) on the side stream + voxel_pooling_v2(coor, ...): same volume and
+    gradients as the plain call; another tensor (or a modified one) is prepared afresh."""
+    from veon_b200.view_transformer import LSSViewTransformer
+    cfg = S.CONFIGS["small"]
+    B, C = 2, 16
+    H, W = cfg.feat_hw
+    neck = LSSViewTransformer(cfg.grid_config, cfg.input_size, cfg.downsample, 8, C, collapse_z=False)
+    coor = torch.from_numpy(S.lidar_coor_np(cfg, batch=B)).cuda()
+    other = torch.from_numpy(S.lidar_coor_np(cfg, batch=B, sample_offset=7)).cuda()
+    g = torch.Generator().manual_seed(9)
+    depth = torch.softmax(torch.randn(B, cfg.n_cams, cfg.D, H, W, generator=g) * 4, dim=2).cuda()
+    feat = torch.randn(B, cfg.n_cams, C, H, W, generator=g).cuda()
+    og = torch.randn(B, C, 16, 200, 200, generator=g).cuda()
+
+    def run(c, prefetch):
+        d, f = depth.clone().requires_grad_(), feat.clone().requires_grad_()
+        if prefetch is not None:
+            neck.prefetch_ranks(prefetch)
+        out = neck.voxel_pooling_v2(c, d, f)
+        out.backward(og)
+        torch.cuda.synchronize()
+        return out.detach(), d.grad, f.grad
+
+    plain = run(coor, None)
+    for a, b in zip(plain, run(coor, coor)):            # prefetched and used
+        assert torch.equal(a, b)
+    assert neck.__dict__["_prefetched"] is None
+    for a, b in zip(plain, run(coor, other)):           # prefetched for another tensor: ignored
+        assert torch.equal(a, b)
+    for a, b in zip(run(other, None), run(other, other)):
+        assert torch.equal(a, b)

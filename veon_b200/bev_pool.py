@@ -237,18 +237,21 @@ def calib_hash(sensor2ego, cam2imgs, post_rots, post_trans, bda):
     return int(out[0])
 
 
-def prepare_ranks(coor, grid_lower_bound, grid_interval, grid_size):
+def prepare_ranks(coor, grid_lower_bound, grid_interval, grid_size, stream=None):
     """Launch the GPU index preparation; returns without a host sync.
 
     coor: [B,N,D,H,W,3] float tensor on CUDA.  The three grid vectors are the
     reference's float32 tensors (view_transformer.py:79-82) or any 3-sequence.
+    stream: a torch.cuda.Stream to launch on instead of the current one; the outputs are still
+    allocated in the CURRENT stream's pool (the caller consumes them there, after waiting for
+    `plan.counts_event`).
     """
     _require_cuda(coor)
     if coor.dim() != 6 or coor.shape[-1] != 3:
         raise ValueError(f"coor must be [B,N,D,H,W,3], got {tuple(coor.shape)}")
     coor = coor.detach().contiguous().float()
     return _prepare(coor, None, tuple(coor.shape[:5]), coor.device, grid_lower_bound,
-                    grid_interval, grid_size)
+                    grid_interval, grid_size, stream=stream)
 
 
 _TENSOR_VALUES = {}
@@ -271,8 +274,10 @@ def _values(x):
 
 
 def _prepare(coor, calib, dims, dev, grid_lower_bound, grid_interval, grid_size, sparse=None,
-             backward_tables=True):
+             backward_tables=True, stream=None):
     lib = _lib.load()
+    launch_on = stream if stream is not None else torch.cuda.current_stream(dev)
+    sp = ctypes.c_void_p(launch_on.cuda_stream)
     B, N, D, H, W = (int(v) for v in dims)
     P = B * N * D * H * W
     # keyed on the VALUES (three small tuples): a list / ndarray mutated in place, or a
@@ -324,22 +329,22 @@ def _prepare(coor, calib, dims, dev, grid_lower_bound, grid_interval, grid_size,
         with _timed("prepare_v2", dev):
             if calib is None:
                 rc = lib.veon_prepare_v2(_ptr(coor), B, N, D, H, W, c_lower, c_interval, c_size,
-                                         *outs, _ptr(ws), ws_bytes, _stream_ptr(dev))
+                                         *outs, _ptr(ws), ws_bytes, sp)
             else:
                 xbytes = lib.veon_lidar_coor_workspace_bytes(B, N)
                 xws = torch.empty(xbytes, dtype=torch.uint8, device=dev)
                 if sparse is None:
                     rc = lib.veon_prepare_v2_calib(*[_ptr(a) for a in calib], B, N, D, H, W,
                                                    c_lower, c_interval, c_size, *outs, _ptr(xws),
-                                                   xbytes, _ptr(ws), ws_bytes, _stream_ptr(dev))
+                                                   xbytes, _ptr(ws), ws_bytes, sp)
                 else:
                     rc = lib.veon_prepare_v2_calib_sparse(
                         *[_ptr(a) for a in calib], _ptr(sparse[0]), sparse[1], B, N, D, H, W,
                         c_lower, c_interval, c_size, *outs, _ptr(xws), xbytes, _ptr(ws), ws_bytes,
-                        _stream_ptr(dev))
+                        sp)
         _lib.check(rc, "veon_prepare_v2")
         ev = torch.cuda.Event()
-        ev.record(torch.cuda.current_stream(dev))
+        ev.record(launch_on)
     plan = PoolPlan()
     plan.tile_start, plan.tile_istart, plan.tile_occ = tiles[0], tiles[1], tiles[2]
     plan.tile_heavy = heavy

@@ -149,8 +149,45 @@ class LSSViewTransformer(nn.Module):
         [B,C,Z,Y,X] (or [B,C*Z,Y,X] with collapse_z) -- reference :175-200."""
         if coor.numel() == 0:
             return self._no_points_dummy(feat)
-        prep = _bp.prepare_ranks(coor, self.grid_lower_bound, self.grid_interval, self.grid_size)
+        prep = self._take_prefetched(coor)
+        if prep is None:
+            prep = _bp.prepare_ranks(coor, self.grid_lower_bound, self.grid_interval,
+                                     self.grid_size)
         return self._pool_prepared(prep, depth, feat)
+
+    # -- pipelined index preparation ----------------------------------------------------------
+    def prefetch_ranks(self, coor):
+        """Queue `voxel_pooling_prepare_v2(coor)` on a side stream, behind everything the caller
+        has launched so far on the current stream; the next `voxel_pooling_v2(coor, ...)` with
+        this very tensor picks the ranks up instead of preparing them.  The preparation depends
+        on the geometry only, so a loop can prepare step i+1 while the backward of step i runs
+        (call this between the forward and the backward): its dozen short, latency-bound
+        launches then cost nothing on the critical path."""
+        if not coor.is_cuda or coor.numel() == 0:
+            return
+        dev = coor.device
+        streams = self.__dict__.setdefault("_prep_streams", {})
+        side = streams.get(dev)
+        if side is None:
+            side = streams[dev] = torch.cuda.Stream(dev)
+        here = torch.cuda.Event()
+        here.record(torch.cuda.current_stream(dev))
+        side.wait_event(here)
+        # launched on the side stream, allocated in the current stream's pool (where the ranks
+        # are consumed): no allocator traffic between the two streams
+        prep = _bp.prepare_ranks(coor, self.grid_lower_bound, self.grid_interval, self.grid_size,
+                                 stream=side)
+        self.__dict__["_prefetched"] = (coor, coor._version, prep, prep.plan.counts_event)
+
+    def _take_prefetched(self, coor):
+        pf = self.__dict__.get("_prefetched")
+        if pf is None:
+            return None
+        self.__dict__["_prefetched"] = None
+        if pf[0] is not coor or pf[1] != coor._version:
+            return None                      # another tensor (or modified since): prepare afresh
+        torch.cuda.current_stream(coor.device).wait_event(pf[3])   # the side stream's kernels are done
+        return pf[2]
 
     def _voxel_pooling_calib(self, calib, depth, feat):
         """voxel_pooling_v2 with get_lidar_coor folded into the index preparation:
