@@ -62,7 +62,10 @@ constexpr int kTileVoxels = 32;  // one warp-wide x-run of the output volume
 // and the forward hands each of them to a whole CTA (pool_fwd.cu).  The list
 // capacity assumes the threshold never goes below kHeavyMinThreshold.
 constexpr int kHeavyMinThreshold = 32;
-constexpr int kHeavyDefaultThreshold = 96;
+#ifndef VEON_HEAVY_THR
+#define VEON_HEAVY_THR 96
+#endif
+constexpr int kHeavyDefaultThreshold = VEON_HEAVY_THR;
 inline int heavy_threshold() { return kHeavyDefaultThreshold; }
 inline int64_t heavy_capacity(int64_t n_points, int64_t n_tiles) {
   const int64_t by_points = n_points / kHeavyMinThreshold;

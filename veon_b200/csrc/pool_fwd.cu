@@ -13,7 +13,7 @@
 // CHANNELS while gathering (feature rows are read as full 128-byte lines, the
 // per-voxel sum lives in registers) and over VOXELS while storing (one 16-byte
 // store per lane = four full 128-byte lines of four channel planes per
-// instruction); a padded, zero-filled shared tile [c][36] does the transposition.
+// instruction); a padded, zero-filled shared tile [c][33] does the transposition.
 // Empty voxels come out as zeros, so the volume is touched exactly once: no
 // memset, no permute pass, no atomics.  Accumulation order inside a voxel is the
 // rank order, fma(feat, depth, acc) starting from 0 -- the same sequence of
@@ -40,7 +40,11 @@ namespace veon {
 // of every channel plane; 7-warp CTAs (896 B) write the same volume 19 % slower
 // (tools/micro/store_pattern.cu: 266 vs 224 us).
 constexpr int kFwdWarps = VEON_FWD_WARPS;
-constexpr int kRowPitch = kTileVoxels + 4;   // 36 floats: rows stay 16-byte aligned
+// Row pitch of the [channel][voxel] shared tiles.  Odd: the per-voxel store of a channel column
+// (lane = channel, address lane * pitch + v) and the write-out reads (4 rows x 8 voxel quads)
+// are then both conflict-free.  (36 kept the rows 16-byte aligned for LDS.128 but made every
+// voxel store a 4-way bank conflict: 65 M of 117 M shared-memory wavefronts at C3, ncu.)
+constexpr int kRowPitch = kTileVoxels + 1;
 
 // ---- per-warp prefetch ring in shared memory (cp.async, no registers held) ----
 // slot (ints): [0]=s [1]=e [2]=tile [3]=cbase, then one int4 per point (lane j):
@@ -75,7 +79,7 @@ __device__ __forceinline__ void cp_async_wait_dist() {
 //  * gather: lanes = channels, up to 16 points' rows in flight (issued in groups of 4,
 //    groups past the tile's last point are skipped), per-voxel sums in registers
 //    (fma(feat, depth, acc) in rank order), one store per occupied voxel into the
-//    zero-filled [c][36] shared tile;
+//    zero-filled [c][33] shared tile;
 //  * write-out: lanes = voxels, LDS.128 + one 16-byte streaming store covers
 //    4 channel planes x 128 B per instruction.
 // (A TMA tensor-store write-out was measured slower here: ~17 B/clk/SM for boxes
@@ -213,7 +217,8 @@ k_pool_fwd(const float* __restrict__ depth, const float* __restrict__ feat,
     {  // zero the tile (empty voxels must read as 0)
       float4* t4 = reinterpret_cast<float4*>(tile);
 #pragma unroll
-      for (int i = 0; i < kTileFloats / 4 / 32; ++i) t4[lane + 32 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int i = 0; i < (kTileFloats / 4 + 31) / 32; ++i)
+        if (lane + 32 * i < kTileFloats / 4) t4[lane + 32 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncwarp();
 
@@ -297,14 +302,12 @@ k_pool_fwd(const float* __restrict__ depth, const float* __restrict__ feat,
     __syncwarp();
 
     // Write-out: lane (r = lane/8, q = lane%8) moves voxels 4q..4q+3 of channel
-    // 4*it + r with one LDS.128 + one 16-byte streaming store.
+    // 4*it + r with four LDS.32 + one 16-byte streaming store.
     const float* trow = tile + r * kRowPitch + q4;
     if (fast) {
 #pragma unroll 4
-      for (int c = r; c < cmax; c += 4, o += ostep, trow += 4 * kRowPitch) {
-        const float4 v4 = *reinterpret_cast<const float4*>(trow);
-        st_stream4(o, v4);
-      }
+      for (int c = r; c < cmax; c += 4, o += ostep, trow += 4 * kRowPitch)
+        st_stream4(o, make_float4(trow[0], trow[1], trow[2], trow[3]));
     } else {  // ragged volume edge / unaligned volume: scalar, bounds-checked
       const int v0 = (int)((uint32_t)g0 - b * Vu);
       for (int c = r; c < cmax; c += 4, o += ostep, trow += 4 * kRowPitch)
@@ -481,7 +484,7 @@ k_pool_fwd_heavy(const float* __restrict__ depth, const float* __restrict__ feat
         float* o = out + ((int64_t)b * C + cbase + c) * V + v0 + q4;
         const float* trow = tile + c * kRowPitch + q4;
         if (fast) {
-          st_stream4(o, *reinterpret_cast<const float4*>(trow));
+          st_stream4(o, make_float4(trow[0], trow[1], trow[2], trow[3]));
         } else {
 #pragma unroll
           for (int i = 0; i < 4; ++i)
