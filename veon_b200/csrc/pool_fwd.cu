@@ -208,8 +208,10 @@ k_pool_fwd(const float* __restrict__ depth, const float* __restrict__ feat,
     const bool fast = vec_ok && (whole_tiles || (uint32_t)g0 - b * Vu + kTileVoxels <= Vu);
 
     if (e0 <= s0 && fast) {  // empty tile
+#ifndef VEON_FWD_X_NOSTORE
 #pragma unroll 4
       for (int c = r; c < cmax; c += 4, o += ostep) st_stream4(o, make_float4(0.f, 0.f, 0.f, 0.f));
+#endif
       continue;
     }
 
@@ -265,7 +267,11 @@ k_pool_fwd(const float* __restrict__ depth, const float* __restrict__ feat,
               const float* row = reinterpret_cast<const float*>(feat_lane + (uint32_t)p[u].y);
 #pragma unroll
               for (int k = 0; k < KCH; ++k)
+#ifdef VEON_FWD_X_NOGATHER   // tools only: elimination timing
+                f[u][k] = (float)p[u].y;
+#else
                 f[u][k] = (FULLC || full_chunk || lane + 32 * k < cmax) ? __ldg(row + 32 * k) : 0.f;
+#endif
             }
           }
         }
@@ -306,8 +312,13 @@ k_pool_fwd(const float* __restrict__ depth, const float* __restrict__ feat,
     const float* trow = tile + r * kRowPitch + q4;
     if (fast) {
 #pragma unroll 4
-      for (int c = r; c < cmax; c += 4, o += ostep, trow += 4 * kRowPitch)
+      for (int c = r; c < cmax; c += 4, o += ostep, trow += 4 * kRowPitch) {
+#ifdef VEON_FWD_X_NOSTORE
+        if (trow[0] == 123.456f) st_stream4(o, make_float4(trow[0], trow[1], trow[2], trow[3]));
+#else
         st_stream4(o, make_float4(trow[0], trow[1], trow[2], trow[3]));
+#endif
+      }
     } else {  // ragged volume edge / unaligned volume: scalar, bounds-checked
       const int v0 = (int)((uint32_t)g0 - b * Vu);
       for (int c = r; c < cmax; c += 4, o += ostep, trow += 4 * kRowPitch)
@@ -992,9 +1003,11 @@ static int launch_fwd_impl(const float* depth, const float* feat, const int32_t*
   // Heavy-tile CTAs behind the main grid (both trigger launch_dependents at their first
   // instruction): they fill the SMs as the persistent CTAs finish one by one, and join the main
   // grid before they complete.
+#ifndef VEON_FWD_X_NOHEAVY
   if (heavy)
     return launch_heavy<KCH>(depth, feat, rd, rf, rb, tile_start, heavy, heavy_ints, B, C, V, out,
                              true, 0, stream);
+#endif
   return 0;
 }
 
