@@ -87,22 +87,31 @@ __device__ __forceinline__ void cp_async_wait_dist() {
 // Slot header: [0]=s [1]=e [2]=g0 (global voxel index of the tile's first voxel)
 //              [3]=sample<<16 | chunk
 // FULLC: C is a multiple of the chunk width, so no channel predicate anywhere.
-template <int KCH, bool FULLC>
+// LOOPC (rows wider than one chunk): an item is a whole TILE and the channel chunks are looped
+// inside it -- the index work (ring, fix-up, the records of the points past the first 32, kept
+// in `ext`) is done once per tile instead of once per (tile, chunk).
+template <int KCH, bool FULLC, bool LOOPC = false>
 __global__ void __launch_bounds__(kFwdWarps * 32)
 k_pool_fwd(const float* __restrict__ depth, const float* __restrict__ feat,
            const int32_t* __restrict__ ranks_depth, const int32_t* __restrict__ ranks_feat,
            const int32_t* __restrict__ ranks_bev, const int32_t* __restrict__ tile_start,
            const int32_t* __restrict__ heavy, uint32_t n_items, uint32_t tiles_per_sample,
-           int64_t V, int C, uint32_t n_chunks, int vec_ok, float* __restrict__ out) {
+           int64_t V, int C, uint32_t n_chunks, int vec_ok, float* __restrict__ out,
+           uint32_t loop_chunks) {
   constexpr int CC = 32 * KCH;
   constexpr int U = (KCH <= 2) ? 16 : 8;  // feature rows in flight per warp
   constexpr int kTileFloats = CC * kRowPitch;
-  constexpr int kWarpFloats = kTileFloats + kRingSlots * kSlotInts;
+  // records of the points past the first 32 of a tile (a tile of the main grid has fewer points
+  // than the plan's heavy threshold)
+  constexpr int kExtInts = LOOPC ? ((kHeavyDefaultThreshold + 31) / 32 - 1) * 128 : 0;
+  constexpr int kWarpFloats = kTileFloats + kRingSlots * kSlotInts + kExtInts;
   extern __shared__ __align__(16) float smem[];
   pdl_launch_dependents();  // the heavy-tile grid may be queued behind this one
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float* tile = smem + warp * kWarpFloats;
   int32_t* ring = reinterpret_cast<int32_t*>(tile + kTileFloats);
+  int32_t* ext = ring + kRingSlots * kSlotInts;
+  (void)ext;
   const uint32_t TW = gridDim.x * kFwdWarps;
   const uint32_t first_item = blockIdx.x * kFwdWarps + warp;
   if (first_item >= n_items) return;
@@ -201,130 +210,155 @@ k_pool_fwd(const float* __restrict__ depth, const float* __restrict__ feat,
     if (e0 - s0 >= heavy_thr) continue;
 
     const uint32_t b = (uint32_t)h.w >> 16;
-    const int cbase = (h.w & 0xffff) * CC;
-    const int cmax = FULLC ? CC : min(CC, C - cbase);
-    // (b*C + cbase + r)*V + v0 + q4  with  v0 = g0 - b*V
-    float* o = out + (int64_t)(b * (uint32_t)(C - 1) + (uint32_t)(cbase + r)) * V + g0 + q4;
     const bool fast = vec_ok && (whole_tiles || (uint32_t)g0 - b * Vu + kTileVoxels <= Vu);
+    const uint32_t n_loop = LOOPC ? loop_chunks : 1u;
 
     if (e0 <= s0 && fast) {  // empty tile
+      const int c_lo = LOOPC ? 0 : (h.w & 0xffff) * CC;
+      const int c_hi = LOOPC ? C : min(c_lo + CC, C);
+      float* o = out + (int64_t)(b * (uint32_t)(C - 1) + (uint32_t)(c_lo + r)) * V + g0 + q4;
 #ifndef VEON_FWD_X_NOSTORE
 #pragma unroll 4
-      for (int c = r; c < cmax; c += 4, o += ostep) st_stream4(o, make_float4(0.f, 0.f, 0.f, 0.f));
+      for (int c = c_lo + r; c < c_hi; c += 4, o += ostep) st_stream4(o, make_float4(0.f, 0.f, 0.f, 0.f));
 #endif
       continue;
     }
 
-    __syncwarp();
-    {  // zero the tile (empty voxels must read as 0)
-      float4* t4 = reinterpret_cast<float4*>(tile);
-#pragma unroll
-      for (int i = 0; i < (kTileFloats / 4 + 31) / 32; ++i)
-        if (lane + 32 * i < kTileFloats / 4) t4[lane + 32 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    __syncwarp();
-
-    float acc[KCH];
-    int acc_vl = -1;
-    const bool full_chunk = FULLC || (cmax == CC);
-    for (int32_t base = s0; base < e0; base += 32) {
-      const int cnt = min(32, e0 - base);
-      if (base != s0) {  // tile with more than 32 points: later chunks are fetched synchronously
-        const int32_t i = base + lane;
-        __syncwarp();
-        int32_t rb = -1, rf = 0;
-        float d = 0.f;
-        if (i < e0) {
-          rb = __ldg(ranks_bev + i);
-          rf = __ldg(ranks_feat + i);
-          d = __ldg(depth + __ldg(ranks_depth + i));
-        }
-        const int32_t up = __shfl_up_sync(0xffffffffu, rb, 1);
-        const bool first = (lane > 0) && (rb != up);  // lane 0 continues or starts: see below
-        int32_t* pt = sl + 4 + 4 * lane;
-        pt[1] = (int32_t)(((uint32_t)rf * (uint32_t)C + (uint32_t)cbase) * 4u);
-        pt[2] = (rb - g0) | (first ? 0x100 : 0);
-        pt[3] = __float_as_int(d);
-        if (lane == 0) {  // first point of the chunk: new voxel iff it differs from the last one
-          const int32_t last = sl[4 + 4 * 31 + 0];
-          pt[2] = (rb - g0) | ((rb != last) ? 0x100 : 0);
-        }
-        __syncwarp();
-        pt[0] = rb;
-        __syncwarp();
+    // records of the points past the first 32 (a tile of the main grid has < heavy_thr <= 96):
+    // fetched synchronously; LOOPC keeps them in `ext` for all channel chunks of the tile
+    auto fetch_block = [&](int32_t base, int32_t* dst, int32_t last_rb, int cb) {
+      const int32_t i = base + lane;
+      int32_t rb = -1, rf = 0;
+      float d = 0.f;
+      if (i < e0) {
+        rb = __ldg(ranks_bev + i);
+        rf = __ldg(ranks_feat + i);
+        d = __ldg(depth + __ldg(ranks_depth + i));
       }
-      const int4* pts = reinterpret_cast<const int4*>(sl + 4);
-      for (int j0 = 0; j0 < cnt; j0 += U) {
-        int4 p[U];
-        float f[U][KCH];
+      int32_t up = __shfl_up_sync(0xffffffffu, rb, 1);
+      if (lane == 0) up = last_rb;   // first point of the block: new voxel iff it differs
+      int32_t* pt = dst + 4 * lane;
+      pt[0] = rb;
+      pt[1] = (int32_t)(((uint32_t)rf * (uint32_t)C + (uint32_t)cb) * 4u);
+      pt[2] = (rb - g0) | ((rb != up) ? 0x100 : 0);
+      pt[3] = __float_as_int(d);
+      return __shfl_sync(0xffffffffu, rb, 31);
+    };
+    if constexpr (LOOPC) {
+      int32_t last = sl[4 + 4 * 31 + 0];
+      int blk = 0;
+      for (int32_t base = s0 + 32; base < e0; base += 32, ++blk)
+        last = fetch_block(base, ext + 128 * blk, last, 0);
+      __syncwarp();
+    }
+
+    for (uint32_t ch = 0; ch < n_loop; ++ch) {
+      const int cbase = LOOPC ? (int)ch * CC : (h.w & 0xffff) * CC;
+      const int cmax = FULLC ? CC : min(CC, C - cbase);
+      // (b*C + cbase + r)*V + v0 + q4  with  v0 = g0 - b*V
+      float* o = out + (int64_t)(b * (uint32_t)(C - 1) + (uint32_t)(cbase + r)) * V + g0 + q4;
+      const char* const feat_ch = feat_lane + (LOOPC ? (uint32_t)cbase * 4u : 0u);
+
+      __syncwarp();
+      {  // zero the tile (empty voxels must read as 0)
+        float4* t4 = reinterpret_cast<float4*>(tile);
 #pragma unroll
-        for (int g = 0; g < U / 4; ++g) {
-          if (j0 + 4 * g < cnt) {  // warp-uniform: skip the groups past the last point
-#pragma unroll
-            for (int uu = 0; uu < 4; ++uu) {
-              const int u = 4 * g + uu;
-              p[u] = pts[min(j0 + u, cnt - 1)];
-              const float* row = reinterpret_cast<const float*>(feat_lane + (uint32_t)p[u].y);
-#pragma unroll
-              for (int k = 0; k < KCH; ++k)
-#ifdef VEON_FWD_X_NOGATHER   // tools only: elimination timing
-                f[u][k] = (float)p[u].y;
-#else
-                f[u][k] = (FULLC || full_chunk || lane + 32 * k < cmax) ? __ldg(row + 32 * k) : 0.f;
-#endif
-            }
+        for (int i = 0; i < (kTileFloats / 4 + 31) / 32; ++i)
+          if (lane + 32 * i < kTileFloats / 4) t4[lane + 32 * i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      __syncwarp();
+
+      float acc[KCH];
+      int acc_vl = -1;
+      const bool full_chunk = FULLC || (cmax == CC);
+      int blk = 0;
+      for (int32_t base = s0; base < e0; base += 32, ++blk) {
+        const int cnt = min(32, e0 - base);
+        const int4* pts = reinterpret_cast<const int4*>(sl + 4);
+        if (base != s0) {
+          if constexpr (LOOPC) {
+            pts = reinterpret_cast<const int4*>(ext + 128 * (blk - 1));
+          } else {  // one chunk per item: the later blocks go through the slot
+            __syncwarp();
+            const int32_t last = sl[4 + 4 * 31 + 0];
+            __syncwarp();
+            fetch_block(base, sl + 4, last, cbase);
+            __syncwarp();
           }
         }
+        for (int j0 = 0; j0 < cnt; j0 += U) {
+          int4 p[U];
+          float f[U][KCH];
 #pragma unroll
-        for (int g = 0; g < U / 4; ++g) {
-          if (j0 + 4 * g < cnt) {
+          for (int g = 0; g < U / 4; ++g) {
+            if (j0 + 4 * g < cnt) {  // warp-uniform: skip the groups past the last point
 #pragma unroll
-            for (int uu = 0; uu < 4; ++uu) {
-              const int u = 4 * g + uu;
-              if (j0 + u < cnt) {
-                const float dj = __int_as_float(p[u].w);
-                if (p[u].z & 0x100) {  // first point of its voxel (warp-uniform)
-                  if (acc_vl >= 0) {
+              for (int uu = 0; uu < 4; ++uu) {
+                const int u = 4 * g + uu;
+                p[u] = pts[min(j0 + u, cnt - 1)];
+                const float* row = reinterpret_cast<const float*>(feat_ch + (uint32_t)p[u].y);
 #pragma unroll
-                    for (int k = 0; k < KCH; ++k) tlane[32 * k * kRowPitch + acc_vl] = acc[k];
+                for (int k = 0; k < KCH; ++k)
+#ifdef VEON_FWD_X_NOGATHER   // tools only: elimination timing
+                  f[u][k] = (float)p[u].y;
+#else
+                  f[u][k] = (FULLC || full_chunk || lane + 32 * k < cmax) ? __ldg(row + 32 * k) : 0.f;
+#endif
+              }
+            }
+          }
+#pragma unroll
+          for (int g = 0; g < U / 4; ++g) {
+            if (j0 + 4 * g < cnt) {
+#pragma unroll
+              for (int uu = 0; uu < 4; ++uu) {
+                const int u = 4 * g + uu;
+                if (j0 + u < cnt) {
+                  const float dj = __int_as_float(p[u].w);
+                  if (p[u].z & 0x100) {  // first point of its voxel (warp-uniform)
+                    if (acc_vl >= 0) {
+#pragma unroll
+                      for (int k = 0; k < KCH; ++k) tlane[32 * k * kRowPitch + acc_vl] = acc[k];
+                    }
+                    acc_vl = p[u].z & 0xff;
+#pragma unroll
+                    for (int k = 0; k < KCH; ++k) acc[k] = fmaf(f[u][k], dj, 0.f);
+                  } else {
+#pragma unroll
+                    for (int k = 0; k < KCH; ++k) acc[k] = fmaf(f[u][k], dj, acc[k]);
                   }
-                  acc_vl = p[u].z & 0xff;
-#pragma unroll
-                  for (int k = 0; k < KCH; ++k) acc[k] = fmaf(f[u][k], dj, 0.f);
-                } else {
-#pragma unroll
-                  for (int k = 0; k < KCH; ++k) acc[k] = fmaf(f[u][k], dj, acc[k]);
                 }
               }
             }
           }
         }
       }
-    }
-    if (acc_vl >= 0) {
+      if (acc_vl >= 0) {
 #pragma unroll
-      for (int k = 0; k < KCH; ++k) tlane[32 * k * kRowPitch + acc_vl] = acc[k];
-    }
-    __syncwarp();
-
-    // Write-out: lane (r = lane/8, q = lane%8) moves voxels 4q..4q+3 of channel
-    // 4*it + r with four LDS.32 + one 16-byte streaming store.
-    const float* trow = tile + r * kRowPitch + q4;
-    if (fast) {
-#pragma unroll 4
-      for (int c = r; c < cmax; c += 4, o += ostep, trow += 4 * kRowPitch) {
-#ifdef VEON_FWD_X_NOSTORE
-        if (trow[0] == 123.456f) st_stream4(o, make_float4(trow[0], trow[1], trow[2], trow[3]));
-#else
-        st_stream4(o, make_float4(trow[0], trow[1], trow[2], trow[3]));
-#endif
+        for (int k = 0; k < KCH; ++k) tlane[32 * k * kRowPitch + acc_vl] = acc[k];
       }
-    } else {  // ragged volume edge / unaligned volume: scalar, bounds-checked
-      const int v0 = (int)((uint32_t)g0 - b * Vu);
-      for (int c = r; c < cmax; c += 4, o += ostep, trow += 4 * kRowPitch)
+      __syncwarp();
+
+      // Write-out: lane (r = lane/8, q = lane%8) moves voxels 4q..4q+3 of channel
+      // 4*it + r with four LDS.32 + one 16-byte streaming store.
+      const float* trow = tile + r * kRowPitch + q4;
+      if (fast) {
+#pragma unroll 4
+        for (int c = r; c < cmax; c += 4, o += ostep, trow += 4 * kRowPitch) {
+#ifdef VEON_FWD_X_NOSTORE
+          if (trow[0] == 123.456f) st_stream4(o, make_float4(trow[0], trow[1], trow[2], trow[3]));
+#else
+          st_stream4(o, make_float4(trow[0], trow[1], trow[2], trow[3]));
+#endif
+        }
+      } else {  // ragged volume edge / unaligned volume: scalar, bounds-checked
+        const int v0 = (int)((uint32_t)g0 - b * Vu);
+        for (int c = r; c < cmax; c += 4, o += ostep, trow += 4 * kRowPitch)
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (v0 + q4 + i < V) st_stream(o + i, trow[i]);
+          for (int i = 0; i < 4; ++i)
+            if (v0 + q4 + i < V) st_stream(o + i, trow[i]);
+      }
+      // (the __syncwarp before the next zero-fill protects the tile reuse)
     }
     // (the __syncwarp before the next zero-fill protects the tile reuse)
   }
@@ -969,20 +1003,21 @@ int launch_heavy_behind(const float* depth, const float* feat, const int32_t* rd
 }
 
 // general route: k_pool_fwd over every (tile, channel chunk), the heavy tiles queued behind it
-template <int KCH, bool FULLC>
+template <int KCH, bool FULLC, bool LOOPC>
 static int launch_fwd_impl(const float* depth, const float* feat, const int32_t* rd,
                            const int32_t* rf, const int32_t* rb, const int32_t* tile_start,
                            const int32_t* heavy, int64_t heavy_ints, int B, int C, int64_t V,
                            bool feat_rows_fit_32bit, float* out, cudaStream_t stream) {
   constexpr int CC = 32 * KCH;
-  const size_t smem = sizeof(float) * kFwdWarps * (CC * kRowPitch + kRingSlots * kSlotInts);
+  constexpr int kExtInts = LOOPC ? ((kHeavyDefaultThreshold + 31) / 32 - 1) * 128 : 0;
+  const size_t smem = sizeof(float) * kFwdWarps * (CC * kRowPitch + kRingSlots * kSlotInts + kExtInts);
   static int ctas_per_sm[kMaxDevices] = {};
   const int dev = current_device();
   if (ctas_per_sm[dev] == 0) {
-    VEON_CUDA_TRY(cudaFuncSetAttribute(k_pool_fwd<KCH, FULLC>,
+    VEON_CUDA_TRY(cudaFuncSetAttribute(k_pool_fwd<KCH, FULLC, LOOPC>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int n = 0;
-    VEON_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_pool_fwd<KCH, FULLC>,
+    VEON_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_pool_fwd<KCH, FULLC, LOOPC>,
                                                                 kFwdWarps * 32, smem));
     ctas_per_sm[dev] = n < 1 ? 1 : n;
   }
@@ -991,22 +1026,23 @@ static int launch_fwd_impl(const float* depth, const float* feat, const int32_t*
   if (n_tiles * n_chunks > 0x7fffffffLL || (int64_t)B * V > 0x7fffffffLL) return VEON_E_RANGE;
   if (!feat_rows_fit_32bit) return VEON_E_RANGE;   // the gather uses 32-bit byte offsets
   const int vec_ok = ((V & 3) == 0) && (((uintptr_t)out & 15) == 0);
-  int64_t blocks = ceil_div64(n_tiles * n_chunks, kFwdWarps);
+  const int64_t n_items = LOOPC ? n_tiles : n_tiles * n_chunks;   // LOOPC: chunks looped per tile
+  int64_t blocks = ceil_div64(n_items, kFwdWarps);
   const int64_t resident = (int64_t)ctas_per_sm[dev] * sm_count();  // persistent grid
   if (blocks > resident) blocks = resident;
   // the heavy-tile kernel stages feature rows with 16-byte copies
   if (heavy && ((C & 3) != 0 || ((uintptr_t)feat & 15) != 0)) heavy = nullptr;
-  k_pool_fwd<KCH, FULLC><<<(unsigned)blocks, kFwdWarps * 32, smem, stream>>>(
-      depth, feat, rd, rf, rb, tile_start, heavy, (uint32_t)(n_tiles * n_chunks), (uint32_t)tps,
-      V, C, (uint32_t)n_chunks, vec_ok, out);
+  k_pool_fwd<KCH, FULLC, LOOPC><<<(unsigned)blocks, kFwdWarps * 32, smem, stream>>>(
+      depth, feat, rd, rf, rb, tile_start, heavy, (uint32_t)n_items, (uint32_t)tps,
+      V, C, (uint32_t)(LOOPC ? 1 : n_chunks), vec_ok, out, (uint32_t)n_chunks);
   VEON_LAUNCH_CHECK();
   // Heavy-tile CTAs behind the main grid (both trigger launch_dependents at their first
   // instruction): they fill the SMs as the persistent CTAs finish one by one, and join the main
   // grid before they complete.
 #ifndef VEON_FWD_X_NOHEAVY
   if (heavy)
-    return launch_heavy<KCH>(depth, feat, rd, rf, rb, tile_start, heavy, heavy_ints, B, C, V, out,
-                             true, 0, stream);
+    return launch_heavy<(KCH > 2 ? 2 : KCH)>(depth, feat, rd, rf, rb, tile_start, heavy, heavy_ints,
+                                             B, C, V, out, true, 0, stream);
 #endif
   return 0;
 }
@@ -1016,11 +1052,22 @@ static int launch_fwd(const float* depth, const float* feat, const int32_t* rd,
                       const int32_t* rf, const int32_t* rb, const int32_t* tile_start,
                       const int32_t* heavy, int64_t heavy_ints, int B, int C, int64_t V,
                       bool feat_rows_fit_32bit, float* out, cudaStream_t stream) {
-  if (C % (32 * KCH) == 0)
-    return launch_fwd_impl<KCH, true>(depth, feat, rd, rf, rb, tile_start, heavy, heavy_ints, B, C,
-                                      V, feat_rows_fit_32bit, out, stream);
-  return launch_fwd_impl<KCH, false>(depth, feat, rd, rf, rb, tile_start, heavy, heavy_ints, B, C,
-                                     V, feat_rows_fit_32bit, out, stream);
+  // rows of several chunks: one item per tile (needs the heavy list: it bounds a tile's points)
+#ifndef VEON_FWD_X_NOLOOPC
+  const bool loopc = heavy && C > 32 * KCH && (C & 3) == 0 && ((uintptr_t)feat & 15) == 0;
+#else
+  const bool loopc = false;
+#endif
+#define VEON_FWD_GO(FULLC_, LOOPC_)                                                            \
+  return launch_fwd_impl<KCH, FULLC_, LOOPC_>(depth, feat, rd, rf, rb, tile_start, heavy,      \
+                                              heavy_ints, B, C, V, feat_rows_fit_32bit, out, stream)
+  if (C % (32 * KCH) == 0) {
+    if (loopc) VEON_FWD_GO(true, true);
+    VEON_FWD_GO(true, false);
+  }
+  if (loopc) VEON_FWD_GO(false, true);
+  VEON_FWD_GO(false, false);
+#undef VEON_FWD_GO
 }
 
 // narrow rows: the heavy tiles (from kNarrowHeavyMin points) first, as a normal launch (a heavy
