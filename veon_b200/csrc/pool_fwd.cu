@@ -489,7 +489,9 @@ k_pool_fwd_heavy(const float* __restrict__ depth, const float* __restrict__ feat
       for (int i = 0; i < kHeavyChunk * kSegs / kHeavyThreads; ++i) {
         const int idx = tid + kHeavyThreads * i;
         const int r = idx / kSegs, seg = (idx % kSegs) * 4;
+#ifndef VEON_FWD_X_HEAVY_NOCOPY   // tools only: elimination timing
         if (r < cnt && seg < cmax) cp_async16(rows + r * CC + seg, feat + off[r] + cbase + seg);
+#endif
       }
       cp_async_commit();
       cp_async_wait_all();
@@ -503,12 +505,14 @@ k_pool_fwd_heavy(const float* __restrict__ depth, const float* __restrict__ feat
         float acc[KCH];
 #pragma unroll
         for (int c = 0; c < KCH; ++c) acc[c] = tile[(lane + 32 * c) * kRowPitch + v];
+#ifndef VEON_FWD_X_HEAVY_NOFMA
 #pragma unroll 4
         for (int j = a; j < e; ++j) {
           const float dj = dep[j];
 #pragma unroll
           for (int c = 0; c < KCH; ++c) acc[c] = fmaf(rows[j * CC + lane + 32 * c], dj, acc[c]);
         }
+#endif
 #pragma unroll
         for (int c = 0; c < KCH; ++c) tile[(lane + 32 * c) * kRowPitch + v] = acc[c];
       }
