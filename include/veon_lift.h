@@ -273,7 +273,7 @@ int veon_bev_pool_v2_fwd_planar(const float* depth, const float* feat,
 
 /* Pooling fused with the 2x2x2 max-downsample VEON's neck applies next
  * (view_transformer_raw.py:549-553), forward only: out is [B, C, Z/2, Y/2, X/2], bit-identical
- * to amax over the volume veon_bev_pool_v2_fwd_planar would write, which is never materialised.
+ * to that maximum over the volume veon_bev_pool_v2_fwd_planar would write (never materialised).
  * Needs even Z, Y, X, C % 64 == 0 and the `voxel_start` array of the prepare workspace. */
 int veon_bev_pool_v2_ds_fwd(const float* depth, const float* feat,
                             const int32_t* ranks_depth, const int32_t* ranks_feat,

@@ -554,13 +554,13 @@ k_pool_fwd_heavy(const float* __restrict__ depth, const float* __restrict__ feat
 
 // ---- fused pooling + 2x2x2 max-downsample, forward ------------------------
 // VEON's neck reduces the pooled volume 8x right away (view_transformer_raw.py:549-553:
-// view(b,c,z/2,2,y/2,2,x/2,2).amax).  Here the full-resolution volume is never written: a CTA
+// rearrange to [..., (dz dh dw)] + torch.max(dim=-1).values).  Here the full-resolution volume is never written: a CTA
 // takes one output row (b, z/2, y/2), pools its four input x-rows one after the other into a
 // shared [c][X] tile -- points of a row are one contiguous slice of the sorted rank arrays,
 // found through the per-voxel prefix `voxel_start` the preparation leaves in its workspace;
 // rows staged by cp.async, rank-ordered fma chains as in k_pool_fwd_heavy -- and folds each
 // into a running [c][X/2] maximum.  Sums are the same bits as the unfused kernel's and max is
-// exact, so the result equals pool + amax bit for bit.  Forward only (inference path).
+// exact, so the result equals pool + that reduction bit for bit.  Forward only (inference path).
 __device__ __forceinline__ float ds_max(float a, float b) { return (b > a || b != b) ? b : a; }
 constexpr int kDsThreads = 256;
 constexpr int kDsRound = 96;   // points staged per round (thread per point)
