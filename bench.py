@@ -432,7 +432,7 @@ def pipeline_leg(dev, world, rank, peak_gbs, batches=(8, 16, 32, 64), Qs=(18, 67
     import torch
     import torch.distributed as dist
     from veon_b200 import synthetic as S
-    from veon_b200.dist import all_gather_occupancy
+    from veon_b200.dist import all_gather_occupancy, reserve_sms
     from veon_b200.pipeline import lift_classify
     from veon_b200.tail import class_of_prompt
     from veon_b200.view_transformer import LSSViewTransformer
@@ -445,6 +445,11 @@ def pipeline_leg(dev, world, rank, peak_gbs, batches=(8, 16, 32, 64), Qs=(18, 67
     side = torch.cuda.Stream(dev)
     rows = []
     g = torch.Generator(device=dev).manual_seed(11 + rank)
+    # with a collective running beside the path, leave it a few SMs: the persistent grids would
+    # otherwise make its CTAs wait for a kernel boundary (veon_reserve_sms; 8 GPUs, 8 samples per
+    # step: 0.773 -> 0.751 ms)
+    reserved = 16 if world > 1 else 0
+    reserve_sms(reserved)
     for Q in Qs:
         refl = list(range(Q - 1)) if Q == 18 else [k for k, n in enumerate(SIZES) for _ in range(n)]
         cls_t = class_of_prompt(refl).to(dev)
@@ -476,13 +481,18 @@ def pipeline_leg(dev, world, rank, peak_gbs, batches=(8, 16, 32, 64), Qs=(18, 67
                 return torch.cat(labs, 0)
 
             def gather(lab):
-                # sample i -> rank i mod world (veon_b200.dist.shard_samples)
-                return all_gather_occupancy(lab, n_total) if world > 1 else lab
-            # correctness of the collective, outside the timed region
+                # sample i -> rank i mod world (veon_b200.dist.shard_samples); the gathered buffer
+                # stays rank-major (the reference's collector orders its results on the host too)
+                return all_gather_occupancy(lab, n_total, sample_order=False) if world > 1 else lab
+            # correctness of the collective, outside the timed region: this rank's block of the
+            # rank-major buffer, and the sample-ordered form against it
             lab = one()
             allv = gather(lab)
             torch.cuda.synchronize()
-            ok = bool(torch.equal(allv[rank::world], lab)) if world > 1 else True
+            ok = True
+            if world > 1:
+                ok = bool(torch.equal(allv[rank * Bp:(rank + 1) * Bp], lab)) and \
+                    bool(torch.equal(all_gather_occupancy(lab, n_total)[rank::world], lab))
             # the all-gather alone
             ag_us = None
             if world > 1:
@@ -536,6 +546,7 @@ def pipeline_leg(dev, world, rank, peak_gbs, batches=(8, 16, 32, 64), Qs=(18, 67
                          "gather_verified": ok})
             del depth, feat, img, metas
             torch.cuda.empty_cache()
+    reserve_sms(0)
     # ---- a static rig: the calibration-keyed rank cache skips the index preparation
     static_row = None
     if rank == 0 or world > 1:
@@ -622,7 +633,9 @@ def pipeline_leg(dev, world, rank, peak_gbs, batches=(8, 16, 32, 64), Qs=(18, 67
                     "bev_pool_v2 of the Q+2 channels with merge/argmax/gate in the pooling kernel's "
                     "registers, the logit volume is never written -> uint8 [B,200,200,16]) + "
                     "all_gather_occupancy over NCCL on a side stream; weak scaling, samples dealt "
-                    "round-robin; max over ranks",
+                    "round-robin (the gathered buffer stays rank-major, as the reference's collector "
+                    "orders results on the host); max over ranks",
+            "reserved_sms": reserved,
             "n_gpus": world, "rows": rows}
 
 

@@ -439,6 +439,12 @@ int veon_voxel_text_argmax_lowres(const float* feat_occ_lr, const float* text_w,
                                   void* workspace, size_t ws_bytes, const void* w_image,
                                   void* stream);
 
+/* Multi-GPU callers that overlap a collective (NCCL on another stream) with the path: the
+ * persistent grids here fill every SM, so the collective's CTAs wait for a kernel boundary.
+ * veon_reserve_sms(n) makes every persistent grid of the library launch on (SM count - n) SMs;
+ * returns the previous value; 0 (the default) uses them all.  Process-wide setting. */
+int veon_reserve_sms(int n);
+
 #ifdef __cplusplus
 }
 #endif

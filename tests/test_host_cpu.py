@@ -185,7 +185,7 @@ def test_shard_samples():
 _WORKER = r"""
 import os, sys, torch, torch.distributed as dist
 sys.path.insert(0, {root!r})
-from veon_b200.dist import shard_samples, all_gather_occupancy
+from veon_b200.dist import shard_samples, all_gather_occupancy, gathered_row
 dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
 r = dist.get_rank()
 for n in (5, 4, 1):
@@ -196,6 +196,10 @@ for n in (5, 4, 1):
     assert full.shape == (n, 3, 4, 2), full.shape
     for i in range(n):
         assert int(full[i, 0, 0, 0]) == 10 * i + 1 and bool((full[i] == 10 * i + 1).all())
+    raw = all_gather_occupancy(local, n, sample_order=False)      # rank-major, no reordering pass
+    assert raw.shape[0] == 2 * ((n + 1) // 2)
+    for i in range(n):
+        assert bool((raw[gathered_row(i, n, 2)] == 10 * i + 1).all())
 dist.destroy_process_group()
 print("rank", r, "ok")
 """

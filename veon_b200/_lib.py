@@ -25,6 +25,7 @@ _P = c_void_p
 _SIGNATURES = {
     # name: (restype, argtypes)
     "veon_abi_version": (c_int, []),
+    "veon_reserve_sms": (c_int, [c_int]),
     "veon_error_string": (c_char_p, [c_int]),
     "veon_kernel_launch_count": (ctypes.c_uint64, []),
     "veon_bev_pool_v2": (c_int, [c_int, c_int, _P, _P, _P, _P, _P, _P, _P, _P, _P]),

@@ -21,3 +21,12 @@ extern "C" const char* veon_error_string(int code) {
   if (code > 0) return cudaGetErrorString((cudaError_t)code);
   return "veon: unknown error";
 }
+
+// Leave `n` SMs free of the path's persistent grids (0 = use them all); returns the previous
+// value.  Process-wide: meant to be set once by a multi-GPU caller that overlaps collectives.
+extern "C" int veon_reserve_sms(int n) {
+  int& r = veon::reserved_sms();
+  const int old = r;
+  r = n < 0 ? 0 : n;
+  return old;
+}

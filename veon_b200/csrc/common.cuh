@@ -82,7 +82,7 @@ inline int current_device() {
   cudaGetDevice(&dev);
   return (dev >= 0 && dev < kMaxDevices) ? dev : 0;
 }
-inline int sm_count() {
+inline int sm_count_total() {
   static int n[kMaxDevices] = {};
   const int dev = current_device();
   if (n[dev] == 0) {
@@ -90,6 +90,18 @@ inline int sm_count() {
     if (n[dev] <= 0) n[dev] = 148;
   }
   return n[dev];
+}
+// SMs the caller wants left free (veon_reserve_sms): a collective running beside the path on
+// another stream (NCCL) needs somewhere to put its CTAs -- persistent grids that fill every SM
+// make it wait for a kernel boundary.
+inline int& reserved_sms() {
+  static int r = 0;
+  return r;
+}
+// what the persistent grids size themselves by
+inline int sm_count() {
+  const int n = sm_count_total() - reserved_sms();
+  return n < 1 ? 1 : n;
 }
 
 // Streaming stores/loads: the feature volume is written once and never re-read

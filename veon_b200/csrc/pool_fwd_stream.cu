@@ -628,7 +628,7 @@ size_t fwd_stream_workspace_bytes(int C) {
   const int CU = C == 64 ? 64 : 128;
   int ns = C == 64 ? 8 : 4;
   while (ns < C / CU) ns *= 2;
-  return (size_t)sm_count() * ns * sizeof(float) * kSlotRows * CU;
+  return (size_t)sm_count_total() * ns * sizeof(float) * kSlotRows * CU;
 }
 
 int launch_fwd_stream(const float* depth, const float* feat, const int32_t* rd, const int32_t* rf,

@@ -597,9 +597,7 @@ int veon_tail_tc_launch(const float* feat_occ, const float* text_w, const int32_
   p.logits = logits;
   p.B = B; p.C = C; p.Q = Q; p.Z = Z; p.Y = Y; p.X = X; p.npad = npad; p.stages = stages;
   p.free_label = free_label; p.V = V;
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int sms = sm_count();
   const int64_t n_tiles = (int64_t)B * ((V + tc::TM - 1) / tc::TM);
   const unsigned grid = (unsigned)(n_tiles < sms ? n_tiles : sms);
   if (w_image) {

@@ -11,7 +11,15 @@ import torch
 import torch.distributed as dist
 
 __all__ = ["shard_samples", "all_gather_occupancy", "shard_cameras", "all_reduce_logit_volume",
-           "lift_classify_camera_sharded"]
+           "lift_classify_camera_sharded", "reserve_sms", "gathered_row"]
+
+
+def reserve_sms(n):
+    """Leave `n` SMs free of the path's persistent grids (`veon_reserve_sms`) so that a collective
+    running on another stream finds room for its CTAs at once instead of at the next kernel
+    boundary; returns the previous value.  0 = use every SM (the default)."""
+    from . import _lib
+    return int(_lib.load().veon_reserve_sms(int(n)))
 
 
 def shard_samples(n_samples, world_size, rank):
@@ -21,10 +29,16 @@ def shard_samples(n_samples, world_size, rank):
     return list(range(rank, n_samples, world_size))
 
 
-def all_gather_occupancy(local_labels, n_samples, group=None):
+def all_gather_occupancy(local_labels, n_samples, group=None, sample_order=True):
     """local_labels: uint8 [B_local, X, Y, Z] for samples shard_samples(n_samples, G, r)
     (in that order).  Returns uint8 [n_samples, X, Y, Z] identical on every rank.
-    One all_gather_into_tensor; shards are padded to the largest B_local."""
+    One all_gather_into_tensor; shards are padded to the largest B_local.
+
+    sample_order=False: skip the device-side reordering pass and return the gathered buffer as it
+    arrives, [G * per, X, Y, Z] rank-major (sample g + j*G at row g*per + j, `gathered_row`): the
+    reference's collector puts its results into dataset order on the HOST as well
+    (mmdet `collect_results_gpu`), and the pass re-reads and re-writes the whole gathered buffer
+    in HBM while the next step's kernels run."""
     if local_labels.dtype != torch.uint8 or local_labels.dim() != 4:
         raise ValueError("local_labels must be uint8 [B_local, X, Y, Z]")
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
@@ -44,9 +58,17 @@ def all_gather_occupancy(local_labels, n_samples, group=None):
     send = send.contiguous()
     recv = torch.empty((G * per,) + vol, dtype=torch.uint8, device=local_labels.device)
     dist.all_gather_into_tensor(recv, send, group=group)
+    if not sample_order:
+        return recv
     # recv[g*per + j] is sample g + j*G  ->  put back in sample order
     recv = recv.view(G, per, *vol).transpose(0, 1).reshape(G * per, *vol)
     return recv[:n_samples].contiguous()
+
+
+def gathered_row(sample, n_samples, world_size):
+    """Row of `sample` in the rank-major buffer all_gather_occupancy(sample_order=False) returns."""
+    per = (n_samples + world_size - 1) // world_size
+    return (sample % world_size) * per + sample // world_size
 
 
 # ---- camera-group sharding (SURVEY.md 8e: fewer samples than GPUs) ---------------------------------
