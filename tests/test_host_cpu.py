@@ -59,6 +59,8 @@ def test_argument_errors_do_not_need_a_gpu():
                                               2, 64, 16, 200, 200, null, null, null, null) == -1
     assert lib.veon_pool_heavy_list_ints(1000, 10) == 12 and lib.veon_pool_heavy_list_ints(64, 10) == 4
     assert lib.veon_prepare_v2_voxel_start_offset(8, 6, 88, 16, 44, gs) % 256 == 0
+    # the SM reservation is a plain process-wide setting (no device needed)
+    assert lib.veon_reserve_sms(5) == 0 and lib.veon_reserve_sms(-3) == 5 and lib.veon_reserve_sms(0) == 0
     # the tail's entry points
     assert lib.veon_semantic_inference_3d(null, null, 1, 64, 18, 8, 100, 100, null, null, null) == -1
     # the classifier's tensor-core operand image: [W_hi ; W_lo] of every 32-channel chunk
