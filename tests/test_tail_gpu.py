@@ -253,12 +253,15 @@ def test_lift_classify_in_logit_space_matches_feature_space_and_oracle():
     assert 0.001 < float((got != 17).float().mean()) < 0.9
 
 
-@pytest.mark.parametrize("cfg_name,Q", [("small", 18), ("small", 67), ("small", 5), ("C3", 18), ("C3", 67)])
+@pytest.mark.parametrize("cfg_name,Q", [("small", 18), ("small", 67), ("small", 5), ("small", 30),
+                                        ("small", 40), ("small", 62), ("small", 94), ("C3", 18),
+                                        ("C3", 40), ("C3", 67)])
 def test_fused_lift_classify_equals_pool_then_classify(cfg_name, Q):
     """veon_lift_classify_fwd (labels straight from the pooling kernel's registers, the logit
     volume never written) against pooling the volume and running classify_logits on it: the same
     labels voxel for voxel -- the sums are the same bits and the rule is the same.  C3 density
-    exercises the CTA-per-tile kernel (tiles of 512+ points), Q = 67 the one-point-per-trip form."""
+    exercises the CTA-per-tile kernel (tiles of 512+ points); Q = 30 / 40, 62 / 67, 94 the widest
+    one-pass row and the two- and three-pass forms (rows of 32 / 48, 64 / 72, 96 channels)."""
     from veon_b200 import synthetic as S
     from veon_b200.pipeline import lift_classify
     from veon_b200.tail import class_of_prompt
