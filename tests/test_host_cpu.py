@@ -59,6 +59,17 @@ def test_argument_errors_do_not_need_a_gpu():
                                               2, 64, 16, 200, 200, null, null, null, null) == -1
     assert lib.veon_pool_heavy_list_ints(1000, 10) == 12 and lib.veon_pool_heavy_list_ints(64, 10) == 4
     assert lib.veon_prepare_v2_voxel_start_offset(8, 6, 88, 16, 44, gs) % 256 == 0
+    # fused lift + classify: argument and shape errors are decided before any launch
+    assert lib.veon_lift_classify_fwd(null, null, null, null, null, null, null, 0, 1, 20, 18, 16, 200,
+                                      200, 10, null, 17, null, null) == -1
+    buf4 = ctypes.cast((ctypes.c_float * 64)(), ctypes.c_void_p)
+    args = lambda Cp, Q, Z: (buf4, buf4, buf4, buf4, buf4, buf4, buf4, 8, 1, Cp, Q, Z, 200, 200, 10, buf4,
+                             17, buf4, null)
+    assert lib.veon_lift_classify_fwd(*args(22, 18, 16)) == -4      # Cp % 4
+    assert lib.veon_lift_classify_fwd(*args(20, 19, 16)) == -4      # Q + 2 > Cp
+    assert lib.veon_lift_classify_fwd(*args(100, 94, 16)) == -4     # Cp > 96
+    assert lib.veon_lift_classify_fwd(buf4, buf4, buf4, buf4, buf4, buf4, buf4, 8, 1, 20, 18, 3, 5, 7,
+                                      10, buf4, 17, buf4, null) == -4   # V = 105: not whole tiles
     # the SM reservation is a plain process-wide setting (no device needed)
     assert lib.veon_reserve_sms(5) == 0 and lib.veon_reserve_sms(-3) == 5 and lib.veon_reserve_sms(0) == 0
     # the tail's entry points
