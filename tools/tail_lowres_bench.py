@@ -5,6 +5,8 @@ import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
 import torch
 import torch.nn.functional as F
+from veon_b200 import _lib
+if os.environ.get("VEON_LIB"): _lib.LIB_PATH = os.environ["VEON_LIB"]
 from veon_b200.tail import (class_of_prompt, semantic_inference_3d, upsample_classify,
                             voxel_text_argmax, voxel_text_argmax_lowres)
 SIZES = [16, 1, 1, 1, 8, 1, 1, 3, 1, 1, 1, 1, 5, 3, 5, 13, 4]

@@ -108,8 +108,11 @@ constexpr int kColThreads = 128;
 // Per prompt row the thread reads the 4 x ZI low-resolution neighbours once (2*ZI/ZO loads per
 // output instead of 8), interpolates in-plane, then along z with compile-time z weights.
 // Threads run along x, so a warp's loads fall into 1-3 sectors per (row, y, z).
+#ifndef VEON_COLS_MINBLOCKS
+#define VEON_COLS_MINBLOCKS 1
+#endif
 template <int ZI, int ZO>
-__global__ void __launch_bounds__(kColThreads)
+__global__ void __launch_bounds__(kColThreads, VEON_COLS_MINBLOCKS)
 k_upsample_classify_cols(const float* __restrict__ logits, const float* __restrict__ bin_occ,
                          const int32_t* __restrict__ class_of_prompt, int Q, int Yi, int Xi,
                          int Y, int X, float sy, float sx, int free_label,
